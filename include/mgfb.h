@@ -1,0 +1,226 @@
+/* mgfb.h -- C ABI of the B200-native implementation of mgf's per-step physics hot path.
+ *
+ * This is the drop-in boundary: every entry point replaces one piece of
+ * the reference's Rust API on that path; the reference item (file:line under the mgf source
+ * tree) is cited on each declaration.  A Rust `mgf-sys` crate binds these 1:1 (see
+ * INTEGRATION.md).  POD only, no callbacks across the boundary, no unwinding: every function
+ * returns an int32 status and mgfb_last_error() gives the message.
+ *
+ * Conventions
+ *   - all reals are IEEE f32; vectors are 3 packed floats (x,y,z); quaternions are 4 floats
+ *     (s, x, y, z) like cgmath's Quaternion{s, v}; matrices are 9 floats column-major.
+ *   - a ctx owns one CUDA device, one stream and all device memory; it is NOT thread-safe.
+ *   - host pointers passed in are only read/written during the call.
+ *   - the reference's closures invoked "0..n times in a defined order" become output arrays
+ *     plus per-item counts, in the same per-item order.
+ *   - there is no CPU fallback: without a CUDA device mgfb_ctx_create fails with MGFB_ERR_CUDA.
+ */
+#ifndef MGFB_H
+#define MGFB_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MGFB_ABI_VERSION 1
+
+enum mgfb_status {
+    MGFB_OK = 0,
+    MGFB_ERR_INVALID_ARG = 1,      /* assert!(radius > 0.0) geom.rs:300,328; bad index (Rust bounds panic) */
+    MGFB_ERR_SINGULAR_INERTIA = 2, /* .invert().unwrap() physics.rs:212 */
+    MGFB_ERR_CAPACITY = 3,         /* a device work list overflowed even after growing */
+    MGFB_ERR_CUDA = 4,
+    MGFB_ERR_NAN_BOUNDS = 5,       /* AABB::combine asserts r >= 0, bounds.rs:125-127 */
+    MGFB_ERR_STATE = 6             /* call order violated (e.g. step without terrain is fine; replay without a step is not) */
+};
+
+enum mgfb_shape_kind {
+    MGFB_SPHERE = 0,    /* geom.rs:290   p = c[3], r                     */
+    MGFB_CAPSULE = 1,   /* geom.rs:316   p = a[3], d[3], r               */
+    MGFB_TRIANGLE = 2,  /* geom.rs:128   p = a[3], b[3], c[3]            */
+    MGFB_RECTANGLE = 3, /* geom.rs:216   p = c[3], u0[3], u1[3], e0, e1  */
+    MGFB_PLANE = 4,     /* geom.rs:32    p = n[3], d                     */
+    MGFB_AABB = 5,      /* geom.rs:257   p = c[3], r[3]                  */
+    MGFB_OBB = 6        /* geom.rs:272   p = c[3], r[3], q[4] (s,x,y,z)  */
+};
+
+/* A shape (optionally swept: geom.rs:357 Moving<T>(T, Vector3)). 64 bytes. */
+typedef struct mgfb_shape {
+    uint32_t kind;      /* mgfb_shape_kind */
+    float p[12];
+    float v[3];         /* Moving<T>.1 ; zero for a static shape */
+} mgfb_shape;
+
+/* collision.rs:431 Contact */
+typedef struct mgfb_contact { float a[3], b[3], n[3], t; } mgfb_contact;
+/* collision.rs:1410 LocalContact */
+typedef struct mgfb_local_contact { float local_a[3], local_b[3]; mgfb_contact global; } mgfb_local_contact;
+
+/* Which `Contacts` impl a homogeneous batch runs: one divergence-free kernel specialisation each. */
+enum mgfb_pair_kind {
+    MGFB_SPHERE_X_MSPHERE = 0,   /* collision.rs:1089 Sphere.contacts(&Moving<Sphere>)   */
+    MGFB_CAPSULE_X_MSPHERE = 1,  /* collision.rs:1145 Capsule.contacts(&Moving<Sphere>)  */
+    MGFB_SPHERE_X_MCAPSULE = 2,  /* collision.rs:1143 commute -> :1368 -> :1145          */
+    MGFB_CAPSULE_X_MCAPSULE = 3, /* collision.rs:1205                                    */
+    MGFB_PLANE_X_MSPHERE = 4,    /* collision.rs:521                                     */
+    MGFB_PLANE_X_MCAPSULE = 5,   /* collision.rs:555                                     */
+    MGFB_TRI_X_MSPHERE = 6,      /* collision.rs:610 (Poly = Triangle)                   */
+    MGFB_TRI_X_MCAPSULE = 7,     /* collision.rs:693 (Poly = Triangle)                   */
+    MGFB_RECT_X_MSPHERE = 8,     /* collision.rs:610 (Poly = Rectangle)                  */
+    MGFB_RECT_X_MCAPSULE = 9,    /* collision.rs:693 (Poly = Rectangle)                  */
+    MGFB_MCOMP_X_MCOMP = 10,     /* compound.rs:192 Moving<Component>.local_contacts(&Moving<Component>) */
+    MGFB_MCOMP_X_TRI = 11,       /* collision.rs:1490 + mesh.rs:119-137: body vs one terrain triangle,
+                                    recv = Moving component, arg = triangle already offset by mesh.x;
+                                    local_b is relative to arg.v (pass mesh.x there)     */
+    MGFB_PAIR_KIND_COUNT = 12
+};
+
+/* solver.rs:265-279 ContactConstraintParams, manifold.rs:27-39 PruningParams, world.rs:181 */
+typedef struct mgfb_config {
+    int32_t device;                 /* CUDA device ordinal */
+    float penetration_slop;         /* 0.05  solver.rs:277 */
+    float baumgarte;                /* 0.2   solver.rs:278 */
+    float persistent_threshold_sq;  /* 0.5   manifold.rs:38 */
+    float fat_margin;               /* 0.25  world.rs:181,237 */
+    uint32_t initial_body_capacity; /* 0 = default */
+    uint32_t reserved[4];
+} mgfb_config;
+void mgfb_config_default(mgfb_config* cfg);
+
+typedef struct mgfb_ctx mgfb_ctx;
+int32_t mgfb_abi_version(void);
+int32_t mgfb_ctx_create(const mgfb_config* cfg, mgfb_ctx** out);
+void mgfb_ctx_destroy(mgfb_ctx* ctx);
+const char* mgfb_last_error(const mgfb_ctx* ctx);   /* valid until the next call on ctx; ctx may be NULL */
+int32_t mgfb_synchronize(mgfb_ctx* ctx);
+
+/* ---------------- RigidBodyVec (physics.rs:141-315) ---------------- */
+/* RigidBodyVec::add_body (physics.rs:200-218) for n bodies.  shapes[i].kind in {SPHERE, CAPSULE};
+ * shapes[i].v is ignored (a new collider is Moving::sweep(collider, 0)).  world_force is the
+ * per-unit-mass force (force = world_force * mass).  *first_id receives the index of the first
+ * new body (RigidBodyRef::Dynamic(id)).  Also inserts the fat AABB (bounds + fat_margin) that
+ * the demo world keeps in its body BVH (world.rs:178-184). */
+int32_t mgfb_bodies_add(mgfb_ctx* ctx, uint32_t n, const mgfb_shape* shapes, const float* mass,
+                        const float* restitution, const float* friction, const float* world_force /* n*3 */,
+                        uint32_t* first_id);
+int32_t mgfb_bodies_count(const mgfb_ctx* ctx, uint32_t* n);
+/* pub fields x, q (physics.rs:142-143) and ConstrainedSet::get's Velocity (physics.rs:273-281).
+ * Any output pointer may be NULL. */
+int32_t mgfb_bodies_get_state(mgfb_ctx* ctx, uint32_t first, uint32_t n, float* x /* n*3 */, float* q /* n*4 */,
+                              float* v /* n*3 */, float* omega /* n*3 */);
+/* ConstrainedSet::set (physics.rs:306-314) for Dynamic(first..first+n). */
+int32_t mgfb_bodies_set_velocity(mgfb_ctx* ctx, uint32_t first, uint32_t n, const float* v, const float* omega);
+/* pub field collider: Vec<Moving<Component>> (physics.rs:154) / colliders() (:256). */
+int32_t mgfb_bodies_get_colliders(mgfb_ctx* ctx, uint32_t first, uint32_t n, mgfb_shape* out);
+/* world inverse inertia (physics.rs:152,232), 9 floats column-major per body. */
+int32_t mgfb_bodies_get_inv_moment(mgfb_ctx* ctx, uint32_t first, uint32_t n, float* out /* n*9 */);
+/* RigidBodyVec::integrate (physics.rs:222-253) */
+int32_t mgfb_integrate(mgfb_ctx* ctx, float dt);
+/* RigidBodyVec::complete_motion (physics.rs:262-269) */
+int32_t mgfb_complete_motion(mgfb_ctx* ctx);
+
+/* ---------------- Mesh (mesh.rs:32-139) ---------------- */
+/* Mesh::new + push_vert* + push_face* + set_pos(x) (mesh.rs:40-73, geom.rs:459).  Builds the
+ * device triangle index that replaces the mesh's BVH<AABB,usize>.  The mesh becomes the
+ * world's terrain (world.rs:72,150).  Face winding decides the normal (world.rs:137-141). */
+int32_t mgfb_terrain_set(mgfb_ctx* ctx, const float* verts /* nverts*3 */, uint32_t nverts,
+                         const uint32_t* faces /* nfaces*3 */, uint32_t nfaces, const float x[3]);
+
+/* ---------------- Contacts / LocalContacts (collision.rs:471,1441) ---------------- */
+/* Runs `recv[i].contacts(&arg[i], cb)` for i in 0..n on the device, one specialised kernel per
+ * pair_kind.  out holds 2 slots per pair (the most any continuous impl emits); counts[i] says
+ * how many are valid, in callback order.  For MGFB_MCOMP_* kinds `out_local` (n*2) is filled as
+ * well (may be NULL otherwise). */
+int32_t mgfb_contacts_batch(mgfb_ctx* ctx, uint32_t pair_kind, const mgfb_shape* recv, const mgfb_shape* arg,
+                            uint32_t n, mgfb_contact* out /* n*2 */, mgfb_local_contact* out_local /* n*2 or NULL */,
+                            uint32_t* counts /* n */);
+
+/* ---------------- Solver / ContactConstraint (solver.rs:53-262) ---------------- */
+/* A batch of ContactConstraint::new inputs (solver.rs:101): obj_a/obj_b, Manifold.
+ * obj < 0 means RigidBodyRef::Static{center, friction} taken from static_center/static_friction.
+ * Manifolds hold up to 4 contacts (manifold.rs:117 SmallVec<[_;4]>). */
+typedef struct mgfb_manifolds {
+    uint32_t n;
+    const int32_t* obj_a;          /* n */
+    const int32_t* obj_b;          /* n */
+    const float* static_center;    /* n*3, used when obj_b < 0 (or obj_a < 0) */
+    const float* static_friction;  /* n */
+    const float* normal;           /* n*3   Manifold.normal */
+    const float* tangent;          /* n*6   Manifold.tangent_vector[2] */
+    const uint32_t* ncontacts;     /* n     1..4 */
+    const float* local_a;          /* n*4*3 Manifold.contacts[k].0 */
+    const float* local_b;          /* n*4*3 Manifold.contacts[k].1 */
+} mgfb_manifolds;
+
+enum mgfb_solve_order {
+    /* Bit-identical to the reference's sequential Gauss-Seidel over the list as given
+     * (solver.rs:72-78): constraints are level-scheduled, level(c) = 1 + max level of any earlier
+     * constraint sharing a dynamic body; levels run in order, a level runs in parallel. */
+    MGFB_ORDER_AS_GIVEN = 0,
+    /* Throughput order: the device greedy-colours the constraint graph and solves colour by
+     * colour.  This equals the reference's sequential sweep over the list permuted colour-major;
+     * the permutation is returned so a caller (or the oracle) can reproduce it exactly. */
+    MGFB_ORDER_COLOURED = 1
+};
+
+typedef struct mgfb_solve_stats {
+    uint32_t constraints;      /* constraints solved per iteration */
+    uint32_t contacts;         /* contact points (sum of ncontacts) */
+    uint32_t groups;           /* levels or colours per iteration */
+    uint32_t iterations;
+    float solve_ms;            /* device time of the solve kernel (CUDA events) */
+    uint32_t reserved[3];
+} mgfb_solve_stats;
+
+/* Solver::new + add_constraint(ContactConstraint::new(&bodies, a, b, manifold, dt))* +
+ * solve(&mut bodies, iters) (solver.rs:59-78,101).  perm_out (n, may be NULL) receives the
+ * solve order: perm_out[k] = index in `m` of the k-th constraint solved in each iteration.
+ * normal_impulse_out (n*4, may be NULL) receives ContactState.normal_impulse after the solve. */
+int32_t mgfb_solver_solve(mgfb_ctx* ctx, const mgfb_manifolds* m, float dt, uint32_t iters, uint32_t order,
+                          uint32_t* perm_out, float* normal_impulse_out, mgfb_solve_stats* stats);
+
+/* ---------------- World::step (mgf_demo/world.rs:227-294) ---------------- */
+typedef struct mgfb_step_stats {
+    uint32_t bodies;
+    uint32_t candidate_pairs;     /* body-body AABB candidates with j < i (world.rs:261-268) */
+    uint32_t terrain_candidates;  /* (body, face) candidates from the mesh query (mesh.rs:121) */
+    uint32_t constraints;         /* ContactConstraints added to the solver */
+    uint32_t terrain_constraints;
+    uint32_t groups;              /* colours (or levels) per solver iteration */
+    uint32_t iterations;
+    uint32_t fat_refreshes;       /* bodies whose stored fat AABB was replaced (world.rs:235-238) */
+    float step_ms;                /* device time of the whole step */
+    float solve_ms;               /* device time of the solve kernel alone */
+    uint32_t overflow;            /* nonzero if a work list had to be regrown and the step rerun */
+    uint32_t reserved[5];
+} mgfb_step_stats;
+
+/* One World::step(dt) with `iters` solver iterations (the demo hard-codes 20, world.rs:293).
+ * The body-pair set is the reference's (fat-AABB query, j < i); constraints are solved in the
+ * device's colour-major order (MGFB_ORDER_COLOURED), exported by mgfb_step_constraints. */
+int32_t mgfb_step(mgfb_ctx* ctx, float dt, uint32_t iters, mgfb_step_stats* stats /* may be NULL */);
+/* Enqueue `nsteps` steps with no host synchronisation in between (stats of the last one). */
+int32_t mgfb_step_n(mgfb_ctx* ctx, float dt, uint32_t iters, uint32_t nsteps, mgfb_step_stats* stats);
+
+/* Identity of the constraints of the most recent step, in the order they were solved:
+ * body_a = i, body_b = j (< i) or -1 for terrain, face = terrain face index, sub = k-th contact
+ * of that (body, face) pair.  Arrays hold stats.constraints entries; any may be NULL. */
+int32_t mgfb_step_constraints(mgfb_ctx* ctx, uint32_t capacity, uint32_t* body_a, int32_t* body_b,
+                              uint32_t* face, uint32_t* sub, uint32_t* colour, uint32_t* count);
+
+/* Device-resident staging used by multi-GPU drivers and benchmarks: raw device pointers to the
+ * SoA body arrays (for NCCL send/recv issued by the host plumbing).  See DESIGN.md. */
+typedef struct mgfb_device_view {
+    void* x;          /* float4[n]: x.xyz, w unused */
+    void* q;          /* float4[n]: s, x, y, z */
+    void* vel;        /* 64-byte records: v[3], omega[3], inv_mass, inv_moment[9] */
+    void* collider;   /* mgfb_shape-like device records, 48 bytes: see DESIGN.md */
+    uint32_t n;
+    void* stream;     /* cudaStream_t */
+} mgfb_device_view;
+int32_t mgfb_device_view_get(mgfb_ctx* ctx, mgfb_device_view* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MGFB_H */

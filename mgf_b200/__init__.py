@@ -1,0 +1,11 @@
+"""mgf_b200 -- B200-native implementation of mgf's per-step physics hot path.
+
+Host-side mirror of the reference's API for that path (RigidBodyVec / Contacts / Solver /
+World::step), over the C ABI in include/mgfb.h.  See DESIGN.md.
+"""
+from . import _lib
+from .api import (Context, MgfbError, World, capsule, contacts_batch, make_shapes, plane, rectangle, sphere,
+                  triangle)
+
+__all__ = ["Context", "MgfbError", "World", "sphere", "capsule", "triangle", "rectangle", "plane", "make_shapes",
+           "contacts_batch", "_lib"]

@@ -1,0 +1,209 @@
+"""Host-side mirror of mgf's API for the step path, over the C ABI (include/mgfb.h).
+
+Names follow the reference: ``World`` is mgf_demo/world.rs ``World`` (bodies: RigidBodyVec,
+terrain: Mesh, ``step``); shape constructors mirror src/geom.rs.  All arithmetic of the path
+runs in the CUDA library; this module only marshals numpy arrays.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib as L
+
+
+class MgfbError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"mgfb error {code}: {msg}")
+        self.code = code
+
+
+# ---------------------------------------------------------------- shapes (geom.rs)
+def make_shapes(n):
+    return np.zeros(n, dtype=L.SHAPE_DTYPE)
+
+
+def _one(kind, p, v=(0.0, 0.0, 0.0)):
+    s = make_shapes(1)
+    s["kind"] = kind
+    s["p"][0, :len(p)] = np.asarray(p, dtype=np.float32)
+    s["v"][0] = np.asarray(v, dtype=np.float32)
+    return s
+
+
+def sphere(c, r, v=(0, 0, 0)):
+    """geom.rs:290 Sphere{c, r} (optionally Moving, geom.rs:357)."""
+    return _one(L.SPHERE, [*c, r], v)
+
+
+def capsule(a, d, r, v=(0, 0, 0)):
+    """geom.rs:316 Capsule{a, d, r}."""
+    return _one(L.CAPSULE, [*a, *d, r], v)
+
+
+def triangle(a, b, c, v=(0, 0, 0)):
+    """geom.rs:128 Triangle{a, b, c}."""
+    return _one(L.TRIANGLE, [*a, *b, *c], v)
+
+
+def rectangle(c, u0, u1, e0, e1):
+    """geom.rs:216 Rectangle{c, u, e} (u must be normalised, as in the reference)."""
+    return _one(L.RECTANGLE, [*c, *u0, *u1, e0, e1])
+
+
+def plane(n, d):
+    """geom.rs:32 Plane{n, d}."""
+    return _one(L.PLANE, [*n, d])
+
+
+class Context:
+    """One mgfb_ctx: one CUDA device, one stream, all device memory."""
+
+    def __init__(self, device=0, **cfg):
+        self.lib = L.load()
+        c = L.Config()
+        self.lib.mgfb_config_default(C.byref(c))
+        c.device = device
+        for k, v in cfg.items():
+            setattr(c, k, v)
+        h = C.c_void_p()
+        st = self.lib.mgfb_ctx_create(C.byref(c), C.byref(h))
+        if st != L.OK:
+            raise MgfbError(st, (self.lib.mgfb_last_error(None) or b"").decode())
+        self.h = h
+        self.cfg = c
+
+    def check(self, st):
+        if st != L.OK:
+            raise MgfbError(st, (self.lib.mgfb_last_error(self.h) or b"").decode())
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.mgfb_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+
+def contacts_batch(ctx, pair_kind, recv, arg, want_local=False):
+    """`recv[i].contacts(&arg[i], cb)` for a homogeneous batch (collision.rs:471).
+
+    Returns (contacts[n,2], counts[n]) and additionally local contacts[n,2] when want_local."""
+    recv = np.ascontiguousarray(recv, dtype=L.SHAPE_DTYPE)
+    arg = np.ascontiguousarray(arg, dtype=L.SHAPE_DTYPE)
+    n = len(recv)
+    assert len(arg) == n
+    out = np.zeros((n, 2), dtype=L.CONTACT_DTYPE)
+    loc = np.zeros((n, 2), dtype=L.LOCAL_CONTACT_DTYPE) if want_local else None
+    counts = np.zeros(n, dtype=np.uint32)
+    ctx.check(ctx.lib.mgfb_contacts_batch(ctx.h, pair_kind, L.ptr(recv), L.ptr(arg), n, L.ptr(out), L.ptr(loc), L.ptr(counts)))
+    return (out, counts, loc) if want_local else (out, counts)
+
+
+class World:
+    """mgf_demo/world.rs World restricted to the physics: bodies + terrain + step."""
+
+    def __init__(self, ctx=None, device=0, **cfg):
+        self.ctx = ctx or Context(device=device, **cfg)
+        self.lib = self.ctx.lib
+
+    # -- RigidBodyVec::add_body (physics.rs:200) + World::add_body (world.rs:178)
+    def add_bodies(self, shapes, mass, restitution, friction, world_force):
+        shapes = np.ascontiguousarray(shapes, dtype=L.SHAPE_DTYPE)
+        n = len(shapes)
+        f32 = lambda a, shape: np.ascontiguousarray(np.broadcast_to(np.asarray(a, dtype=np.float32), shape))
+        mass, restitution, friction = f32(mass, (n,)), f32(restitution, (n,)), f32(friction, (n,))
+        world_force = f32(world_force, (n, 3))
+        first = C.c_uint32()
+        self.ctx.check(self.lib.mgfb_bodies_add(self.ctx.h, n, L.ptr(shapes), L.ptr(mass), L.ptr(restitution), L.ptr(friction),
+                                                L.ptr(world_force), C.byref(first)))
+        return first.value
+
+    def __len__(self):
+        n = C.c_uint32()
+        self.ctx.check(self.lib.mgfb_bodies_count(self.ctx.h, C.byref(n)))
+        return n.value
+
+    # -- Mesh (mesh.rs:40-73) as the world's terrain
+    def set_terrain(self, verts, faces, x=(0.0, 0.0, 0.0)):
+        verts = np.ascontiguousarray(verts, dtype=np.float32).reshape(-1, 3)
+        faces = np.ascontiguousarray(faces, dtype=np.uint32).reshape(-1, 3)
+        x = np.asarray(x, dtype=np.float32)
+        self.ctx.check(self.lib.mgfb_terrain_set(self.ctx.h, L.ptr(verts), len(verts), L.ptr(faces), len(faces), L.ptr(x)))
+
+    def state(self, first=0, n=None):
+        n = len(self) - first if n is None else n
+        x = np.zeros((n, 3), np.float32); q = np.zeros((n, 4), np.float32)
+        v = np.zeros((n, 3), np.float32); w = np.zeros((n, 3), np.float32)
+        self.ctx.check(self.lib.mgfb_bodies_get_state(self.ctx.h, first, n, L.ptr(x), L.ptr(q), L.ptr(v), L.ptr(w)))
+        return x, q, v, w
+
+    def set_velocity(self, first, v, omega):
+        v = np.ascontiguousarray(v, dtype=np.float32).reshape(-1, 3)
+        omega = np.ascontiguousarray(omega, dtype=np.float32).reshape(-1, 3)
+        self.ctx.check(self.lib.mgfb_bodies_set_velocity(self.ctx.h, first, len(v), L.ptr(v), L.ptr(omega)))
+
+    def colliders(self, first=0, n=None):
+        n = len(self) - first if n is None else n
+        out = np.zeros(n, dtype=L.SHAPE_DTYPE)
+        self.ctx.check(self.lib.mgfb_bodies_get_colliders(self.ctx.h, first, n, L.ptr(out)))
+        return out
+
+    def inv_moment(self, first=0, n=None):
+        n = len(self) - first if n is None else n
+        out = np.zeros((n, 9), np.float32)
+        self.ctx.check(self.lib.mgfb_bodies_get_inv_moment(self.ctx.h, first, n, L.ptr(out)))
+        return out
+
+    def integrate(self, dt):
+        self.ctx.check(self.lib.mgfb_integrate(self.ctx.h, dt))
+
+    def complete_motion(self):
+        self.ctx.check(self.lib.mgfb_complete_motion(self.ctx.h))
+
+    # -- World::step (world.rs:227-294)
+    def step(self, dt, iters=20, nsteps=1):
+        st = L.StepStats()
+        self.ctx.check(self.lib.mgfb_step_n(self.ctx.h, dt, iters, nsteps, C.byref(st)))
+        return st.as_dict()
+
+    def constraints(self):
+        """Identity of the last step's constraints in solve order."""
+        cnt = C.c_uint32()
+        st = self.lib.mgfb_step_constraints(self.ctx.h, 0, None, None, None, None, None, C.byref(cnt))
+        m = cnt.value
+        a = np.zeros(m, np.uint32); b = np.zeros(m, np.int32); face = np.zeros(m, np.uint32)
+        sub = np.zeros(m, np.uint32); colour = np.zeros(m, np.uint32)
+        if m:
+            self.ctx.check(self.lib.mgfb_step_constraints(self.ctx.h, m, L.ptr(a), L.ptr(b), L.ptr(face), L.ptr(sub), L.ptr(colour),
+                                                          C.byref(cnt)))
+        elif st not in (L.OK, L.ERR_CAPACITY):
+            self.ctx.check(st)
+        return a, b, face, sub, colour
+
+    # -- Solver::solve over caller-built manifolds (solver.rs:53-79, 101)
+    def solve_manifolds(self, obj_a, obj_b, normal, tangent, ncontacts, local_a, local_b, dt, iters, order=L.ORDER_AS_GIVEN,
+                        static_center=None, static_friction=None):
+        n = len(obj_a)
+        arrs = dict(
+            obj_a=np.ascontiguousarray(obj_a, np.int32), obj_b=np.ascontiguousarray(obj_b, np.int32),
+            normal=np.ascontiguousarray(normal, np.float32).reshape(n, 3), tangent=np.ascontiguousarray(tangent, np.float32).reshape(n, 6),
+            ncontacts=np.ascontiguousarray(ncontacts, np.uint32), local_a=np.ascontiguousarray(local_a, np.float32).reshape(n, 12),
+            local_b=np.ascontiguousarray(local_b, np.float32).reshape(n, 12),
+            static_center=None if static_center is None else np.ascontiguousarray(static_center, np.float32).reshape(n, 3),
+            static_friction=None if static_friction is None else np.ascontiguousarray(static_friction, np.float32))
+        m = L.Manifolds(n=n, **{k: L.ptr(v) for k, v in arrs.items()})
+        perm = np.zeros(n, np.uint32); imp = np.zeros((n, 4), np.float32)
+        st = L.SolveStats()
+        self.ctx.check(self.lib.mgfb_solver_solve(self.ctx.h, C.byref(m), dt, iters, order, L.ptr(perm), L.ptr(imp), C.byref(st)))
+        stats = {k: getattr(st, k) for k, _ in st._fields_ if k != "reserved"}
+        return perm, imp, stats

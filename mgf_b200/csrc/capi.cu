@@ -1,0 +1,848 @@
+// capi.cu -- context, device memory arenas and the extern "C" entry points of include/mgfb.h.
+// Host code here only stages buffers and enqueues kernels; every arithmetic step of the hot
+// path runs in the kernels of kernels.cuh.  There is no CPU fallback: without a CUDA device
+// mgfb_ctx_create fails.
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+#include "../../include/mgfb.h"
+#include "kernels.cuh"
+
+using namespace mgfb;
+
+namespace {
+
+struct Buf {
+    void* p = nullptr;
+    size_t bytes = 0;
+    template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct TerrainData {
+    bool present = false;
+    Buf verts, faces, boxes, cell_count, cell_start, ent_id, ent_key, max_bits;
+    unsigned nverts = 0, nfaces = 0, table = 0, ent_cap = 0;
+    float inv_cell = 1.0f;
+    float x[3] = {0, 0, 0};
+};
+
+}  // namespace
+
+struct mgfb_ctx {
+    mgfb_config cfg;
+    int device = 0;
+    int num_sms = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    unsigned n = 0, cap = 0;
+    unsigned n_capsules = 0;
+    // body SoA
+    Buf x, q, vel, force, torque, imb, col, tight, fat;
+    // counters
+    Buf ctr;
+    Counters* h_ctr = nullptr;  // pinned
+    // work lists
+    Buf pair_list[4]; unsigned pair_cap = 0;
+    Buf tpair_list[2]; unsigned tpair_cap = 0;
+    Buf c_a, c_b, c_face, c_sub, c_la, c_lb, c_nt; unsigned contact_cap = 0;
+    // ordering scratch
+    Buf body_best, body_scratch /* mask[n] u64 + last[n] u32 */, group, group_count, group_start, perm;
+    unsigned group_cap = 0;
+    // rows
+    Buf r_ab, r_n, r_t0, r_t1, r_ra, r_rb, r_imp, r_xra, r_xrb, r_xtm; unsigned row_cap = 0, xrow_cap = 0;
+    // body grid
+    Buf cell_count, cell_start, ent_id, ent_key, scan_sums; unsigned table = 0, ent_cap = 0;
+    TerrainData terrain;
+    // user-path staging
+    Buf u_a, u_b, u_sc, u_sf, u_n, u_t, u_nc, u_la, u_lb;
+    // cooperative grid sizes
+    int coop_order = 0, coop_solve = 0;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    // last step
+    unsigned last_constraints = 0;
+    bool have_step = false;
+};
+
+namespace {
+
+#define CU(call)                                                                              \
+    do {                                                                                      \
+        cudaError_t _e = (call);                                                              \
+        if (_e != cudaSuccess) {                                                              \
+            ctx->err = std::string(#call) + ": " + cudaGetErrorString(_e);                    \
+            return MGFB_ERR_CUDA;                                                             \
+        }                                                                                     \
+    } while (0)
+#define TRY(call) do { int32_t _s = (call); if (_s != MGFB_OK) return _s; } while (0)
+
+int32_t fail(mgfb_ctx* ctx, int32_t code, const char* msg) { if (ctx) ctx->err = msg; return code; }
+
+// (re)allocate to at least `bytes`, optionally keeping the old contents
+int32_t ensure(mgfb_ctx* ctx, Buf& b, size_t bytes, bool keep = false, bool zero = false) {
+    if (b.bytes >= bytes && b.p) return MGFB_OK;
+    void* np = nullptr;
+    CU(cudaMalloc(&np, bytes));
+    if (zero) CU(cudaMemsetAsync(np, 0, bytes, ctx->stream));
+    if (keep && b.p && b.bytes) CU(cudaMemcpyAsync(np, b.p, b.bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+    if (b.p) { CU(cudaStreamSynchronize(ctx->stream)); CU(cudaFree(b.p)); }
+    b.p = np; b.bytes = bytes;
+    return MGFB_OK;
+}
+void release(Buf& b) { if (b.p) cudaFree(b.p); b.p = nullptr; b.bytes = 0; }
+
+unsigned next_pow2(unsigned v) { unsigned p = 1; while (p < v) p <<= 1; return p; }
+int grid_for(const mgfb_ctx* ctx, size_t items) {
+    size_t blocks = (items + MGFB_THREADS - 1) / MGFB_THREADS;
+    size_t cap = (size_t)ctx->num_sms * 8;
+    return (int)std::max<size_t>(1, std::min(blocks, cap));
+}
+
+BodyArrays body_arrays(const mgfb_ctx* ctx) {
+    BodyArrays B;
+    B.x = ctx->x.as<float4>(); B.q = ctx->q.as<float4>(); B.vel = ctx->vel.as<BodyVel>();
+    B.force = ctx->force.as<float4>(); B.torque = ctx->torque.as<float4>(); B.imb = ctx->imb.as<float4>();
+    B.col = ctx->col.as<Collider>(); B.tight = ctx->tight.as<Box>(); B.fat = ctx->fat.as<Box>();
+    return B;
+}
+int32_t grow_bodies(mgfb_ctx* ctx, unsigned need) {
+    if (need <= ctx->cap) return MGFB_OK;
+    unsigned nc = std::max(need, std::max(1024u, ctx->cap * 2));
+    TRY(ensure(ctx, ctx->x, (size_t)nc * sizeof(float4), true));
+    TRY(ensure(ctx, ctx->q, (size_t)nc * sizeof(float4), true));
+    TRY(ensure(ctx, ctx->vel, (size_t)nc * sizeof(BodyVel), true));
+    TRY(ensure(ctx, ctx->force, (size_t)nc * sizeof(float4), true));
+    TRY(ensure(ctx, ctx->torque, (size_t)nc * sizeof(float4), true));
+    TRY(ensure(ctx, ctx->imb, (size_t)nc * 3 * sizeof(float4), true));
+    TRY(ensure(ctx, ctx->col, (size_t)nc * sizeof(Collider), true));
+    TRY(ensure(ctx, ctx->tight, (size_t)nc * sizeof(Box), true));
+    TRY(ensure(ctx, ctx->fat, (size_t)nc * sizeof(Box), true));
+    TRY(ensure(ctx, ctx->body_best, (size_t)nc * 8, false, true));
+    TRY(ensure(ctx, ctx->body_scratch, (size_t)nc * 12, false, true));
+    ctx->cap = nc;
+    return MGFB_OK;
+}
+// Work-list capacities scale with the body count; a step that overflows one regrows and reruns.
+int32_t ensure_step_buffers(mgfb_ctx* ctx, unsigned scale) {
+    unsigned n = std::max(ctx->n, 1024u);
+    unsigned pc = n * 8 * scale, tc = n * 8 * scale, cc = n * 8 * scale;
+    if (pc > ctx->pair_cap) { for (auto& b : ctx->pair_list) TRY(ensure(ctx, b, (size_t)pc * sizeof(int2))); ctx->pair_cap = pc; }
+    if (tc > ctx->tpair_cap) { for (auto& b : ctx->tpair_list) TRY(ensure(ctx, b, (size_t)tc * sizeof(int2))); ctx->tpair_cap = tc; }
+    if (cc > ctx->contact_cap) {
+        TRY(ensure(ctx, ctx->c_a, (size_t)cc * 4)); TRY(ensure(ctx, ctx->c_b, (size_t)cc * 4));
+        TRY(ensure(ctx, ctx->c_face, (size_t)cc * 4)); TRY(ensure(ctx, ctx->c_sub, (size_t)cc * 4));
+        TRY(ensure(ctx, ctx->c_la, (size_t)cc * 16)); TRY(ensure(ctx, ctx->c_lb, (size_t)cc * 16)); TRY(ensure(ctx, ctx->c_nt, (size_t)cc * 16));
+        ctx->contact_cap = cc;
+    }
+    return MGFB_OK;
+}
+int32_t ensure_rows(mgfb_ctx* ctx, unsigned m, bool extras, unsigned groups) {
+    if (m > ctx->row_cap) {
+        unsigned rc = std::max(m, 1024u);
+        TRY(ensure(ctx, ctx->r_ab, (size_t)rc * 8)); TRY(ensure(ctx, ctx->r_n, (size_t)rc * 16)); TRY(ensure(ctx, ctx->r_t0, (size_t)rc * 16));
+        TRY(ensure(ctx, ctx->r_t1, (size_t)rc * 16)); TRY(ensure(ctx, ctx->r_ra, (size_t)rc * 16)); TRY(ensure(ctx, ctx->r_rb, (size_t)rc * 16));
+        TRY(ensure(ctx, ctx->r_imp, (size_t)rc * 4)); TRY(ensure(ctx, ctx->group, (size_t)rc * 4)); TRY(ensure(ctx, ctx->perm, (size_t)rc * 4));
+        ctx->row_cap = rc;
+    }
+    if (extras && m > ctx->xrow_cap) {
+        unsigned rc = std::max(m, 1024u);
+        TRY(ensure(ctx, ctx->r_xra, (size_t)rc * 48)); TRY(ensure(ctx, ctx->r_xrb, (size_t)rc * 48)); TRY(ensure(ctx, ctx->r_xtm, (size_t)rc * 48));
+        ctx->xrow_cap = rc;
+    }
+    if (groups > ctx->group_cap) {
+        unsigned gc = std::max(groups, 4096u);
+        TRY(ensure(ctx, ctx->group_count, (size_t)gc * 4)); TRY(ensure(ctx, ctx->group_start, ((size_t)gc + 1) * 4));
+        ctx->group_cap = gc;
+    }
+    return MGFB_OK;
+}
+int32_t ensure_grid(mgfb_ctx* ctx, unsigned scale) {
+    unsigned table = next_pow2(std::max(4096u, ctx->n * 4));
+    unsigned ecap = std::max(ctx->n, 1024u) * 12 * scale;
+    if (table > ctx->table) {
+        TRY(ensure(ctx, ctx->cell_count, (size_t)table * 4)); TRY(ensure(ctx, ctx->cell_start, ((size_t)table + 1) * 4));
+        TRY(ensure(ctx, ctx->scan_sums, ((size_t)table / SCAN_ITEMS + 2) * 4));
+        ctx->table = table;
+    }
+    if (ecap > ctx->ent_cap) { TRY(ensure(ctx, ctx->ent_id, (size_t)ecap * 4)); TRY(ensure(ctx, ctx->ent_key, (size_t)ecap * 8)); ctx->ent_cap = ecap; }
+    return MGFB_OK;
+}
+// exclusive scan of `in[0..n)` into out[0..n], out[n] = total (also stored at *total_dev if given)
+int32_t scan_u32(mgfb_ctx* ctx, const unsigned* in, unsigned* out, unsigned n, unsigned* sums, unsigned* total_dev) {
+    unsigned nb = (n + SCAN_ITEMS - 1) / SCAN_ITEMS;
+    k_scan_reduce<<<nb, 256, 0, ctx->stream>>>(in, n, sums);
+    k_scan_sums<<<1, 1024, 0, ctx->stream>>>(sums, nb, total_dev);
+    k_scan_final<<<nb, 256, 0, ctx->stream>>>(in, n, sums, out, total_dev);
+    CU(cudaGetLastError());
+    return MGFB_OK;
+}
+
+GridView body_grid(const mgfb_ctx* ctx) {
+    GridView G;
+    G.cell_count = ctx->cell_count.as<unsigned>(); G.cell_start = ctx->cell_start.as<unsigned>();
+    G.ent_id = ctx->ent_id.as<unsigned>(); G.ent_key = ctx->ent_key.as<unsigned long long>();
+    G.table_mask = ctx->table - 1; G.ent_cap = ctx->ent_cap;
+    return G;
+}
+TerrainView terrain_view(const mgfb_ctx* ctx) {
+    TerrainView T;
+    const TerrainData& t = ctx->terrain;
+    T.verts = t.verts.as<float4>(); T.faces = t.faces.as<uint4>(); T.boxes = t.boxes.as<Box>();
+    T.G.cell_count = t.cell_count.as<unsigned>(); T.G.cell_start = t.cell_start.as<unsigned>();
+    T.G.ent_id = t.ent_id.as<unsigned>(); T.G.ent_key = t.ent_key.as<unsigned long long>();
+    T.G.table_mask = t.table - 1; T.G.ent_cap = t.ent_cap;
+    T.inv_cell = t.inv_cell; T.nfaces = t.nfaces;
+    T.x = make_float4(t.x[0], t.x[1], t.x[2], 0.0f);
+    return T;
+}
+ContactList contact_list(const mgfb_ctx* ctx) {
+    ContactList L;
+    L.a = ctx->c_a.as<int>(); L.b = ctx->c_b.as<int>(); L.face = ctx->c_face.as<uint32_t>(); L.sub = ctx->c_sub.as<uint32_t>();
+    L.la = ctx->c_la.as<float4>(); L.lb = ctx->c_lb.as<float4>(); L.nt = ctx->c_nt.as<float4>();
+    return L;
+}
+ConstraintRows rows_view(const mgfb_ctx* ctx) {
+    ConstraintRows R;
+    R.ab = ctx->r_ab.as<int2>(); R.n = ctx->r_n.as<float4>(); R.t0 = ctx->r_t0.as<float4>(); R.t1 = ctx->r_t1.as<float4>();
+    R.ra = ctx->r_ra.as<float4>(); R.rb = ctx->r_rb.as<float4>(); R.impulse = ctx->r_imp.as<float>();
+    R.xra = ctx->r_xra.as<float4>(); R.xrb = ctx->r_xrb.as<float4>(); R.xtm = ctx->r_xtm.as<float4>();
+    return R;
+}
+BodyInfoView body_info(const mgfb_ctx* ctx) {
+    BodyInfoView B;
+    B.x = ctx->x.as<float4>(); B.vel = ctx->vel.as<BodyVel>(); B.col = ctx->col.as<Collider>();
+    B.force = ctx->force.as<float4>(); B.torque = ctx->torque.as<float4>();
+    return B;
+}
+OrderView order_view(const mgfb_ctx* ctx, const int* a, const int* b, const uint32_t* face, const uint32_t* sub) {
+    OrderView O;
+    O.a = a; O.b = b; O.face = face; O.sub = sub;
+    O.body_best = ctx->body_best.as<unsigned long long>();
+    O.body_mask = ctx->body_scratch.as<unsigned long long>();
+    O.body_last = reinterpret_cast<unsigned*>(ctx->body_scratch.as<unsigned long long>() + ctx->cap);
+    O.group = ctx->group.as<int>(); O.group_count = ctx->group_count.as<unsigned>(); O.gcap = ctx->group_cap;
+    return O;
+}
+Counters* dctr(const mgfb_ctx* ctx) { return ctx->ctr.as<Counters>(); }
+
+template <class K>
+int coop_blocks(const mgfb_ctx* ctx, K kernel) {
+    int per_sm = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, MGFB_THREADS, 0);
+    per_sm = std::max(1, std::min(per_sm, 4));
+    return per_sm * ctx->num_sms;
+}
+
+// order -> scan -> scatter -> build -> solve, for `m` constraints counted on the device
+// (m_ptr) or known on the host (m_host).
+int32_t enqueue_order_and_solve(mgfb_ctx* ctx, const OrderView& O, const ManifoldInput& M, const unsigned* m_ptr, unsigned m_host,
+                                unsigned m_bound, bool as_given, float dt, unsigned iters, bool time_solve) {
+    Counters* c = dctr(ctx);
+    ConstraintRows R = rows_view(ctx);
+    BodyInfoView BI = body_info(ctx);
+    unsigned* gcount = ctx->group_count.as<unsigned>();
+    unsigned* gstart = ctx->group_start.as<unsigned>();
+    unsigned* perm = ctx->perm.as<unsigned>();
+    BodyVel* vel = ctx->vel.as<BodyVel>();
+    unsigned gcap = ctx->group_cap;
+    {
+        OrderView Ov = O; bool ag = as_given; unsigned mh = m_host; const unsigned* mp = m_ptr;
+        void* args[] = {&Ov, &mp, &mh, &ag, &c};
+        CU(cudaLaunchCooperativeKernel((void*)k_order, dim3(ctx->coop_order), dim3(MGFB_THREADS), args, 0, ctx->stream));
+    }
+    k_group_scan<<<1, 1024, 0, ctx->stream>>>(gcount, gstart, c, gcap);
+    int g = grid_for(ctx, m_bound);
+    k_scatter_rows<<<g, MGFB_THREADS, 0, ctx->stream>>>(O.group, gcount, gstart, perm, m_ptr, m_host, c);
+    k_build_rows<<<g, MGFB_THREADS, 0, ctx->stream>>>(M, BI, perm, R, m_ptr, m_host, dt, ctx->cfg.baumgarte, ctx->cfg.penetration_slop, c);
+    CU(cudaGetLastError());
+    if (time_solve) CU(cudaEventRecord(ctx->ev[2], ctx->stream));
+    {
+        const unsigned* gs = gstart; unsigned it = iters;
+        void* args[] = {&R, &vel, &gs, &it, &c};
+        CU(cudaLaunchCooperativeKernel((void*)k_solve, dim3(ctx->coop_solve), dim3(MGFB_THREADS), args, 0, ctx->stream));
+    }
+    if (time_solve) CU(cudaEventRecord(ctx->ev[3], ctx->stream));
+    return MGFB_OK;
+}
+
+// One World::step.  `from_integrate` = false re-runs only the part after integration (used when
+// a work list overflowed and was regrown).
+int32_t enqueue_step(mgfb_ctx* ctx, float dt, unsigned iters, bool from_integrate, bool timed) {
+    Counters* c = dctr(ctx);
+    unsigned n = ctx->n;
+    BodyArrays B = body_arrays(ctx);
+    CU(cudaMemsetAsync(c, 0, offsetof(Counters, overflow), ctx->stream));
+    CU(cudaMemsetAsync(ctx->body_scratch.p, 0, (size_t)ctx->cap * 12, ctx->stream));
+    CU(cudaMemsetAsync(ctx->group_count.p, 0, (size_t)ctx->group_cap * 4, ctx->stream));
+    CU(cudaMemsetAsync(ctx->cell_count.p, 0, (size_t)ctx->table * 4, ctx->stream));
+    int gb = grid_for(ctx, n);
+    if (from_integrate) k_integrate<true, true, true><<<gb, MGFB_THREADS, 0, ctx->stream>>>(B, n, dt, ctx->cfg.fat_margin, c);
+    else k_integrate<false, false, true><<<gb, MGFB_THREADS, 0, ctx->stream>>>(B, n, dt, ctx->cfg.fat_margin, c);
+    // broadphase over the stored fat boxes
+    GridView G = body_grid(ctx);
+    k_grid_insert<false><<<gb, MGFB_THREADS, 0, ctx->stream>>>(B.fat, n, G, c, 0.0f);
+    TRY(scan_u32(ctx, G.cell_count, G.cell_start, ctx->table, ctx->scan_sums.as<unsigned>(), &c->grid_entries));
+    k_grid_insert<true><<<gb, MGFB_THREADS, 0, ctx->stream>>>(B.fat, n, G, c, 0.0f);
+    PairLists PL; for (int k = 0; k < 4; ++k) PL.p[k] = ctx->pair_list[k].as<int2>();
+    k_body_pairs<<<gb, MGFB_THREADS, 0, ctx->stream>>>(B.tight, B.fat, B.col, n, G, PL, ctx->pair_cap, c);
+    ContactList L = contact_list(ctx);
+    TerrainView T{};
+    if (ctx->terrain.present) {
+        T = terrain_view(ctx);
+        PairLists TL; for (int k = 0; k < 4; ++k) TL.p[k] = k < 2 ? ctx->tpair_list[k].as<int2>() : nullptr;
+        k_terrain_pairs<<<gb, MGFB_THREADS, 0, ctx->stream>>>(B.tight, B.col, n, T, TL, ctx->tpair_cap, c);
+    }
+    // narrowphase, one specialisation per shape pair
+    bool caps = ctx->n_capsules > 0, sph = ctx->n_capsules < ctx->n;
+    int gp = grid_for(ctx, (size_t)n * 4);
+    if (sph) k_narrow_bodies<0, 0><<<gp, MGFB_THREADS, 0, ctx->stream>>>(B.col, PL.p[0], L, ctx->contact_cap, c);
+    if (sph && caps) {
+        k_narrow_bodies<0, 1><<<gp, MGFB_THREADS, 0, ctx->stream>>>(B.col, PL.p[1], L, ctx->contact_cap, c);
+        k_narrow_bodies<1, 0><<<gp, MGFB_THREADS, 0, ctx->stream>>>(B.col, PL.p[2], L, ctx->contact_cap, c);
+    }
+    if (caps) k_narrow_bodies<1, 1><<<gp, MGFB_THREADS, 0, ctx->stream>>>(B.col, PL.p[3], L, ctx->contact_cap, c);
+    if (ctx->terrain.present) {
+        if (sph) k_narrow_terrain<0><<<gp, MGFB_THREADS, 0, ctx->stream>>>(B.col, ctx->tpair_list[0].as<int2>(), T, L, ctx->contact_cap, c);
+        if (caps) k_narrow_terrain<1><<<gp, MGFB_THREADS, 0, ctx->stream>>>(B.col, ctx->tpair_list[1].as<int2>(), T, L, ctx->contact_cap, c);
+    }
+    CU(cudaGetLastError());
+    // constraints: colour, build rows in solve order, solve
+    OrderView O = order_view(ctx, L.a, L.b, L.face, L.sub);
+    ManifoldInput M{};
+    M.a = L.a; M.b = L.b; M.la = L.la; M.lb = L.lb; M.nt = L.nt; M.user = false;
+    M.terrain_center = make_float4(ctx->terrain.x[0], ctx->terrain.x[1], ctx->terrain.x[2], 0.0f);
+    TRY(enqueue_order_and_solve(ctx, O, M, &c->contacts, 0, ctx->contact_cap, false, dt, iters, timed));
+    k_step_done<<<1, 1, 0, ctx->stream>>>(c);
+    CU(cudaGetLastError());
+    return MGFB_OK;
+}
+
+int32_t read_counters(mgfb_ctx* ctx) {
+    CU(cudaMemcpyAsync(ctx->h_ctr, dctr(ctx), sizeof(Counters), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return MGFB_OK;
+}
+int32_t clear_sticky(mgfb_ctx* ctx) {
+    CU(cudaMemsetAsync(reinterpret_cast<char*>(dctr(ctx)) + offsetof(Counters, overflow), 0, 8, ctx->stream));
+    return MGFB_OK;
+}
+
+Collider shape_to_collider(const mgfb_shape& s, float half_h) {
+    Collider k;
+    if (s.kind == MGFB_SPHERE) {
+        k.p0 = make_float4(s.p[0], s.p[1], s.p[2], s.p[3]);
+        k.p1 = make_float4(0, 0, 0, ibits(0));
+    } else {
+        k.p0 = make_float4(s.p[0], s.p[1], s.p[2], s.p[6]);
+        k.p1 = make_float4(s.p[3], s.p[4], s.p[5], ibits(1));
+    }
+    k.v = make_float4(s.v[0], s.v[1], s.v[2], half_h);
+    return k;
+}
+
+// physics.rs:30-46
+M3 sphere_tensor(V3 c, float r, float m) {
+    float i = 0.4f * m * r * r;
+    M3 I = m_diag(i, i, i);
+    M3 outer = mkm(c * c.x, c * c.y, c * c.z);
+    return madd(I, smul(m, msub(mscale(m_ident(), dot3(c, c)), outer)));
+}
+// physics.rs:48-84
+M3 capsule_tensor(V3 a, V3 d, float r, float m) {
+    float h = len(d);
+    float mh = m * 2.0f * r / (4.0f * r + 3.0f * h);
+    float mc = m * h / (4.0f / 3.0f * r + h);
+    float ic_x = 1.0f / 12.0f * mc * (3.0f * r * r + h * h);
+    float ic_y = 0.5f * mc * r * r;
+    float ic_z = ic_x;
+    float is_x = mh * (3.0f * r + 2.0f * h) / 4.0f * h;
+    float is_y = 4.0f / 5.0f * mh * r * r;
+    float is_z = is_x;
+    float i_x = ic_x + is_x, i_y = ic_y + is_y, i_z = ic_z + is_z;
+    M3 rot = m_from_q(q_from_arc(mk3(0.0f, 1.0f, 0.0f) * h, d));
+    M3 I = mmul(mmul(rot, m_diag(i_x, i_y, i_z)), mtrans(rot));
+    V3 disp = a + d * 0.5f;
+    M3 outer = mkm(disp * disp.x, disp * disp.y, disp * disp.z);
+    return madd(I, smul(m, msub(mscale(m_ident(), dot3(disp, disp)), outer)));
+}
+
+}  // namespace
+
+// ============================================================================ C ABI
+extern "C" {
+
+int32_t mgfb_abi_version(void) { return MGFB_ABI_VERSION; }
+
+void mgfb_config_default(mgfb_config* cfg) {
+    if (!cfg) return;
+    std::memset(cfg, 0, sizeof(*cfg));
+    cfg->device = 0;
+    cfg->penetration_slop = 0.05f;
+    cfg->baumgarte = 0.2f;
+    cfg->persistent_threshold_sq = 0.5f;
+    cfg->fat_margin = 0.25f;
+}
+
+static std::string g_create_err;
+const char* mgfb_last_error(const mgfb_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
+
+int32_t mgfb_ctx_create(const mgfb_config* cfg, mgfb_ctx** out) {
+    if (!out) return MGFB_ERR_INVALID_ARG;
+    *out = nullptr;
+    mgfb_ctx* ctx = new mgfb_ctx();
+    if (cfg) ctx->cfg = *cfg; else mgfb_config_default(&ctx->cfg);
+    ctx->device = ctx->cfg.device;
+    auto bail = [&](cudaError_t e, const char* what) {
+        g_create_err = std::string(what) + ": " + cudaGetErrorString(e);
+        delete ctx;
+        return (int32_t)MGFB_ERR_CUDA;
+    };
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) return bail(e == cudaSuccess ? cudaErrorNoDevice : e, "no CUDA device (mgfb has no CPU fallback)");
+    if ((e = cudaSetDevice(ctx->device)) != cudaSuccess) return bail(e, "cudaSetDevice");
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties(&prop, ctx->device)) != cudaSuccess) return bail(e, "cudaGetDeviceProperties");
+    ctx->num_sms = prop.multiProcessorCount;
+    if (!prop.cooperativeLaunch) return bail(cudaErrorNotSupported, "device lacks cooperative launch");
+    if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "cudaStreamCreate");
+    for (auto& ev : ctx->ev) if ((e = cudaEventCreate(&ev)) != cudaSuccess) return bail(e, "cudaEventCreate");
+    if ((e = cudaMallocHost(&ctx->h_ctr, sizeof(Counters))) != cudaSuccess) return bail(e, "cudaMallocHost");
+    if ((e = cudaMalloc(&ctx->ctr.p, sizeof(Counters))) != cudaSuccess) return bail(e, "cudaMalloc");
+    ctx->ctr.bytes = sizeof(Counters);
+    cudaMemsetAsync(ctx->ctr.p, 0, sizeof(Counters), ctx->stream);
+    ctx->coop_order = coop_blocks(ctx, k_order);
+    ctx->coop_solve = coop_blocks(ctx, k_solve);
+    int32_t s = grow_bodies(ctx, std::max(ctx->cfg.initial_body_capacity, 1024u));
+    if (s == MGFB_OK) s = ensure_rows(ctx, 1024, false, 4096);
+    if (s != MGFB_OK) { g_create_err = ctx->err; delete ctx; return s; }
+    *out = ctx;
+    return MGFB_OK;
+}
+
+void mgfb_ctx_destroy(mgfb_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    Buf* all[] = {&ctx->x, &ctx->q, &ctx->vel, &ctx->force, &ctx->torque, &ctx->imb, &ctx->col, &ctx->tight, &ctx->fat, &ctx->ctr,
+                  &ctx->pair_list[0], &ctx->pair_list[1], &ctx->pair_list[2], &ctx->pair_list[3], &ctx->tpair_list[0], &ctx->tpair_list[1],
+                  &ctx->c_a, &ctx->c_b, &ctx->c_face, &ctx->c_sub, &ctx->c_la, &ctx->c_lb, &ctx->c_nt, &ctx->body_best, &ctx->body_scratch,
+                  &ctx->group, &ctx->group_count, &ctx->group_start, &ctx->perm, &ctx->r_ab, &ctx->r_n, &ctx->r_t0, &ctx->r_t1, &ctx->r_ra,
+                  &ctx->r_rb, &ctx->r_imp, &ctx->r_xra, &ctx->r_xrb, &ctx->r_xtm, &ctx->cell_count, &ctx->cell_start, &ctx->ent_id,
+                  &ctx->ent_key, &ctx->scan_sums, &ctx->u_a, &ctx->u_b, &ctx->u_sc, &ctx->u_sf, &ctx->u_n, &ctx->u_t, &ctx->u_nc, &ctx->u_la,
+                  &ctx->u_lb, &ctx->terrain.verts, &ctx->terrain.faces, &ctx->terrain.boxes, &ctx->terrain.cell_count,
+                  &ctx->terrain.cell_start, &ctx->terrain.ent_id, &ctx->terrain.ent_key, &ctx->terrain.max_bits};
+    for (Buf* b : all) release(*b);
+    if (ctx->h_ctr) cudaFreeHost(ctx->h_ctr);
+    for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+int32_t mgfb_synchronize(mgfb_ctx* ctx) {
+    if (!ctx) return MGFB_ERR_INVALID_ARG;
+    CU(cudaStreamSynchronize(ctx->stream));
+    return MGFB_OK;
+}
+
+int32_t mgfb_bodies_count(const mgfb_ctx* ctx, uint32_t* n) {
+    if (!ctx || !n) return MGFB_ERR_INVALID_ARG;
+    *n = ctx->n;
+    return MGFB_OK;
+}
+
+int32_t mgfb_bodies_add(mgfb_ctx* ctx, uint32_t n, const mgfb_shape* shapes, const float* mass, const float* restitution,
+                        const float* friction, const float* world_force, uint32_t* first_id) {
+    if (!ctx) return MGFB_ERR_INVALID_ARG;
+    if (n == 0) { if (first_id) *first_id = ctx->n; return MGFB_OK; }
+    if (!shapes || !mass || !restitution || !friction || !world_force) return fail(ctx, MGFB_ERR_INVALID_ARG, "null input array");
+    CU(cudaSetDevice(ctx->device));
+    std::vector<float4> hx(n), hq(n), hforce(n), htorque(n), himb((size_t)n * 3);
+    std::vector<BodyVel> hvel(n);
+    std::vector<Collider> hcol(n);
+    std::vector<Box> htight(n), hfat(n);
+    unsigned ncaps = 0;
+    for (uint32_t i = 0; i < n; ++i) {
+        const mgfb_shape& s = shapes[i];
+        V3 x; Q4 q; float half_h = 0.0f; M3 tensor;
+        float m = mass[i];
+        if (s.kind == MGFB_SPHERE) {  // compound.rs:44-45
+            float r = s.p[3];
+            if (!(r > 0.0f)) return fail(ctx, MGFB_ERR_INVALID_ARG, "sphere radius must be > 0 (geom.rs:300)");
+            x = mk3(s.p[0], s.p[1], s.p[2]); q = qident();
+            V3 c0 = x + (-x);  // collider - x (physics.rs:212)
+            tensor = sphere_tensor(c0, r, m);
+        } else if (s.kind == MGFB_CAPSULE) {  // compound.rs:46-50
+            float r = s.p[6];
+            if (!(r > 0.0f)) return fail(ctx, MGFB_ERR_INVALID_ARG, "capsule radius must be > 0 (geom.rs:328)");
+            V3 a = mk3(s.p[0], s.p[1], s.p[2]), d = mk3(s.p[3], s.p[4], s.p[5]);
+            float h = len(d);
+            q = q_from_arc(mk3(0.0f, 1.0f, 0.0f) * h, d);
+            x = a + d * 0.5f; half_h = h * 0.5f;
+            tensor = capsule_tensor(a + (-x), d, r, m);
+            ncaps++;
+        } else {
+            return fail(ctx, MGFB_ERR_INVALID_ARG, "RigidBodyVec holds Component::{Sphere,Capsule} only (physics.rs:153-154)");
+        }
+        M3 inv;
+        if (!minv(tensor, &inv)) return fail(ctx, MGFB_ERR_SINGULAR_INERTIA, "inertia tensor is singular (physics.rs:212 unwrap)");
+        hx[i] = v4(x, 0.0f);
+        hq[i] = make_float4(q.s, q.v.x, q.v.y, q.v.z);
+        BodyVel bv; bv.a = make_float4(0, 0, 0, 0); bv.b = make_float4(0, 0, 1.0f / m, 0);
+        bv.c = make_float4(0, 0, 0, 0); bv.d = make_float4(0, 0, 0, 0);
+        vel_set_inertia(bv, inv);
+        hvel[i] = bv;
+        V3 wf = mk3(world_force[3 * i], world_force[3 * i + 1], world_force[3 * i + 2]);
+        hforce[i] = v4(wf * m, restitution[i]);          // physics.rs:207
+        htorque[i] = make_float4(0, 0, 0, friction[i]);
+        himb[3 * i] = v4(inv.c0, 0); himb[3 * i + 1] = v4(inv.c1, 0); himb[3 * i + 2] = v4(inv.c2, 0);
+        mgfb_shape s0 = s; s0.v[0] = s0.v[1] = s0.v[2] = 0.0f;  // Moving::sweep(collider, 0)
+        hcol[i] = shape_to_collider(s0, half_h);
+        V3 tc, tr;
+        if (!swept_bounds(hcol[i], &tc, &tr)) return fail(ctx, MGFB_ERR_NAN_BOUNDS, "AABB::combine: r >= 0 violated (bounds.rs:125)");
+        htight[i].c = v4(tc, 0); htight[i].r = v4(tr, 0);
+        float mg = ctx->cfg.fat_margin;
+        hfat[i].c = v4(tc, 0); hfat[i].r = v4(tr + mk3(mg, mg, mg), 0);  // world.rs:180-181
+    }
+    unsigned first = ctx->n;
+    TRY(grow_bodies(ctx, first + n));
+    auto up = [&](Buf& b, const void* src, size_t elem, size_t per = 1) {
+        return cudaMemcpyAsync(reinterpret_cast<char*>(b.p) + (size_t)first * elem * per, src, (size_t)n * elem * per, cudaMemcpyHostToDevice, ctx->stream);
+    };
+    CU(up(ctx->x, hx.data(), sizeof(float4))); CU(up(ctx->q, hq.data(), sizeof(float4))); CU(up(ctx->vel, hvel.data(), sizeof(BodyVel)));
+    CU(up(ctx->force, hforce.data(), sizeof(float4))); CU(up(ctx->torque, htorque.data(), sizeof(float4)));
+    CU(up(ctx->imb, himb.data(), sizeof(float4), 3)); CU(up(ctx->col, hcol.data(), sizeof(Collider)));
+    CU(up(ctx->tight, htight.data(), sizeof(Box))); CU(up(ctx->fat, hfat.data(), sizeof(Box)));
+    CU(cudaStreamSynchronize(ctx->stream));
+    ctx->n += n; ctx->n_capsules += ncaps;
+    if (first_id) *first_id = first;
+    return MGFB_OK;
+}
+
+int32_t mgfb_bodies_get_state(mgfb_ctx* ctx, uint32_t first, uint32_t n, float* x, float* q, float* v, float* omega) {
+    if (!ctx || (uint64_t)first + n > ctx->n) return fail(ctx, MGFB_ERR_INVALID_ARG, "body range out of bounds");
+    if (n == 0) return MGFB_OK;
+    CU(cudaSetDevice(ctx->device));
+    std::vector<float4> tmp(n);
+    if (x) {
+        CU(cudaMemcpyAsync(tmp.data(), ctx->x.as<float4>() + first, (size_t)n * 16, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        for (uint32_t i = 0; i < n; ++i) { x[3 * i] = tmp[i].x; x[3 * i + 1] = tmp[i].y; x[3 * i + 2] = tmp[i].z; }
+    }
+    if (q) {
+        CU(cudaMemcpyAsync(tmp.data(), ctx->q.as<float4>() + first, (size_t)n * 16, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        for (uint32_t i = 0; i < n; ++i) { q[4 * i] = tmp[i].x; q[4 * i + 1] = tmp[i].y; q[4 * i + 2] = tmp[i].z; q[4 * i + 3] = tmp[i].w; }
+    }
+    if (v || omega) {
+        std::vector<BodyVel> bv(n);
+        CU(cudaMemcpyAsync(bv.data(), ctx->vel.as<BodyVel>() + first, (size_t)n * sizeof(BodyVel), cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        for (uint32_t i = 0; i < n; ++i) {
+            if (v) { v[3 * i] = bv[i].a.x; v[3 * i + 1] = bv[i].a.y; v[3 * i + 2] = bv[i].a.z; }
+            if (omega) { omega[3 * i] = bv[i].a.w; omega[3 * i + 1] = bv[i].b.x; omega[3 * i + 2] = bv[i].b.y; }
+        }
+    }
+    return MGFB_OK;
+}
+
+int32_t mgfb_bodies_set_velocity(mgfb_ctx* ctx, uint32_t first, uint32_t n, const float* v, const float* omega) {
+    if (!ctx || (uint64_t)first + n > ctx->n || !v || !omega) return fail(ctx, MGFB_ERR_INVALID_ARG, "bad arguments");
+    if (n == 0) return MGFB_OK;
+    CU(cudaSetDevice(ctx->device));
+    std::vector<BodyVel> bv(n);
+    CU(cudaMemcpyAsync(bv.data(), ctx->vel.as<BodyVel>() + first, (size_t)n * sizeof(BodyVel), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    for (uint32_t i = 0; i < n; ++i) {
+        bv[i].a = make_float4(v[3 * i], v[3 * i + 1], v[3 * i + 2], omega[3 * i]);
+        bv[i].b.x = omega[3 * i + 1]; bv[i].b.y = omega[3 * i + 2];
+    }
+    CU(cudaMemcpyAsync(ctx->vel.as<BodyVel>() + first, bv.data(), (size_t)n * sizeof(BodyVel), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return MGFB_OK;
+}
+
+int32_t mgfb_bodies_get_colliders(mgfb_ctx* ctx, uint32_t first, uint32_t n, mgfb_shape* out) {
+    if (!ctx || (uint64_t)first + n > ctx->n || !out) return fail(ctx, MGFB_ERR_INVALID_ARG, "bad arguments");
+    if (n == 0) return MGFB_OK;
+    CU(cudaSetDevice(ctx->device));
+    std::vector<Collider> hc(n);
+    CU(cudaMemcpyAsync(hc.data(), ctx->col.as<Collider>() + first, (size_t)n * sizeof(Collider), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    for (uint32_t i = 0; i < n; ++i) {
+        mgfb_shape s; std::memset(&s, 0, sizeof(s));
+        const Collider& k = hc[i];
+        if (col_kind(k) == 0) { s.kind = MGFB_SPHERE; s.p[0] = k.p0.x; s.p[1] = k.p0.y; s.p[2] = k.p0.z; s.p[3] = k.p0.w; }
+        else { s.kind = MGFB_CAPSULE; s.p[0] = k.p0.x; s.p[1] = k.p0.y; s.p[2] = k.p0.z; s.p[3] = k.p1.x; s.p[4] = k.p1.y; s.p[5] = k.p1.z; s.p[6] = k.p0.w; }
+        s.v[0] = k.v.x; s.v[1] = k.v.y; s.v[2] = k.v.z;
+        out[i] = s;
+    }
+    return MGFB_OK;
+}
+
+int32_t mgfb_bodies_get_inv_moment(mgfb_ctx* ctx, uint32_t first, uint32_t n, float* out) {
+    if (!ctx || (uint64_t)first + n > ctx->n || !out) return fail(ctx, MGFB_ERR_INVALID_ARG, "bad arguments");
+    if (n == 0) return MGFB_OK;
+    CU(cudaSetDevice(ctx->device));
+    std::vector<BodyVel> bv(n);
+    CU(cudaMemcpyAsync(bv.data(), ctx->vel.as<BodyVel>() + first, (size_t)n * sizeof(BodyVel), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    for (uint32_t i = 0; i < n; ++i) {
+        M3 I = vel_inertia(bv[i]);
+        float* o = out + 9 * i;
+        o[0] = I.c0.x; o[1] = I.c0.y; o[2] = I.c0.z; o[3] = I.c1.x; o[4] = I.c1.y; o[5] = I.c1.z; o[6] = I.c2.x; o[7] = I.c2.y; o[8] = I.c2.z;
+    }
+    return MGFB_OK;
+}
+
+int32_t mgfb_integrate(mgfb_ctx* ctx, float dt) {
+    if (!ctx) return MGFB_ERR_INVALID_ARG;
+    if (ctx->n == 0) return MGFB_OK;
+    CU(cudaSetDevice(ctx->device));
+    k_integrate<false, true, false><<<grid_for(ctx, ctx->n), MGFB_THREADS, 0, ctx->stream>>>(body_arrays(ctx), ctx->n, dt, ctx->cfg.fat_margin, dctr(ctx));
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(ctx->stream));
+    return MGFB_OK;
+}
+
+int32_t mgfb_complete_motion(mgfb_ctx* ctx) {
+    if (!ctx) return MGFB_ERR_INVALID_ARG;
+    if (ctx->n == 0) return MGFB_OK;
+    CU(cudaSetDevice(ctx->device));
+    k_integrate<true, false, false><<<grid_for(ctx, ctx->n), MGFB_THREADS, 0, ctx->stream>>>(body_arrays(ctx), ctx->n, 0.0f, ctx->cfg.fat_margin, dctr(ctx));
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(ctx->stream));
+    return MGFB_OK;
+}
+
+int32_t mgfb_terrain_set(mgfb_ctx* ctx, const float* verts, uint32_t nverts, const uint32_t* faces, uint32_t nfaces, const float x[3]) {
+    if (!ctx || !verts || !faces || !x) return fail(ctx, MGFB_ERR_INVALID_ARG, "null terrain arrays");
+    if (nfaces >= (1u << 30)) return fail(ctx, MGFB_ERR_INVALID_ARG, "too many faces");
+    for (uint32_t i = 0; i < nfaces * 3; ++i)
+        if (faces[i] >= nverts) return fail(ctx, MGFB_ERR_INVALID_ARG, "face index out of range (Rust bounds panic, mesh.rs:65-67)");
+    CU(cudaSetDevice(ctx->device));
+    TerrainData& t = ctx->terrain;
+    t.present = false;
+    t.nverts = nverts; t.nfaces = nfaces;
+    t.x[0] = x[0]; t.x[1] = x[1]; t.x[2] = x[2];
+    if (nfaces == 0) return MGFB_OK;
+    std::vector<float4> hv(nverts); std::vector<uint4> hf(nfaces);
+    for (uint32_t i = 0; i < nverts; ++i) hv[i] = make_float4(verts[3 * i], verts[3 * i + 1], verts[3 * i + 2], 0);
+    for (uint32_t i = 0; i < nfaces; ++i) hf[i] = make_uint4(faces[3 * i], faces[3 * i + 1], faces[3 * i + 2], 0);
+    TRY(ensure(ctx, t.verts, (size_t)nverts * 16)); TRY(ensure(ctx, t.faces, (size_t)nfaces * 16)); TRY(ensure(ctx, t.boxes, (size_t)nfaces * sizeof(Box)));
+    TRY(ensure(ctx, t.max_bits, 16));
+    CU(cudaMemcpyAsync(t.verts.p, hv.data(), (size_t)nverts * 16, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(t.faces.p, hf.data(), (size_t)nfaces * 16, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemsetAsync(t.max_bits.p, 0, 16, ctx->stream));
+    k_face_boxes<<<(nfaces + 255) / 256, 256, 0, ctx->stream>>>(t.verts.as<float4>(), t.faces.as<uint4>(), nfaces, t.boxes.as<Box>(), t.max_bits.as<unsigned>());
+    CU(cudaGetLastError());
+    unsigned bits = 0;
+    CU(cudaMemcpyAsync(&bits, t.max_bits.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    float cell; std::memcpy(&cell, &bits, 4);
+    if (!(cell > 0.0f) || !std::isfinite(cell)) cell = 1.0f;
+    t.inv_cell = 1.0f / cell;
+    t.table = next_pow2(std::max(1024u, nfaces * 4));
+    TRY(ensure(ctx, t.cell_count, (size_t)t.table * 4)); TRY(ensure(ctx, t.cell_start, ((size_t)t.table + 1) * 4));
+    Buf sums; TRY(ensure(ctx, sums, ((size_t)t.table / SCAN_ITEMS + 2) * 4));
+    // entries: count first (the count pass needs no entry storage), then size exactly
+    GridView G; G.cell_count = t.cell_count.as<unsigned>(); G.cell_start = t.cell_start.as<unsigned>();
+    G.ent_id = nullptr; G.ent_key = nullptr; G.table_mask = t.table - 1; G.ent_cap = 0;
+    CU(cudaMemsetAsync(t.cell_count.p, 0, (size_t)t.table * 4, ctx->stream));
+    int gb = grid_for(ctx, nfaces);
+    k_grid_insert<false><<<gb, MGFB_THREADS, 0, ctx->stream>>>(t.boxes.as<Box>(), nfaces, G, dctr(ctx), t.inv_cell);
+    TRY(scan_u32(ctx, G.cell_count, G.cell_start, t.table, sums.as<unsigned>(), t.max_bits.as<unsigned>() + 1));
+    unsigned total = 0;
+    CU(cudaMemcpyAsync(&total, t.max_bits.as<unsigned>() + 1, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    t.ent_cap = std::max(total, 1u);
+    TRY(ensure(ctx, t.ent_id, (size_t)t.ent_cap * 4)); TRY(ensure(ctx, t.ent_key, (size_t)t.ent_cap * 8));
+    G.ent_id = t.ent_id.as<unsigned>(); G.ent_key = t.ent_key.as<unsigned long long>(); G.ent_cap = t.ent_cap;
+    k_grid_insert<true><<<gb, MGFB_THREADS, 0, ctx->stream>>>(t.boxes.as<Box>(), nfaces, G, dctr(ctx), t.inv_cell);
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(ctx->stream));
+    release(sums);
+    t.present = true;
+    return MGFB_OK;
+}
+
+static void fill_step_stats(mgfb_ctx* ctx, mgfb_step_stats* st, unsigned iters, bool timed, unsigned overflowed) {
+    const Counters& h = *ctx->h_ctr;
+    std::memset(st, 0, sizeof(*st));
+    st->bodies = ctx->n;
+    st->candidate_pairs = h.pairs[0] + h.pairs[1] + h.pairs[2] + h.pairs[3];
+    st->terrain_candidates = h.tpairs[0] + h.tpairs[1];
+    st->constraints = h.contacts;
+    st->terrain_constraints = h.tcontacts;
+    st->groups = h.ngroups;
+    st->iterations = iters;
+    st->fat_refreshes = h.fat_refreshes;
+    st->overflow = overflowed;
+    if (timed) {
+        cudaEventElapsedTime(&st->step_ms, ctx->ev[0], ctx->ev[1]);
+        cudaEventElapsedTime(&st->solve_ms, ctx->ev[2], ctx->ev[3]);
+    }
+}
+
+int32_t mgfb_step_n(mgfb_ctx* ctx, float dt, uint32_t iters, uint32_t nsteps, mgfb_step_stats* stats) {
+    if (!ctx) return MGFB_ERR_INVALID_ARG;
+    if (!(dt > 0.0f)) return fail(ctx, MGFB_ERR_INVALID_ARG, "dt must be > 0");
+    CU(cudaSetDevice(ctx->device));
+    if (ctx->n == 0 || nsteps == 0) { if (stats) std::memset(stats, 0, sizeof(*stats)); return MGFB_OK; }
+    unsigned scale = 1, overflowed = 0;
+    TRY(ensure_step_buffers(ctx, scale));
+    TRY(ensure_grid(ctx, scale));
+    TRY(ensure_rows(ctx, ctx->contact_cap, false, 4096));
+    TRY(read_counters(ctx));
+    unsigned done0 = ctx->h_ctr->steps_done, target = done0 + nsteps;
+    bool resume_after_integrate = false;
+    for (int attempt = 0; attempt < 8; ++attempt) {
+        unsigned todo = target - ctx->h_ctr->steps_done;
+        for (unsigned s = 0; s < todo; ++s) {
+            bool last = (s + 1 == todo);
+            if (last) CU(cudaEventRecord(ctx->ev[0], ctx->stream));
+            TRY(enqueue_step(ctx, dt, iters, !(s == 0 && resume_after_integrate), last));
+            if (last) CU(cudaEventRecord(ctx->ev[1], ctx->stream));
+        }
+        TRY(read_counters(ctx));
+        if (ctx->h_ctr->nan_bounds) { clear_sticky(ctx); return fail(ctx, MGFB_ERR_NAN_BOUNDS, "AABB::combine: r >= 0 violated (NaN in body state; bounds.rs:125-127)"); }
+        if (!ctx->h_ctr->overflow) break;
+        // a work list overflowed inside step (steps_done): that step already integrated.
+        overflowed |= ctx->h_ctr->overflow;
+        if (ctx->h_ctr->overflow & OVF_GROUPS) { clear_sticky(ctx); return fail(ctx, MGFB_ERR_CAPACITY, "more constraint groups than group capacity"); }
+        scale *= 2;
+        TRY(clear_sticky(ctx));
+        TRY(ensure_step_buffers(ctx, scale));
+        TRY(ensure_grid(ctx, scale));
+        TRY(ensure_rows(ctx, ctx->contact_cap, false, 4096));
+        resume_after_integrate = true;
+        if (attempt == 7) return fail(ctx, MGFB_ERR_CAPACITY, "work lists still overflow after growing 128x");
+    }
+    ctx->last_constraints = ctx->h_ctr->contacts;
+    ctx->have_step = true;
+    if (stats) fill_step_stats(ctx, stats, iters, true, overflowed);
+    return MGFB_OK;
+}
+
+int32_t mgfb_step(mgfb_ctx* ctx, float dt, uint32_t iters, mgfb_step_stats* stats) { return mgfb_step_n(ctx, dt, iters, 1, stats); }
+
+int32_t mgfb_step_constraints(mgfb_ctx* ctx, uint32_t capacity, uint32_t* body_a, int32_t* body_b, uint32_t* face, uint32_t* sub,
+                              uint32_t* colour, uint32_t* count) {
+    if (!ctx) return MGFB_ERR_INVALID_ARG;
+    if (!ctx->have_step) return fail(ctx, MGFB_ERR_STATE, "no step has been run");
+    CU(cudaSetDevice(ctx->device));
+    unsigned m = ctx->last_constraints;
+    if (count) *count = m;
+    if (capacity < m) return fail(ctx, MGFB_ERR_CAPACITY, "output arrays too small");
+    if (m == 0) return MGFB_OK;
+    std::vector<unsigned> perm(m), hface(m), hsub(m); std::vector<int> ha(m), hb(m), hg(m);
+    auto dl = [&](void* dst, const Buf& b) { return cudaMemcpyAsync(dst, b.p, (size_t)m * 4, cudaMemcpyDeviceToHost, ctx->stream); };
+    CU(dl(perm.data(), ctx->perm)); CU(dl(ha.data(), ctx->c_a)); CU(dl(hb.data(), ctx->c_b)); CU(dl(hface.data(), ctx->c_face));
+    CU(dl(hsub.data(), ctx->c_sub)); CU(dl(hg.data(), ctx->group));
+    CU(cudaStreamSynchronize(ctx->stream));
+    for (unsigned r = 0; r < m; ++r) {
+        unsigned k = perm[r];
+        if (body_a) body_a[r] = (uint32_t)ha[k];
+        if (body_b) body_b[r] = hb[k];
+        if (face) face[r] = hface[k];
+        if (sub) sub[r] = hsub[k];
+        if (colour) colour[r] = (uint32_t)hg[k];
+    }
+    return MGFB_OK;
+}
+
+int32_t mgfb_solver_solve(mgfb_ctx* ctx, const mgfb_manifolds* m, float dt, uint32_t iters, uint32_t order, uint32_t* perm_out,
+                          float* normal_impulse_out, mgfb_solve_stats* stats) {
+    if (!ctx || !m) return MGFB_ERR_INVALID_ARG;
+    if (order > MGFB_ORDER_COLOURED) return fail(ctx, MGFB_ERR_INVALID_ARG, "unknown solve order");
+    if (!(dt > 0.0f)) return fail(ctx, MGFB_ERR_INVALID_ARG, "dt must be > 0");
+    unsigned n = m->n;
+    if (stats) std::memset(stats, 0, sizeof(*stats));
+    if (n == 0) return MGFB_OK;
+    if (!m->obj_a || !m->obj_b || !m->normal || !m->tangent || !m->ncontacts || !m->local_a || !m->local_b)
+        return fail(ctx, MGFB_ERR_INVALID_ARG, "null manifold array");
+    CU(cudaSetDevice(ctx->device));
+    unsigned total_contacts = 0;
+    std::vector<float> zc, zf;
+    for (unsigned k = 0; k < n; ++k) {
+        int a = m->obj_a[k], b = m->obj_b[k];
+        if (a >= (int)ctx->n || b >= (int)ctx->n) return fail(ctx, MGFB_ERR_INVALID_ARG, "constraint refers to a body that does not exist");
+        if (a >= 0 && a == b) return fail(ctx, MGFB_ERR_INVALID_ARG, "constraint joins a body to itself");
+        if ((a < 0 || b < 0) && (!m->static_center || !m->static_friction)) return fail(ctx, MGFB_ERR_INVALID_ARG, "static body without static_center/static_friction");
+        if (m->ncontacts[k] < 1 || m->ncontacts[k] > 4) return fail(ctx, MGFB_ERR_INVALID_ARG, "ncontacts must be 1..4");
+        total_contacts += m->ncontacts[k];
+    }
+    const float* sc = m->static_center; const float* sf = m->static_friction;
+    if (!sc) { zc.assign((size_t)n * 3, 0.0f); sc = zc.data(); }
+    if (!sf) { zf.assign(n, 0.0f); sf = zf.data(); }
+    bool as_given = order == MGFB_ORDER_AS_GIVEN;
+    TRY(ensure_rows(ctx, n, true, as_given ? n + 1 : 4096));
+    auto up = [&](Buf& b, const void* src, size_t bytes) -> int32_t {
+        TRY(ensure(ctx, b, bytes));
+        CU(cudaMemcpyAsync(b.p, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+        return MGFB_OK;
+    };
+    TRY(up(ctx->u_a, m->obj_a, (size_t)n * 4)); TRY(up(ctx->u_b, m->obj_b, (size_t)n * 4));
+    TRY(up(ctx->u_sc, sc, (size_t)n * 12)); TRY(up(ctx->u_sf, sf, (size_t)n * 4));
+    TRY(up(ctx->u_n, m->normal, (size_t)n * 12)); TRY(up(ctx->u_t, m->tangent, (size_t)n * 24));
+    TRY(up(ctx->u_nc, m->ncontacts, (size_t)n * 4));
+    TRY(up(ctx->u_la, m->local_a, (size_t)n * 48)); TRY(up(ctx->u_lb, m->local_b, (size_t)n * 48));
+    Counters* c = dctr(ctx);
+    CU(cudaMemsetAsync(c, 0, offsetof(Counters, overflow), ctx->stream));
+    CU(cudaMemsetAsync(ctx->body_scratch.p, 0, (size_t)ctx->cap * 12, ctx->stream));
+    CU(cudaMemsetAsync(ctx->group_count.p, 0, (size_t)ctx->group_cap * 4, ctx->stream));
+    // a static endpoint may sit in slot a: the ordering only cares about dynamic endpoints,
+    // so present (dynamic, other) to it with the dynamic one first.
+    std::vector<int> oa(n), ob(n);
+    for (unsigned k = 0; k < n; ++k) {
+        int a = m->obj_a[k], b = m->obj_b[k];
+        if (a < 0) { oa[k] = b; ob[k] = -1; } else { oa[k] = a; ob[k] = b; }
+        if (oa[k] < 0) return fail(ctx, MGFB_ERR_INVALID_ARG, "constraint between two static bodies");
+    }
+    Buf d_oa, d_ob;
+    TRY(up(d_oa, oa.data(), (size_t)n * 4)); TRY(up(d_ob, ob.data(), (size_t)n * 4));
+    OrderView O = order_view(ctx, d_oa.as<int>(), d_ob.as<int>(), nullptr, nullptr);
+    ManifoldInput M{};
+    M.user = true; M.a = ctx->u_a.as<int>(); M.b = ctx->u_b.as<int>();
+    M.normal = ctx->u_n.as<float>(); M.tangent = ctx->u_t.as<float>(); M.ncontacts = ctx->u_nc.as<uint32_t>();
+    M.ula = ctx->u_la.as<float>(); M.ulb = ctx->u_lb.as<float>(); M.static_center = ctx->u_sc.as<float>(); M.static_friction = ctx->u_sf.as<float>();
+    int32_t s = enqueue_order_and_solve(ctx, O, M, nullptr, n, n, as_given, dt, iters, true);
+    if (s == MGFB_OK) s = read_counters(ctx);
+    release(d_oa); release(d_ob);
+    TRY(s);
+    if (ctx->h_ctr->overflow) { clear_sticky(ctx); return fail(ctx, MGFB_ERR_CAPACITY, "group capacity exceeded"); }
+    std::vector<unsigned> perm(n);
+    CU(cudaMemcpyAsync(perm.data(), ctx->perm.p, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    std::vector<float> imp(n); std::vector<float4> xtm;
+    CU(cudaMemcpyAsync(imp.data(), ctx->r_imp.p, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (normal_impulse_out && total_contacts > n) {
+        xtm.resize((size_t)n * 3);
+        CU(cudaMemcpyAsync(xtm.data(), ctx->r_xtm.p, (size_t)n * 48, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (perm_out) std::memcpy(perm_out, perm.data(), (size_t)n * 4);
+    if (normal_impulse_out) {
+        std::memset(normal_impulse_out, 0, (size_t)n * 16);
+        for (unsigned r = 0; r < n; ++r) {
+            unsigned k = perm[r];
+            normal_impulse_out[4 * k] = imp[r];
+            for (unsigned cidx = 1; cidx < m->ncontacts[k]; ++cidx) normal_impulse_out[4 * k + cidx] = xtm[(size_t)r * 3 + cidx - 1].z;
+        }
+    }
+    if (stats) {
+        stats->constraints = n; stats->contacts = total_contacts; stats->groups = ctx->h_ctr->ngroups; stats->iterations = iters;
+        cudaEventElapsedTime(&stats->solve_ms, ctx->ev[2], ctx->ev[3]);
+    }
+    return MGFB_OK;
+}
+
+int32_t mgfb_device_view_get(mgfb_ctx* ctx, mgfb_device_view* out) {
+    if (!ctx || !out) return MGFB_ERR_INVALID_ARG;
+    out->x = ctx->x.p; out->q = ctx->q.p; out->vel = ctx->vel.p; out->collider = ctx->col.p; out->n = ctx->n; out->stream = ctx->stream;
+    return MGFB_OK;
+}
+
+}  // extern "C"
+
+#include "batch.cuh"

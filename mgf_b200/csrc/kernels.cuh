@@ -1,0 +1,769 @@
+// kernels.cuh -- the device kernels of the step path (see DESIGN.md section 4 for the list,
+// the HBM bytes each moves and the roofline that bounds it).  All kernels are grid-stride
+// over counts that live in device memory, so a whole step is enqueued without a single
+// host round trip.
+#pragma once
+#include "layout.cuh"
+
+namespace mgfb {
+
+#define MGFB_THREADS 256
+
+// Device-resident counters of one step.  Zeroed (except the sticky ones) at step start.
+struct Counters {
+    unsigned pairs[4];       // body-pair candidates per kind: [ki*2+kj], k = 0 sphere / 1 capsule
+    unsigned tpairs[2];      // (body, face) terrain candidates per body kind
+    unsigned contacts;       // contacts emitted = constraints
+    unsigned tcontacts;      // of which terrain
+    unsigned grid_entries;
+    unsigned fat_refreshes;
+    unsigned max_fat_bits;   // float bits of the largest fat-box diameter (cell size)
+    unsigned ngroups;
+    unsigned remaining;      // uncoloured constraints
+    unsigned bar;            // grid barrier arrival counter
+    unsigned rounds;         // colouring rounds taken
+    unsigned pad0;
+    // sticky until the host clears them
+    unsigned overflow;       // bit0 pairs, bit1 tpairs, bit2 contacts, bit3 grid entries
+    unsigned nan_bounds;     // AABB::combine assert (bounds.rs:125-127)
+    unsigned steps_done;
+    unsigned pad1;
+};
+enum { OVF_PAIRS = 1, OVF_TPAIRS = 2, OVF_CONTACTS = 4, OVF_GRID = 8, OVF_GROUPS = 16 };
+struct PairLists { int2* p[4]; };
+
+// ---------------------------------------------------------------- grid barrier
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+// All CTAs of a cooperative launch.  `bar` is zero at kernel entry; phase counts barriers.
+__device__ __forceinline__ void grid_barrier(unsigned* bar, unsigned& phase) {
+    __syncthreads();
+    phase++;
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(bar, 1u);
+        unsigned target = phase * gridDim.x;
+        while (ld_acquire_u32(bar) < target) { }
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+// ---------------------------------------------------------------- integrate (+ AABB)
+// physics.rs:262-269 complete_motion, :222-253 integrate, bounds.rs:60-68 swept AABB,
+// world.rs:235-238 fat-box refresh -- one pass, 272 algorithmic bytes per body.
+struct BodyArrays {
+    float4* x;        // position
+    float4* q;        // s, x, y, z
+    BodyVel* vel;
+    float4* force;    // force.xyz, restitution
+    float4* torque;   // torque.xyz, friction
+    float4* imb;      // inv_moment_body: 3 float4 per body (columns)
+    Collider* col;
+    Box* tight;
+    Box* fat;
+};
+
+HD void collider_bounds(const Collider& k, V3* c, V3* r) {
+    if (col_kind(k) == 0) {  // bounds.rs:170-177
+        *c = f4v(k.p0); *r = mk3(k.p0.w, k.p0.w, k.p0.w);
+    } else {                  // bounds.rs:179-188
+        V3 d = f4v(k.p1);
+        float rr = k.p0.w + len(d) * 0.5f;
+        *c = f4v(k.p0) + d * 0.5f; *r = mk3(rr, rr, rr);
+    }
+}
+// bounds.rs:60-68 + :113-130; returns false when the reference's assert!(r >= 0) would fire.
+HD bool swept_bounds(const Collider& k, V3* oc, V3* orr) {
+    V3 sc, sr; collider_bounds(k, &sc, &sr);
+    V3 ec = sc + f4v(k.v);
+    V3 lo = mk3(fminf(sc.x - sr.x, ec.x - sr.x), fminf(sc.y - sr.y, ec.y - sr.y), fminf(sc.z - sr.z, ec.z - sr.z));
+    V3 hi = mk3(fmaxf(sc.x + sr.x, ec.x + sr.x), fmaxf(sc.y + sr.y, ec.y + sr.y), fmaxf(sc.z + sr.z, ec.z + sr.z));
+    V3 r = (hi - lo) / 2.0f;
+    *oc = (hi + lo) / 2.0f; *orr = r;
+    return (r.x >= 0.0f) && (r.y >= 0.0f) && (r.z >= 0.0f);
+}
+HD bool box_contains_pt(V3 c, V3 r, V3 p) {  // collision.rs:114-120
+    return fabsf(c.x - p.x) <= r.x && fabsf(c.y - p.y) <= r.y && fabsf(c.z - p.z) <= r.z;
+}
+HD bool box_overlaps(V3 ac, V3 ar, V3 bc, V3 br) {  // collision.rs:22-29 (closed)
+    return fabsf(ac.x - bc.x) <= (ar.x + br.x) && fabsf(ac.y - bc.y) <= (ar.y + br.y) && fabsf(ac.z - bc.z) <= (ar.z + br.z);
+}
+
+template <bool COMPLETE, bool INTEGRATE, bool BOUNDS>
+__global__ void __launch_bounds__(MGFB_THREADS) k_integrate(BodyArrays B, unsigned n, float dt, float margin, Counters* ctr) {
+    if (ctr->overflow | ctr->nan_bounds) return;  // poisoned: the host will resume from steps_done
+    float my_fat = 0.0f;
+    unsigned refreshed = 0;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        Collider k = B.col[i];
+        V3 xi = f4v(B.x[i]);
+        if (COMPLETE) {  // x += collider.delta()
+            xi = xi + f4v(k.v);
+            B.x[i] = v4(xi, 0.0f);
+        }
+        if (INTEGRATE) {
+            float4 q4 = B.q[i];
+            Q4 qi = mkq(q4.x, mk3(q4.y, q4.z, q4.w));
+            BodyVel bv = B.vel[i];
+            V3 v = mk3(bv.a.x, bv.a.y, bv.a.z), w = mk3(bv.a.w, bv.b.x, bv.b.y);
+            float inv_mass = bv.b.z;
+            // q <- normalize(q + (Quat(0, w*dt) * 0.5) * q)                       physics.rs:226-227
+            qi = qunit(qadd(qi, qmul(qscale(mkq(0.0f, w * dt), 0.5f), qi)));
+            // I^-1 <- R * I^-1_body * R^T                                        physics.rs:231-232
+            M3 R = m_from_q(qi);
+            M3 Ib = mkm(f4v(B.imb[3 * i]), f4v(B.imb[3 * i + 1]), f4v(B.imb[3 * i + 2]));
+            M3 I = mmul(mmul(R, Ib), mtrans(R));
+            float4 f4 = B.force[i], t4 = B.torque[i];
+            v = v + f4v(f4) * inv_mass * dt;                                    // physics.rs:236
+            w = w + mmulv(I, f4v(t4)) * dt;                                     // physics.rs:240
+            bv.a = make_float4(v.x, v.y, v.z, w.x);
+            bv.b.x = w.y; bv.b.y = w.z;
+            vel_set_inertia(bv, I);
+            B.vel[i] = bv;
+            B.q[i] = make_float4(qi.s, qi.v.x, qi.v.y, qi.v.z);
+            // collider <- sweep(construct(x, q), v*dt)                          physics.rs:243-250
+            if (col_kind(k) == 0) {
+                k.p0 = v4(xi, k.p0.w);
+            } else {
+                V3 d = qrot(qi, mk3(0.0f, 1.0f, 0.0f) * k.v.w);                 // compound.rs:222-225
+                k.p0 = v4(xi + (-d), k.p0.w);
+                V3 d2 = d * 2.0f;
+                k.p1 = make_float4(d2.x, d2.y, d2.z, k.p1.w);
+            }
+            V3 delta = v * dt;
+            k.v = make_float4(delta.x, delta.y, delta.z, k.v.w);
+            B.col[i] = k;
+        }
+        if (BOUNDS) {
+            V3 tc, tr;
+            if (!swept_bounds(k, &tc, &tr)) atomicOr(&ctr->nan_bounds, 1u);
+            Box tb; tb.c = v4(tc, 0.0f); tb.r = v4(tr, 0.0f);
+            B.tight[i] = tb;
+            Box fb = B.fat[i];
+            V3 fc = f4v(fb.c), fr = f4v(fb.r);
+            // world.rs:235: if !stored.contains(&bounds)  (collision.rs:129-135)
+            if (!(box_contains_pt(fc, fr, tc + tr) && box_contains_pt(fc, fr, tc + (-tr)))) {
+                fr = tr + mk3(margin, margin, margin);   // bounds.rs:91-98
+                fb.c = v4(tc, 0.0f); fb.r = v4(fr, 0.0f);
+                B.fat[i] = fb;
+                refreshed++;
+            }
+            my_fat = fmaxf(my_fat, 2.0f * fmaxf(fr.x, fmaxf(fr.y, fr.z)));
+        }
+    }
+    if (BOUNDS) {
+        for (int o = 16; o > 0; o >>= 1) {
+            my_fat = fmaxf(my_fat, __shfl_xor_sync(0xffffffffu, my_fat, o));
+            refreshed += __shfl_xor_sync(0xffffffffu, refreshed, o);
+        }
+        if ((threadIdx.x & 31) == 0) {
+            atomicMax(&ctr->max_fat_bits, __float_as_uint(my_fat));
+            if (refreshed) atomicAdd(&ctr->fat_refreshes, refreshed);
+        }
+    }
+}
+
+// ---------------------------------------------------------------- uniform hashed grid
+struct GridView {
+    unsigned* cell_count;   // [T]   (consumed by the fill)
+    unsigned* cell_start;   // [T+1] exclusive scan of counts
+    unsigned* ent_id;       // [E]
+    unsigned long long* ent_key;  // [E] packed cell coordinates
+    unsigned table_mask;    // T - 1
+    unsigned ent_cap;
+};
+__device__ __forceinline__ int cell_coord(float x, float inv) {
+    float f = floorf(x * inv);
+    f = fminf(fmaxf(f, -1048576.0f), 1048575.0f);
+    return (int)f;
+}
+__device__ __forceinline__ unsigned long long cell_key(int x, int y, int z) {
+    return ((unsigned long long)(x & 0x1FFFFF) << 42) | ((unsigned long long)(y & 0x1FFFFF) << 21) | (unsigned long long)(z & 0x1FFFFF);
+}
+__device__ __forceinline__ unsigned long long mix64(unsigned long long z) {  // splitmix64 finaliser (bijective)
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    return z ^ (z >> 31);
+}
+__device__ __forceinline__ unsigned cell_hash(unsigned long long key, unsigned mask) { return (unsigned)(mix64(key) >> 20) & mask; }
+struct CellRange { int lo[3], hi[3]; };
+// Cells covered by a stored box.  `slop` widens the range of INSERTED boxes by a few ulps so
+// that a closed, rounded overlap test that passes always finds a shared cell.
+__device__ __forceinline__ CellRange cell_range(V3 c, V3 r, float inv, bool slop) {
+    CellRange cr;
+    float cs[3] = {c.x, c.y, c.z}, rs[3] = {r.x, r.y, r.z};
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        float lo = cs[a] - rs[a], hi = cs[a] + rs[a];
+        if (slop) { float e = (fabsf(cs[a]) + rs[a]) * 2e-6f + 1e-30f; lo -= e; hi += e; }
+        cr.lo[a] = cell_coord(lo, inv); cr.hi[a] = cell_coord(hi, inv);
+    }
+    return cr;
+}
+__device__ __forceinline__ float grid_inv_cell(const Counters* ctr) {
+    float s = __uint_as_float(ctr->max_fat_bits);
+    if (!(s > 0.0f)) s = 1.0f;
+    return 1.0f / s;
+}
+
+// pass 1: count entries per hashed cell; pass 2 (FILL): write them.
+template <bool FILL>
+__global__ void __launch_bounds__(MGFB_THREADS) k_grid_insert(const Box* __restrict__ boxes, unsigned n, GridView G, Counters* ctr, float fixed_inv) {
+    if (ctr->overflow | ctr->nan_bounds) return;
+    float inv = fixed_inv > 0.0f ? fixed_inv : grid_inv_cell(ctr);
+    for (unsigned j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+        Box b = boxes[j];
+        CellRange cr = cell_range(f4v(b.c), f4v(b.r), inv, true);
+        for (int x = cr.lo[0]; x <= cr.hi[0]; ++x)
+            for (int y = cr.lo[1]; y <= cr.hi[1]; ++y)
+                for (int z = cr.lo[2]; z <= cr.hi[2]; ++z) {
+                    unsigned long long key = cell_key(x, y, z);
+                    unsigned h = cell_hash(key, G.table_mask);
+                    if (!FILL) {
+                        atomicAdd(&G.cell_count[h], 1u);
+                    } else {
+                        unsigned pos = G.cell_start[h] + (atomicSub(&G.cell_count[h], 1u) - 1u);
+                        if (pos < G.ent_cap) { G.ent_id[pos] = j; G.ent_key[pos] = key; }
+                        else atomicOr(&ctr->overflow, (unsigned)OVF_GRID);
+                    }
+                }
+    }
+}
+
+// Body-pair sweep: P = {(i, j): j < i, tight_i overlaps fat_j}  (world.rs:261-268).
+__global__ void __launch_bounds__(MGFB_THREADS) k_body_pairs(const Box* __restrict__ tight, const Box* __restrict__ fat,
+                                                            const Collider* __restrict__ col, unsigned n, GridView G,
+                                                            PairLists lists, unsigned cap, Counters* ctr) {
+    if (ctr->overflow | ctr->nan_bounds) return;
+    float inv = grid_inv_cell(ctr);
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        if (i == 0) continue;  // world.rs:256
+        Box tb = tight[i];
+        V3 tc = f4v(tb.c), tr = f4v(tb.r);
+        CellRange qi = cell_range(tc, tr, inv, false);
+        int ki = col_kind(col[i]);
+        for (int x = qi.lo[0]; x <= qi.hi[0]; ++x)
+            for (int y = qi.lo[1]; y <= qi.hi[1]; ++y)
+                for (int z = qi.lo[2]; z <= qi.hi[2]; ++z) {
+                    unsigned long long key = cell_key(x, y, z);
+                    unsigned h = cell_hash(key, G.table_mask);
+                    unsigned e0 = G.cell_start[h], e1 = G.cell_start[h + 1];
+                    for (unsigned e = e0; e < e1; ++e) {
+                        if (G.ent_key[e] != key) continue;
+                        unsigned j = G.ent_id[e];
+                        if (j >= i) continue;  // world.rs:266
+                        Box fb = fat[j];
+                        V3 fc = f4v(fb.c), fr = f4v(fb.r);
+                        if (!box_overlaps(tc, tr, fc, fr)) continue;
+                        // report the pair only from the first cell both ranges share
+                        CellRange qj = cell_range(fc, fr, inv, true);
+                        if (x != max(qi.lo[0], qj.lo[0]) || y != max(qi.lo[1], qj.lo[1]) || z != max(qi.lo[2], qj.lo[2])) continue;
+                        int kind = ki * 2 + col_kind(col[j]);
+                        unsigned pos = atomicAdd(&ctr->pairs[kind], 1u);
+                        if (pos < cap) lists.p[kind][pos] = make_int2((int)i, (int)j);
+                        else atomicOr(&ctr->overflow, (unsigned)OVF_PAIRS);
+                    }
+                }
+    }
+}
+
+// Terrain candidates: Mesh::contacts' BVH query (mesh.rs:121) as a grid lookup over the
+// triangles' AABBs (bounds.rs:137-152, precomputed).
+struct TerrainView {
+    const float4* verts;   // xyz
+    const uint4* faces;    // a, b, c, unused
+    const Box* boxes;      // per face, mesh-local
+    GridView G;
+    float inv_cell;
+    unsigned nfaces;
+    float4 x;              // Mesh.x
+};
+__global__ void __launch_bounds__(MGFB_THREADS) k_terrain_pairs(const Box* __restrict__ tight, const Collider* __restrict__ col, unsigned n,
+                                                               TerrainView T, PairLists lists, unsigned cap, Counters* ctr) {
+    if (ctr->overflow | ctr->nan_bounds) return;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        Box tb = tight[i];
+        V3 tc = f4v(tb.c) + (-f4v(T.x));  // rhs.bounds() - self.x  (mesh.rs:121)
+        V3 tr = f4v(tb.r);
+        CellRange qi = cell_range(tc, tr, T.inv_cell, false);
+        int ki = col_kind(col[i]);
+        for (int x = qi.lo[0]; x <= qi.hi[0]; ++x)
+            for (int y = qi.lo[1]; y <= qi.hi[1]; ++y)
+                for (int z = qi.lo[2]; z <= qi.hi[2]; ++z) {
+                    unsigned long long key = cell_key(x, y, z);
+                    unsigned h = cell_hash(key, T.G.table_mask);
+                    unsigned e0 = T.G.cell_start[h], e1 = T.G.cell_start[h + 1];
+                    for (unsigned e = e0; e < e1; ++e) {
+                        if (T.G.ent_key[e] != key) continue;
+                        unsigned f = T.G.ent_id[e];
+                        Box fb = T.boxes[f];
+                        V3 fc = f4v(fb.c), fr = f4v(fb.r);
+                        if (!box_overlaps(tc, tr, fc, fr)) continue;
+                        CellRange qj = cell_range(fc, fr, T.inv_cell, true);
+                        if (x != max(qi.lo[0], qj.lo[0]) || y != max(qi.lo[1], qj.lo[1]) || z != max(qi.lo[2], qj.lo[2])) continue;
+                        unsigned pos = atomicAdd(&ctr->tpairs[ki], 1u);
+                        if (pos < cap) lists.p[ki][pos] = make_int2((int)i, (int)f);
+                        else atomicOr(&ctr->overflow, (unsigned)OVF_TPAIRS);
+                    }
+                }
+    }
+}
+// per-face AABB, bounds.rs:137-152 (centroid-centred box, not the tight one)
+__global__ void k_face_boxes(const float4* verts, const uint4* faces, unsigned nfaces, Box* out, unsigned* max_bits) {
+    unsigned f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= nfaces) return;
+    uint4 fc = faces[f];
+    V3 a = f4v(verts[fc.x]), b = f4v(verts[fc.y]), c = f4v(verts[fc.z]);
+    V3 ctr = (a + b + c) / 3.0f;
+    float d0 = fmaxf(fabsf(a.x - ctr.x), fmaxf(fabsf(b.x - ctr.x), fabsf(c.x - ctr.x)));
+    float d1 = fmaxf(fabsf(a.y - ctr.y), fmaxf(fabsf(b.y - ctr.y), fabsf(c.y - ctr.y)));
+    float d2 = fmaxf(fabsf(a.z - ctr.z), fmaxf(fabsf(b.z - ctr.z), fabsf(c.z - ctr.z)));
+    Box bx; bx.c = v4(ctr, 0.0f); bx.r = make_float4(d0, d1, d2, 0.0f);
+    out[f] = bx;
+    atomicMax(max_bits, __float_as_uint(2.0f * fmaxf(d0, fmaxf(d1, d2))));
+}
+
+// ---------------------------------------------------------------- narrowphase
+__device__ __forceinline__ void emit_contact(const ContactList& L, unsigned cap, Counters* ctr, int a, int b, unsigned face,
+                                             unsigned sub, V3 la, V3 lb, V3 n, float t) {
+    unsigned k = atomicAdd(&ctr->contacts, 1u);
+    if (k >= cap) { atomicOr(&ctr->overflow, (unsigned)OVF_CONTACTS); return; }
+    L.a[k] = a; L.b[k] = b; L.face[k] = face; L.sub[k] = sub;
+    L.la[k] = v4(la, n.x); L.lb[k] = v4(lb, n.y); L.nt[k] = make_float4(n.z, t, 0.0f, 0.0f);
+}
+
+// Body i (receiver, kind KI) vs body j (argument, kind KJ): compound.rs:192-207 resolved per
+// SURVEY Appendix B to ga.contacts(&Moving(gb, vb - va)) + frame shift (collision.rs:1387).
+template <int KI, int KJ>
+__device__ __forceinline__ bool body_pair_contact(const Collider& A, const Collider& Bc, Hit* h, V3* la, V3* lb) {
+    V3 va = f4v(A.v), vb = f4v(Bc.v);
+    V3 vrel = vb - va;
+    bool ok;
+    if (KI == 0 && KJ == 0) ok = sphere_msphere(col_sphere(A), col_sphere(Bc), vrel, h);
+    else if (KI == 1 && KJ == 0) ok = capsule_msphere(col_capsule(A), col_sphere(Bc), vrel, h);
+    else if (KI == 0 && KJ == 1) ok = sphere_mcapsule(col_sphere(A), col_capsule(Bc), vrel, h);
+    else ok = capsule_mcapsule(col_capsule(A), col_capsule(Bc), vrel, h);
+    if (!ok) return false;
+    h->a = h->a + va * h->t;
+    h->b = h->b + va * h->t;
+    *la = h->a + (-(col_center(A) + va * h->t));
+    *lb = h->b + (-(col_center(Bc) + vb * h->t));
+    return true;
+}
+template <int KI, int KJ>
+__global__ void __launch_bounds__(MGFB_THREADS) k_narrow_bodies(const Collider* __restrict__ col, const int2* __restrict__ pairs,
+                                                               ContactList L, unsigned cap, Counters* ctr) {
+    if (ctr->overflow | ctr->nan_bounds) return;
+    unsigned np = ctr->pairs[KI * 2 + KJ];
+    for (unsigned p = blockIdx.x * blockDim.x + threadIdx.x; p < np; p += gridDim.x * blockDim.x) {
+        int2 ij = pairs[p];
+        Collider A = col[ij.x], Bc = col[ij.y];
+        Hit h; V3 la, lb;
+        if (!body_pair_contact<KI, KJ>(A, Bc, &h, &la, &lb)) continue;
+        // ContactPruner with one contact -> Manifold::from(pruner): normal = (0 + n) / 1  (manifold.rs:135-140)
+        V3 n = (zero3() + h.n) / 1.0f;
+        emit_contact(L, cap, ctr, ij.x, ij.y, 0u, 0u, la, lb, n, h.t);
+    }
+}
+// Body i vs terrain face f: mesh.rs:119-137 + collision.rs:1490-1506 + compound.rs:179-190.
+// Leaf hit has a on the triangle, b on the body, n = triangle normal; the delivered
+// LocalContact has local_a = body point - body centre(t), local_b = triangle point - mesh.x,
+// normal = -n_tri.
+template <int KI>
+__device__ __forceinline__ int body_tri_contacts(const Collider& A, const Tri& tri, V3 mesh_x, Hit out[2], V3 la[2], V3 lb[2]) {
+    Hits hs; hs.n = 0;
+    V3 v = f4v(A.v);
+    if (KI == 0) { Hit h; if (poly_msphere(tri, col_sphere(A), v, &h)) push(hs, h); }
+    else hs = poly_mcapsule(tri, col_capsule(A), v);
+    for (int k = 0; k < hs.n; ++k) {
+        Hit c = hs.h[k];
+        V3 a_c = col_center(A) + v * c.t;
+        la[k] = c.b + (-a_c);
+        lb[k] = c.a + (-mesh_x);
+        out[k] = flip(c);
+    }
+    return hs.n;
+}
+template <int KI>
+__global__ void __launch_bounds__(MGFB_THREADS) k_narrow_terrain(const Collider* __restrict__ col, const int2* __restrict__ pairs,
+                                                                TerrainView T, ContactList L, unsigned cap, Counters* ctr) {
+    if (ctr->overflow | ctr->nan_bounds) return;
+    unsigned np = ctr->tpairs[KI];
+    V3 mx = f4v(T.x);
+    for (unsigned p = blockIdx.x * blockDim.x + threadIdx.x; p < np; p += gridDim.x * blockDim.x) {
+        int2 bf = pairs[p];
+        Collider A = col[bf.x];
+        uint4 fc = T.faces[bf.y];
+        Tri tri; tri.a = f4v(T.verts[fc.x]) + mx; tri.b = f4v(T.verts[fc.y]) + mx; tri.c = f4v(T.verts[fc.z]) + mx;
+        Hit hs[2]; V3 la[2], lb[2];
+        int nh = body_tri_contacts<KI>(A, tri, mx, hs, la, lb);
+        for (int k = 0; k < nh; ++k) {
+            emit_contact(L, cap, ctr, bf.x, -1, (unsigned)bf.y, (unsigned)k, la[k], lb[k], hs[k].n, hs[k].t);
+            atomicAdd(&ctr->tcontacts, 1u);
+        }
+    }
+}
+
+// ---------------------------------------------------------------- constraint ordering
+// Jones-Plassmann greedy edge colouring (MGFB_ORDER_COLOURED) or order-preserving level
+// scheduling (MGFB_ORDER_AS_GIVEN) of the constraint graph, in one cooperative kernel.
+struct OrderView {
+    const int* a; const int* b;        // constraint endpoints (b < 0: static)
+    const uint32_t* face; const uint32_t* sub;  // identity for the priority hash (may be NULL)
+    unsigned long long* body_best;     // [nbodies]
+    unsigned long long* body_mask;     // [nbodies] colours used (coloured mode)
+    unsigned* body_last;               // [nbodies] last level / highest overflow colour
+    int* group;                        // [m] out: colour / level, -1 = unassigned
+    unsigned* group_count;             // [gcap]
+    unsigned gcap;
+};
+__device__ __forceinline__ unsigned long long order_key(const OrderView& O, unsigned k, bool as_given) {
+    if (as_given) return ~(unsigned long long)k;             // earlier in the list = higher priority
+    if (!O.face) { unsigned long long key = mix64((unsigned long long)k + 1ULL); return key ? key : 1ULL; }
+    int a = O.a[k], b = O.b[k];
+    unsigned lo = b >= 0 ? (unsigned)b : (0x80000000u | ((O.face ? O.face[k] : 0u) << 1) | (O.sub ? O.sub[k] : 0u));
+    unsigned long long key = mix64(((unsigned long long)(unsigned)a << 32) | lo);
+    return key ? key : 1ULL;
+}
+__global__ void __launch_bounds__(MGFB_THREADS) k_order(OrderView O, const unsigned* m_ptr, unsigned m_host, bool as_given, Counters* ctr) {
+    if (ctr->overflow | ctr->nan_bounds) return;
+    const unsigned m = m_ptr ? *m_ptr : m_host;
+    const unsigned tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+    unsigned phase = 0;
+    for (unsigned k = tid; k < m; k += nth) __stcg(&O.group[k], -1);
+    if (tid == 0) { ctr->remaining = m; ctr->ngroups = 0; ctr->rounds = 0; }
+    grid_barrier(&ctr->bar, phase);
+    for (unsigned round = 0; round < 100000u; ++round) {
+        if (__ldcg(&ctr->remaining) == 0) break;
+        // propose
+        for (unsigned k = tid; k < m; k += nth) {
+            if (__ldcg(&O.group[k]) >= 0) continue;
+            unsigned long long key = order_key(O, k, as_given);
+            atomicMax(&O.body_best[O.a[k]], key);
+            int b = O.b[k];
+            if (b >= 0) atomicMax(&O.body_best[b], key);
+        }
+        grid_barrier(&ctr->bar, phase);
+        // commit
+        unsigned done = 0;
+        for (unsigned k = tid; k < m; k += nth) {
+            if (__ldcg(&O.group[k]) >= 0) continue;
+            unsigned long long key = order_key(O, k, as_given);
+            int a = O.a[k], b = O.b[k];
+            if (__ldcg(&O.body_best[a]) != key) continue;
+            if (b >= 0 && __ldcg(&O.body_best[b]) != key) continue;
+            unsigned g;
+            if (as_given) {
+                unsigned la = __ldcg(&O.body_last[a]);
+                unsigned lb = b >= 0 ? __ldcg(&O.body_last[b]) : 0u;
+                g = max(la, lb);             // level index = (1 + max) - 1
+                __stcg(&O.body_last[a], g + 1);
+                if (b >= 0) __stcg(&O.body_last[b], g + 1);
+            } else {
+                unsigned long long ma = __ldcg(&O.body_mask[a]);
+                unsigned long long mb = b >= 0 ? __ldcg(&O.body_mask[b]) : 0ULL;
+                unsigned long long fr = ~(ma | mb);
+                if (fr) {
+                    g = (unsigned)__ffsll((long long)fr) - 1u;
+                    __stcg(&O.body_mask[a], ma | (1ULL << g));
+                    if (b >= 0) __stcg(&O.body_mask[b], mb | (1ULL << g));
+                } else {  // more than 64 colours around one body: stack further colours above
+                    unsigned la = max(__ldcg(&O.body_last[a]), 63u);
+                    unsigned lb = b >= 0 ? max(__ldcg(&O.body_last[b]), 63u) : 63u;
+                    g = max(la, lb) + 1u;
+                    __stcg(&O.body_last[a], g);
+                    if (b >= 0) __stcg(&O.body_last[b], g);
+                }
+            }
+            __stcg(&O.group[k], (int)g);
+            __stcg(&O.body_best[a], 0ULL);
+            if (b >= 0) __stcg(&O.body_best[b], 0ULL);
+            if (g < O.gcap) atomicAdd(&O.group_count[g], 1u);
+            else atomicOr(&ctr->overflow, (unsigned)OVF_GROUPS);
+            atomicMax(&ctr->ngroups, g + 1u);
+            done++;
+        }
+        for (int o = 16; o > 0; o >>= 1) done += __shfl_xor_sync(0xffffffffu, done, o);
+        if ((threadIdx.x & 31) == 0 && done) atomicSub(&ctr->remaining, done);
+        if (tid == 0) ctr->rounds = round + 1;
+        grid_barrier(&ctr->bar, phase);
+    }
+}
+// Exclusive scan of group_count[0..ngroups) into group_start (single block, chunked).
+__global__ void __launch_bounds__(1024) k_group_scan(const unsigned* count, unsigned* start, Counters* ctr, unsigned gcap) {
+    __shared__ unsigned warp_sums[32];
+    __shared__ unsigned carry;
+    unsigned n = min(ctr->ngroups, gcap);
+    if (threadIdx.x == 0) { carry = 0; ctr->bar = 0; }  // re-arm the grid barrier for the solve kernel
+    __syncthreads();
+    for (unsigned base = 0; base < n; base += 1024) {
+        unsigned i = base + threadIdx.x;
+        unsigned v = i < n ? count[i] : 0u;
+        unsigned x = v;
+        for (int o = 1; o < 32; o <<= 1) { unsigned y = __shfl_up_sync(0xffffffffu, x, o); if ((threadIdx.x & 31) >= o) x += y; }
+        if ((threadIdx.x & 31) == 31) warp_sums[threadIdx.x >> 5] = x;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            unsigned w = warp_sums[threadIdx.x], ws = w;
+            for (int o = 1; o < 32; o <<= 1) { unsigned y = __shfl_up_sync(0xffffffffu, ws, o); if (threadIdx.x >= o) ws += y; }
+            warp_sums[threadIdx.x] = ws - w;
+        }
+        __syncthreads();
+        unsigned excl = carry + warp_sums[threadIdx.x >> 5] + x - v;
+        if (i < n) start[i] = excl;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = excl + v;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) start[n] = carry;
+}
+// row = group_start[g] + (slot within the group); perm[row] = k
+__global__ void __launch_bounds__(MGFB_THREADS) k_scatter_rows(const int* __restrict__ group, unsigned* group_count, const unsigned* __restrict__ group_start,
+                                                              unsigned* perm, const unsigned* m_ptr, unsigned m_host, Counters* ctr) {
+    if (ctr->overflow | ctr->nan_bounds) return;
+    const unsigned m = m_ptr ? *m_ptr : m_host;
+    for (unsigned k = blockIdx.x * blockDim.x + threadIdx.x; k < m; k += gridDim.x * blockDim.x) {
+        int g = group[k];
+        unsigned row = group_start[g] + (atomicSub(&group_count[g], 1u) - 1u);
+        perm[row] = k;
+    }
+}
+
+// ---------------------------------------------------------------- ContactConstraint::new
+// solver.rs:101-191.  Input manifolds come either from the step's ContactList (one contact,
+// tangents from compute_basis) or from user arrays (mgfb_solver_solve).
+struct ManifoldInput {
+    const int* a; const int* b;
+    const float4* la; const float4* lb; const float4* nt;   // step path (ContactList)
+    // user path
+    const float* normal; const float* tangent; const uint32_t* ncontacts;
+    const float* ula; const float* ulb; const float* static_center; const float* static_friction;
+    float4 terrain_center;   // step path: Static{center: terrain.center(), friction: 0}
+    bool user;
+};
+struct BodyInfoView {
+    const float4* x; const BodyVel* vel; const Collider* col; const float4* force; const float4* torque;
+};
+HD void basis_from_normal(V3 n, V3* t0, V3* t1) {  // geom.rs:1138-1145
+    V3 b = fabsf(n.x) >= 0.57735f ? mk3(n.y, -n.x, 0.0f) : mk3(0.0f, n.z, -n.y);
+    b = unit(b);
+    *t0 = b; *t1 = cross3(n, b);
+}
+struct BodyState { V3 v, w, x; float inv_mass, rest, fric; M3 I; };
+__device__ __forceinline__ BodyState load_body_info(const BodyInfoView& B, int i) {
+    BodyState s;
+    BodyVel r = B.vel[i];
+    s.v = mk3(r.a.x, r.a.y, r.a.z); s.w = mk3(r.a.w, r.b.x, r.b.y); s.inv_mass = r.b.z; s.I = vel_inertia(r);
+    s.x = f4v(B.x[i]) + f4v(B.col[i].v);   // physics.rs:282  x + collider.delta()
+    s.rest = B.force[i].w; s.fric = B.torque[i].w;
+    return s;
+}
+__device__ __forceinline__ BodyState static_body_info(V3 center, float fric) {  // physics.rs:289-302
+    BodyState s; s.v = zero3(); s.w = zero3(); s.x = center; s.inv_mass = 0.0f; s.rest = 0.0f; s.fric = fric; s.I = m_zero();
+    return s;
+}
+__device__ __forceinline__ void contact_state(const BodyState& A, const BodyState& Bs, V3 ra, V3 rb, V3 n, V3 t0, V3 t1, float dt,
+                                              float baumgarte, float slop, float restitution, float* bias, float* nmass, float* tm0, float* tm1) {
+    V3 ca = ra + A.x, cb = rb + Bs.x;
+    V3 ra_cn = cross3(ra, n), rb_cn = cross3(rb, n);
+    float pen = dot3(cb - ca, n);
+    V3 dv = Bs.v + cross3(Bs.w, rb) - A.v - cross3(A.w, ra);
+    float rel_v = dot3(dv, n);
+    *bias = -baumgarte / dt * (pen > 0.0f ? 0.0f : pen + slop) + (rel_v < -1.0f ? -restitution * rel_v : 0.0f);
+    *nmass = 1.0f / (A.inv_mass + dot3(ra_cn, mmulv(A.I, ra_cn)) + Bs.inv_mass + dot3(rb_cn, mmulv(Bs.I, rb_cn)));
+    V3 ra_ct = cross3(ra, t0), rb_ct = cross3(rb, t0);
+    *tm0 = 1.0f / (A.inv_mass + dot3(ra_ct, mmulv(A.I, ra_ct)) + Bs.inv_mass + dot3(rb_ct, mmulv(Bs.I, rb_ct)));
+    ra_ct = cross3(ra, t1); rb_ct = cross3(rb, t1);
+    *tm1 = 1.0f / (A.inv_mass + dot3(ra_ct, mmulv(A.I, ra_ct)) + Bs.inv_mass + dot3(rb_ct, mmulv(Bs.I, rb_ct)));
+}
+__global__ void __launch_bounds__(MGFB_THREADS) k_build_rows(ManifoldInput M, BodyInfoView B, const unsigned* __restrict__ perm, ConstraintRows R,
+                                                            const unsigned* m_ptr, unsigned m_host, float dt, float baumgarte, float slop, Counters* ctr) {
+    if (ctr->overflow | ctr->nan_bounds) return;
+    const unsigned m = m_ptr ? *m_ptr : m_host;
+    for (unsigned row = blockIdx.x * blockDim.x + threadIdx.x; row < m; row += gridDim.x * blockDim.x) {
+        unsigned k = perm[row];
+        int a = M.a[k], b = M.b[k];
+        V3 n, t0, t1; unsigned nc = 1;
+        BodyState A, Bs;
+        if (!M.user) {
+            float4 la4 = M.la[k], lb4 = M.lb[k], nt4 = M.nt[k];
+            n = mk3(la4.w, lb4.w, nt4.x);
+            basis_from_normal(n, &t0, &t1);
+            A = load_body_info(B, a);
+            Bs = b >= 0 ? load_body_info(B, b) : static_body_info(f4v(M.terrain_center), 0.0f);
+        } else {
+            n = mk3(M.normal[3 * k], M.normal[3 * k + 1], M.normal[3 * k + 2]);
+            t0 = mk3(M.tangent[6 * k], M.tangent[6 * k + 1], M.tangent[6 * k + 2]);
+            t1 = mk3(M.tangent[6 * k + 3], M.tangent[6 * k + 4], M.tangent[6 * k + 5]);
+            nc = M.ncontacts[k];
+            V3 sc = mk3(M.static_center[3 * k], M.static_center[3 * k + 1], M.static_center[3 * k + 2]);
+            A = a >= 0 ? load_body_info(B, a) : static_body_info(sc, M.static_friction[k]);
+            Bs = b >= 0 ? load_body_info(B, b) : static_body_info(sc, M.static_friction[k]);
+        }
+        float restitution = fmaxf(A.rest, Bs.rest);   // solver.rs:125
+        for (unsigned c = 0; c < nc; ++c) {
+            V3 ra, rb;
+            if (!M.user) { ra = f4v(M.la[k]); rb = f4v(M.lb[k]); }
+            else {
+                ra = mk3(M.ula[12 * k + 3 * c], M.ula[12 * k + 3 * c + 1], M.ula[12 * k + 3 * c + 2]);
+                rb = mk3(M.ulb[12 * k + 3 * c], M.ulb[12 * k + 3 * c + 1], M.ulb[12 * k + 3 * c + 2]);
+            }
+            float bias, nmass, tm0, tm1;
+            contact_state(A, Bs, ra, rb, n, t0, t1, dt, baumgarte, slop, restitution, &bias, &nmass, &tm0, &tm1);
+            if (c == 0) {
+                R.ab[row] = make_int2(a, b);
+                R.n[row] = v4(n, bias);
+                R.t0[row] = v4(t0, tm0);
+                R.t1[row] = v4(t1, tm1);
+                R.ra[row] = v4(ra, nmass);
+                R.rb[row] = v4(rb, ibits((int)nc));
+                R.impulse[row] = 0.0f;
+            } else {
+                unsigned e = row * 3 + (c - 1);
+                R.xra[e] = v4(ra, nmass);
+                R.xrb[e] = v4(rb, bias);
+                R.xtm[e] = make_float4(tm0, tm1, 0.0f, 0.0f);
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------- Solver::solve
+// solver.rs:72-78 + :203-252.  Persistent cooperative kernel: for each iteration, for each
+// group (colour / level) in order, every row of the group in parallel, then a grid barrier.
+// Rows of a group share no dynamic body, so the result equals the reference's sequential
+// sweep over the rows in row order, bit for bit.
+__device__ __forceinline__ void load_vel(const BodyVel* p, V3* v, V3* w, float* im, M3* I) {
+    const float4* q = reinterpret_cast<const float4*>(p);
+    float4 a = __ldcg(q), b = __ldcg(q + 1), c = __ldcg(q + 2), d = __ldcg(q + 3);
+    *v = mk3(a.x, a.y, a.z); *w = mk3(a.w, b.x, b.y); *im = b.z;
+    *I = mkm(mk3(b.w, c.x, c.y), mk3(c.z, c.w, d.x), mk3(d.y, d.z, d.w));
+}
+__device__ __forceinline__ void store_vel(BodyVel* p, V3 v, V3 w, float im, const M3& I) {
+    float4* q = reinterpret_cast<float4*>(p);
+    __stcg(q, make_float4(v.x, v.y, v.z, w.x));
+    __stcg(q + 1, make_float4(w.y, w.z, im, I.c0.x));
+}
+__device__ __forceinline__ void apply_impulse(V3 J, V3 ra, V3 rb, float ima, float imb, const M3& IA, const M3& IB, V3& va, V3& oa, V3& vb, V3& ob) {
+    va = va - J * ima;                       // solver.rs:228-231 / :244-247
+    oa = oa - mmulv(IA, cross3(ra, J));
+    vb = vb + J * imb;
+    ob = ob + mmulv(IB, cross3(rb, J));
+}
+__device__ __forceinline__ void solve_row(const ConstraintRows& R, BodyVel* vel, unsigned row) {
+    int2 ab = R.ab[row];
+    V3 va = zero3(), oa = zero3(), vb = zero3(), ob = zero3();
+    float ima = 0.0f, imb = 0.0f; M3 IA = m_zero(), IB = m_zero();
+    if (ab.x >= 0) load_vel(vel + ab.x, &va, &oa, &ima, &IA);
+    if (ab.y >= 0) load_vel(vel + ab.y, &vb, &ob, &imb, &IB);
+    float4 n4 = R.n[row], t04 = R.t0[row], t14 = R.t1[row], ra4 = R.ra[row], rb4 = R.rb[row];
+    V3 n = f4v(n4), t0 = f4v(t04), t1 = f4v(t14);
+    int nc = (int)fbits(rb4.w);
+    for (int c = 0; c < nc; ++c) {
+        V3 ra, rb; float bias, nmass, tm0, tm1, imp;
+        if (c == 0) { ra = f4v(ra4); rb = f4v(rb4); bias = n4.w; nmass = ra4.w; tm0 = t04.w; tm1 = t14.w; imp = __ldcg(&R.impulse[row]); }
+        else {
+            unsigned e = row * 3 + (c - 1);
+            float4 xa = R.xra[e], xb = R.xrb[e], xt = __ldcg(&R.xtm[e]);
+            ra = f4v(xa); rb = f4v(xb); nmass = xa.w; bias = xb.w; tm0 = xt.x; tm1 = xt.y; imp = xt.z;
+        }
+        // friction: both tangents use the SAME dv, impulses are applied unclamped (solver.rs:217-232)
+        V3 dv = vb + cross3(ob, rb) - va - cross3(oa, ra);
+        float l0 = -dot3(dv, t0) * tm0;
+        apply_impulse(t0 * l0, ra, rb, ima, imb, IA, IB, va, oa, vb, ob);
+        float l1 = -dot3(dv, t1) * tm1;
+        apply_impulse(t1 * l1, ra, rb, ima, imb, IA, IB, va, oa, vb, ob);
+        // normal (solver.rs:234-247)
+        V3 dv2 = vb + cross3(ob, rb) - va - cross3(oa, ra);
+        float vn = dot3(dv2, n);
+        float lambda = nmass * (-vn + bias);
+        float prev = imp;
+        imp = fmaxf(prev + lambda, 0.0f);
+        lambda = imp - prev;
+        apply_impulse(n * lambda, ra, rb, ima, imb, IA, IB, va, oa, vb, ob);
+        if (c == 0) __stcg(&R.impulse[row], imp);
+        else { unsigned e = row * 3 + (c - 1); __stcg(&R.xtm[e], make_float4(tm0, tm1, imp, 0.0f)); }
+    }
+    if (ab.x >= 0) store_vel(vel + ab.x, va, oa, ima, IA);
+    if (ab.y >= 0) store_vel(vel + ab.y, vb, ob, imb, IB);
+}
+__global__ void __launch_bounds__(MGFB_THREADS) k_solve(ConstraintRows R, BodyVel* vel, const unsigned* __restrict__ group_start,
+                                                       unsigned iters, Counters* ctr) {
+    if (ctr->overflow | ctr->nan_bounds) return;
+    const unsigned ngroups = ctr->ngroups;
+    const unsigned tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+    unsigned phase = 0;
+    for (unsigned it = 0; it < iters; ++it) {
+        for (unsigned g = 0; g < ngroups; ++g) {
+            unsigned r0 = group_start[g], r1 = group_start[g + 1];
+            for (unsigned row = r0 + tid; row < r1; row += nth) solve_row(R, vel, row);
+            grid_barrier(&ctr->bar, phase);
+        }
+    }
+}
+__global__ void k_step_done(Counters* ctr) { if (!(ctr->overflow | ctr->nan_bounds)) ctr->steps_done++; }
+
+// ---------------------------------------------------------------- multi-block exclusive scan (u32)
+#define SCAN_ITEMS 2048
+__global__ void __launch_bounds__(256) k_scan_reduce(const unsigned* __restrict__ in, unsigned n, unsigned* block_sums) {
+    __shared__ unsigned ws[8];
+    unsigned base = blockIdx.x * SCAN_ITEMS, s = 0;
+    for (unsigned i = threadIdx.x; i < SCAN_ITEMS; i += 256) { unsigned idx = base + i; if (idx < n) s += in[idx]; }
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) { unsigned t = 0; for (int w = 0; w < 8; ++w) t += ws[w]; block_sums[blockIdx.x] = t; }
+}
+__global__ void __launch_bounds__(1024) k_scan_sums(unsigned* block_sums, unsigned nblocks, unsigned* total) {
+    __shared__ unsigned warp_sums[32];
+    __shared__ unsigned carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (unsigned base = 0; base < nblocks; base += 1024) {
+        unsigned i = base + threadIdx.x;
+        unsigned v = i < nblocks ? block_sums[i] : 0u, x = v;
+        for (int o = 1; o < 32; o <<= 1) { unsigned y = __shfl_up_sync(0xffffffffu, x, o); if ((threadIdx.x & 31) >= o) x += y; }
+        if ((threadIdx.x & 31) == 31) warp_sums[threadIdx.x >> 5] = x;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            unsigned w = warp_sums[threadIdx.x], wsum = w;
+            for (int o = 1; o < 32; o <<= 1) { unsigned y = __shfl_up_sync(0xffffffffu, wsum, o); if (threadIdx.x >= o) wsum += y; }
+            warp_sums[threadIdx.x] = wsum - w;
+        }
+        __syncthreads();
+        unsigned excl = carry + warp_sums[threadIdx.x >> 5] + x - v;
+        if (i < nblocks) block_sums[i] = excl;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = excl + v;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0 && total) *total = carry;
+}
+__global__ void __launch_bounds__(256) k_scan_final(const unsigned* __restrict__ in, unsigned n, const unsigned* __restrict__ block_sums, unsigned* out, const unsigned* total) {
+    __shared__ unsigned ws[8];
+    __shared__ unsigned carry;
+    unsigned base = blockIdx.x * SCAN_ITEMS;
+    if (threadIdx.x == 0) carry = block_sums[blockIdx.x];
+    __syncthreads();
+    for (unsigned c = 0; c < SCAN_ITEMS; c += 256) {
+        unsigned idx = base + c + threadIdx.x;
+        unsigned v = idx < n ? in[idx] : 0u, x = v;
+        for (int o = 1; o < 32; o <<= 1) { unsigned y = __shfl_up_sync(0xffffffffu, x, o); if ((threadIdx.x & 31) >= o) x += y; }
+        if ((threadIdx.x & 31) == 31) ws[threadIdx.x >> 5] = x;
+        __syncthreads();
+        unsigned woff = 0;
+        for (int w = 0; w < (int)(threadIdx.x >> 5); ++w) woff += ws[w];
+        unsigned excl = carry + woff + x - v;
+        if (idx < n) out[idx] = excl;
+        __syncthreads();
+        if (threadIdx.x == 255) carry = excl + v;
+        __syncthreads();
+    }
+    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) out[n] = *total;
+}
+
+}  // namespace mgfb

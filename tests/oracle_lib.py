@@ -1,0 +1,184 @@
+"""ctypes binding of the CPU oracle (oracle/liboracle.so).  TEST INFRASTRUCTURE ONLY: nothing
+under mgf_b200/ imports this; it is the checker, never the thing measured or shipped."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ODIR = os.path.join(ROOT, "oracle")
+SO = os.path.join(ODIR, "liboracle.so")
+
+import sys
+sys.path.insert(0, ROOT)
+from mgf_b200 import _lib as L  # POD struct layouts only (numpy dtypes); does not load libmgfb
+
+_P = C.c_void_p
+_lib = None
+
+
+def build():
+    subprocess.run(["make", "-C", ODIR, "-s", "all"], check=True)
+
+
+def load():
+    global _lib
+    if _lib is not None:
+        return _lib
+    srcs = [os.path.join(ODIR, f) for f in os.listdir(ODIR) if f.endswith((".hpp", ".cpp"))]
+    if not os.path.exists(SO) or any(os.path.getmtime(s) > os.path.getmtime(SO) for s in srcs):
+        build()
+    lib = C.CDLL(SO)
+    lib.mgfo_contacts_batch.restype = C.c_int32
+    lib.mgfo_contacts_batch.argtypes = [C.c_uint32, _P, _P, C.c_uint32, _P, _P, _P]
+    lib.mgfo_world_create.restype = _P
+    lib.mgfo_world_create.argtypes = [C.c_float]
+    lib.mgfo_world_destroy.argtypes = [_P]
+    lib.mgfo_world_add_bodies.restype = C.c_int32
+    lib.mgfo_world_add_bodies.argtypes = [_P, C.c_uint32, _P, _P, _P, _P, _P]
+    lib.mgfo_world_set_terrain.restype = C.c_int32
+    lib.mgfo_world_set_terrain.argtypes = [_P, _P, C.c_uint32, _P, C.c_uint32, _P]
+    lib.mgfo_world_count.restype = C.c_uint32
+    lib.mgfo_world_count.argtypes = [_P]
+    lib.mgfo_world_get_state.argtypes = [_P, _P, _P, _P, _P]
+    lib.mgfo_world_set_velocity.argtypes = [_P, C.c_uint32, C.c_uint32, _P, _P]
+    lib.mgfo_world_get_colliders.argtypes = [_P, _P]
+    lib.mgfo_world_get_inv_moment.argtypes = [_P, _P]
+    lib.mgfo_world_integrate.argtypes = [_P, C.c_float]
+    lib.mgfo_world_complete_motion.argtypes = [_P]
+    lib.mgfo_world_step.restype = C.c_int32
+    lib.mgfo_world_step.argtypes = [_P, C.c_float, C.c_uint32, C.c_uint32]
+    lib.mgfo_world_build.restype = C.c_int32
+    lib.mgfo_world_build.argtypes = [_P, C.c_float, C.POINTER(C.c_uint32)]
+    lib.mgfo_world_constraints.argtypes = [_P, _P, _P, _P, _P]
+    lib.mgfo_world_manifolds.argtypes = [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P]
+    lib.mgfo_world_stats.argtypes = [_P, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+    lib.mgfo_world_solve_order.argtypes = [_P, _P, C.c_uint32, C.c_uint32]
+    lib.mgfo_world_solve_manifolds.restype = C.c_int32
+    lib.mgfo_world_solve_manifolds.argtypes = [_P, C.POINTER(L.Manifolds), C.c_float, C.c_uint32, _P, _P]
+    lib.mgfo_world_time_steps.restype = C.c_double
+    lib.mgfo_world_time_steps.argtypes = [_P, C.c_float, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+    lib.mgfo_gjk_batch.restype = C.c_int32
+    lib.mgfo_gjk_batch.argtypes = [_P, _P, C.c_uint32, _P, _P, _P]
+    _lib = lib
+    return lib
+
+
+def contacts_batch(pair_kind, recv, arg, want_local=False):
+    lib = load()
+    recv = np.ascontiguousarray(recv, dtype=L.SHAPE_DTYPE)
+    arg = np.ascontiguousarray(arg, dtype=L.SHAPE_DTYPE)
+    n = len(recv)
+    out = np.zeros((n, 2), dtype=L.CONTACT_DTYPE)
+    loc = np.zeros((n, 2), dtype=L.LOCAL_CONTACT_DTYPE) if want_local else None
+    counts = np.zeros(n, dtype=np.uint32)
+    st = lib.mgfo_contacts_batch(pair_kind, L.ptr(recv), L.ptr(arg), n, L.ptr(out), L.ptr(loc), L.ptr(counts))
+    assert st == 0
+    return (out, counts, loc) if want_local else (out, counts)
+
+
+class OracleWorld:
+    """mgf_demo World::step on the CPU restatement."""
+
+    def __init__(self, fat_margin=0.25):
+        self.lib = load()
+        self.h = self.lib.mgfo_world_create(fat_margin)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.lib.mgfo_world_destroy(self.h)
+            self.h = None
+
+    def add_bodies(self, shapes, mass, restitution, friction, world_force):
+        shapes = np.ascontiguousarray(shapes, dtype=L.SHAPE_DTYPE)
+        n = len(shapes)
+        f32 = lambda a, shape: np.ascontiguousarray(np.broadcast_to(np.asarray(a, dtype=np.float32), shape))
+        st = self.lib.mgfo_world_add_bodies(self.h, n, L.ptr(shapes), L.ptr(f32(mass, (n,))), L.ptr(f32(restitution, (n,))),
+                                            L.ptr(f32(friction, (n,))), L.ptr(f32(world_force, (n, 3))))
+        assert st == 0, st
+
+    def set_terrain(self, verts, faces, x=(0, 0, 0)):
+        verts = np.ascontiguousarray(verts, dtype=np.float32).reshape(-1, 3)
+        faces = np.ascontiguousarray(faces, dtype=np.uint32).reshape(-1, 3)
+        x = np.asarray(x, dtype=np.float32)
+        self.lib.mgfo_world_set_terrain(self.h, L.ptr(verts), len(verts), L.ptr(faces), len(faces), L.ptr(x))
+
+    def __len__(self):
+        return self.lib.mgfo_world_count(self.h)
+
+    def state(self):
+        n = len(self)
+        x = np.zeros((n, 3), np.float32); q = np.zeros((n, 4), np.float32)
+        v = np.zeros((n, 3), np.float32); w = np.zeros((n, 3), np.float32)
+        self.lib.mgfo_world_get_state(self.h, L.ptr(x), L.ptr(q), L.ptr(v), L.ptr(w))
+        return x, q, v, w
+
+    def set_velocity(self, first, v, omega):
+        v = np.ascontiguousarray(v, dtype=np.float32).reshape(-1, 3)
+        omega = np.ascontiguousarray(omega, dtype=np.float32).reshape(-1, 3)
+        self.lib.mgfo_world_set_velocity(self.h, first, len(v), L.ptr(v), L.ptr(omega))
+
+    def colliders(self):
+        out = np.zeros(len(self), dtype=L.SHAPE_DTYPE)
+        self.lib.mgfo_world_get_colliders(self.h, L.ptr(out))
+        return out
+
+    def inv_moment(self):
+        out = np.zeros((len(self), 9), np.float32)
+        self.lib.mgfo_world_get_inv_moment(self.h, L.ptr(out))
+        return out
+
+    def integrate(self, dt):
+        self.lib.mgfo_world_integrate(self.h, dt)
+
+    def complete_motion(self):
+        self.lib.mgfo_world_complete_motion(self.h)
+
+    def step(self, dt, iters=20, nsteps=1):
+        st = self.lib.mgfo_world_step(self.h, dt, iters, nsteps)
+        assert st == 0, st
+
+    def build(self, dt):
+        cnt = C.c_uint32()
+        st = self.lib.mgfo_world_build(self.h, dt, C.byref(cnt))
+        assert st == 0, st
+        return cnt.value
+
+    def constraints(self, m):
+        a = np.zeros(m, np.uint32); b = np.zeros(m, np.int32); face = np.zeros(m, np.uint32); sub = np.zeros(m, np.uint32)
+        self.lib.mgfo_world_constraints(self.h, L.ptr(a), L.ptr(b), L.ptr(face), L.ptr(sub))
+        return a, b, face, sub
+
+    def manifolds(self, m):
+        d = dict(obj_a=np.zeros(m, np.int32), obj_b=np.zeros(m, np.int32), static_center=np.zeros((m, 3), np.float32),
+                 static_friction=np.zeros(m, np.float32), normal=np.zeros((m, 3), np.float32), tangent=np.zeros((m, 6), np.float32),
+                 ncontacts=np.zeros(m, np.uint32), local_a=np.zeros((m, 12), np.float32), local_b=np.zeros((m, 12), np.float32))
+        self.lib.mgfo_world_manifolds(self.h, *[L.ptr(d[k]) for k in ("obj_a", "obj_b", "static_center", "static_friction", "normal",
+                                                                       "tangent", "ncontacts", "local_a", "local_b")])
+        return d
+
+    def stats(self):
+        a = C.c_uint64(); b = C.c_uint64()
+        self.lib.mgfo_world_stats(self.h, C.byref(a), C.byref(b))
+        return a.value, b.value
+
+    def solve_order(self, perm, iters):
+        perm = np.ascontiguousarray(perm, dtype=np.uint32)
+        self.lib.mgfo_world_solve_order(self.h, L.ptr(perm), len(perm), iters)
+
+    def solve_manifolds(self, d, dt, iters, perm=None):
+        n = len(d["obj_a"])
+        m = L.Manifolds(n=n, **{k: L.ptr(np.ascontiguousarray(v)) for k, v in d.items()})
+        keep = [np.ascontiguousarray(v) for v in d.values()]  # noqa: F841 keep alive
+        m = L.Manifolds(n=n, **{k: L.ptr(v) for k, v in zip(d.keys(), keep)})
+        imp = np.zeros((n, 4), np.float32)
+        p = None if perm is None else np.ascontiguousarray(perm, dtype=np.uint32)
+        st = self.lib.mgfo_world_solve_manifolds(self.h, C.byref(m), dt, iters, L.ptr(p), L.ptr(imp))
+        assert st == 0
+        return imp
+
+    def time_steps(self, dt, iters, nsteps):
+        ci = C.c_uint64(); pr = C.c_uint64()
+        sec = self.lib.mgfo_world_time_steps(self.h, dt, iters, nsteps, C.byref(ci), C.byref(pr))
+        return sec, ci.value, pr.value
