@@ -1,0 +1,277 @@
+#!/usr/bin/env python
+"""bench.py -- mgf step hot path on B200: contact-constraint iterations/s (+ narrowphase pairs/s).
+
+Contract (see the task statement): `python bench.py --gpus N --steps K --warmup W` prints ONE
+JSON line from rank 0.  A "step" is one World::step (mgf_demo/world.rs:227-294) of the
+workload below with 20 solver iterations; `value` is whole-job constraint-iterations/s with
+all inputs resident in HBM, timed on the device with CUDA events (the library's own events
+on its launching stream), L2 flushed between timed steps; `e2e` is the same metric through
+the public API with host buffers (pinned H2D of velocities + D2H of the full body state every
+step, wall clock).  `roofline` is for the dominant kernel (k_solve), `cpu_baseline` is the
+oracle (a C++ port of the reference: the Rust reference cannot be built here) on one core.
+
+`--impl reference` times that CPU port alone on the same workload (bounded sample).
+
+Workload "C2pile": BASELINE.json configs[1] body set (100 000 spheres r=0.5, balls.rs lattice
+46^3 + 2664, LCG jitter +-0.01 seed 1, box 160x160x40, restitution 0.3, friction 0.6, g=-9.8,
+dt=1/60, 20 iterations) arranged as a pile already in contact (lattice spacing squeezed to
+0.98*2r, bottom layer on the floor) so that the ~295 k contact constraints per step of the
+settled pile exist from step 0 in BOTH arms; the free-fall variant needs ~600 steps (10 min of
+CPU time) before its first dense contact.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+ALGO_BYTES_PER_CONSTRAINT_ITER = 268.0   # 216 B read + 52 B written
+WORKLOAD = "C2pile"
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); smax = float(r[2])
+                for k, nm in enumerate(names):
+                    if r[4 + k].lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                continue
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def build_scene():
+    from mgf_b200 import scenes
+    return scenes.build_config(WORKLOAD)
+
+
+def run_reference(args, rank):
+    """CPU arm: the oracle port of the reference, single thread (mgf is single-threaded and its
+    Gauss-Seidel sweep is inherently serial, solver.rs:73-77)."""
+    if rank != 0:
+        return
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import numpy as np
+    import oracle_lib   # bench.py's reference arm is one of the two places allowed to execute oracle/
+    bodies, terrain, iters = build_scene()
+    w = oracle_lib.OracleWorld()
+    w.add_bodies(*bodies); w.set_terrain(*terrain)
+    dt = np.float32(1.0 / 60.0)
+    budget_s = 150.0
+    t_start = time.time()
+    warm = 0
+    for _ in range(args.warmup):
+        if time.time() - t_start > budget_s * 0.3:
+            break
+        w.step(dt, iters); warm += 1
+    sec = 0.0; ci = 0; pairs = 0; steps = 0
+    for _ in range(args.steps):
+        s, c, p = w.time_steps(dt, iters, 1)
+        sec += s; ci += c; pairs += p; steps += 1
+        if time.time() - t_start > budget_s:
+            break
+    val = ci / sec
+    line = {
+        "impl": "reference", "metric": "contact_constraint_iterations_per_second", "value": val, "unit": "constraint-iters/s",
+        "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": 1e3 * sec / steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "bodies": len(bodies[0]), "solver_iterations": iters, "dt": 1.0 / 60.0,
+                   "constraints_per_step": ci / iters / steps, "candidate_pairs_per_step": pairs / steps},
+        "narrowphase_pairs_per_second": pairs / sec,
+        "cpu_baseline": {"value": val, "unit": "constraint-iters/s", "cores": 1, "kind": "port",
+                         "sample": f"{steps} full World::step of {WORKLOAD} after {warm} warm-up steps, C++ port of the reference "
+                                   "(oracle/), g++ -O2 -ffp-contract=off, whole step timed like balls.rs:107-109; host has "
+                                   f"{os.cpu_count()} cores, 1 used (reference is single-threaded)"},
+        "e2e": {"value": val, "unit": "constraint-iters/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="mgf_b200", choices=["mgf_b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "mgf_b200" else args.warmup
+    rank = int(os.environ.get("RANK", "0")); local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    assert torch.cuda.is_available(), "bench.py needs a GPU: mgf_b200 has no CPU fallback"
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    import mgf_b200
+
+    bodies, terrain, iters = build_scene()
+    n = len(bodies[0])
+    dt = np.float32(1.0 / 60.0)
+    g = mgf_b200.World(device=local_rank)
+    g.add_bodies(*bodies); g.set_terrain(*terrain)
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device="cuda")   # 256 MB > 126 MB L2
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up
+    g.step(dt, iters, nsteps=args.warmup)
+    g.totals(reset=True)
+    # ---- timed: K steps, device time from the library's CUDA events, L2 flushed between steps
+    sampler = ClockSampler(local_rank); sampler.start()
+    barrier()
+    step_ms = []; solve_ms = []; cons = []; pairs = []; groups = []
+    t_wall0 = time.perf_counter()
+    for _ in range(args.steps):
+        flush.fill_(1.0); torch.cuda.synchronize()
+        st = g.step(dt, iters)
+        step_ms.append(st["step_ms"]); solve_ms.append(st["solve_ms"]); cons.append(st["constraints"])
+        pairs.append(st["candidate_pairs"] + st["terrain_candidates"]); groups.append(st["groups"])
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    clocks = sampler.stop()
+    tot = g.totals(reset=True)
+    total_ms = float(sum(step_ms)); units = float(sum(cons)) * iters; npairs = float(sum(pairs))
+    if world > 1:
+        t = torch.tensor([total_ms], device="cuda", dtype=torch.float64); dist.all_reduce(t, op=dist.ReduceOp.MAX); total_ms_max = t.item()
+        u = torch.tensor([units, npairs], device="cuda", dtype=torch.float64); dist.all_reduce(u, op=dist.ReduceOp.SUM)
+        units_all, pairs_all = u[0].item(), u[1].item()
+    else:
+        total_ms_max, units_all, pairs_all = total_ms, units, npairs
+    value = units_all / (total_ms_max * 1e-3)
+
+    # ---- end to end: public API with host buffers; pinned H2D (v, omega) + D2H (x, q, v, omega) per step
+    pin = lambda shape: torch.empty(shape, dtype=torch.float32, pin_memory=True).numpy()
+    hx, hq, hv, hw = pin((n, 3)), pin((n, 4)), pin((n, 3)), pin((n, 3))
+    _, _, v0, w0 = g.state()
+    hv[:] = v0; hw[:] = w0
+    from mgf_b200 import _lib as L
+    lib, h = g.ctx.lib, g.ctx.h
+    barrier()
+    e2e_units = 0.0
+    t0 = time.perf_counter()
+    import ctypes as C
+    st = L.StepStats()
+    for _ in range(args.steps):
+        g.ctx.check(lib.mgfb_bodies_set_velocity(h, 0, n, L.ptr(hv), L.ptr(hw)))            # H2D
+        g.ctx.check(lib.mgfb_step(h, dt, iters, C.byref(st)))
+        g.ctx.check(lib.mgfb_bodies_get_state(h, 0, n, L.ptr(hx), L.ptr(hq), L.ptr(hv), L.ptr(hw)))   # D2H
+        e2e_units += st.constraints * iters
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64); dist.all_reduce(t, op=dist.ReduceOp.MAX); e2e_s = t.item()
+        u = torch.tensor([e2e_units], device="cuda", dtype=torch.float64); dist.all_reduce(u, op=dist.ReduceOp.SUM); e2e_units = u.item()
+    e2e_val = e2e_units / e2e_s
+    assert np.isfinite(hx).all()
+
+    # ---- roofline of the dominant kernel (k_solve), live CUDA-event durations
+    peak, peak_src = measured_peak()
+    solve_s = sum(solve_ms) * 1e-3
+    achieved = ALGO_BYTES_PER_CONSTRAINT_ITER * units / solve_s / 1e9
+    roofline = {"kernel": "k_solve (persistent cooperative sequential-impulse solver)", "bound": "hbm", "achieved": achieved, "peak": peak,
+                "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": ALGO_BYTES_PER_CONSTRAINT_ITER * units / len(solve_ms),
+                "avg_launch_ms": sum(solve_ms) / len(solve_ms), "share_of_step": sum(solve_ms) / total_ms,
+                "note": "268 B per constraint-iteration x constraints x 20 iterations per launch; the per-step working set "
+                        "(~75 MB) fits the 126 MB L2, so iterations 2..20 are L2-served by construction"}
+
+    # ---- CPU baseline (rank 0, N=1): bounded sample of the same workload on the oracle
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import oracle_lib
+        o = oracle_lib.OracleWorld()
+        o.add_bodies(*bodies); o.set_terrain(*terrain)
+        o.step(dt, iters, min(args.warmup, 3))
+        sec, ci, pr = o.time_steps(dt, iters, 8)
+        cpu = {"value": ci / sec, "unit": "constraint-iters/s", "cores": 1, "kind": "port",
+               "pairs_per_second": pr / sec, "ms_per_step": 1e3 * sec / 8,
+               "sample": f"8 full World::step of {WORKLOAD} after {min(args.warmup, 3)} warm-up steps on the C++ port of the reference "
+                         f"(the Rust reference cannot be built: no rustc); 1 of {os.cpu_count()} host cores (reference is single-threaded)"}
+
+    if rank == 0:
+        line = {
+            "metric": "contact_constraint_iterations_per_second", "value": value, "unit": "constraint-iters/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms_max / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "bodies_per_gpu": n, "solver_iterations": iters, "dt": 1.0 / 60.0,
+                       "constraints_per_step": sum(cons) / len(cons), "candidate_pairs_per_step": sum(pairs) / len(pairs),
+                       "colour_groups": sum(groups) / len(groups), "l2": "flushed between timed steps (256 MB write)",
+                       "parallelism": "one tile per GPU, no cross-tile exchange" if world > 1 else "single GPU",
+                       "arithmetic": "--fmad=false, IEEE div/sqrt: bit-exact vs the CPU port"},
+            "narrowphase_pairs_per_second": pairs_all / (total_ms_max * 1e-3),
+            "solver_only_constraint_iters_per_second": units / solve_s,
+            "roofline": roofline, "cpu_baseline": cpu,
+            "e2e": {"value": e2e_val, "unit": "constraint-iters/s", "h2d_bytes_per_step": n * 24, "d2h_bytes_per_step": n * 52,
+                    "ms_per_step": 1e3 * e2e_s / args.steps},
+            "gpu_launches": tot["kernel_launches"], "clocks": clocks, "wall_s_timed_region": t_wall,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

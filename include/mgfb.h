@@ -208,6 +208,13 @@ int32_t mgfb_step_n(mgfb_ctx* ctx, float dt, uint32_t iters, uint32_t nsteps, mg
 int32_t mgfb_step_constraints(mgfb_ctx* ctx, uint32_t capacity, uint32_t* body_a, int32_t* body_b,
                               uint32_t* face, uint32_t* sub, uint32_t* colour, uint32_t* count);
 
+/* Running totals over all steps since the last reset (device-side accumulators, one readback):
+ * steps completed, ContactConstraints solved per iteration summed over steps, candidate pairs
+ * (body-body + terrain) summed over steps, colour groups summed over steps, and the number of
+ * CUDA kernels this ctx launched.  Any pointer may be NULL. */
+int32_t mgfb_step_totals(mgfb_ctx* ctx, uint64_t* steps, uint64_t* constraints, uint64_t* candidate_pairs, uint64_t* groups,
+                         uint64_t* kernel_launches, int32_t reset);
+
 /* Device-resident staging used by multi-GPU drivers and benchmarks: raw device pointers to the
  * SoA body arrays (for NCCL send/recv issued by the host plumbing).  See DESIGN.md. */
 typedef struct mgfb_device_view {

@@ -82,6 +82,7 @@ SYMBOLS = [
     ("mgfb_step", C.c_int32, [_P, C.c_float, C.c_uint32, C.POINTER(StepStats)]),
     ("mgfb_step_n", C.c_int32, [_P, C.c_float, C.c_uint32, C.c_uint32, C.POINTER(StepStats)]),
     ("mgfb_step_constraints", C.c_int32, [_P, C.c_uint32, _P, _P, _P, _P, _P, C.POINTER(C.c_uint32)]),
+    ("mgfb_step_totals", C.c_int32, [_P] + [C.POINTER(C.c_uint64)] * 5 + [C.c_int32]),
     ("mgfb_device_view_get", C.c_int32, [_P, C.POINTER(DeviceView)]),
 ]
 

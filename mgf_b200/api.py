@@ -176,6 +176,12 @@ class World:
         self.ctx.check(self.lib.mgfb_step_n(self.ctx.h, dt, iters, nsteps, C.byref(st)))
         return st.as_dict()
 
+    def totals(self, reset=False):
+        """Running totals since the last reset (see mgfb_step_totals)."""
+        v = [C.c_uint64() for _ in range(5)]
+        self.ctx.check(self.lib.mgfb_step_totals(self.ctx.h, *[C.byref(x) for x in v], 1 if reset else 0))
+        return dict(zip(("steps", "constraints", "candidate_pairs", "groups", "kernel_launches"), [x.value for x in v]))
+
     def constraints(self):
         """Identity of the last step's constraints in solve order."""
         cnt = C.c_uint32()

@@ -55,6 +55,8 @@ struct mgfb_ctx {
     // body grid
     Buf cell_count, cell_start, ent_id, ent_key, scan_sums; unsigned table = 0, ent_cap = 0;
     TerrainData terrain;
+    Buf stage;          // packed state staging for get_state / set_velocity
+    unsigned long long launches = 0;   // kernels launched since the last mgfb_step_totals(reset)
     // user-path staging
     Buf u_a, u_b, u_sc, u_sf, u_n, u_t, u_nc, u_la, u_lb;
     // cooperative grid sizes
@@ -263,6 +265,7 @@ int32_t enqueue_order_and_solve(mgfb_ctx* ctx, const OrderView& O, const Manifol
         CU(cudaLaunchCooperativeKernel((void*)k_solve, dim3(ctx->coop_solve), dim3(MGFB_THREADS), args, 0, ctx->stream));
     }
     if (time_solve) CU(cudaEventRecord(ctx->ev[3], ctx->stream));
+    ctx->launches += 5;   // k_order, k_group_scan, k_scatter_rows, k_build_rows, k_solve
     return MGFB_OK;
 }
 
@@ -315,6 +318,9 @@ int32_t enqueue_step(mgfb_ctx* ctx, float dt, unsigned iters, bool from_integrat
     TRY(enqueue_order_and_solve(ctx, O, M, &c->contacts, 0, ctx->contact_cap, false, dt, iters, timed));
     k_step_done<<<1, 1, 0, ctx->stream>>>(c);
     CU(cudaGetLastError());
+    // k_integrate, 2x k_grid_insert, 3 scan kernels, k_body_pairs, k_step_done (+ terrain, narrowphase)
+    ctx->launches += 8 + (ctx->terrain.present ? 1 : 0) + (sph ? 1 : 0) + (sph && caps ? 2 : 0) + (caps ? 1 : 0) +
+                     (ctx->terrain.present ? (sph ? 1 : 0) + (caps ? 1 : 0) : 0);
     return MGFB_OK;
 }
 
@@ -431,7 +437,7 @@ void mgfb_ctx_destroy(mgfb_ctx* ctx) {
                   &ctx->group, &ctx->group_count, &ctx->group_start, &ctx->perm, &ctx->r_ab, &ctx->r_n, &ctx->r_t0, &ctx->r_t1, &ctx->r_ra,
                   &ctx->r_rb, &ctx->r_imp, &ctx->r_xra, &ctx->r_xrb, &ctx->r_xtm, &ctx->cell_count, &ctx->cell_start, &ctx->ent_id,
                   &ctx->ent_key, &ctx->scan_sums, &ctx->u_a, &ctx->u_b, &ctx->u_sc, &ctx->u_sf, &ctx->u_n, &ctx->u_t, &ctx->u_nc, &ctx->u_la,
-                  &ctx->u_lb, &ctx->terrain.verts, &ctx->terrain.faces, &ctx->terrain.boxes, &ctx->terrain.cell_count,
+                  &ctx->u_lb, &ctx->stage, &ctx->terrain.verts, &ctx->terrain.faces, &ctx->terrain.boxes, &ctx->terrain.cell_count,
                   &ctx->terrain.cell_start, &ctx->terrain.ent_id, &ctx->terrain.ent_key, &ctx->terrain.max_bits};
     for (Buf* b : all) release(*b);
     if (ctx->h_ctr) cudaFreeHost(ctx->h_ctr);
@@ -524,26 +530,17 @@ int32_t mgfb_bodies_get_state(mgfb_ctx* ctx, uint32_t first, uint32_t n, float* 
     if (!ctx || (uint64_t)first + n > ctx->n) return fail(ctx, MGFB_ERR_INVALID_ARG, "body range out of bounds");
     if (n == 0) return MGFB_OK;
     CU(cudaSetDevice(ctx->device));
-    std::vector<float4> tmp(n);
-    if (x) {
-        CU(cudaMemcpyAsync(tmp.data(), ctx->x.as<float4>() + first, (size_t)n * 16, cudaMemcpyDeviceToHost, ctx->stream));
-        CU(cudaStreamSynchronize(ctx->stream));
-        for (uint32_t i = 0; i < n; ++i) { x[3 * i] = tmp[i].x; x[3 * i + 1] = tmp[i].y; x[3 * i + 2] = tmp[i].z; }
-    }
-    if (q) {
-        CU(cudaMemcpyAsync(tmp.data(), ctx->q.as<float4>() + first, (size_t)n * 16, cudaMemcpyDeviceToHost, ctx->stream));
-        CU(cudaStreamSynchronize(ctx->stream));
-        for (uint32_t i = 0; i < n; ++i) { q[4 * i] = tmp[i].x; q[4 * i + 1] = tmp[i].y; q[4 * i + 2] = tmp[i].z; q[4 * i + 3] = tmp[i].w; }
-    }
-    if (v || omega) {
-        std::vector<BodyVel> bv(n);
-        CU(cudaMemcpyAsync(bv.data(), ctx->vel.as<BodyVel>() + first, (size_t)n * sizeof(BodyVel), cudaMemcpyDeviceToHost, ctx->stream));
-        CU(cudaStreamSynchronize(ctx->stream));
-        for (uint32_t i = 0; i < n; ++i) {
-            if (v) { v[3 * i] = bv[i].a.x; v[3 * i + 1] = bv[i].a.y; v[3 * i + 2] = bv[i].a.z; }
-            if (omega) { omega[3 * i] = bv[i].a.w; omega[3 * i + 1] = bv[i].b.x; omega[3 * i + 2] = bv[i].b.y; }
-        }
-    }
+    TRY(ensure(ctx, ctx->stage, (size_t)n * 13 * 4));
+    float* sx = ctx->stage.as<float>(); float* sq = sx + (size_t)3 * n; float* sv = sq + (size_t)4 * n; float* sw = sv + (size_t)3 * n;
+    k_pack_state<<<(n + MGFB_THREADS - 1) / MGFB_THREADS, MGFB_THREADS, 0, ctx->stream>>>(body_arrays(ctx), first, n, x ? sx : nullptr,
+                                                                                           q ? sq : nullptr, v ? sv : nullptr, omega ? sw : nullptr);
+    CU(cudaGetLastError());
+    ctx->launches += 1;
+    if (x) CU(cudaMemcpyAsync(x, sx, (size_t)n * 12, cudaMemcpyDeviceToHost, ctx->stream));
+    if (q) CU(cudaMemcpyAsync(q, sq, (size_t)n * 16, cudaMemcpyDeviceToHost, ctx->stream));
+    if (v) CU(cudaMemcpyAsync(v, sv, (size_t)n * 12, cudaMemcpyDeviceToHost, ctx->stream));
+    if (omega) CU(cudaMemcpyAsync(omega, sw, (size_t)n * 12, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
     return MGFB_OK;
 }
 
@@ -551,14 +548,13 @@ int32_t mgfb_bodies_set_velocity(mgfb_ctx* ctx, uint32_t first, uint32_t n, cons
     if (!ctx || (uint64_t)first + n > ctx->n || !v || !omega) return fail(ctx, MGFB_ERR_INVALID_ARG, "bad arguments");
     if (n == 0) return MGFB_OK;
     CU(cudaSetDevice(ctx->device));
-    std::vector<BodyVel> bv(n);
-    CU(cudaMemcpyAsync(bv.data(), ctx->vel.as<BodyVel>() + first, (size_t)n * sizeof(BodyVel), cudaMemcpyDeviceToHost, ctx->stream));
-    CU(cudaStreamSynchronize(ctx->stream));
-    for (uint32_t i = 0; i < n; ++i) {
-        bv[i].a = make_float4(v[3 * i], v[3 * i + 1], v[3 * i + 2], omega[3 * i]);
-        bv[i].b.x = omega[3 * i + 1]; bv[i].b.y = omega[3 * i + 2];
-    }
-    CU(cudaMemcpyAsync(ctx->vel.as<BodyVel>() + first, bv.data(), (size_t)n * sizeof(BodyVel), cudaMemcpyHostToDevice, ctx->stream));
+    TRY(ensure(ctx, ctx->stage, (size_t)n * 13 * 4));
+    float* sv = ctx->stage.as<float>(); float* sw = sv + (size_t)3 * n;
+    CU(cudaMemcpyAsync(sv, v, (size_t)n * 12, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(sw, omega, (size_t)n * 12, cudaMemcpyHostToDevice, ctx->stream));
+    k_set_velocity<<<(n + MGFB_THREADS - 1) / MGFB_THREADS, MGFB_THREADS, 0, ctx->stream>>>(body_arrays(ctx), first, n, sv, sw);
+    CU(cudaGetLastError());
+    ctx->launches += 1;
     CU(cudaStreamSynchronize(ctx->stream));
     return MGFB_OK;
 }
@@ -833,6 +829,23 @@ int32_t mgfb_solver_solve(mgfb_ctx* ctx, const mgfb_manifolds* m, float dt, uint
     if (stats) {
         stats->constraints = n; stats->contacts = total_contacts; stats->groups = ctx->h_ctr->ngroups; stats->iterations = iters;
         cudaEventElapsedTime(&stats->solve_ms, ctx->ev[2], ctx->ev[3]);
+    }
+    return MGFB_OK;
+}
+
+int32_t mgfb_step_totals(mgfb_ctx* ctx, uint64_t* steps, uint64_t* constraints, uint64_t* candidate_pairs, uint64_t* groups,
+                         uint64_t* kernel_launches, int32_t reset) {
+    if (!ctx) return MGFB_ERR_INVALID_ARG;
+    CU(cudaSetDevice(ctx->device));
+    TRY(read_counters(ctx));
+    if (steps) *steps = ctx->h_ctr->acc_steps;
+    if (constraints) *constraints = ctx->h_ctr->acc_constraints;
+    if (candidate_pairs) *candidate_pairs = ctx->h_ctr->acc_pairs;
+    if (groups) *groups = ctx->h_ctr->acc_groups;
+    if (kernel_launches) *kernel_launches = ctx->launches;
+    if (reset) {
+        CU(cudaMemsetAsync(reinterpret_cast<char*>(dctr(ctx)) + offsetof(Counters, acc_constraints), 0, 32, ctx->stream));
+        ctx->launches = 0;
     }
     return MGFB_OK;
 }

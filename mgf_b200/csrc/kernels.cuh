@@ -28,6 +28,11 @@ struct Counters {
     unsigned nan_bounds;     // AABB::combine assert (bounds.rs:125-127)
     unsigned steps_done;
     unsigned pad1;
+    // running totals since the last mgfb_step_totals(reset)
+    unsigned long long acc_constraints;
+    unsigned long long acc_pairs;        // body-body + terrain candidates
+    unsigned long long acc_groups;
+    unsigned long long acc_steps;
 };
 enum { OVF_PAIRS = 1, OVF_TPAIRS = 2, OVF_CONTACTS = 4, OVF_GRID = 8, OVF_GROUPS = 16 };
 struct PairLists { int2* p[4]; };
@@ -705,7 +710,34 @@ __global__ void __launch_bounds__(MGFB_THREADS) k_solve(ConstraintRows R, BodyVe
         }
     }
 }
-__global__ void k_step_done(Counters* ctr) { if (!(ctr->overflow | ctr->nan_bounds)) ctr->steps_done++; }
+__global__ void k_step_done(Counters* ctr) {
+    if (ctr->overflow | ctr->nan_bounds) return;
+    ctr->steps_done++;
+    ctr->acc_steps++;
+    ctr->acc_constraints += ctr->contacts;
+    ctr->acc_pairs += (unsigned long long)ctr->pairs[0] + ctr->pairs[1] + ctr->pairs[2] + ctr->pairs[3] + ctr->tpairs[0] + ctr->tpairs[1];
+    ctr->acc_groups += ctr->ngroups;
+}
+// state marshalling for the host API: packed f32 arrays <-> SoA records
+__global__ void __launch_bounds__(MGFB_THREADS) k_pack_state(BodyArrays B, unsigned first, unsigned n, float* x, float* q, float* v, float* w) {
+    unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    unsigned b = first + i;
+    if (x) { float4 p = B.x[b]; x[3 * i] = p.x; x[3 * i + 1] = p.y; x[3 * i + 2] = p.z; }
+    if (q) { float4 p = B.q[b]; q[4 * i] = p.x; q[4 * i + 1] = p.y; q[4 * i + 2] = p.z; q[4 * i + 3] = p.w; }
+    if (v || w) {
+        BodyVel r = B.vel[b];
+        if (v) { v[3 * i] = r.a.x; v[3 * i + 1] = r.a.y; v[3 * i + 2] = r.a.z; }
+        if (w) { w[3 * i] = r.a.w; w[3 * i + 1] = r.b.x; w[3 * i + 2] = r.b.y; }
+    }
+}
+__global__ void __launch_bounds__(MGFB_THREADS) k_set_velocity(BodyArrays B, unsigned first, unsigned n, const float* v, const float* w) {
+    unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    BodyVel* r = B.vel + first + i;
+    r->a = make_float4(v[3 * i], v[3 * i + 1], v[3 * i + 2], w[3 * i]);
+    r->b.x = w[3 * i + 1]; r->b.y = w[3 * i + 2];
+}
 
 // ---------------------------------------------------------------- multi-block exclusive scan (u32)
 #define SCAN_ITEMS 2048

@@ -136,17 +136,40 @@ def capsules_scene(num=11, jitter=0.0, seed=1, count=None):
             np.tile(np.array([0.0, -9.8, 0.0], np.float32), (n, 1)))
 
 
+def pile_scene(num=46, extra=2664, jitter=0.01, seed=1, rad=0.5, squeeze=0.98, floor_y=-10.0):
+    """The C2 body set as a pile that is already in contact: the balls.rs lattice (same loop
+    order, same `extra` top layer, same LCG jitter) with the spacing squeezed from 2.5*rad to
+    squeeze*2*rad and the bottom layer resting on the floor, so contact-constraint work is
+    present from step 0 (the free-fall version needs ~600 steps before the pile forms)."""
+    shapes, mass, rest, fric, force = balls_scene(num, extra, 0.0, seed, rad)
+    pos = shapes["p"][:, 0:3].astype(np.float32)
+    scale = F(squeeze * 2.0 * rad) / (F(2.5) * F(rad))
+    pos = (pos * scale).astype(np.float32)
+    pos[:, 1] += F(floor_y + rad) - pos[:, 1].min()
+    n = len(pos)
+    if jitter:
+        u = lcg_uniform_fast(3 * n, seed).reshape(n, 3)
+        pos = (pos + (u * F(2.0) - F(1.0)) * F(jitter)).astype(np.float32)
+    shapes["p"][:, 0:3] = pos
+    return shapes, mass, rest, fric, force
+
+
 CONFIGS = {
     # name: (scene kwargs, terrain kwargs, iters)
     "C1": dict(kind="balls", num=8, extra=0, jitter=0.0, box=(10.0, 10.0, 10.0), iters=10),
     "demo": dict(kind="balls", num=11, extra=0, jitter=0.0, box=(10.0, 10.0, 10.0), iters=20, demo_extra_ball=True),
     "C2": dict(kind="balls", num=46, extra=2664, jitter=0.01, box=(80.0, 40.0, 80.0), iters=20),
+    "C2pile": dict(kind="pile", num=46, extra=2664, jitter=0.01, box=(80.0, 40.0, 80.0), iters=20),
     "C4tile": dict(kind="balls", num=63, extra=0, jitter=0.01, box=(80.0, 60.0, 80.0), iters=20),
 }
 
 
 def build_config(name):
     cfg = CONFIGS[name]
+    if cfg["kind"] == "pile":
+        bodies = pile_scene(cfg["num"], cfg["extra"], cfg["jitter"], 1)
+        hx, wh, hz = cfg["box"]
+        return bodies, box_terrain(hx, wh, hz), cfg["iters"]
     bodies = balls_scene(cfg["num"], cfg["extra"], cfg["jitter"], 1, demo_extra_ball=cfg.get("demo_extra_ball", False))
     hx, wh, hz = cfg["box"]
     terrain = box_terrain(hx, wh, hz)

@@ -166,6 +166,19 @@ void mgfo_world_manifolds(const mgfo_world* h, int32_t* obj_a, int32_t* obj_b, f
         }
     }
 }
+// O(n^2) count of {(i, j): j < i, tight_i overlaps stored fat_j} over the LEAF boxes of the last
+// build.  The reference's BVH query can return fewer: its internal nodes are rounded unions
+// ((hi+lo)/2, (hi-lo)/2 in bounds.rs:113-130), so a leaf that only TOUCHES the query box can be
+// pruned at a parent.  Such pairs are >= fat_margin apart and never produce a contact.
+uint64_t mgfo_world_brute_pairs(const mgfo_world* h) {
+    const World& w = h->w;
+    uint64_t cnt = 0;
+    for (size_t i = 1; i < w.bodies.len(); ++i) {
+        AABB t = bounds(w.bodies.collider[i]);
+        for (size_t j = 0; j < i; ++j) cnt += overlaps(t, w.bvh[w.bvh_ids[j]]) ? 1 : 0;
+    }
+    return cnt;
+}
 void mgfo_world_stats(const mgfo_world* h, uint64_t* candidate_pairs, uint64_t* terrain_candidates) {
     *candidate_pairs = h->w.candidate_pairs; *terrain_candidates = h->w.terrain_candidates;
 }

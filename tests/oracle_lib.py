@@ -53,6 +53,8 @@ def load():
     lib.mgfo_world_build.argtypes = [_P, C.c_float, C.POINTER(C.c_uint32)]
     lib.mgfo_world_constraints.argtypes = [_P, _P, _P, _P, _P]
     lib.mgfo_world_manifolds.argtypes = [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P]
+    lib.mgfo_world_brute_pairs.restype = C.c_uint64
+    lib.mgfo_world_brute_pairs.argtypes = [_P]
     lib.mgfo_world_stats.argtypes = [_P, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
     lib.mgfo_world_solve_order.argtypes = [_P, _P, C.c_uint32, C.c_uint32]
     lib.mgfo_world_solve_manifolds.restype = C.c_int32
@@ -162,6 +164,9 @@ class OracleWorld:
         a = C.c_uint64(); b = C.c_uint64()
         self.lib.mgfo_world_stats(self.h, C.byref(a), C.byref(b))
         return a.value, b.value
+
+    def brute_pairs(self):
+        return self.lib.mgfo_world_brute_pairs(self.h)
 
     def solve_order(self, perm, iters):
         perm = np.ascontiguousarray(perm, dtype=np.uint32)

@@ -76,8 +76,11 @@ KINDS = [
 
 
 def _assert_bit_equal(got, want, what):
-    g = np.ascontiguousarray(got).view(np.uint32); w = np.ascontiguousarray(want).view(np.uint32)
-    bad = np.nonzero((g != w).reshape(len(got), -1).any(axis=1))[0]
+    # bit-exact, except that NaN payload/sign is not part of IEEE arithmetic (x86 SSE makes
+    # 0xFFC00000, the GPU 0x7FFFFFFF): degenerate inputs (zero-area triangle) must give NaN on both.
+    gf = np.ascontiguousarray(got).view(np.float32); wf = np.ascontiguousarray(want).view(np.float32)
+    g = gf.view(np.uint32); w = wf.view(np.uint32)
+    bad = np.nonzero(((g != w) & ~(np.isnan(gf) & np.isnan(wf))).reshape(len(got), -1).any(axis=1))[0]
     assert len(bad) == 0, f"{what}: {len(bad)} rows differ, first {bad[:5].tolist()}"
 
 
