@@ -51,7 +51,9 @@ class StepStats(C.Structure):
                 ("solve_ms", C.c_float), ("overflow", C.c_uint32), ("reserved", C.c_uint32 * 5)]
 
     def as_dict(self):
-        return {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}
+        d = {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}
+        d["colouring_rounds"] = self.reserved[0]
+        return d
 
 
 class DeviceView(C.Structure):

@@ -53,7 +53,7 @@ struct mgfb_ctx {
     // rows
     Buf r_ab, r_n, r_t0, r_t1, r_ra, r_rb, r_imp, r_xra, r_xrb, r_xtm; unsigned row_cap = 0, xrow_cap = 0;
     // body grid
-    Buf cell_count, cell_start, ent_id, ent_key, scan_sums; unsigned table = 0, ent_cap = 0;
+    Buf cell_count, cell_start, bg_ent, scan_sums; unsigned table = 0, ent_cap = 0;
     TerrainData terrain;
     Buf stage;          // packed state staging for get_state / set_velocity
     unsigned long long launches = 0;   // kernels launched since the last mgfb_step_totals(reset)
@@ -167,7 +167,8 @@ int32_t ensure_grid(mgfb_ctx* ctx, unsigned scale) {
         TRY(ensure(ctx, ctx->scan_sums, ((size_t)table / SCAN_ITEMS + 2) * 4));
         ctx->table = table;
     }
-    if (ecap > ctx->ent_cap) { TRY(ensure(ctx, ctx->ent_id, (size_t)ecap * 4)); TRY(ensure(ctx, ctx->ent_key, (size_t)ecap * 8)); ctx->ent_cap = ecap; }
+    (void)ecap;
+    if (ctx->cap > ctx->ent_cap) { TRY(ensure(ctx, ctx->bg_ent, (size_t)ctx->cap * 32)); ctx->ent_cap = ctx->cap; }
     return MGFB_OK;
 }
 // exclusive scan of `in[0..n)` into out[0..n], out[n] = total (also stored at *total_dev if given)
@@ -180,11 +181,10 @@ int32_t scan_u32(mgfb_ctx* ctx, const unsigned* in, unsigned* out, unsigned n, u
     return MGFB_OK;
 }
 
-GridView body_grid(const mgfb_ctx* ctx) {
-    GridView G;
+BodyGrid body_grid(const mgfb_ctx* ctx) {
+    BodyGrid G;
     G.cell_count = ctx->cell_count.as<unsigned>(); G.cell_start = ctx->cell_start.as<unsigned>();
-    G.ent_id = ctx->ent_id.as<unsigned>(); G.ent_key = ctx->ent_key.as<unsigned long long>();
-    G.table_mask = ctx->table - 1; G.ent_cap = ctx->ent_cap;
+    G.ent = ctx->bg_ent.as<float4>(); G.table_mask = ctx->table - 1;
     return G;
 }
 TerrainView terrain_view(const mgfb_ctx* ctx) {
@@ -229,10 +229,10 @@ OrderView order_view(const mgfb_ctx* ctx, const int* a, const int* b, const uint
 Counters* dctr(const mgfb_ctx* ctx) { return ctx->ctr.as<Counters>(); }
 
 template <class K>
-int coop_blocks(const mgfb_ctx* ctx, K kernel) {
+int coop_blocks(const mgfb_ctx* ctx, K kernel, int threads, int max_per_sm) {
     int per_sm = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, MGFB_THREADS, 0);
-    per_sm = std::max(1, std::min(per_sm, 4));
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, 0);
+    per_sm = std::max(1, std::min(per_sm, max_per_sm));
     return per_sm * ctx->num_sms;
 }
 
@@ -262,7 +262,7 @@ int32_t enqueue_order_and_solve(mgfb_ctx* ctx, const OrderView& O, const Manifol
     {
         const unsigned* gs = gstart; unsigned it = iters;
         void* args[] = {&R, &vel, &gs, &it, &c};
-        CU(cudaLaunchCooperativeKernel((void*)k_solve, dim3(ctx->coop_solve), dim3(MGFB_THREADS), args, 0, ctx->stream));
+        CU(cudaLaunchCooperativeKernel((void*)k_solve, dim3(ctx->coop_solve), dim3(MGFB_SOLVE_THREADS), args, 0, ctx->stream));
     }
     if (time_solve) CU(cudaEventRecord(ctx->ev[3], ctx->stream));
     ctx->launches += 5;   // k_order, k_group_scan, k_scatter_rows, k_build_rows, k_solve
@@ -283,12 +283,12 @@ int32_t enqueue_step(mgfb_ctx* ctx, float dt, unsigned iters, bool from_integrat
     if (from_integrate) k_integrate<true, true, true><<<gb, MGFB_THREADS, 0, ctx->stream>>>(B, n, dt, ctx->cfg.fat_margin, c);
     else k_integrate<false, false, true><<<gb, MGFB_THREADS, 0, ctx->stream>>>(B, n, dt, ctx->cfg.fat_margin, c);
     // broadphase over the stored fat boxes
-    GridView G = body_grid(ctx);
-    k_grid_insert<false><<<gb, MGFB_THREADS, 0, ctx->stream>>>(B.fat, n, G, c, 0.0f);
+    BodyGrid G = body_grid(ctx);
+    k_bgrid_insert<false><<<gb, MGFB_THREADS, 0, ctx->stream>>>(B.fat, B.col, n, G, c);
     TRY(scan_u32(ctx, G.cell_count, G.cell_start, ctx->table, ctx->scan_sums.as<unsigned>(), &c->grid_entries));
-    k_grid_insert<true><<<gb, MGFB_THREADS, 0, ctx->stream>>>(B.fat, n, G, c, 0.0f);
+    k_bgrid_insert<true><<<gb, MGFB_THREADS, 0, ctx->stream>>>(B.fat, B.col, n, G, c);
     PairLists PL; for (int k = 0; k < 4; ++k) PL.p[k] = ctx->pair_list[k].as<int2>();
-    k_body_pairs<<<gb, MGFB_THREADS, 0, ctx->stream>>>(B.tight, B.fat, B.col, n, G, PL, ctx->pair_cap, c);
+    k_body_pairs_warp<<<std::max(1, std::min((int)((n + BP_WARPS - 1) / BP_WARPS), ctx->num_sms * 8)), MGFB_THREADS, 0, ctx->stream>>>(B.tight, B.col, n, G, PL, ctx->pair_cap, c);
     ContactList L = contact_list(ctx);
     TerrainView T{};
     if (ctx->terrain.present) {
@@ -418,8 +418,8 @@ int32_t mgfb_ctx_create(const mgfb_config* cfg, mgfb_ctx** out) {
     if ((e = cudaMalloc(&ctx->ctr.p, sizeof(Counters))) != cudaSuccess) return bail(e, "cudaMalloc");
     ctx->ctr.bytes = sizeof(Counters);
     cudaMemsetAsync(ctx->ctr.p, 0, sizeof(Counters), ctx->stream);
-    ctx->coop_order = coop_blocks(ctx, k_order);
-    ctx->coop_solve = coop_blocks(ctx, k_solve);
+    ctx->coop_order = coop_blocks(ctx, k_order, MGFB_THREADS, 2);
+    ctx->coop_solve = coop_blocks(ctx, k_solve, MGFB_SOLVE_THREADS, 1);
     int32_t s = grow_bodies(ctx, std::max(ctx->cfg.initial_body_capacity, 1024u));
     if (s == MGFB_OK) s = ensure_rows(ctx, 1024, false, 4096);
     if (s != MGFB_OK) { g_create_err = ctx->err; delete ctx; return s; }
@@ -435,8 +435,8 @@ void mgfb_ctx_destroy(mgfb_ctx* ctx) {
                   &ctx->pair_list[0], &ctx->pair_list[1], &ctx->pair_list[2], &ctx->pair_list[3], &ctx->tpair_list[0], &ctx->tpair_list[1],
                   &ctx->c_a, &ctx->c_b, &ctx->c_face, &ctx->c_sub, &ctx->c_la, &ctx->c_lb, &ctx->c_nt, &ctx->body_best, &ctx->body_scratch,
                   &ctx->group, &ctx->group_count, &ctx->group_start, &ctx->perm, &ctx->r_ab, &ctx->r_n, &ctx->r_t0, &ctx->r_t1, &ctx->r_ra,
-                  &ctx->r_rb, &ctx->r_imp, &ctx->r_xra, &ctx->r_xrb, &ctx->r_xtm, &ctx->cell_count, &ctx->cell_start, &ctx->ent_id,
-                  &ctx->ent_key, &ctx->scan_sums, &ctx->u_a, &ctx->u_b, &ctx->u_sc, &ctx->u_sf, &ctx->u_n, &ctx->u_t, &ctx->u_nc, &ctx->u_la,
+                  &ctx->r_rb, &ctx->r_imp, &ctx->r_xra, &ctx->r_xrb, &ctx->r_xtm, &ctx->cell_count, &ctx->cell_start, &ctx->bg_ent,
+                  &ctx->scan_sums, &ctx->u_a, &ctx->u_b, &ctx->u_sc, &ctx->u_sf, &ctx->u_n, &ctx->u_t, &ctx->u_nc, &ctx->u_la,
                   &ctx->u_lb, &ctx->stage, &ctx->terrain.verts, &ctx->terrain.faces, &ctx->terrain.boxes, &ctx->terrain.cell_count,
                   &ctx->terrain.cell_start, &ctx->terrain.ent_id, &ctx->terrain.ent_key, &ctx->terrain.max_bits};
     for (Buf* b : all) release(*b);
@@ -675,6 +675,7 @@ static void fill_step_stats(mgfb_ctx* ctx, mgfb_step_stats* st, unsigned iters, 
     st->iterations = iters;
     st->fat_refreshes = h.fat_refreshes;
     st->overflow = overflowed;
+    st->reserved[0] = h.rounds;   // colouring rounds (diagnostic)
     if (timed) {
         cudaEventElapsedTime(&st->step_ms, ctx->ev[0], ctx->ev[1]);
         cudaEventElapsedTime(&st->solve_ms, ctx->ev[2], ctx->ev[3]);

@@ -17,12 +17,12 @@ struct Counters {
     unsigned tcontacts;      // of which terrain
     unsigned grid_entries;
     unsigned fat_refreshes;
-    unsigned max_fat_bits;   // float bits of the largest fat-box diameter (cell size)
+    unsigned max_fat_bits;   // float bits of the largest stored fat-box half extent
     unsigned ngroups;
     unsigned remaining;      // uncoloured constraints
     unsigned bar;            // grid barrier arrival counter
     unsigned rounds;         // colouring rounds taken
-    unsigned pad0;
+    unsigned max_tight_bits; // float bits of the largest tight (swept) box half extent
     // sticky until the host clears them
     unsigned overflow;       // bit0 pairs, bit1 tpairs, bit2 contacts, bit3 grid entries
     unsigned nan_bounds;     // AABB::combine assert (bounds.rs:125-127)
@@ -44,15 +44,16 @@ __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
     return v;
 }
 // All CTAs of a cooperative launch.  `bar` is zero at kernel entry; phase counts barriers.
+// One release-add + acquire-poll per CTA: the CTA barrier in front makes every thread's earlier
+// writes happen-before thread 0's release, the one behind orders the acquire before every
+// thread's later reads (PTX memory model: causality order is transitive across bar.sync).
 __device__ __forceinline__ void grid_barrier(unsigned* bar, unsigned& phase) {
     __syncthreads();
     phase++;
     if (threadIdx.x == 0) {
-        __threadfence();
-        atomicAdd(bar, 1u);
+        asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(bar) : "memory");
         unsigned target = phase * gridDim.x;
         while (ld_acquire_u32(bar) < target) { }
-        __threadfence();
     }
     __syncthreads();
 }
@@ -101,7 +102,7 @@ HD bool box_overlaps(V3 ac, V3 ar, V3 bc, V3 br) {  // collision.rs:22-29 (close
 template <bool COMPLETE, bool INTEGRATE, bool BOUNDS>
 __global__ void __launch_bounds__(MGFB_THREADS) k_integrate(BodyArrays B, unsigned n, float dt, float margin, Counters* ctr) {
     if (ctr->overflow | ctr->nan_bounds) return;  // poisoned: the host will resume from steps_done
-    float my_fat = 0.0f;
+    float my_fat = 0.0f, my_tight = 0.0f;
     unsigned refreshed = 0;
     for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         Collider k = B.col[i];
@@ -157,16 +158,19 @@ __global__ void __launch_bounds__(MGFB_THREADS) k_integrate(BodyArrays B, unsign
                 B.fat[i] = fb;
                 refreshed++;
             }
-            my_fat = fmaxf(my_fat, 2.0f * fmaxf(fr.x, fmaxf(fr.y, fr.z)));
+            my_fat = fmaxf(my_fat, fmaxf(fr.x, fmaxf(fr.y, fr.z)));
+            my_tight = fmaxf(my_tight, fmaxf(tr.x, fmaxf(tr.y, tr.z)));
         }
     }
     if (BOUNDS) {
         for (int o = 16; o > 0; o >>= 1) {
             my_fat = fmaxf(my_fat, __shfl_xor_sync(0xffffffffu, my_fat, o));
+            my_tight = fmaxf(my_tight, __shfl_xor_sync(0xffffffffu, my_tight, o));
             refreshed += __shfl_xor_sync(0xffffffffu, refreshed, o);
         }
         if ((threadIdx.x & 31) == 0) {
             atomicMax(&ctr->max_fat_bits, __float_as_uint(my_fat));
+            atomicMax(&ctr->max_tight_bits, __float_as_uint(my_tight));
             if (refreshed) atomicAdd(&ctr->fat_refreshes, refreshed);
         }
     }
@@ -209,10 +213,133 @@ __device__ __forceinline__ CellRange cell_range(V3 c, V3 r, float inv, bool slop
     }
     return cr;
 }
+// Body grid: every body is binned ONCE, by the centre of its stored fat box, into cells of
+// edge s >= max tight half extent + max fat half extent.  Then |c_i - c_j| <= r_i + R_j (the
+// closed overlap test) implies the two centres are at most one cell apart on every axis, so a
+// query looks at the 27 cells around the tight box's centre and no pair can be seen twice.
 __device__ __forceinline__ float grid_inv_cell(const Counters* ctr) {
-    float s = __uint_as_float(ctr->max_fat_bits);
-    if (!(s > 0.0f)) s = 1.0f;
+    float s = (__uint_as_float(ctr->max_fat_bits) + __uint_as_float(ctr->max_tight_bits)) * 1.001f;
+    if (!(s > 0.0f) || !(s < 3.0e38f)) s = 1.0f;
     return 1.0f / s;
+}
+struct BodyGrid {
+    unsigned* cell_count;   // [T]
+    unsigned* cell_start;   // [T+1]
+    float4* ent;            // [2n]: (fat.c.xyz, body index bits), (fat.r.xyz, shape kind bits)
+    unsigned table_mask;
+};
+template <bool FILL>
+__global__ void __launch_bounds__(MGFB_THREADS) k_bgrid_insert(const Box* __restrict__ fat, const Collider* __restrict__ col, unsigned n, BodyGrid G, Counters* ctr) {
+    if (ctr->overflow | ctr->nan_bounds) return;
+    float inv = grid_inv_cell(ctr);
+    for (unsigned j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+        Box b = fat[j];
+        unsigned h = cell_hash(cell_key(cell_coord(b.c.x, inv), cell_coord(b.c.y, inv), cell_coord(b.c.z, inv)), G.table_mask);
+        if (!FILL) atomicAdd(&G.cell_count[h], 1u);
+        else {
+            unsigned pos = G.cell_start[h] + (atomicSub(&G.cell_count[h], 1u) - 1u);
+            G.ent[2 * pos] = make_float4(b.c.x, b.c.y, b.c.z, __uint_as_float(j));
+            G.ent[2 * pos + 1] = make_float4(b.r.x, b.r.y, b.r.z, __int_as_float(col_kind(col[j])));
+        }
+    }
+}
+// Body-pair sweep, one warp per body i: lanes 0..26 take the 27 neighbouring cells.  Hits are
+// staged in shared memory and appended with ONE global atomic per block per batch of 8 bodies
+// (a single global cursor would otherwise serialise ~4 atomics per body at one L2 address).
+// P = {(i, j): j < i, tight_i overlaps stored fat_j}  (world.rs:261-268).
+#define BP_WARPS (MGFB_THREADS / 32)
+#define BP_BUF 128
+__device__ __forceinline__ void bp_flush_warp(unsigned* buf, unsigned cnt, unsigned i, const unsigned base[4], PairLists lists, unsigned cap,
+                                              Counters* ctr, unsigned lane) {
+    // buf entries: j | kind << 30.  base[k]: where this warp's kind-k entries start in list k.
+    unsigned run[4] = {0, 0, 0, 0};
+    for (unsigned s0 = 0; s0 < cnt; s0 += 32) {
+        unsigned e = s0 + lane < cnt ? buf[s0 + lane] : 0xffffffffu;
+        int kind = e == 0xffffffffu ? -1 : (int)(e >> 30);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            unsigned m = __ballot_sync(0xffffffffu, kind == k);
+            if (kind == k) {
+                unsigned pos = base[k] + run[k] + __popc(m & ((1u << lane) - 1u));
+                if (pos < cap) lists.p[k][pos] = make_int2((int)i, (int)(e & 0x3fffffffu));
+                else atomicOr(&ctr->overflow, (unsigned)OVF_PAIRS);
+            }
+            run[k] += __popc(m);
+        }
+    }
+}
+__global__ void __launch_bounds__(MGFB_THREADS) k_body_pairs_warp(const Box* __restrict__ tight, const Collider* __restrict__ col, unsigned n,
+                                                                 BodyGrid G, PairLists lists, unsigned cap, Counters* ctr) {
+    __shared__ unsigned s_buf[BP_WARPS][BP_BUF];
+    __shared__ unsigned s_cnt[BP_WARPS][4];     // per warp, per kind
+    __shared__ unsigned s_base[BP_WARPS][4];
+    if (ctr->overflow | ctr->nan_bounds) return;
+    const float inv = grid_inv_cell(ctr);
+    const unsigned lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
+    for (unsigned batch = blockIdx.x * BP_WARPS; batch < n; batch += gridDim.x * BP_WARPS) {   // uniform per block
+        const unsigned i = batch + w;
+        unsigned cnt = 0, kcnt[4] = {0, 0, 0, 0};
+        if (i < n && i != 0) {   // world.rs:256
+            Box tb = tight[i];
+            V3 tc = f4v(tb.c), tr = f4v(tb.r);
+            int ki = col_kind(col[i]);
+            int cx = cell_coord(tc.x, inv), cy = cell_coord(tc.y, inv), cz = cell_coord(tc.z, inv);
+            unsigned e = 0, e1 = 0;
+            int x = 0, y = 0, z = 0;
+            if (lane < 27) {
+                x = cx + (int)(lane % 3) - 1; y = cy + (int)((lane / 3) % 3) - 1; z = cz + (int)(lane / 9) - 1;
+                unsigned h = cell_hash(cell_key(x, y, z), G.table_mask);
+                e = G.cell_start[h]; e1 = G.cell_start[h + 1];
+            }
+            while (__any_sync(0xffffffffu, e < e1)) {
+                int kind = -1; unsigned j = 0;
+                if (e < e1) {
+                    float4 a = G.ent[2 * e], b = G.ent[2 * e + 1];
+                    ++e;
+                    j = __float_as_uint(a.w);
+                    // the bucket may also hold other cells (hash collisions): take only this cell's bodies
+                    if (j < i && cell_coord(a.x, inv) == x && cell_coord(a.y, inv) == y && cell_coord(a.z, inv) == z &&
+                        box_overlaps(tc, tr, mk3(a.x, a.y, a.z), mk3(b.x, b.y, b.z)))
+                        kind = ki * 2 + __float_as_int(b.w);
+                }
+                unsigned m = __ballot_sync(0xffffffffu, kind >= 0);
+                if (!m) continue;
+                unsigned nh = __popc(m);
+                if (cnt + nh > BP_BUF) {   // staging full (a very dense blob): spill with a per-warp reservation
+                    unsigned base[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        unsigned b0 = 0;
+                        if (lane == 0 && kcnt[k]) b0 = atomicAdd(&ctr->pairs[k], kcnt[k]);
+                        base[k] = __shfl_sync(0xffffffffu, b0, 0);
+                        kcnt[k] = 0;
+                    }
+                    __syncwarp();
+                    bp_flush_warp(s_buf[w], cnt, i, base, lists, cap, ctr, lane);
+                    __syncwarp();
+                    cnt = 0;
+                }
+                if (kind >= 0) s_buf[w][cnt + __popc(m & ((1u << lane) - 1u))] = j | ((unsigned)kind << 30);
+                cnt += nh;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) kcnt[k] += __popc(__ballot_sync(0xffffffffu, kind == k));
+            }
+        }
+        if (lane < 4) s_cnt[w][lane] = kcnt[lane];
+        __syncthreads();
+        if (threadIdx.x < 4) {   // one reservation per kind for the whole block
+            unsigned tot = 0;
+            for (int ww = 0; ww < BP_WARPS; ++ww) { s_base[ww][threadIdx.x] = tot; tot += s_cnt[ww][threadIdx.x]; }
+            unsigned b0 = tot ? atomicAdd(&ctr->pairs[threadIdx.x], tot) : 0u;
+            for (int ww = 0; ww < BP_WARPS; ++ww) s_base[ww][threadIdx.x] += b0;
+        }
+        __syncthreads();
+        if (cnt) {
+            unsigned base[4] = {s_base[w][0], s_base[w][1], s_base[w][2], s_base[w][3]};
+            bp_flush_warp(s_buf[w], cnt, i, base, lists, cap, ctr, lane);
+        }
+        __syncthreads();
+    }
 }
 
 // pass 1: count entries per hashed cell; pass 2 (FILL): write them.
@@ -234,43 +361,6 @@ __global__ void __launch_bounds__(MGFB_THREADS) k_grid_insert(const Box* __restr
                         unsigned pos = G.cell_start[h] + (atomicSub(&G.cell_count[h], 1u) - 1u);
                         if (pos < G.ent_cap) { G.ent_id[pos] = j; G.ent_key[pos] = key; }
                         else atomicOr(&ctr->overflow, (unsigned)OVF_GRID);
-                    }
-                }
-    }
-}
-
-// Body-pair sweep: P = {(i, j): j < i, tight_i overlaps fat_j}  (world.rs:261-268).
-__global__ void __launch_bounds__(MGFB_THREADS) k_body_pairs(const Box* __restrict__ tight, const Box* __restrict__ fat,
-                                                            const Collider* __restrict__ col, unsigned n, GridView G,
-                                                            PairLists lists, unsigned cap, Counters* ctr) {
-    if (ctr->overflow | ctr->nan_bounds) return;
-    float inv = grid_inv_cell(ctr);
-    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        if (i == 0) continue;  // world.rs:256
-        Box tb = tight[i];
-        V3 tc = f4v(tb.c), tr = f4v(tb.r);
-        CellRange qi = cell_range(tc, tr, inv, false);
-        int ki = col_kind(col[i]);
-        for (int x = qi.lo[0]; x <= qi.hi[0]; ++x)
-            for (int y = qi.lo[1]; y <= qi.hi[1]; ++y)
-                for (int z = qi.lo[2]; z <= qi.hi[2]; ++z) {
-                    unsigned long long key = cell_key(x, y, z);
-                    unsigned h = cell_hash(key, G.table_mask);
-                    unsigned e0 = G.cell_start[h], e1 = G.cell_start[h + 1];
-                    for (unsigned e = e0; e < e1; ++e) {
-                        if (G.ent_key[e] != key) continue;
-                        unsigned j = G.ent_id[e];
-                        if (j >= i) continue;  // world.rs:266
-                        Box fb = fat[j];
-                        V3 fc = f4v(fb.c), fr = f4v(fb.r);
-                        if (!box_overlaps(tc, tr, fc, fr)) continue;
-                        // report the pair only from the first cell both ranges share
-                        CellRange qj = cell_range(fc, fr, inv, true);
-                        if (x != max(qi.lo[0], qj.lo[0]) || y != max(qi.lo[1], qj.lo[1]) || z != max(qi.lo[2], qj.lo[2])) continue;
-                        int kind = ki * 2 + col_kind(col[j]);
-                        unsigned pos = atomicAdd(&ctr->pairs[kind], 1u);
-                        if (pos < cap) lists.p[kind][pos] = make_int2((int)i, (int)j);
-                        else atomicOr(&ctr->overflow, (unsigned)OVF_PAIRS);
                     }
                 }
     }
@@ -659,13 +749,20 @@ __device__ __forceinline__ void apply_impulse(V3 J, V3 ra, V3 rb, float ima, flo
     vb = vb + J * imb;
     ob = ob + mmulv(IB, cross3(rb, J));
 }
-__device__ __forceinline__ void solve_row(const ConstraintRows& R, BodyVel* vel, unsigned row) {
-    int2 ab = R.ab[row];
+// Immutable part of a row (everything but the bodies' velocities and the accumulated impulse).
+struct RowData { int2 ab; float4 n, t0, t1, ra, rb; };
+__device__ __forceinline__ RowData load_row(const ConstraintRows& R, unsigned row) {
+    RowData d;
+    d.ab = R.ab[row]; d.n = R.n[row]; d.t0 = R.t0[row]; d.t1 = R.t1[row]; d.ra = R.ra[row]; d.rb = R.rb[row];
+    return d;
+}
+__device__ __forceinline__ void solve_row(const ConstraintRows& R, BodyVel* vel, unsigned row, const RowData& d) {
+    int2 ab = d.ab;
     V3 va = zero3(), oa = zero3(), vb = zero3(), ob = zero3();
     float ima = 0.0f, imb = 0.0f; M3 IA = m_zero(), IB = m_zero();
     if (ab.x >= 0) load_vel(vel + ab.x, &va, &oa, &ima, &IA);
     if (ab.y >= 0) load_vel(vel + ab.y, &vb, &ob, &imb, &IB);
-    float4 n4 = R.n[row], t04 = R.t0[row], t14 = R.t1[row], ra4 = R.ra[row], rb4 = R.rb[row];
+    float4 n4 = d.n, t04 = d.t0, t14 = d.t1, ra4 = d.ra, rb4 = d.rb;
     V3 n = f4v(n4), t0 = f4v(t04), t1 = f4v(t14);
     int nc = (int)fbits(rb4.w);
     for (int c = 0; c < nc; ++c) {
@@ -696,16 +793,32 @@ __device__ __forceinline__ void solve_row(const ConstraintRows& R, BodyVel* vel,
     if (ab.x >= 0) store_vel(vel + ab.x, va, oa, ima, IA);
     if (ab.y >= 0) store_vel(vel + ab.y, vb, ob, imb, IB);
 }
-__global__ void __launch_bounds__(MGFB_THREADS) k_solve(ConstraintRows R, BodyVel* vel, const unsigned* __restrict__ group_start,
-                                                       unsigned iters, Counters* ctr) {
+#define MGFB_SOLVE_THREADS 512
+__global__ void __launch_bounds__(MGFB_SOLVE_THREADS, 1) k_solve(ConstraintRows R, BodyVel* vel, const unsigned* __restrict__ group_start,
+                                                                unsigned iters, Counters* ctr) {
     if (ctr->overflow | ctr->nan_bounds) return;
     const unsigned ngroups = ctr->ngroups;
-    const unsigned tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+    if (ngroups == 0) return;
+    // Rows are dealt to warps round-robin ACROSS the SMs (warp w of CTA b is global warp
+    // w*gridDim + b), so a group with fewer rows than threads still spreads over all 148 SMs
+    // instead of saturating the issue slots of the first few.
+    const unsigned tid = (((threadIdx.x >> 5) * gridDim.x + blockIdx.x) << 5) | (threadIdx.x & 31u), nth = gridDim.x * blockDim.x;
     unsigned phase = 0;
+    // The first row this thread owns in the next group is fetched BEFORE the grid barrier: rows
+    // are immutable during the solve, so only the body gather sits behind the barrier.
+    unsigned r0 = group_start[0], r1 = group_start[1];
+    RowData pre; bool have = false;
+    if (r0 + tid < r1) { pre = load_row(R, r0 + tid); have = true; }
     for (unsigned it = 0; it < iters; ++it) {
         for (unsigned g = 0; g < ngroups; ++g) {
-            unsigned r0 = group_start[g], r1 = group_start[g + 1];
-            for (unsigned row = r0 + tid; row < r1; row += nth) solve_row(R, vel, row);
+            unsigned row = r0 + tid;
+            if (have) solve_row(R, vel, row, pre);
+            for (row += nth; row < r1; row += nth) { RowData d = load_row(R, row); solve_row(R, vel, row, d); }
+            unsigned gn = g + 1 == ngroups ? 0 : g + 1;
+            bool more = (g + 1 < ngroups) || (it + 1 < iters);
+            r0 = group_start[gn]; r1 = group_start[gn + 1];
+            have = false;
+            if (more && r0 + tid < r1) { pre = load_row(R, r0 + tid); have = true; }
             grid_barrier(&ctr->bar, phase);
         }
     }
