@@ -31,7 +31,8 @@ enum mgfb_status {
     MGFB_ERR_CAPACITY = 3,         /* a device work list overflowed even after growing */
     MGFB_ERR_CUDA = 4,
     MGFB_ERR_NAN_BOUNDS = 5,       /* AABB::combine asserts r >= 0, bounds.rs:125-127 */
-    MGFB_ERR_STATE = 6             /* call order violated (e.g. step without terrain is fine; replay without a step is not) */
+    MGFB_ERR_STATE = 6,            /* call order violated (e.g. step without terrain is fine; replay without a step is not) */
+    MGFB_ERR_TILE = 7              /* tiled world: a neighbour tile did not answer in time, or the tile is thinner than its ghost layers */
 };
 
 enum mgfb_shape_kind {
@@ -83,7 +84,9 @@ typedef struct mgfb_config {
     float persistent_threshold_sq;  /* 0.5   manifold.rs:38 */
     float fat_margin;               /* 0.25  world.rs:181,237 */
     uint32_t initial_body_capacity; /* 0 = default */
-    uint32_t reserved[4];
+    uint32_t max_cooperative_ctas;  /* 0 = one CTA per SM; lower it when several contexts must share one GPU */
+    uint32_t tile_timeout_ms;       /* 0 = 20000: how long a tile waits for a neighbour before MGFB_ERR_TILE */
+    uint32_t reserved[2];
 } mgfb_config;
 void mgfb_config_default(mgfb_config* cfg);
 
@@ -192,7 +195,11 @@ typedef struct mgfb_step_stats {
     float step_ms;                /* device time of the whole step */
     float solve_ms;               /* device time of the solve kernel alone */
     uint32_t overflow;            /* nonzero if a work list had to be regrown and the step rerun */
-    uint32_t reserved[5];
+    uint32_t colouring_rounds;    /* Jones-Plassmann rounds (diagnostic) */
+    uint32_t ghosts;              /* tiled world: bodies received from the right neighbour this step */
+    uint32_t boundary_constraints;/* tiled world: constraints between an owned body and a ghost */
+    uint32_t phases;              /* non-empty groups = grid-wide phases per solver iteration */
+    uint32_t reserved;
 } mgfb_step_stats;
 
 /* One World::step(dt) with `iters` solver iterations (the demo hard-codes 20, world.rs:293).
@@ -214,6 +221,32 @@ int32_t mgfb_step_constraints(mgfb_ctx* ctx, uint32_t capacity, uint32_t* body_a
  * CUDA kernels this ctx launched.  Any pointer may be NULL. */
 int32_t mgfb_step_totals(mgfb_ctx* ctx, uint64_t* steps, uint64_t* constraints, uint64_t* candidate_pairs, uint64_t* groups,
                          uint64_t* kernel_launches, int32_t reset);
+
+/* ---------------- one world tiled across GPUs (no counterpart in mgf) ----------------
+ * Each GPU (one process per GPU, or one ctx per GPU) owns a slab of the bodies.  Once per step the
+ * right neighbour's bodies that can touch this tile arrive as "ghosts" (written by the neighbour's
+ * kernel straight into this ctx's body arrays over NVLink peer memory); constraints between an owned
+ * body and a ghost are solved here, inside the same persistent solver kernel, with the ghost
+ * velocities exchanged every iteration.  The executed constraint order is a valid sequential order
+ * (per iteration: every tile's interior constraints, then every tile's boundary constraints), exported
+ * by mgfb_step_constraints with GLOBAL body ids so a caller (or the oracle) can replay it.
+ *
+ *   setup:  add this tile's bodies; mgfb_bodies_set_gid; mgfb_terrain_set (same mesh on every tile);
+ *           mgfb_tile_export; exchange the descriptors between ranks (host plumbing, e.g.
+ *           torch.distributed all_gather); mgfb_tile_connect; then every rank calls mgfb_step /
+ *           mgfb_step_n the same number of times.
+ *   rules:  tiles are ordered along x; rank r's bodies must only ever touch bodies of ranks r-1, r, r+1
+ *           and no body may touch both neighbours (MGFB_ERR_TILE otherwise): tiles must stay wider than
+ *           two ghost layers.  Ownership is fixed until the caller re-tiles. */
+/* The global id of bodies first..first+n (default: the local index).  Pairs are generated as
+ * (i, j) with gid_j < gid_i (world.rs:266), so the global ids define which body is the receiver. */
+int32_t mgfb_bodies_set_gid(mgfb_ctx* ctx, uint32_t first, uint32_t n, const uint32_t* gids);
+typedef struct mgfb_tile_desc { uint64_t opaque[112]; } mgfb_tile_desc;   /* 896 bytes, plain data: send it to the other ranks */
+/* Freezes the body set, reserves room for `ghost_capacity` ghosts and describes this tile's device
+ * memory (pointers for contexts of the same process, cudaIpc handles for other processes). */
+int32_t mgfb_tile_export(mgfb_ctx* ctx, uint32_t ghost_capacity, mgfb_tile_desc* out);
+/* descs[0..nranks) in tile order along x; maps the neighbours' memory (rank-1, rank+1). */
+int32_t mgfb_tile_connect(mgfb_ctx* ctx, uint32_t rank, uint32_t nranks, const mgfb_tile_desc* descs);
 
 /* Device-resident staging used by multi-GPU drivers and benchmarks: raw device pointers to the
  * SoA body arrays (for NCCL send/recv issued by the host plumbing).  See DESIGN.md. */

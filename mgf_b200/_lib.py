@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libmgfb.so")
 
 # enum mgfb_status
-OK, ERR_INVALID_ARG, ERR_SINGULAR_INERTIA, ERR_CAPACITY, ERR_CUDA, ERR_NAN_BOUNDS, ERR_STATE = range(7)
+OK, ERR_INVALID_ARG, ERR_SINGULAR_INERTIA, ERR_CAPACITY, ERR_CUDA, ERR_NAN_BOUNDS, ERR_STATE, ERR_TILE = range(8)
 # enum mgfb_shape_kind
 SPHERE, CAPSULE, TRIANGLE, RECTANGLE, PLANE, AABB, OBB = range(7)
 # enum mgfb_pair_kind
@@ -30,7 +30,8 @@ assert SHAPE_DTYPE.itemsize == 64 and CONTACT_DTYPE.itemsize == 40 and LOCAL_CON
 class Config(C.Structure):
     _fields_ = [("device", C.c_int32), ("penetration_slop", C.c_float), ("baumgarte", C.c_float),
                 ("persistent_threshold_sq", C.c_float), ("fat_margin", C.c_float),
-                ("initial_body_capacity", C.c_uint32), ("reserved", C.c_uint32 * 4)]
+                ("initial_body_capacity", C.c_uint32), ("max_cooperative_ctas", C.c_uint32), ("tile_timeout_ms", C.c_uint32),
+                ("reserved", C.c_uint32 * 2)]
 
 
 class Manifolds(C.Structure):
@@ -48,12 +49,15 @@ class StepStats(C.Structure):
     _fields_ = [("bodies", C.c_uint32), ("candidate_pairs", C.c_uint32), ("terrain_candidates", C.c_uint32),
                 ("constraints", C.c_uint32), ("terrain_constraints", C.c_uint32), ("groups", C.c_uint32),
                 ("iterations", C.c_uint32), ("fat_refreshes", C.c_uint32), ("step_ms", C.c_float),
-                ("solve_ms", C.c_float), ("overflow", C.c_uint32), ("reserved", C.c_uint32 * 5)]
+                ("solve_ms", C.c_float), ("overflow", C.c_uint32), ("colouring_rounds", C.c_uint32), ("ghosts", C.c_uint32),
+                ("boundary_constraints", C.c_uint32), ("phases", C.c_uint32), ("reserved", C.c_uint32)]
 
     def as_dict(self):
-        d = {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}
-        d["colouring_rounds"] = self.reserved[0]
-        return d
+        return {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}
+
+
+class TileDesc(C.Structure):
+    _fields_ = [("opaque", C.c_uint64 * 112)]
 
 
 class DeviceView(C.Structure):
@@ -86,6 +90,9 @@ SYMBOLS = [
     ("mgfb_step_constraints", C.c_int32, [_P, C.c_uint32, _P, _P, _P, _P, _P, C.POINTER(C.c_uint32)]),
     ("mgfb_step_totals", C.c_int32, [_P] + [C.POINTER(C.c_uint64)] * 5 + [C.c_int32]),
     ("mgfb_device_view_get", C.c_int32, [_P, C.POINTER(DeviceView)]),
+    ("mgfb_bodies_set_gid", C.c_int32, [_P, C.c_uint32, C.c_uint32, _P]),
+    ("mgfb_tile_export", C.c_int32, [_P, C.c_uint32, C.POINTER(TileDesc)]),
+    ("mgfb_tile_connect", C.c_int32, [_P, C.c_uint32, C.c_uint32, _P]),
 ]
 
 _lib = None

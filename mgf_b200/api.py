@@ -176,6 +176,24 @@ class World:
         self.ctx.check(self.lib.mgfb_step_n(self.ctx.h, dt, iters, nsteps, C.byref(st)))
         return st.as_dict()
 
+    # -- one world tiled across GPUs (mgfb.h "one world tiled across GPUs"; driver in tiling.py)
+    def set_gid(self, gids, first=0):
+        gids = np.ascontiguousarray(gids, dtype=np.uint32)
+        self.ctx.check(self.lib.mgfb_bodies_set_gid(self.ctx.h, first, len(gids), L.ptr(gids)))
+
+    def tile_export(self, ghost_capacity):
+        """Freeze the body set and describe this tile's device memory; returns the descriptor bytes."""
+        d = L.TileDesc()
+        self.ctx.check(self.lib.mgfb_tile_export(self.ctx.h, ghost_capacity, C.byref(d)))
+        return bytes(d)
+
+    def tile_connect(self, rank, descs):
+        """descs: the descriptor bytes of every tile, in tile order along x."""
+        arr = (L.TileDesc * len(descs))()
+        for k, b in enumerate(descs):
+            C.memmove(C.byref(arr[k]), b, C.sizeof(L.TileDesc))
+        self.ctx.check(self.lib.mgfb_tile_connect(self.ctx.h, rank, len(descs), arr))
+
     def totals(self, reset=False):
         """Running totals since the last reset (see mgfb_step_totals)."""
         v = [C.c_uint64() for _ in range(5)]

@@ -2,6 +2,7 @@
 // Host code here only stages buffers and enqueues kernels; every arithmetic step of the hot
 // path runs in the kernels of kernels.cuh.  There is no CPU fallback: without a CUDA device
 // mgfb_ctx_create fails.
+#include <unistd.h>
 #include <algorithm>
 #include <cstdio>
 #include <cstring>
@@ -39,7 +40,7 @@ struct mgfb_ctx {
     unsigned n = 0, cap = 0;
     unsigned n_capsules = 0;
     // body SoA
-    Buf x, q, vel, force, torque, imb, col, tight, fat;
+    Buf x, q, vel, force, torque, imb, col, tight, fat, gid;
     // counters
     Buf ctr;
     Counters* h_ctr = nullptr;  // pinned
@@ -48,7 +49,7 @@ struct mgfb_ctx {
     Buf tpair_list[2]; unsigned tpair_cap = 0;
     Buf c_a, c_b, c_face, c_sub, c_la, c_lb, c_nt; unsigned contact_cap = 0;
     // ordering scratch
-    Buf body_best, body_scratch /* mask[n] u64 + last[n] u32 */, group, group_count, group_start, perm;
+    Buf body_best, body_scratch /* mask[n] u64 + last[n] u32 */, group, group_count, group_start, phase_start, perm;
     unsigned group_cap = 0;
     // rows
     Buf r_ab, r_n, r_t0, r_t1, r_ra, r_rb, r_imp, r_xra, r_xrb, r_xtm; unsigned row_cap = 0, xrow_cap = 0;
@@ -65,6 +66,15 @@ struct mgfb_ctx {
     // last step
     unsigned last_constraints = 0;
     bool have_step = false;
+    // spatial tiling (tile.cuh): this ctx owns one slab of a world spread over several GPUs
+    bool tile_exported = false, tiled = false;
+    unsigned ghost_cap = 0;
+    Buf edge_idx, edge_mark, ridx, mbox;
+    TileLink link{};
+    unsigned long long tile_step = 0;
+    std::vector<void*> ipc_opened;
+    int max_ctas = 0;                    // cfg.reserved[0]: cap on cooperative grids (two tiles sharing one GPU in tests)
+    unsigned long long tile_timeout_ns = 20000000000ULL;
 };
 
 namespace {
@@ -98,6 +108,7 @@ unsigned next_pow2(unsigned v) { unsigned p = 1; while (p < v) p <<= 1; return p
 int grid_for(const mgfb_ctx* ctx, size_t items) {
     size_t blocks = (items + MGFB_THREADS - 1) / MGFB_THREADS;
     size_t cap = (size_t)ctx->num_sms * 8;
+    if (ctx->max_ctas) cap = std::min<size_t>(cap, (size_t)ctx->max_ctas * 4);
     return (int)std::max<size_t>(1, std::min(blocks, cap));
 }
 
@@ -106,10 +117,14 @@ BodyArrays body_arrays(const mgfb_ctx* ctx) {
     B.x = ctx->x.as<float4>(); B.q = ctx->q.as<float4>(); B.vel = ctx->vel.as<BodyVel>();
     B.force = ctx->force.as<float4>(); B.torque = ctx->torque.as<float4>(); B.imb = ctx->imb.as<float4>();
     B.col = ctx->col.as<Collider>(); B.tight = ctx->tight.as<Box>(); B.fat = ctx->fat.as<Box>();
+    B.gid = ctx->gid.as<unsigned>();
     return B;
 }
+// bodies this ctx may hold in a step: its own plus the ghosts a tiled world sends it
+unsigned body_slots(const mgfb_ctx* ctx) { return ctx->n + ctx->ghost_cap; }
 int32_t grow_bodies(mgfb_ctx* ctx, unsigned need) {
     if (need <= ctx->cap) return MGFB_OK;
+    if (ctx->tile_exported) return fail(ctx, MGFB_ERR_STATE, "body arrays are exported to neighbour tiles and cannot grow");
     unsigned nc = std::max(need, std::max(1024u, ctx->cap * 2));
     TRY(ensure(ctx, ctx->x, (size_t)nc * sizeof(float4), true));
     TRY(ensure(ctx, ctx->q, (size_t)nc * sizeof(float4), true));
@@ -120,6 +135,7 @@ int32_t grow_bodies(mgfb_ctx* ctx, unsigned need) {
     TRY(ensure(ctx, ctx->col, (size_t)nc * sizeof(Collider), true));
     TRY(ensure(ctx, ctx->tight, (size_t)nc * sizeof(Box), true));
     TRY(ensure(ctx, ctx->fat, (size_t)nc * sizeof(Box), true));
+    TRY(ensure(ctx, ctx->gid, (size_t)nc * 4, true));
     TRY(ensure(ctx, ctx->body_best, (size_t)nc * 8, false, true));
     TRY(ensure(ctx, ctx->body_scratch, (size_t)nc * 12, false, true));
     ctx->cap = nc;
@@ -127,7 +143,7 @@ int32_t grow_bodies(mgfb_ctx* ctx, unsigned need) {
 }
 // Work-list capacities scale with the body count; a step that overflows one regrows and reruns.
 int32_t ensure_step_buffers(mgfb_ctx* ctx, unsigned scale) {
-    unsigned n = std::max(ctx->n, 1024u);
+    unsigned n = std::max(body_slots(ctx), 1024u);
     unsigned pc = n * 8 * scale, tc = n * 8 * scale, cc = n * 8 * scale;
     if (pc > ctx->pair_cap) { for (auto& b : ctx->pair_list) TRY(ensure(ctx, b, (size_t)pc * sizeof(int2))); ctx->pair_cap = pc; }
     if (tc > ctx->tpair_cap) { for (auto& b : ctx->tpair_list) TRY(ensure(ctx, b, (size_t)tc * sizeof(int2))); ctx->tpair_cap = tc; }
@@ -155,13 +171,14 @@ int32_t ensure_rows(mgfb_ctx* ctx, unsigned m, bool extras, unsigned groups) {
     if (groups > ctx->group_cap) {
         unsigned gc = std::max(groups, 4096u);
         TRY(ensure(ctx, ctx->group_count, (size_t)gc * 4)); TRY(ensure(ctx, ctx->group_start, ((size_t)gc + 1) * 4));
+        TRY(ensure(ctx, ctx->phase_start, ((size_t)gc + 1) * 4));
         ctx->group_cap = gc;
     }
     return MGFB_OK;
 }
 int32_t ensure_grid(mgfb_ctx* ctx, unsigned scale) {
-    unsigned table = next_pow2(std::max(4096u, ctx->n * 4));
-    unsigned ecap = std::max(ctx->n, 1024u) * 12 * scale;
+    unsigned table = next_pow2(std::max(4096u, body_slots(ctx) * 4));
+    unsigned ecap = std::max(body_slots(ctx), 1024u) * 12 * scale;
     if (table > ctx->table) {
         TRY(ensure(ctx, ctx->cell_count, (size_t)table * 4)); TRY(ensure(ctx, ctx->cell_start, ((size_t)table + 1) * 4));
         TRY(ensure(ctx, ctx->scan_sums, ((size_t)table / SCAN_ITEMS + 2) * 4));
@@ -224,6 +241,7 @@ OrderView order_view(const mgfb_ctx* ctx, const int* a, const int* b, const uint
     O.body_mask = ctx->body_scratch.as<unsigned long long>();
     O.body_last = reinterpret_cast<unsigned*>(ctx->body_scratch.as<unsigned long long>() + ctx->cap);
     O.group = ctx->group.as<int>(); O.group_count = ctx->group_count.as<unsigned>(); O.gcap = ctx->group_cap;
+    O.gid = ctx->gid.as<unsigned>(); O.n_own = ctx->tiled ? ctx->n : 0xffffffffu;
     return O;
 }
 Counters* dctr(const mgfb_ctx* ctx) { return ctx->ctr.as<Counters>(); }
@@ -233,7 +251,8 @@ int coop_blocks(const mgfb_ctx* ctx, K kernel, int threads, int max_per_sm) {
     int per_sm = 0;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, 0);
     per_sm = std::max(1, std::min(per_sm, max_per_sm));
-    return per_sm * ctx->num_sms;
+    int blocks = per_sm * ctx->num_sms;
+    return ctx->max_ctas ? std::min(blocks, ctx->max_ctas) : blocks;
 }
 
 // order -> scan -> scatter -> build -> solve, for `m` constraints counted on the device
@@ -245,7 +264,9 @@ int32_t enqueue_order_and_solve(mgfb_ctx* ctx, const OrderView& O, const Manifol
     BodyInfoView BI = body_info(ctx);
     unsigned* gcount = ctx->group_count.as<unsigned>();
     unsigned* gstart = ctx->group_start.as<unsigned>();
+    unsigned* pstart = ctx->phase_start.as<unsigned>();
     unsigned* perm = ctx->perm.as<unsigned>();
+    const bool tiled = ctx->tiled && !M.user;
     BodyVel* vel = ctx->vel.as<BodyVel>();
     unsigned gcap = ctx->group_cap;
     {
@@ -253,16 +274,19 @@ int32_t enqueue_order_and_solve(mgfb_ctx* ctx, const OrderView& O, const Manifol
         void* args[] = {&Ov, &mp, &mh, &ag, &c};
         CU(cudaLaunchCooperativeKernel((void*)k_order, dim3(ctx->coop_order), dim3(MGFB_THREADS), args, 0, ctx->stream));
     }
-    k_group_scan<<<1, 1024, 0, ctx->stream>>>(gcount, gstart, c, gcap);
+    k_group_scan<<<1, 1024, 0, ctx->stream>>>(gcount, gstart, pstart, c, gcap, tiled ? (unsigned)TILE_INTERIOR_COLOURS : 0xffffffffu);
     int g = grid_for(ctx, m_bound);
     k_scatter_rows<<<g, MGFB_THREADS, 0, ctx->stream>>>(O.group, gcount, gstart, perm, m_ptr, m_host, c);
-    k_build_rows<<<g, MGFB_THREADS, 0, ctx->stream>>>(M, BI, perm, R, m_ptr, m_host, dt, ctx->cfg.baumgarte, ctx->cfg.penetration_slop, c);
+    k_build_rows<<<g, MGFB_THREADS, 0, ctx->stream>>>(M, BI, perm, R, m_ptr, m_host, dt, ctx->cfg.baumgarte, ctx->cfg.penetration_slop, c,
+                                                      tiled ? ctx->edge_mark.as<unsigned char>() : nullptr, tiled ? ctx->n : 0xffffffffu);
     CU(cudaGetLastError());
     if (time_solve) CU(cudaEventRecord(ctx->ev[2], ctx->stream));
     {
-        const unsigned* gs = gstart; unsigned it = iters;
-        void* args[] = {&R, &vel, &gs, &it, &c};
-        CU(cudaLaunchCooperativeKernel((void*)k_solve, dim3(ctx->coop_solve), dim3(MGFB_SOLVE_THREADS), args, 0, ctx->stream));
+        const unsigned* ps = pstart; unsigned it = iters;
+        TileLink T = ctx->link;
+        void* args[] = {&R, &vel, &ps, &it, &c, &T};
+        void* fn = tiled ? (void*)k_solve<true> : (void*)k_solve<false>;
+        CU(cudaLaunchCooperativeKernel(fn, dim3(ctx->coop_solve), dim3(MGFB_SOLVE_THREADS), args, 0, ctx->stream));
     }
     if (time_solve) CU(cudaEventRecord(ctx->ev[3], ctx->stream));
     ctx->launches += 5;   // k_order, k_group_scan, k_scatter_rows, k_build_rows, k_solve
@@ -280,15 +304,39 @@ int32_t enqueue_step(mgfb_ctx* ctx, float dt, unsigned iters, bool from_integrat
     CU(cudaMemsetAsync(ctx->group_count.p, 0, (size_t)ctx->group_cap * 4, ctx->stream));
     CU(cudaMemsetAsync(ctx->cell_count.p, 0, (size_t)ctx->table * 4, ctx->stream));
     int gb = grid_for(ctx, n);
-    if (from_integrate) k_integrate<true, true, true><<<gb, MGFB_THREADS, 0, ctx->stream>>>(B, n, dt, ctx->cfg.fat_margin, c);
-    else k_integrate<false, false, true><<<gb, MGFB_THREADS, 0, ctx->stream>>>(B, n, dt, ctx->cfg.fat_margin, c);
+    const bool tiled = ctx->tiled;
+    const unsigned slots = body_slots(ctx);   // upper bound of n_total (device-resident: own + this step's ghosts)
+    if (!tiled) {
+        if (from_integrate) k_integrate<true, true, true><<<gb, MGFB_THREADS, 0, ctx->stream>>>(B, n, dt, ctx->cfg.fat_margin, c);
+        else k_integrate<false, false, true><<<gb, MGFB_THREADS, 0, ctx->stream>>>(B, n, dt, ctx->cfg.fat_margin, c);
+    } else {
+        // tile.cuh: my right extent -> right neighbour; my edge bodies -> left neighbour's ghost slots
+        ctx->tile_step++;
+        ctx->link.step = ctx->tile_step;
+        const TileLink& T = ctx->link;
+        CU(cudaMemsetAsync(ctx->edge_mark.p, 0, ctx->n, ctx->stream));
+        k_integrate<true, true, true, true><<<gb, MGFB_THREADS, 0, ctx->stream>>>(B, n, dt, ctx->cfg.fat_margin, c);
+        k_tile_publish<<<1, 1, 0, ctx->stream>>>(T, c);
+        if (T.has_left) {
+            k_tile_wait<<<1, 1, 0, ctx->stream>>>(&T.mine->xr.flag, T.step, T.timeout_ns, c);
+            k_ghost_send<<<gb, 256, 0, ctx->stream>>>(B, T, c);
+        }
+        if (T.has_right) k_tile_wait<<<1, 1, 0, ctx->stream>>>(&T.mine->ghosts.flag, T.step, T.timeout_ns, c);
+        k_ghost_recv<<<grid_for(ctx, std::max(ctx->ghost_cap, 1u)), 256, 0, ctx->stream>>>(B, T, c);
+        ctx->launches += 2 + (T.has_left ? 2 : 0) + (T.has_right ? 1 : 0);
+    }
+    int gs = grid_for(ctx, slots);
     // broadphase over the stored fat boxes
     BodyGrid G = body_grid(ctx);
-    k_bgrid_insert<false><<<gb, MGFB_THREADS, 0, ctx->stream>>>(B.fat, B.col, n, G, c);
+    k_bgrid_insert<false><<<gs, MGFB_THREADS, 0, ctx->stream>>>(B.fat, B.col, B.gid, G, c);
     TRY(scan_u32(ctx, G.cell_count, G.cell_start, ctx->table, ctx->scan_sums.as<unsigned>(), &c->grid_entries));
-    k_bgrid_insert<true><<<gb, MGFB_THREADS, 0, ctx->stream>>>(B.fat, B.col, n, G, c);
+    k_bgrid_insert<true><<<gs, MGFB_THREADS, 0, ctx->stream>>>(B.fat, B.col, B.gid, G, c);
     PairLists PL; for (int k = 0; k < 4; ++k) PL.p[k] = ctx->pair_list[k].as<int2>();
-    k_body_pairs_warp<<<std::max(1, std::min((int)((n + BP_WARPS - 1) / BP_WARPS), ctx->num_sms * 8)), MGFB_THREADS, 0, ctx->stream>>>(B.tight, B.col, n, G, PL, ctx->pair_cap, c);
+    {
+        int gw = std::max(1, std::min((int)((slots + BP_WARPS - 1) / BP_WARPS), ctx->num_sms * 8));
+        if (ctx->max_ctas) gw = std::min(gw, ctx->max_ctas * 4);
+        k_body_pairs_warp<<<gw, MGFB_THREADS, 0, ctx->stream>>>(B.tight, B.col, B.gid, tiled ? n : 0xffffffffu, G, PL, ctx->pair_cap, c);
+    }
     ContactList L = contact_list(ctx);
     TerrainView T{};
     if (ctx->terrain.present) {
@@ -298,7 +346,7 @@ int32_t enqueue_step(mgfb_ctx* ctx, float dt, unsigned iters, bool from_integrat
     }
     // narrowphase, one specialisation per shape pair
     bool caps = ctx->n_capsules > 0, sph = ctx->n_capsules < ctx->n;
-    int gp = grid_for(ctx, (size_t)n * 4);
+    int gp = grid_for(ctx, (size_t)slots * 4);
     if (sph) k_narrow_bodies<0, 0><<<gp, MGFB_THREADS, 0, ctx->stream>>>(B.col, PL.p[0], L, ctx->contact_cap, c);
     if (sph && caps) {
         k_narrow_bodies<0, 1><<<gp, MGFB_THREADS, 0, ctx->stream>>>(B.col, PL.p[1], L, ctx->contact_cap, c);
@@ -418,8 +466,26 @@ int32_t mgfb_ctx_create(const mgfb_config* cfg, mgfb_ctx** out) {
     if ((e = cudaMalloc(&ctx->ctr.p, sizeof(Counters))) != cudaSuccess) return bail(e, "cudaMalloc");
     ctx->ctr.bytes = sizeof(Counters);
     cudaMemsetAsync(ctx->ctr.p, 0, sizeof(Counters), ctx->stream);
+    {
+        // Load every step kernel NOW.  With CUDA's lazy module loading the first launch of a kernel
+        // may have to wait for the device to go idle -- which never happens while a neighbour tile's
+        // kernel is spinning on a flag this very launch would set.
+        const void* fns[] = {(const void*)k_integrate<true, true, true, false>, (const void*)k_integrate<true, true, true, true>,
+                             (const void*)k_integrate<false, false, true, false>, (const void*)k_tile_publish, (const void*)k_tile_wait,
+                             (const void*)k_ghost_send, (const void*)k_ghost_recv, (const void*)k_bgrid_insert<false>,
+                             (const void*)k_bgrid_insert<true>, (const void*)k_scan_reduce, (const void*)k_scan_sums, (const void*)k_scan_final,
+                             (const void*)k_body_pairs_warp, (const void*)k_terrain_pairs, (const void*)k_narrow_bodies<0, 0>,
+                             (const void*)k_narrow_bodies<0, 1>, (const void*)k_narrow_bodies<1, 0>, (const void*)k_narrow_bodies<1, 1>,
+                             (const void*)k_narrow_terrain<0>, (const void*)k_narrow_terrain<1>, (const void*)k_order, (const void*)k_group_scan,
+                             (const void*)k_scatter_rows, (const void*)k_build_rows, (const void*)k_solve<false>, (const void*)k_solve<true>,
+                             (const void*)k_step_done, (const void*)k_pack_state, (const void*)k_set_velocity};
+        cudaFuncAttributes fa;
+        for (const void* f : fns) if ((e = cudaFuncGetAttributes(&fa, f)) != cudaSuccess) return bail(e, "cudaFuncGetAttributes");
+    }
+    ctx->max_ctas = (int)ctx->cfg.max_cooperative_ctas;
+    if (ctx->cfg.tile_timeout_ms) ctx->tile_timeout_ns = (unsigned long long)ctx->cfg.tile_timeout_ms * 1000000ULL;
     ctx->coop_order = coop_blocks(ctx, k_order, MGFB_THREADS, 2);
-    ctx->coop_solve = coop_blocks(ctx, k_solve, MGFB_SOLVE_THREADS, 1);
+    ctx->coop_solve = std::min(coop_blocks(ctx, k_solve<false>, MGFB_SOLVE_THREADS, 1), coop_blocks(ctx, k_solve<true>, MGFB_SOLVE_THREADS, 1));
     int32_t s = grow_bodies(ctx, std::max(ctx->cfg.initial_body_capacity, 1024u));
     if (s == MGFB_OK) s = ensure_rows(ctx, 1024, false, 4096);
     if (s != MGFB_OK) { g_create_err = ctx->err; delete ctx; return s; }
@@ -438,7 +504,9 @@ void mgfb_ctx_destroy(mgfb_ctx* ctx) {
                   &ctx->r_rb, &ctx->r_imp, &ctx->r_xra, &ctx->r_xrb, &ctx->r_xtm, &ctx->cell_count, &ctx->cell_start, &ctx->bg_ent,
                   &ctx->scan_sums, &ctx->u_a, &ctx->u_b, &ctx->u_sc, &ctx->u_sf, &ctx->u_n, &ctx->u_t, &ctx->u_nc, &ctx->u_la,
                   &ctx->u_lb, &ctx->stage, &ctx->terrain.verts, &ctx->terrain.faces, &ctx->terrain.boxes, &ctx->terrain.cell_count,
-                  &ctx->terrain.cell_start, &ctx->terrain.ent_id, &ctx->terrain.ent_key, &ctx->terrain.max_bits};
+                  &ctx->terrain.cell_start, &ctx->terrain.ent_id, &ctx->terrain.ent_key, &ctx->terrain.max_bits,
+                  &ctx->gid, &ctx->phase_start, &ctx->edge_idx, &ctx->edge_mark, &ctx->ridx, &ctx->mbox};
+    for (void* ptr : ctx->ipc_opened) cudaIpcCloseMemHandle(ptr);
     for (Buf* b : all) release(*b);
     if (ctx->h_ctr) cudaFreeHost(ctx->h_ctr);
     for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
@@ -468,6 +536,8 @@ int32_t mgfb_bodies_add(mgfb_ctx* ctx, uint32_t n, const mgfb_shape* shapes, con
     std::vector<BodyVel> hvel(n);
     std::vector<Collider> hcol(n);
     std::vector<Box> htight(n), hfat(n);
+    std::vector<unsigned> hgid(n);
+    if (ctx->tile_exported) return fail(ctx, MGFB_ERR_STATE, "bodies cannot be added after mgfb_tile_export");
     unsigned ncaps = 0;
     for (uint32_t i = 0; i < n; ++i) {
         const mgfb_shape& s = shapes[i];
@@ -510,6 +580,7 @@ int32_t mgfb_bodies_add(mgfb_ctx* ctx, uint32_t n, const mgfb_shape* shapes, con
         htight[i].c = v4(tc, 0); htight[i].r = v4(tr, 0);
         float mg = ctx->cfg.fat_margin;
         hfat[i].c = v4(tc, 0); hfat[i].r = v4(tr + mk3(mg, mg, mg), 0);  // world.rs:180-181
+        hgid[i] = ctx->n + i;
     }
     unsigned first = ctx->n;
     TRY(grow_bodies(ctx, first + n));
@@ -520,6 +591,7 @@ int32_t mgfb_bodies_add(mgfb_ctx* ctx, uint32_t n, const mgfb_shape* shapes, con
     CU(up(ctx->force, hforce.data(), sizeof(float4))); CU(up(ctx->torque, htorque.data(), sizeof(float4)));
     CU(up(ctx->imb, himb.data(), sizeof(float4), 3)); CU(up(ctx->col, hcol.data(), sizeof(Collider)));
     CU(up(ctx->tight, htight.data(), sizeof(Box))); CU(up(ctx->fat, hfat.data(), sizeof(Box)));
+    CU(up(ctx->gid, hgid.data(), 4));
     CU(cudaStreamSynchronize(ctx->stream));
     ctx->n += n; ctx->n_capsules += ncaps;
     if (first_id) *first_id = first;
@@ -675,7 +747,10 @@ static void fill_step_stats(mgfb_ctx* ctx, mgfb_step_stats* st, unsigned iters, 
     st->iterations = iters;
     st->fat_refreshes = h.fat_refreshes;
     st->overflow = overflowed;
-    st->reserved[0] = h.rounds;   // colouring rounds (diagnostic)
+    st->colouring_rounds = h.rounds;
+    st->ghosts = h.n_total - ctx->n;
+    st->boundary_constraints = h.contacts - h.n_int_rows;
+    st->phases = h.n_phases;
     if (timed) {
         cudaEventElapsedTime(&st->step_ms, ctx->ev[0], ctx->ev[1]);
         cudaEventElapsedTime(&st->solve_ms, ctx->ev[2], ctx->ev[3]);
@@ -704,6 +779,15 @@ int32_t mgfb_step_n(mgfb_ctx* ctx, float dt, uint32_t iters, uint32_t nsteps, mg
         }
         TRY(read_counters(ctx));
         if (ctx->h_ctr->nan_bounds) { clear_sticky(ctx); return fail(ctx, MGFB_ERR_NAN_BOUNDS, "AABB::combine: r >= 0 violated (NaN in body state; bounds.rs:125-127)"); }
+        if (ctx->tiled) {
+            // a tile cannot rerun part of a step on its own: its neighbours have moved on
+            if (ctx->h_ctr->comm_error & COMM_TILE_TOO_THIN)
+                return fail(ctx, MGFB_ERR_TILE, "tile too thin: a body is a ghost on the left neighbour and touches a ghost from the right (or reaches two tiles away); use fewer, wider tiles");
+            if (ctx->h_ctr->comm_error) return fail(ctx, MGFB_ERR_TILE, "neighbour tile did not answer within the time limit");
+            if (ctx->h_ctr->overflow & OVF_GHOSTS) return fail(ctx, MGFB_ERR_CAPACITY, "more ghost bodies than the neighbour's ghost capacity (mgfb_tile_export)");
+            if (ctx->h_ctr->overflow) return fail(ctx, MGFB_ERR_CAPACITY, "a work list overflowed in a tiled step (lists are sized for own + ghost capacity; raise ghost_capacity)");
+            break;
+        }
         if (!ctx->h_ctr->overflow) break;
         // a work list overflowed inside step (steps_done): that step already integrated.
         overflowed |= ctx->h_ctr->overflow;
@@ -734,14 +818,19 @@ int32_t mgfb_step_constraints(mgfb_ctx* ctx, uint32_t capacity, uint32_t* body_a
     if (capacity < m) return fail(ctx, MGFB_ERR_CAPACITY, "output arrays too small");
     if (m == 0) return MGFB_OK;
     std::vector<unsigned> perm(m), hface(m), hsub(m); std::vector<int> ha(m), hb(m), hg(m);
+    std::vector<unsigned> hgid;
+    if (ctx->tiled) {   // a tile reports GLOBAL body ids
+        hgid.resize(body_slots(ctx));
+        CU(cudaMemcpyAsync(hgid.data(), ctx->gid.p, (size_t)hgid.size() * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    }
     auto dl = [&](void* dst, const Buf& b) { return cudaMemcpyAsync(dst, b.p, (size_t)m * 4, cudaMemcpyDeviceToHost, ctx->stream); };
     CU(dl(perm.data(), ctx->perm)); CU(dl(ha.data(), ctx->c_a)); CU(dl(hb.data(), ctx->c_b)); CU(dl(hface.data(), ctx->c_face));
     CU(dl(hsub.data(), ctx->c_sub)); CU(dl(hg.data(), ctx->group));
     CU(cudaStreamSynchronize(ctx->stream));
     for (unsigned r = 0; r < m; ++r) {
         unsigned k = perm[r];
-        if (body_a) body_a[r] = (uint32_t)ha[k];
-        if (body_b) body_b[r] = hb[k];
+        if (body_a) body_a[r] = ctx->tiled ? hgid[ha[k]] : (uint32_t)ha[k];
+        if (body_b) body_b[r] = (ctx->tiled && hb[k] >= 0) ? (int32_t)hgid[hb[k]] : hb[k];
         if (face) face[r] = hface[k];
         if (sub) sub[r] = hsub[k];
         if (colour) colour[r] = (uint32_t)hg[k];
@@ -800,6 +889,7 @@ int32_t mgfb_solver_solve(mgfb_ctx* ctx, const mgfb_manifolds* m, float dt, uint
     Buf d_oa, d_ob;
     TRY(up(d_oa, oa.data(), (size_t)n * 4)); TRY(up(d_ob, ob.data(), (size_t)n * 4));
     OrderView O = order_view(ctx, d_oa.as<int>(), d_ob.as<int>(), nullptr, nullptr);
+    O.n_own = 0xffffffffu;   // caller-built manifolds never involve ghosts
     ManifoldInput M{};
     M.user = true; M.a = ctx->u_a.as<int>(); M.b = ctx->u_b.as<int>();
     M.normal = ctx->u_n.as<float>(); M.tangent = ctx->u_t.as<float>(); M.ncontacts = ctx->u_nc.as<uint32_t>();
@@ -848,6 +938,96 @@ int32_t mgfb_step_totals(mgfb_ctx* ctx, uint64_t* steps, uint64_t* constraints, 
         CU(cudaMemsetAsync(reinterpret_cast<char*>(dctr(ctx)) + offsetof(Counters, acc_constraints), 0, 32, ctx->stream));
         ctx->launches = 0;
     }
+    return MGFB_OK;
+}
+
+// ---------------------------------------------------------------- spatial tiling (tile.cuh)
+namespace {
+struct TileDescRaw {           // what one tile tells the others (fits mgfb_tile_desc)
+    uint64_t magic;
+    int64_t pid;
+    int32_t device; uint32_t n_own, ghost_cap, pad;
+    void* ptr[10];             // x vel force torque col tight fat gid ridx mbox (valid inside the exporting process)
+    cudaIpcMemHandle_t ipc[10];
+};
+static_assert(sizeof(TileDescRaw) <= sizeof(mgfb_tile_desc), "mgfb_tile_desc too small");
+const uint64_t TILE_MAGIC = 0x6d6766625f74696cULL;
+}  // namespace
+
+int32_t mgfb_bodies_set_gid(mgfb_ctx* ctx, uint32_t first, uint32_t n, const uint32_t* gids) {
+    if (!ctx || (uint64_t)first + n > ctx->n || !gids) return fail(ctx, MGFB_ERR_INVALID_ARG, "bad arguments");
+    if (n == 0) return MGFB_OK;
+    for (uint32_t i = 0; i < n; ++i) if (gids[i] >= (1u << 30)) return fail(ctx, MGFB_ERR_INVALID_ARG, "global ids must be < 2^30");
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaMemcpyAsync(ctx->gid.as<unsigned>() + first, gids, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return MGFB_OK;
+}
+
+int32_t mgfb_tile_export(mgfb_ctx* ctx, uint32_t ghost_capacity, mgfb_tile_desc* out) {
+    if (!ctx || !out) return MGFB_ERR_INVALID_ARG;
+    if (ctx->tile_exported) return fail(ctx, MGFB_ERR_STATE, "tile already exported");
+    CU(cudaSetDevice(ctx->device));
+    ghost_capacity = std::max(ghost_capacity, 1u);
+    TRY(grow_bodies(ctx, ctx->n + ghost_capacity));
+    ctx->ghost_cap = ghost_capacity;
+    TRY(ensure(ctx, ctx->edge_idx, (size_t)std::max(ctx->n, 1u) * 4));
+    TRY(ensure(ctx, ctx->edge_mark, (size_t)std::max(ctx->n, 1u), false, true));
+    TRY(ensure(ctx, ctx->ridx, (size_t)ghost_capacity * 4, false, true));
+    TRY(ensure(ctx, ctx->mbox, sizeof(TileMailbox), false, true));
+    // every per-step buffer at its final size now: nothing may be reallocated while neighbours hold pointers
+    TRY(ensure_step_buffers(ctx, 1));
+    TRY(ensure_grid(ctx, 1));
+    TRY(ensure_rows(ctx, ctx->contact_cap, false, 4096));
+    CU(cudaStreamSynchronize(ctx->stream));
+    TileDescRaw d; std::memset(&d, 0, sizeof(d));
+    d.magic = TILE_MAGIC; d.pid = (int64_t)getpid(); d.device = ctx->device; d.n_own = ctx->n; d.ghost_cap = ghost_capacity;
+    void* ptrs[10] = {ctx->x.p, ctx->vel.p, ctx->force.p, ctx->torque.p, ctx->col.p, ctx->tight.p, ctx->fat.p, ctx->gid.p, ctx->ridx.p, ctx->mbox.p};
+    for (int k = 0; k < 10; ++k) { d.ptr[k] = ptrs[k]; CU(cudaIpcGetMemHandle(&d.ipc[k], ptrs[k])); }
+    std::memset(out, 0, sizeof(*out));
+    std::memcpy(out, &d, sizeof(d));
+    ctx->tile_exported = true;
+    return MGFB_OK;
+}
+
+static int32_t tile_open_peer(mgfb_ctx* ctx, const mgfb_tile_desc* desc, TilePeer* P) {
+    TileDescRaw d; std::memcpy(&d, desc, sizeof(d));
+    if (d.magic != TILE_MAGIC) return fail(ctx, MGFB_ERR_INVALID_ARG, "not a tile descriptor");
+    void* p[10];
+    if (d.pid == (int64_t)getpid()) {   // a context of this very process: its pointers are ours already
+        if (d.device != ctx->device) {
+            cudaError_t e = cudaDeviceEnablePeerAccess(d.device, 0);
+            if (e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+            else if (e != cudaSuccess) { ctx->err = std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(e); return MGFB_ERR_CUDA; }
+        }
+        for (int k = 0; k < 10; ++k) p[k] = d.ptr[k];
+    } else {                            // another process: map its allocations over NVLink
+        for (int k = 0; k < 10; ++k) {
+            CU(cudaIpcOpenMemHandle(&p[k], d.ipc[k], cudaIpcMemLazyEnablePeerAccess));
+            ctx->ipc_opened.push_back(p[k]);
+        }
+    }
+    P->x = (float4*)p[0]; P->vel = (BodyVel*)p[1]; P->force = (float4*)p[2]; P->torque = (float4*)p[3]; P->col = (Collider*)p[4];
+    P->tight = (Box*)p[5]; P->fat = (Box*)p[6]; P->gid = (unsigned*)p[7]; P->ridx = (unsigned*)p[8]; P->mbox = (TileMailbox*)p[9];
+    P->n_own = d.n_own; P->ghost_cap = d.ghost_cap;
+    return MGFB_OK;
+}
+
+int32_t mgfb_tile_connect(mgfb_ctx* ctx, uint32_t rank, uint32_t nranks, const mgfb_tile_desc* descs) {
+    if (!ctx || !descs || nranks == 0 || rank >= nranks) return fail(ctx, MGFB_ERR_INVALID_ARG, "bad arguments");
+    if (!ctx->tile_exported) return fail(ctx, MGFB_ERR_STATE, "mgfb_tile_export first");
+    if (ctx->tiled) return fail(ctx, MGFB_ERR_STATE, "tile already connected");
+    CU(cudaSetDevice(ctx->device));
+    TileLink T{};
+    T.has_left = rank > 0; T.has_right = rank + 1 < nranks;
+    if (T.has_left) TRY(tile_open_peer(ctx, &descs[rank - 1], &T.left));
+    if (T.has_right) TRY(tile_open_peer(ctx, &descs[rank + 1], &T.right));
+    T.mine = ctx->mbox.as<TileMailbox>();
+    T.edge_idx = ctx->edge_idx.as<unsigned>(); T.edge_mark = ctx->edge_mark.as<unsigned char>(); T.ridx = ctx->ridx.as<unsigned>();
+    T.n_own = ctx->n; T.ghost_cap = ctx->ghost_cap; T.step = 0; T.timeout_ns = ctx->tile_timeout_ns;
+    ctx->link = T;
+    ctx->tile_step = 0;
+    ctx->tiled = true;
     return MGFB_OK;
 }
 

@@ -3,39 +3,11 @@
 // over counts that live in device memory, so a whole step is enqueued without a single
 // host round trip.
 #pragma once
-#include "layout.cuh"
+#include "tile.cuh"
 
 namespace mgfb {
 
 #define MGFB_THREADS 256
-
-// Device-resident counters of one step.  Zeroed (except the sticky ones) at step start.
-struct Counters {
-    unsigned pairs[4];       // body-pair candidates per kind: [ki*2+kj], k = 0 sphere / 1 capsule
-    unsigned tpairs[2];      // (body, face) terrain candidates per body kind
-    unsigned contacts;       // contacts emitted = constraints
-    unsigned tcontacts;      // of which terrain
-    unsigned grid_entries;
-    unsigned fat_refreshes;
-    unsigned max_fat_bits;   // float bits of the largest stored fat-box half extent
-    unsigned ngroups;
-    unsigned remaining;      // uncoloured constraints
-    unsigned bar;            // grid barrier arrival counter
-    unsigned rounds;         // colouring rounds taken
-    unsigned max_tight_bits; // float bits of the largest tight (swept) box half extent
-    // sticky until the host clears them
-    unsigned overflow;       // bit0 pairs, bit1 tpairs, bit2 contacts, bit3 grid entries
-    unsigned nan_bounds;     // AABB::combine assert (bounds.rs:125-127)
-    unsigned steps_done;
-    unsigned pad1;
-    // running totals since the last mgfb_step_totals(reset)
-    unsigned long long acc_constraints;
-    unsigned long long acc_pairs;        // body-body + terrain candidates
-    unsigned long long acc_groups;
-    unsigned long long acc_steps;
-};
-enum { OVF_PAIRS = 1, OVF_TPAIRS = 2, OVF_CONTACTS = 4, OVF_GRID = 8, OVF_GROUPS = 16 };
-struct PairLists { int2* p[4]; };
 
 // ---------------------------------------------------------------- grid barrier
 __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
@@ -61,18 +33,6 @@ __device__ __forceinline__ void grid_barrier(unsigned* bar, unsigned& phase) {
 // ---------------------------------------------------------------- integrate (+ AABB)
 // physics.rs:262-269 complete_motion, :222-253 integrate, bounds.rs:60-68 swept AABB,
 // world.rs:235-238 fat-box refresh -- one pass, 272 algorithmic bytes per body.
-struct BodyArrays {
-    float4* x;        // position
-    float4* q;        // s, x, y, z
-    BodyVel* vel;
-    float4* force;    // force.xyz, restitution
-    float4* torque;   // torque.xyz, friction
-    float4* imb;      // inv_moment_body: 3 float4 per body (columns)
-    Collider* col;
-    Box* tight;
-    Box* fat;
-};
-
 HD void collider_bounds(const Collider& k, V3* c, V3* r) {
     if (col_kind(k) == 0) {  // bounds.rs:170-177
         *c = f4v(k.p0); *r = mk3(k.p0.w, k.p0.w, k.p0.w);
@@ -99,11 +59,12 @@ HD bool box_overlaps(V3 ac, V3 ar, V3 bc, V3 br) {  // collision.rs:22-29 (close
     return fabsf(ac.x - bc.x) <= (ar.x + br.x) && fabsf(ac.y - bc.y) <= (ar.y + br.y) && fabsf(ac.z - bc.z) <= (ar.z + br.z);
 }
 
-template <bool COMPLETE, bool INTEGRATE, bool BOUNDS>
+template <bool COMPLETE, bool INTEGRATE, bool BOUNDS, bool TILED_XR = false>
 __global__ void __launch_bounds__(MGFB_THREADS) k_integrate(BodyArrays B, unsigned n, float dt, float margin, Counters* ctr) {
     if (ctr->overflow | ctr->nan_bounds) return;  // poisoned: the host will resume from steps_done
-    float my_fat = 0.0f, my_tight = 0.0f;
+    float my_fat = 0.0f, my_tight = 0.0f, my_xr = -3.0e38f;
     unsigned refreshed = 0;
+    if (BOUNDS && blockIdx.x == 0 && threadIdx.x == 0) ctr->n_total = n;   // a tiled world adds its ghosts in k_ghost_recv
     for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         Collider k = B.col[i];
         V3 xi = f4v(B.x[i]);
@@ -160,17 +121,20 @@ __global__ void __launch_bounds__(MGFB_THREADS) k_integrate(BodyArrays B, unsign
             }
             my_fat = fmaxf(my_fat, fmaxf(fr.x, fmaxf(fr.y, fr.z)));
             my_tight = fmaxf(my_tight, fmaxf(tr.x, fmaxf(tr.y, tr.z)));
+            my_xr = fmaxf(my_xr, fb.c.x + fr.x);
         }
     }
     if (BOUNDS) {
         for (int o = 16; o > 0; o >>= 1) {
             my_fat = fmaxf(my_fat, __shfl_xor_sync(0xffffffffu, my_fat, o));
             my_tight = fmaxf(my_tight, __shfl_xor_sync(0xffffffffu, my_tight, o));
+            my_xr = fmaxf(my_xr, __shfl_xor_sync(0xffffffffu, my_xr, o));
             refreshed += __shfl_xor_sync(0xffffffffu, refreshed, o);
         }
         if ((threadIdx.x & 31) == 0) {
             atomicMax(&ctr->max_fat_bits, __float_as_uint(my_fat));
             atomicMax(&ctr->max_tight_bits, __float_as_uint(my_tight));
+            if (TILED_XR) atomicMax(&ctr->xr_bits, ordered_bits(my_xr));
             if (refreshed) atomicAdd(&ctr->fat_refreshes, refreshed);
         }
     }
@@ -225,28 +189,31 @@ __device__ __forceinline__ float grid_inv_cell(const Counters* ctr) {
 struct BodyGrid {
     unsigned* cell_count;   // [T]
     unsigned* cell_start;   // [T+1]
-    float4* ent;            // [2n]: (fat.c.xyz, body index bits), (fat.r.xyz, shape kind bits)
+    float4* ent;            // [2n]: (fat.c.xyz, body index | kind << 31), (fat.r.xyz, global id)
     unsigned table_mask;
 };
 template <bool FILL>
-__global__ void __launch_bounds__(MGFB_THREADS) k_bgrid_insert(const Box* __restrict__ fat, const Collider* __restrict__ col, unsigned n, BodyGrid G, Counters* ctr) {
+__global__ void __launch_bounds__(MGFB_THREADS) k_bgrid_insert(const Box* __restrict__ fat, const Collider* __restrict__ col, const unsigned* __restrict__ gid,
+                                                               BodyGrid G, Counters* ctr) {
     if (ctr->overflow | ctr->nan_bounds) return;
     float inv = grid_inv_cell(ctr);
+    const unsigned n = ctr->n_total;
     for (unsigned j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
         Box b = fat[j];
         unsigned h = cell_hash(cell_key(cell_coord(b.c.x, inv), cell_coord(b.c.y, inv), cell_coord(b.c.z, inv)), G.table_mask);
         if (!FILL) atomicAdd(&G.cell_count[h], 1u);
         else {
             unsigned pos = G.cell_start[h] + (atomicSub(&G.cell_count[h], 1u) - 1u);
-            G.ent[2 * pos] = make_float4(b.c.x, b.c.y, b.c.z, __uint_as_float(j));
-            G.ent[2 * pos + 1] = make_float4(b.r.x, b.r.y, b.r.z, __int_as_float(col_kind(col[j])));
+            G.ent[2 * pos] = make_float4(b.c.x, b.c.y, b.c.z, __uint_as_float(j | ((unsigned)col_kind(col[j]) << 31)));
+            G.ent[2 * pos + 1] = make_float4(b.r.x, b.r.y, b.r.z, __uint_as_float(gid[j]));
         }
     }
 }
 // Body-pair sweep, one warp per body i: lanes 0..26 take the 27 neighbouring cells.  Hits are
 // staged in shared memory and appended with ONE global atomic per block per batch of 8 bodies
 // (a single global cursor would otherwise serialise ~4 atomics per body at one L2 address).
-// P = {(i, j): j < i, tight_i overlaps stored fat_j}  (world.rs:261-268).
+// P = {(i, j): j < i, tight_i overlaps stored fat_j}  (world.rs:261-268), "<" on GLOBAL ids.  In
+// a tiled world bodies >= n_own are ghosts: they take part as i or as j, never both.
 #define BP_WARPS (MGFB_THREADS / 32)
 #define BP_BUF 128
 __device__ __forceinline__ void bp_flush_warp(unsigned* buf, unsigned cnt, unsigned i, const unsigned base[4], PairLists lists, unsigned cap,
@@ -261,25 +228,28 @@ __device__ __forceinline__ void bp_flush_warp(unsigned* buf, unsigned cnt, unsig
             unsigned m = __ballot_sync(0xffffffffu, kind == k);
             if (kind == k) {
                 unsigned pos = base[k] + run[k] + __popc(m & ((1u << lane) - 1u));
-                if (pos < cap) lists.p[k][pos] = make_int2((int)i, (int)(e & 0x3fffffffu));
+                if (pos < cap) lists.p[k][pos] = make_int2((int)i, (int)(e & 0x3fffffffu));   // (bodies < 2^30)
                 else atomicOr(&ctr->overflow, (unsigned)OVF_PAIRS);
             }
             run[k] += __popc(m);
         }
     }
 }
-__global__ void __launch_bounds__(MGFB_THREADS) k_body_pairs_warp(const Box* __restrict__ tight, const Collider* __restrict__ col, unsigned n,
-                                                                 BodyGrid G, PairLists lists, unsigned cap, Counters* ctr) {
+__global__ void __launch_bounds__(MGFB_THREADS) k_body_pairs_warp(const Box* __restrict__ tight, const Collider* __restrict__ col, const unsigned* __restrict__ gid,
+                                                                 unsigned n_own, BodyGrid G, PairLists lists, unsigned cap, Counters* ctr) {
     __shared__ unsigned s_buf[BP_WARPS][BP_BUF];
     __shared__ unsigned s_cnt[BP_WARPS][4];     // per warp, per kind
     __shared__ unsigned s_base[BP_WARPS][4];
     if (ctr->overflow | ctr->nan_bounds) return;
     const float inv = grid_inv_cell(ctr);
+    const unsigned n = ctr->n_total;
     const unsigned lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
     for (unsigned batch = blockIdx.x * BP_WARPS; batch < n; batch += gridDim.x * BP_WARPS) {   // uniform per block
         const unsigned i = batch + w;
         unsigned cnt = 0, kcnt[4] = {0, 0, 0, 0};
-        if (i < n && i != 0) {   // world.rs:256
+        if (i < n) {   // (world.rs:256 skips body 0: it has no j < i)
+            const unsigned gi = gid[i];
+            const bool ghost_i = i >= n_own;
             Box tb = tight[i];
             V3 tc = f4v(tb.c), tr = f4v(tb.r);
             int ki = col_kind(col[i]);
@@ -296,11 +266,12 @@ __global__ void __launch_bounds__(MGFB_THREADS) k_body_pairs_warp(const Box* __r
                 if (e < e1) {
                     float4 a = G.ent[2 * e], b = G.ent[2 * e + 1];
                     ++e;
-                    j = __float_as_uint(a.w);
+                    unsigned jw = __float_as_uint(a.w);
+                    j = jw & 0x7fffffffu;
                     // the bucket may also hold other cells (hash collisions): take only this cell's bodies
-                    if (j < i && cell_coord(a.x, inv) == x && cell_coord(a.y, inv) == y && cell_coord(a.z, inv) == z &&
-                        box_overlaps(tc, tr, mk3(a.x, a.y, a.z), mk3(b.x, b.y, b.z)))
-                        kind = ki * 2 + __float_as_int(b.w);
+                    if (__float_as_uint(b.w) < gi && !(ghost_i && j >= n_own) && cell_coord(a.x, inv) == x && cell_coord(a.y, inv) == y &&
+                        cell_coord(a.z, inv) == z && box_overlaps(tc, tr, mk3(a.x, a.y, a.z), mk3(b.x, b.y, b.z)))
+                        kind = ki * 2 + (int)(jw >> 31);
                 }
                 unsigned m = __ballot_sync(0xffffffffu, kind >= 0);
                 if (!m) continue;
@@ -515,13 +486,16 @@ struct OrderView {
     int* group;                        // [m] out: colour / level, -1 = unassigned
     unsigned* group_count;             // [gcap]
     unsigned gcap;
+    const unsigned* gid;               // global body ids: priorities do not depend on the tiling
+    unsigned n_own;                    // tiled world: bodies >= n_own are ghosts; 0xffffffff otherwise
 };
+#define TILE_INTERIOR_COLOURS 32
 __device__ __forceinline__ unsigned long long order_key(const OrderView& O, unsigned k, bool as_given) {
     if (as_given) return ~(unsigned long long)k;             // earlier in the list = higher priority
     if (!O.face) { unsigned long long key = mix64((unsigned long long)k + 1ULL); return key ? key : 1ULL; }
     int a = O.a[k], b = O.b[k];
-    unsigned lo = b >= 0 ? (unsigned)b : (0x80000000u | ((O.face ? O.face[k] : 0u) << 1) | (O.sub ? O.sub[k] : 0u));
-    unsigned long long key = mix64(((unsigned long long)(unsigned)a << 32) | lo);
+    unsigned lo = b >= 0 ? O.gid[b] : (0x80000000u | ((O.face ? O.face[k] : 0u) << 1) | (O.sub ? O.sub[k] : 0u));
+    unsigned long long key = mix64(((unsigned long long)O.gid[a] << 32) | lo);
     return key ? key : 1ULL;
 }
 __global__ void __launch_bounds__(MGFB_THREADS) k_order(OrderView O, const unsigned* m_ptr, unsigned m_host, bool as_given, Counters* ctr) {
@@ -562,6 +536,13 @@ __global__ void __launch_bounds__(MGFB_THREADS) k_order(OrderView O, const unsig
                 unsigned long long ma = __ldcg(&O.body_mask[a]);
                 unsigned long long mb = b >= 0 ? __ldcg(&O.body_mask[b]) : 0ULL;
                 unsigned long long fr = ~(ma | mb);
+                if (O.n_own != 0xffffffffu) {
+                    // tiled world: interior constraints take colours 0..31, boundary ones (a ghost
+                    // endpoint) 32..63, so every iteration runs interior | exchange | boundary
+                    bool boundary = (unsigned)a >= O.n_own || (b >= 0 && (unsigned)b >= O.n_own);
+                    fr &= boundary ? 0xFFFFFFFF00000000ULL : 0x00000000FFFFFFFFULL;
+                    if (!fr) { atomicOr(&ctr->overflow, (unsigned)OVF_GROUPS); fr = boundary ? (1ULL << 63) : (1ULL << 31); }
+                }
                 if (fr) {
                     g = (unsigned)__ffsll((long long)fr) - 1u;
                     __stcg(&O.body_mask[a], ma | (1ULL << g));
@@ -588,33 +569,53 @@ __global__ void __launch_bounds__(MGFB_THREADS) k_order(OrderView O, const unsig
         grid_barrier(&ctr->bar, phase);
     }
 }
-// Exclusive scan of group_count[0..ngroups) into group_start (single block, chunked).
-__global__ void __launch_bounds__(1024) k_group_scan(const unsigned* count, unsigned* start, Counters* ctr, unsigned gcap) {
-    __shared__ unsigned warp_sums[32];
-    __shared__ unsigned carry;
-    unsigned n = min(ctr->ngroups, gcap);
-    if (threadIdx.x == 0) { carry = 0; ctr->bar = 0; }  // re-arm the grid barrier for the solve kernel
+// Exclusive scan of group_count[0..ngroups) into group_start (single block, chunked), then the
+// compact list of NON-EMPTY groups: phase p of the solver covers rows [phase_start[p],
+// phase_start[p+1]).  `split` = first boundary colour of a tiled world (else >= ngroups).
+__device__ __forceinline__ unsigned block_excl_scan_1024(unsigned v, unsigned* warp_sums, unsigned* total) {
+    unsigned x = v;
+    for (int o = 1; o < 32; o <<= 1) { unsigned y = __shfl_up_sync(0xffffffffu, x, o); if ((threadIdx.x & 31) >= o) x += y; }
+    if ((threadIdx.x & 31) == 31) warp_sums[threadIdx.x >> 5] = x;
     __syncthreads();
+    if (threadIdx.x < 32) {
+        unsigned w = warp_sums[threadIdx.x], ws = w;
+        for (int o = 1; o < 32; o <<= 1) { unsigned y = __shfl_up_sync(0xffffffffu, ws, o); if (threadIdx.x >= o) ws += y; }
+        warp_sums[threadIdx.x] = ws - w;
+        if (threadIdx.x == 31) *total = ws;
+    }
+    __syncthreads();
+    unsigned excl = warp_sums[threadIdx.x >> 5] + x - v;
+    __syncthreads();
+    return excl;
+}
+__global__ void __launch_bounds__(1024) k_group_scan(const unsigned* count, unsigned* start, unsigned* phase_start, Counters* ctr, unsigned gcap,
+                                                     unsigned split) {
+    __shared__ unsigned warp_sums[32];
+    __shared__ unsigned tot;
+    unsigned n = min(ctr->ngroups, gcap);
+    if (threadIdx.x == 0) ctr->bar = 0;   // re-arm the grid barrier for the solve kernel
+    unsigned carry = 0, pcarry = 0, pint = 0, int_rows = 0;   // every thread keeps the running totals
     for (unsigned base = 0; base < n; base += 1024) {
         unsigned i = base + threadIdx.x;
         unsigned v = i < n ? count[i] : 0u;
-        unsigned x = v;
-        for (int o = 1; o < 32; o <<= 1) { unsigned y = __shfl_up_sync(0xffffffffu, x, o); if ((threadIdx.x & 31) >= o) x += y; }
-        if ((threadIdx.x & 31) == 31) warp_sums[threadIdx.x >> 5] = x;
-        __syncthreads();
-        if (threadIdx.x < 32) {
-            unsigned w = warp_sums[threadIdx.x], ws = w;
-            for (int o = 1; o < 32; o <<= 1) { unsigned y = __shfl_up_sync(0xffffffffu, ws, o); if (threadIdx.x >= o) ws += y; }
-            warp_sums[threadIdx.x] = ws - w;
-        }
-        __syncthreads();
-        unsigned excl = carry + warp_sums[threadIdx.x >> 5] + x - v;
+        unsigned f = v > 0u ? 1u : 0u;
+        unsigned excl = carry + block_excl_scan_1024(v, warp_sums, &tot);
+        carry += tot;
+        unsigned pos = pcarry + block_excl_scan_1024(f, warp_sums, &tot);
+        pcarry += tot;
         if (i < n) start[i] = excl;
-        __syncthreads();
-        if (threadIdx.x == 1023) carry = excl + v;
-        __syncthreads();
+        if (f) phase_start[pos] = excl;
+        // interior = groups below `split`
+        (void)block_excl_scan_1024((f && i < split) ? 1u : 0u, warp_sums, &tot);
+        pint += tot;
+        (void)block_excl_scan_1024(i < split ? v : 0u, warp_sums, &tot);
+        int_rows += tot;
     }
-    if (threadIdx.x == 0) start[n] = carry;
+    if (threadIdx.x == 0) {
+        start[n] = carry;
+        phase_start[pcarry] = carry;
+        ctr->n_phases = pcarry; ctr->n_int_phases = pint; ctr->n_int_rows = int_rows;
+    }
 }
 // row = group_start[g] + (slot within the group); perm[row] = k
 __global__ void __launch_bounds__(MGFB_THREADS) k_scatter_rows(const int* __restrict__ group, unsigned* group_count, const unsigned* __restrict__ group_start,
@@ -676,12 +677,19 @@ __device__ __forceinline__ void contact_state(const BodyState& A, const BodyStat
     *tm1 = 1.0f / (A.inv_mass + dot3(ra_ct, mmulv(A.I, ra_ct)) + Bs.inv_mass + dot3(rb_ct, mmulv(Bs.I, rb_ct)));
 }
 __global__ void __launch_bounds__(MGFB_THREADS) k_build_rows(ManifoldInput M, BodyInfoView B, const unsigned* __restrict__ perm, ConstraintRows R,
-                                                            const unsigned* m_ptr, unsigned m_host, float dt, float baumgarte, float slop, Counters* ctr) {
+                                                            const unsigned* m_ptr, unsigned m_host, float dt, float baumgarte, float slop, Counters* ctr,
+                                                            const unsigned char* __restrict__ edge_mark, unsigned n_own) {
     if (ctr->overflow | ctr->nan_bounds) return;
     const unsigned m = m_ptr ? *m_ptr : m_host;
     for (unsigned row = blockIdx.x * blockDim.x + threadIdx.x; row < m; row += gridDim.x * blockDim.x) {
         unsigned k = perm[row];
         int a = M.a[k], b = M.b[k];
+        if (edge_mark && b >= 0 && (((unsigned)a >= n_own) != ((unsigned)b >= n_own))) {
+            // boundary constraint: its owned body is updated here while the left neighbour may update
+            // the bodies it holds as ghosts -- the two sets must not meet (tile too thin otherwise)
+            unsigned own = (unsigned)a >= n_own ? (unsigned)b : (unsigned)a;
+            if (edge_mark[own]) atomicOr(&ctr->comm_error, (unsigned)COMM_TILE_TOO_THIN);
+        }
         V3 n, t0, t1; unsigned nc = 1;
         BodyState A, Bs;
         if (!M.user) {
@@ -794,34 +802,71 @@ __device__ __forceinline__ void solve_row(const ConstraintRows& R, BodyVel* vel,
     if (ab.y >= 0) store_vel(vel + ab.y, vb, ob, imb, IB);
 }
 #define MGFB_SOLVE_THREADS 512
-__global__ void __launch_bounds__(MGFB_SOLVE_THREADS, 1) k_solve(ConstraintRows R, BodyVel* vel, const unsigned* __restrict__ group_start,
-                                                                unsigned iters, Counters* ctr) {
+// TILED: every iteration runs  interior phases | edge velocities to the left neighbour's ghost
+// slots | boundary phases | ghost velocities back to the right neighbour  (see tile.cuh).
+template <bool TILED>
+__global__ void __launch_bounds__(MGFB_SOLVE_THREADS, 1) k_solve(ConstraintRows R, BodyVel* vel, const unsigned* __restrict__ phase_start,
+                                                                unsigned iters, Counters* ctr, TileLink T) {
     if (ctr->overflow | ctr->nan_bounds) return;
-    const unsigned ngroups = ctr->ngroups;
-    if (ngroups == 0) return;
+    const unsigned P = ctr->n_phases;
+    const unsigned Pint = TILED ? ctr->n_int_phases : P;
+    if (!TILED && P == 0) return;
     // Rows are dealt to warps round-robin ACROSS the SMs (warp w of CTA b is global warp
     // w*gridDim + b), so a group with fewer rows than threads still spreads over all 148 SMs
     // instead of saturating the issue slots of the first few.
     const unsigned tid = (((threadIdx.x >> 5) * gridDim.x + blockIdx.x) << 5) | (threadIdx.x & 31u), nth = gridDim.x * blockDim.x;
     unsigned phase = 0;
-    // The first row this thread owns in the next group is fetched BEFORE the grid barrier: rows
+    unsigned n_edge = 0, n_ghost = 0;
+    if (TILED) {
+        n_edge = min(ctr->n_edge, T.left.ghost_cap);
+        n_ghost = ctr->n_total - T.n_own;
+        // the right neighbour may start overwriting my ghost velocities: the rows are built
+        if (T.has_right && blockIdx.x == 0 && threadIdx.x == 0) st_release_sys_u64(&T.right.mbox->vel_from_left.flag, tile_seq(T.step, 1));
+    }
+    // The first row this thread owns in the next phase is fetched BEFORE the grid barrier: rows
     // are immutable during the solve, so only the body gather sits behind the barrier.
-    unsigned r0 = group_start[0], r1 = group_start[1];
+    unsigned r0 = 0, r1 = 0;
     RowData pre; bool have = false;
-    if (r0 + tid < r1) { pre = load_row(R, r0 + tid); have = true; }
+    if (P) { r0 = phase_start[0]; r1 = phase_start[1]; if (r0 + tid < r1) { pre = load_row(R, r0 + tid); have = true; } }
     for (unsigned it = 0; it < iters; ++it) {
-        for (unsigned g = 0; g < ngroups; ++g) {
+        // my edge bodies carry the left neighbour's boundary results of the previous iteration
+        if (TILED && T.has_left && it > 0) tile_wait_cta(&T.mine->vel_from_left.flag, tile_seq(T.step, 1 + it), T.timeout_ns, ctr);
+        for (unsigned p = 0; p < P; ++p) {
+            if (TILED && p == Pint) {
+                if (T.has_left) {
+                    if (it == 0) tile_wait_cta(&T.mine->vel_from_left.flag, tile_seq(T.step, 1), T.timeout_ns, ctr);
+                    tile_push_edges(T, vel, n_edge, tid, nth);
+                    grid_barrier(&ctr->bar, phase);
+                    if (blockIdx.x == 0 && threadIdx.x == 0) st_release_sys_u64(&T.left.mbox->vel_from_right.flag, tile_seq(T.step, 1 + it));
+                }
+                if (T.has_right) tile_wait_cta(&T.mine->vel_from_right.flag, tile_seq(T.step, 1 + it), T.timeout_ns, ctr);
+            }
             unsigned row = r0 + tid;
             if (have) solve_row(R, vel, row, pre);
             for (row += nth; row < r1; row += nth) { RowData d = load_row(R, row); solve_row(R, vel, row, d); }
-            unsigned gn = g + 1 == ngroups ? 0 : g + 1;
-            bool more = (g + 1 < ngroups) || (it + 1 < iters);
-            r0 = group_start[gn]; r1 = group_start[gn + 1];
+            unsigned pn = p + 1 == P ? 0 : p + 1;
+            bool more = (p + 1 < P) || (it + 1 < iters);
+            r0 = phase_start[pn]; r1 = phase_start[pn + 1];
             have = false;
             if (more && r0 + tid < r1) { pre = load_row(R, r0 + tid); have = true; }
             grid_barrier(&ctr->bar, phase);
         }
+        if (TILED) {
+            if (Pint == P && T.has_left) {   // no boundary phase on this rank: the exchange still happens
+                if (it == 0) tile_wait_cta(&T.mine->vel_from_left.flag, tile_seq(T.step, 1), T.timeout_ns, ctr);
+                tile_push_edges(T, vel, n_edge, tid, nth);
+                grid_barrier(&ctr->bar, phase);
+                if (blockIdx.x == 0 && threadIdx.x == 0) st_release_sys_u64(&T.left.mbox->vel_from_right.flag, tile_seq(T.step, 1 + it));
+            }
+            if (T.has_right) {
+                if (Pint == P) tile_wait_cta(&T.mine->vel_from_right.flag, tile_seq(T.step, 1 + it), T.timeout_ns, ctr);
+                tile_return_ghosts(T, vel, n_ghost, tid, nth);
+                grid_barrier(&ctr->bar, phase);
+                if (blockIdx.x == 0 && threadIdx.x == 0) st_release_sys_u64(&T.right.mbox->vel_from_left.flag, tile_seq(T.step, 2 + it));
+            }
+        }
     }
+    if (TILED && T.has_left) tile_wait_cta(&T.mine->vel_from_left.flag, tile_seq(T.step, 1 + iters), T.timeout_ns, ctr);
 }
 __global__ void k_step_done(Counters* ctr) {
     if (ctr->overflow | ctr->nan_bounds) return;

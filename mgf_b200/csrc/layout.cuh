@@ -77,4 +77,55 @@ struct ConstraintRows {
     float4* xtm;     // tangent_mass0, tangent_mass1, normal_impulse, unused
 };
 
+
+// Device-resident counters of one step.  Zeroed (except the sticky ones) at step start.
+struct Counters {
+    unsigned pairs[4];       // body-pair candidates per kind: [ki*2+kj], k = 0 sphere / 1 capsule
+    unsigned tpairs[2];      // (body, face) terrain candidates per body kind
+    unsigned contacts;       // contacts emitted = constraints
+    unsigned tcontacts;      // of which terrain
+    unsigned grid_entries;
+    unsigned fat_refreshes;
+    unsigned max_fat_bits;   // float bits of the largest stored fat-box half extent
+    unsigned ngroups;
+    unsigned remaining;      // uncoloured constraints
+    unsigned bar;            // grid barrier arrival counter
+    unsigned rounds;         // colouring rounds taken
+    unsigned max_tight_bits; // float bits of the largest tight (swept) box half extent
+    unsigned n_total;        // owned bodies + ghost bodies received this step (= n when not tiled)
+    unsigned n_edge;         // owned bodies sent to the left neighbour as ghosts this step
+    unsigned blocks_done;    // last-block-done counter of k_ghost_send
+    unsigned xr_bits;        // ordered-float bits of max(fat.c.x + fat.r.x) over owned bodies
+    unsigned n_phases;       // non-empty groups (solver phases per iteration)
+    unsigned n_int_phases;   // of which interior (before the boundary exchange); = n_phases when not tiled
+    unsigned n_int_rows;     // constraints in interior phases
+    unsigned pad0;
+    // sticky until the host clears them
+    unsigned overflow;       // bit0 pairs, bit1 tpairs, bit2 contacts, bit3 grid entries, bit4 groups, bit5 ghosts
+    unsigned nan_bounds;     // AABB::combine assert (bounds.rs:125-127)
+    unsigned steps_done;
+    unsigned comm_error;     // tiled mode: bit0 neighbour timed out, bit1 tile thinner than its two ghost layers
+    // running totals since the last mgfb_step_totals(reset)
+    unsigned long long acc_constraints;
+    unsigned long long acc_pairs;        // body-body + terrain candidates
+    unsigned long long acc_groups;
+    unsigned long long acc_steps;
+};
+enum { OVF_PAIRS = 1, OVF_TPAIRS = 2, OVF_CONTACTS = 4, OVF_GRID = 8, OVF_GROUPS = 16, OVF_GHOSTS = 32 };
+enum { COMM_TIMEOUT = 1, COMM_TILE_TOO_THIN = 2 };
+struct PairLists { int2* p[4]; };
+
+struct BodyArrays {
+    float4* x;        // position
+    float4* q;        // s, x, y, z
+    BodyVel* vel;
+    float4* force;    // force.xyz, restitution
+    float4* torque;   // torque.xyz, friction
+    float4* imb;      // inv_moment_body: 3 float4 per body (columns)
+    Collider* col;
+    Box* tight;
+    Box* fat;
+    unsigned* gid;    // global body id (= index when the world is not tiled): orders pairs (j < i, world.rs:266)
+};
+
 }  // namespace mgfb

@@ -154,6 +154,39 @@ def pile_scene(num=46, extra=2664, jitter=0.01, seed=1, rad=0.5, squeeze=0.98, f
     return shapes, mass, rest, fric, force
 
 
+def pile_xyz(nx, ny, nz, jitter=0.01, seed=1, rad=0.5, squeeze=0.98, floor_y=-10.0):
+    """A pile already in contact on an nx x ny x nz lattice (x-major order, like balls.rs:80-92), used
+    for worlds tiled along x: ids ascend with x, so a slab is a contiguous id range."""
+    step = F(squeeze * 2.0 * rad)
+    ii, jj, kk = np.meshgrid(np.arange(nx), np.arange(ny), np.arange(nz), indexing="ij")
+    pos = np.stack([(ii.ravel().astype(np.float32) - F(nx - 1) / F(2.0)) * step,
+                    F(floor_y + rad) + jj.ravel().astype(np.float32) * step,
+                    (kk.ravel().astype(np.float32) - F(nz - 1) / F(2.0)) * step], axis=1).astype(np.float32)
+    n = len(pos)
+    if jitter:
+        u = lcg_uniform_fast(3 * n, seed).reshape(n, 3)
+        pos = (pos + (u * F(2.0) - F(1.0)) * F(jitter)).astype(np.float32)
+    shapes = np.zeros(n, dtype=L.SHAPE_DTYPE)
+    shapes["kind"] = L.SPHERE
+    shapes["p"][:, 0:3] = pos
+    shapes["p"][:, 3] = rad
+    return (shapes, np.full(n, 1.0, np.float32), np.full(n, 0.3, np.float32), np.full(n, 0.6, np.float32),
+            np.tile(np.array([0.0, -9.8, 0.0], np.float32), (n, 1)))
+
+
+def tiled_pile(ntiles, tile=0, nx=50, ny=40, nz=50):
+    """Tile `tile` of ONE pile of ntiles*nx x ny x nz spheres in one box, split along x (weak
+    scaling: nx*ny*nz = 100 000 bodies per tile by default, the C2 body count).  Tiles abut at the
+    lattice spacing; jitter comes from the LCG seeded 1 + tile.  Returns the tile's bodies, their
+    global ids (tile-major, ascending with x) and the terrain of the whole world."""
+    shapes, mass, rest, fric, force = pile_xyz(nx, ny, nz, 0.01, 1 + tile)
+    pitch = F(nx * 0.98)
+    shapes["p"][:, 0] += (F(tile) - F(ntiles - 1) / F(2.0)) * pitch
+    n = len(shapes)
+    ids = (np.arange(n, dtype=np.uint32) + np.uint32(tile * n))
+    return (shapes, mass, rest, fric, force), ids, box_terrain(0.8 * nx * ntiles, 40.0, 0.8 * nz)
+
+
 CONFIGS = {
     # name: (scene kwargs, terrain kwargs, iters)
     "C1": dict(kind="balls", num=8, extra=0, jitter=0.0, box=(10.0, 10.0, 10.0), iters=10),

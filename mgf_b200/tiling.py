@@ -1,0 +1,113 @@
+"""One world tiled across GPUs: host-side driver of include/mgfb.h's tile API.
+
+mgf itself is single-threaded; this is the scale-out the north star asks for.  Bodies are split
+into slabs along x, one slab per GPU (one process per GPU under torchrun, or several contexts in
+one process).  This module only PLANS (which body goes where) and WIRES (swaps the tiles'
+memory descriptors between ranks through torch.distributed -- plumbing); every byte of the
+per-step exchange moves GPU to GPU inside the CUDA kernels (mgf_b200/csrc/tile.cuh).
+"""
+import numpy as np
+
+from . import _lib as L
+from .api import World
+
+INTERIOR_COLOURS = 32   # csrc/kernels.cuh TILE_INTERIOR_COLOURS: colours >= 32 are boundary colours
+
+
+def slab_partition(x, nranks):
+    """Split bodies into `nranks` slabs of (nearly) equal count by x coordinate.
+
+    Returns a list of ascending global-id arrays, slab 0 leftmost.  Ties are broken by id, so the
+    result is deterministic."""
+    x = np.asarray(x, dtype=np.float64).reshape(-1)
+    n = len(x)
+    order = np.lexsort((np.arange(n), x))
+    cuts = [(n * r) // nranks for r in range(nranks + 1)]
+    return [np.sort(order[cuts[r]:cuts[r + 1]]).astype(np.uint32) for r in range(nranks)]
+
+
+def shape_centres_x(shapes):
+    """x of Shape::center for an array of mgfb_shape (sphere: c.x; capsule: a.x + d.x/2)."""
+    p = shapes["p"]
+    return np.where(shapes["kind"] == L.CAPSULE, p[:, 0] + 0.5 * p[:, 3], p[:, 0])
+
+
+def all_gather_bytes(blob, group=None):
+    """Every rank's `blob`, in rank order (torch.distributed; gloo or nccl -- host plumbing)."""
+    import torch.distributed as dist
+    out = [None] * dist.get_world_size(group)
+    dist.all_gather_object(out, blob, group=group)
+    return out
+
+
+class TiledWorld:
+    """Rank `rank`'s tile.  Usage (every rank):
+
+        tw = TiledWorld(rank, nranks, device=local_rank)
+        tw.add_bodies(owned_ids, shapes, mass, restitution, friction, world_force)   # GLOBAL arrays
+        tw.set_terrain(verts, faces, x)
+        tw.connect(all_gather_bytes)         # or connect_local([...]) for contexts of one process
+        tw.step(dt, iters)
+    """
+
+    def __init__(self, rank, nranks, device=0, **cfg):
+        self.rank, self.nranks = rank, nranks
+        self.world = World(device=device, **cfg)
+        self.ids = np.zeros(0, np.uint32)
+        self.desc = None
+
+    def add_bodies(self, owned_ids, shapes, mass, restitution, friction, world_force):
+        ids = np.ascontiguousarray(owned_ids, dtype=np.uint32)
+        assert len(ids) > 0, "a tile needs at least one body"
+        assert np.all(np.diff(ids.astype(np.int64)) > 0), "owned ids must be ascending"
+        n = len(shapes)
+        pick = lambda a, shape: np.ascontiguousarray(np.broadcast_to(np.asarray(a, dtype=np.float32), shape)[ids])
+        self.world.add_bodies(np.ascontiguousarray(shapes[ids]), pick(mass, (n,)), pick(restitution, (n,)), pick(friction, (n,)),
+                              pick(world_force, (n, 3)))
+        self.world.set_gid(ids)
+        self.ids = ids
+
+    def set_terrain(self, verts, faces, x=(0.0, 0.0, 0.0)):
+        self.world.set_terrain(verts, faces, x)
+
+    def export(self, ghost_capacity=None):
+        if ghost_capacity is None:
+            ghost_capacity = max(4096, len(self.ids) // 2)
+        self.desc = self.world.tile_export(ghost_capacity)
+        return self.desc
+
+    def connect(self, gather=all_gather_bytes, ghost_capacity=None):
+        descs = gather(self.desc or self.export(ghost_capacity))
+        assert len(descs) == self.nranks
+        self.world.tile_connect(self.rank, descs)
+
+    def step(self, dt, iters=20, nsteps=1):
+        return self.world.step(dt, iters, nsteps)
+
+    def state(self):
+        return self.world.state()
+
+    def constraints(self):
+        """(gid_a, gid_b, face, sub, colour) of the last step in solve order, and the number of
+        interior rows (they come first; the rest are boundary rows)."""
+        a, b, face, sub, colour = self.world.constraints()
+        return a, b, face, sub, colour, int(np.count_nonzero(colour < INTERIOR_COLOURS))
+
+
+def connect_local(tiles, ghost_capacity=None):
+    """Wire tiles that live in ONE process (tests; several GPUs driven by one host thread each)."""
+    descs = [t.export(ghost_capacity) for t in tiles]
+    for t in tiles:
+        t.world.tile_connect(t.rank, descs)
+
+
+def executed_order(per_rank):
+    """The sequential Gauss-Seidel order the tiled solver is equivalent to, per iteration: every
+    rank's interior rows (rank by rank), then every rank's boundary rows.  `per_rank` is a list of
+    TiledWorld.constraints() results; returns (a, b, face, sub) arrays in that global order."""
+    parts = []
+    for a, b, f, s, _, ni in per_rank:
+        parts.append((a[:ni], b[:ni], f[:ni], s[:ni]))
+    for a, b, f, s, _, ni in per_rank:
+        parts.append((a[ni:], b[ni:], f[ni:], s[ni:]))
+    return tuple(np.concatenate([p[k] for p in parts]) for k in range(4))
