@@ -56,7 +56,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20",
                                           "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -67,9 +67,14 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append([c.strip() for c in line.split(",")])
 
-    def stop(self):
+    def mark(self):
+        """Index of the next sample: brackets the timed region inside a longer-running sampler."""
+        return len(self.rows)
+
+    def stop(self, first=0, last=None):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.05)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
@@ -77,7 +82,8 @@ class ClockSampler:
             self.proc.kill()
         sm, smax, reasons = [], None, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        last = len(self.rows) if last is None else max(last, first + 1)
+        for r in self.rows[first:last + 1]:
             try:
                 sm.append(float(r[1])); smax = float(r[2])
                 for k, nm in enumerate(names):
@@ -102,7 +108,15 @@ def run_reference(args, rank):
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import numpy as np
     import oracle_lib   # bench.py's reference arm is one of the two places allowed to execute oracle/
-    bodies, terrain, iters = build_scene()
+    if args.gpus == 1:
+        bodies, terrain, iters = build_scene()
+        workload = WORKLOAD
+    else:   # the same one-box world the N-GPU arm tiles, whole, on one core
+        from mgf_b200 import scenes
+        tiles = [scenes.tiled_pile(args.gpus, t) for t in range(args.gpus)]
+        bodies = tuple(np.concatenate([t[0][k] for t in tiles]) for k in range(5))
+        terrain = tiles[0][2]; iters = 20
+        workload = f"pile of {args.gpus} x 100000 spheres (50x40x50 lattice per tile, same radius/spacing/material as C2pile), one box"
     w = oracle_lib.OracleWorld()
     w.add_bodies(*bodies); w.set_terrain(*terrain)
     dt = np.float32(1.0 / 60.0)
@@ -124,11 +138,11 @@ def run_reference(args, rank):
         "impl": "reference", "metric": "contact_constraint_iterations_per_second", "value": val, "unit": "constraint-iters/s",
         "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": 1e3 * sec / steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "bodies": len(bodies[0]), "solver_iterations": iters, "dt": 1.0 / 60.0,
+        "config": {"workload": workload, "bodies": len(bodies[0]), "solver_iterations": iters, "dt": 1.0 / 60.0,
                    "constraints_per_step": ci / iters / steps, "candidate_pairs_per_step": pairs / steps},
         "narrowphase_pairs_per_second": pairs / sec,
         "cpu_baseline": {"value": val, "unit": "constraint-iters/s", "cores": 1, "kind": "port",
-                         "sample": f"{steps} full World::step of {WORKLOAD} after {warm} warm-up steps, C++ port of the reference "
+                         "sample": f"{steps} full World::step of {workload} after {warm} warm-up steps, C++ port of the reference "
                                    "(oracle/), g++ -O2 -ffp-contract=off, whole step timed like balls.rs:107-109; host has "
                                    f"{os.cpu_count()} cores, 1 used (reference is single-threaded)"},
         "e2e": {"value": val, "unit": "constraint-iters/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -140,7 +154,7 @@ def run_reference(args, rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="mgf_b200", choices=["mgf_b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -162,11 +176,28 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     import mgf_b200
 
-    bodies, terrain, iters = build_scene()
-    n = len(bodies[0])
     dt = np.float32(1.0 / 60.0)
-    g = mgf_b200.World(device=local_rank)
-    g.add_bodies(*bodies); g.set_terrain(*terrain)
+    if world == 1:
+        bodies, terrain, iters = build_scene()
+        g = mgf_b200.World(device=local_rank)
+        g.add_bodies(*bodies); g.set_terrain(*terrain)
+        workload = WORKLOAD
+        parallelism = "single GPU"
+    else:
+        # ONE world of `world` x 100 000 spheres in one box, one slab per GPU (weak scaling).  Ghost
+        # bodies and boundary velocities cross NVLink inside the kernels (csrc/tile.cuh); torch.distributed
+        # only swaps the tiles' memory descriptors once, here.
+        from mgf_b200 import scenes, tiling
+        bodies, ids, terrain = scenes.tiled_pile(world, rank)
+        iters = 20
+        tw = tiling.TiledWorld(rank, world, device=local_rank)
+        tw.add_owned(ids, *bodies); tw.set_terrain(*terrain)
+        tw.connect(tiling.all_gather_bytes, ghost_capacity=32768)
+        g = tw.world
+        workload = f"pile of {world} x 100000 spheres (50x40x50 lattice per tile, same radius/spacing/material as C2pile), one box"
+        parallelism = (f"{world} slabs along x, one per GPU; ghost bodies once per step and boundary velocities every solver "
+                       "iteration through NVLink peer memory inside the kernels")
+    n = len(bodies[0])
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device="cuda")   # 256 MB > 126 MB L2
 
     def barrier():
@@ -175,22 +206,25 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- warm-up
+    # ---- warm-up (the clock sampler starts here: nvidia-smi needs ~0.1 s before its first sample)
+    sampler = ClockSampler(local_rank); sampler.start()
+    barrier()
     g.step(dt, iters, nsteps=args.warmup)
     g.totals(reset=True)
     # ---- timed: K steps, device time from the library's CUDA events, L2 flushed between steps
-    sampler = ClockSampler(local_rank); sampler.start()
     barrier()
-    step_ms = []; solve_ms = []; cons = []; pairs = []; groups = []
+    mark0 = sampler.mark()
+    step_ms = []; solve_ms = []; cons = []; pairs = []; groups = []; ghosts = []; bcons = []
     t_wall0 = time.perf_counter()
     for _ in range(args.steps):
         flush.fill_(1.0); torch.cuda.synchronize()
         st = g.step(dt, iters)
         step_ms.append(st["step_ms"]); solve_ms.append(st["solve_ms"]); cons.append(st["constraints"])
-        pairs.append(st["candidate_pairs"] + st["terrain_candidates"]); groups.append(st["groups"])
+        pairs.append(st["candidate_pairs"] + st["terrain_candidates"]); groups.append(st["phases"])
+        ghosts.append(st["ghosts"]); bcons.append(st["boundary_constraints"])
     barrier()
     t_wall = time.perf_counter() - t_wall0
-    clocks = sampler.stop()
+    clocks = sampler.stop(mark0, sampler.mark())
     tot = g.totals(reset=True)
     total_ms = float(sum(step_ms)); units = float(sum(cons)) * iters; npairs = float(sum(pairs))
     if world > 1:
@@ -256,10 +290,11 @@ def main():
             "metric": "contact_constraint_iterations_per_second", "value": value, "unit": "constraint-iters/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms_max / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "bodies_per_gpu": n, "solver_iterations": iters, "dt": 1.0 / 60.0,
-                       "constraints_per_step": sum(cons) / len(cons), "candidate_pairs_per_step": sum(pairs) / len(pairs),
+            "config": {"workload": workload, "bodies_per_gpu": n, "solver_iterations": iters, "dt": 1.0 / 60.0,
+                       "constraints_per_step": units_all / iters / args.steps, "candidate_pairs_per_step": pairs_all / args.steps,
                        "colour_groups": sum(groups) / len(groups), "l2": "flushed between timed steps (256 MB write)",
-                       "parallelism": "one tile per GPU, no cross-tile exchange" if world > 1 else "single GPU",
+                       "parallelism": parallelism,
+                       "rank0_ghosts_per_step": sum(ghosts) / len(ghosts), "rank0_boundary_constraints_per_step": sum(bcons) / len(bcons),
                        "arithmetic": "--fmad=false, IEEE div/sqrt: bit-exact vs the CPU port"},
             "narrowphase_pairs_per_second": pairs_all / (total_ms_max * 1e-3),
             "solver_only_constraint_iters_per_second": units / solve_s,

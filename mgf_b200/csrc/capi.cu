@@ -762,7 +762,7 @@ int32_t mgfb_step_n(mgfb_ctx* ctx, float dt, uint32_t iters, uint32_t nsteps, mg
     if (!(dt > 0.0f)) return fail(ctx, MGFB_ERR_INVALID_ARG, "dt must be > 0");
     CU(cudaSetDevice(ctx->device));
     if (ctx->n == 0 || nsteps == 0) { if (stats) std::memset(stats, 0, sizeof(*stats)); return MGFB_OK; }
-    unsigned scale = 1, overflowed = 0;
+    unsigned scale = ctx->tile_exported ? 2 : 1, overflowed = 0;   // a tile cannot regrow mid-run: sized once, generously
     TRY(ensure_step_buffers(ctx, scale));
     TRY(ensure_grid(ctx, scale));
     TRY(ensure_rows(ctx, ctx->contact_cap, false, 4096));
@@ -781,11 +781,15 @@ int32_t mgfb_step_n(mgfb_ctx* ctx, float dt, uint32_t iters, uint32_t nsteps, mg
         if (ctx->h_ctr->nan_bounds) { clear_sticky(ctx); return fail(ctx, MGFB_ERR_NAN_BOUNDS, "AABB::combine: r >= 0 violated (NaN in body state; bounds.rs:125-127)"); }
         if (ctx->tiled) {
             // a tile cannot rerun part of a step on its own: its neighbours have moved on
+            // (an overflow makes this tile's kernels return early, so its neighbours -- and then it -- time out: report the cause)
+            if (ctx->h_ctr->overflow & OVF_GHOSTS) return fail(ctx, MGFB_ERR_CAPACITY, "more ghost bodies than the neighbour's ghost capacity (mgfb_tile_export)");
+            if (ctx->h_ctr->overflow) {
+                ctx->err = "a work list overflowed in a tiled step (bits " + std::to_string(ctx->h_ctr->overflow) + "): lists hold 16 pairs / 16 contacts per body slot; raise ghost_capacity";
+                return MGFB_ERR_CAPACITY;
+            }
             if (ctx->h_ctr->comm_error & COMM_TILE_TOO_THIN)
                 return fail(ctx, MGFB_ERR_TILE, "tile too thin: a body is a ghost on the left neighbour and touches a ghost from the right (or reaches two tiles away); use fewer, wider tiles");
             if (ctx->h_ctr->comm_error) return fail(ctx, MGFB_ERR_TILE, "neighbour tile did not answer within the time limit");
-            if (ctx->h_ctr->overflow & OVF_GHOSTS) return fail(ctx, MGFB_ERR_CAPACITY, "more ghost bodies than the neighbour's ghost capacity (mgfb_tile_export)");
-            if (ctx->h_ctr->overflow) return fail(ctx, MGFB_ERR_CAPACITY, "a work list overflowed in a tiled step (lists are sized for own + ghost capacity; raise ghost_capacity)");
             break;
         }
         if (!ctx->h_ctr->overflow) break;
@@ -976,8 +980,8 @@ int32_t mgfb_tile_export(mgfb_ctx* ctx, uint32_t ghost_capacity, mgfb_tile_desc*
     TRY(ensure(ctx, ctx->ridx, (size_t)ghost_capacity * 4, false, true));
     TRY(ensure(ctx, ctx->mbox, sizeof(TileMailbox), false, true));
     // every per-step buffer at its final size now: nothing may be reallocated while neighbours hold pointers
-    TRY(ensure_step_buffers(ctx, 1));
-    TRY(ensure_grid(ctx, 1));
+    TRY(ensure_step_buffers(ctx, 2));
+    TRY(ensure_grid(ctx, 2));
     TRY(ensure_rows(ctx, ctx->contact_cap, false, 4096));
     CU(cudaStreamSynchronize(ctx->stream));
     TileDescRaw d; std::memset(&d, 0, sizeof(d));

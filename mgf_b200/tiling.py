@@ -67,6 +67,15 @@ class TiledWorld:
         self.world.set_gid(ids)
         self.ids = ids
 
+    def add_owned(self, ids, shapes, mass, restitution, friction, world_force):
+        """Like add_bodies, but the arrays hold ONLY this tile's bodies (big worlds: no rank ever
+        materialises the whole scene)."""
+        ids = np.ascontiguousarray(ids, dtype=np.uint32)
+        assert len(ids) == len(shapes) > 0 and np.all(np.diff(ids.astype(np.int64)) > 0)
+        self.world.add_bodies(shapes, mass, restitution, friction, world_force)
+        self.world.set_gid(ids)
+        self.ids = ids
+
     def set_terrain(self, verts, faces, x=(0.0, 0.0, 0.0)):
         self.world.set_terrain(verts, faces, x)
 
