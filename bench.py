@@ -45,54 +45,69 @@ def measured_peak():
 
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock + throttle reasons sampled every ~5 ms by NVML during the timed region (the same
+    counters `nvidia-smi --query-gpu=clocks.sm,clocks_event_reasons.*` prints; B200_PROFILING.md)."""
+    REASONS = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
 
     def __init__(self, gpu_index):
         self.idx = gpu_index
-        self.rows = []
-        self.proc = None
+        self.rows = []          # (sm_mhz, reasons bitmask)
+        self.smax = None
+        self.h = None
+        self._stop = False
+        self.t = None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20",
-                                          "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
+            import pynvml
+            pynvml.nvmlInit()
+            # NVML enumerates by PCI order like CUDA_VISIBLE_DEVICES-less CUDA; map through the UUID to be safe
+            import torch
+            uuid = str(torch.cuda.get_device_properties(self.idx).uuid)
+            self.h = None
+            for k in range(pynvml.nvmlDeviceGetCount()):
+                hk = pynvml.nvmlDeviceGetHandleByIndex(k)
+                u = pynvml.nvmlDeviceGetUUID(hk)
+                u = u.decode() if isinstance(u, bytes) else u
+                if uuid in u or u.replace("GPU-", "") == uuid:
+                    self.h = hk
+            if self.h is None:
+                self.h = pynvml.nvmlDeviceGetHandleByIndex(self.idx)
+            self.nv = pynvml
+            self.smax = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.t = threading.Thread(target=self._run, daemon=True)
             self.t.start()
-        except Exception:
-            self.proc = None
+        except Exception as e:   # noqa: BLE001
+            self.err = repr(e)
+            self.h = None
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+    def _run(self):
+        nv = self.nv
+        while not self._stop:
+            try:
+                self.rows.append((float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)),
+                                  int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))))
+            except Exception:   # noqa: BLE001
+                pass
+            time.sleep(0.005)
 
     def mark(self):
         """Index of the next sample: brackets the timed region inside a longer-running sampler."""
         return len(self.rows)
 
     def stop(self, first=0, last=None):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.05)
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, smax, reasons = [], None, set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        if self.h is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["NVML unavailable: " + getattr(self, "err", "?")]}
+        self._stop = True
+        self.t.join(1.0)
         last = len(self.rows) if last is None else max(last, first + 1)
-        for r in self.rows[first:last + 1]:
-            try:
-                sm.append(float(r[1])); smax = float(r[2])
-                for k, nm in enumerate(names):
-                    if r[4 + k].lower().startswith("active"):
-                        reasons.add(nm)
-            except Exception:
-                continue
-        sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons), "samples": len(sm)}
+        rows = self.rows[first:last + 1]
+        sm = sorted(r[0] for r in rows)
+        mask = 0
+        for r in rows:
+            mask |= r[1]
+        reasons = sorted(k for k, bit in self.REASONS.items() if mask & bit)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.smax, "reasons": reasons, "samples": len(sm)}
 
 
 def build_scene():

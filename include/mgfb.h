@@ -138,6 +138,22 @@ int32_t mgfb_contacts_batch(mgfb_ctx* ctx, uint32_t pair_kind, const mgfb_shape*
                             uint32_t n, mgfb_contact* out /* n*2 */, mgfb_local_contact* out_local /* n*2 or NULL */,
                             uint32_t* counts /* n */);
 
+/* ---------------- discrete path: GJK + EPA (simplex.rs:172-553) ---------------- */
+/* `a[i].contacts(&b[i], cb)` for static convex pairs through the generic impl for Convex + Volumetric shapes
+ * (collision.rs:497-519): GJK seeded along +-y (simplex.rs:172-200), then EPA (simplex.rs:456-553, at most
+ * 101 iterations); the contact has t = 0, `a` on shape a, `b = a - depth * n`.  Shapes: SPHERE, CAPSULE, AABB,
+ * OBB (the Convex implementors, geom.rs:1027-1072).  status[i]: 0 = no contact (the callback is not invoked),
+ * 1 = contact in out[i], 2 = EPA polytope outgrew the device's fixed capacity (254 faces), 3 = GJK did not
+ * converge in 4096 steps (the reference's loop has no other exit there: NaN input, or separated polytopes whose
+ * support point never satisfies |min|^2 >= |support|^2, simplex.rs:195), 4 = the reference panics (EPA indexes a
+ * free Pool slot, pool.rs:111).  epa_iters may be NULL. */
+int32_t mgfb_gjk_batch(mgfb_ctx* ctx, const mgfb_shape* a, const mgfb_shape* b, uint32_t n, mgfb_contact* out /* n */,
+                       uint32_t* status /* n */, uint32_t* epa_iters /* n or NULL */);
+/* Penetrates::separation (collision.rs:404-425): GJK seeded along +-x; status[i] = 1 and separation[i] =
+ * distance for Some(d), status[i] = 0 for None (the shapes overlap). */
+int32_t mgfb_separation_batch(mgfb_ctx* ctx, const mgfb_shape* a, const mgfb_shape* b, uint32_t n, float* separation /* n */,
+                              uint32_t* status /* n */);
+
 /* ---------------- Solver / ContactConstraint (solver.rs:53-262) ---------------- */
 /* A batch of ContactConstraint::new inputs (solver.rs:101): obj_a/obj_b, Manifold.
  * obj < 0 means RigidBodyRef::Static{center, friction} taken from static_center/static_friction.

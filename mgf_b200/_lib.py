@@ -90,6 +90,8 @@ SYMBOLS = [
     ("mgfb_step_constraints", C.c_int32, [_P, C.c_uint32, _P, _P, _P, _P, _P, C.POINTER(C.c_uint32)]),
     ("mgfb_step_totals", C.c_int32, [_P] + [C.POINTER(C.c_uint64)] * 5 + [C.c_int32]),
     ("mgfb_device_view_get", C.c_int32, [_P, C.POINTER(DeviceView)]),
+    ("mgfb_gjk_batch", C.c_int32, [_P, _P, _P, C.c_uint32, _P, _P, _P]),
+    ("mgfb_separation_batch", C.c_int32, [_P, _P, _P, C.c_uint32, _P, _P]),
     ("mgfb_bodies_set_gid", C.c_int32, [_P, C.c_uint32, C.c_uint32, _P]),
     ("mgfb_tile_export", C.c_int32, [_P, C.c_uint32, C.POINTER(TileDesc)]),
     ("mgfb_tile_connect", C.c_int32, [_P, C.c_uint32, C.c_uint32, _P]),

@@ -94,6 +94,37 @@ class Context:
         self.close()
 
 
+def aabb(c, r):
+    """geom.rs:257 AABB{c, r}."""
+    return _one(L.AABB, [*c, *r])
+
+
+def obb(c, r, q=(1.0, 0.0, 0.0, 0.0)):
+    """geom.rs:272 OBB{c, q, r}; q = (s, x, y, z)."""
+    return _one(L.OBB, [*c, *r, *q])
+
+
+def gjk_batch(ctx, a, b):
+    """`a[i].contacts(&b[i], cb)` through the discrete GJK + EPA path (collision.rs:497-519).
+    Returns (contacts[n], status[n], epa_iterations[n]); status 1 = a contact was delivered."""
+    a = np.ascontiguousarray(a, dtype=L.SHAPE_DTYPE); b = np.ascontiguousarray(b, dtype=L.SHAPE_DTYPE)
+    n = len(a)
+    assert len(b) == n
+    out = np.zeros(n, dtype=L.CONTACT_DTYPE); status = np.zeros(n, np.uint32); iters = np.zeros(n, np.uint32)
+    ctx.check(ctx.lib.mgfb_gjk_batch(ctx.h, L.ptr(a), L.ptr(b), n, L.ptr(out), L.ptr(status), L.ptr(iters)))
+    return out, status, iters
+
+
+def separation_batch(ctx, a, b):
+    """Penetrates::separation (collision.rs:404-425): (distance[n], is_some[n])."""
+    a = np.ascontiguousarray(a, dtype=L.SHAPE_DTYPE); b = np.ascontiguousarray(b, dtype=L.SHAPE_DTYPE)
+    n = len(a)
+    assert len(b) == n
+    sep = np.zeros(n, np.float32); status = np.zeros(n, np.uint32)
+    ctx.check(ctx.lib.mgfb_separation_batch(ctx.h, L.ptr(a), L.ptr(b), n, L.ptr(sep), L.ptr(status)))
+    return sep, status
+
+
 def contacts_batch(ctx, pair_kind, recv, arg, want_local=False):
     """`recv[i].contacts(&arg[i], cb)` for a homogeneous batch (collision.rs:471).
 

@@ -1044,3 +1044,4 @@ int32_t mgfb_device_view_get(mgfb_ctx* ctx, mgfb_device_view* out) {
 }  // extern "C"
 
 #include "batch.cuh"
+#include "gjk.cuh"

@@ -230,14 +230,25 @@ double mgfo_world_time_steps(mgfo_world* h, float dt, uint32_t iters, uint32_t n
 }
 
 // ---- discrete path (collision.rs:404-425, 497-519) ----
-static bool gjk_dispatch(const mgfb_shape& A, const mgfb_shape& B, Contact* c, int* it);
+static bool gjk_dispatch(const mgfb_shape& A, const mgfb_shape& B, Contact* c, int* it, int* st);
 int32_t mgfo_gjk_batch(const mgfb_shape* a, const mgfb_shape* b, uint32_t n, mgfb_contact* out, uint32_t* hit, uint32_t* epa_iters) {
     for (uint32_t i = 0; i < n; ++i) {
         Contact c{}; int it = 0;
-        bool ok = gjk_dispatch(a[i], b[i], &c, &it);
-        hit[i] = ok ? 1u : 0u;
+        int st = 0;
+        bool ok = gjk_dispatch(a[i], b[i], &c, &it, &st);
+        hit[i] = ok ? 1u : (uint32_t)st;   // 0 no contact, 1 contact, 3 GJK step cap (same codes as mgfb_gjk_batch)
         if (epa_iters) epa_iters[i] = (uint32_t)it;
         if (ok) put_contact(&out[i], c); else std::memset(&out[i], 0, sizeof(mgfb_contact));
+    }
+    return MGFB_OK;
+}
+static bool sep_dispatch(const mgfb_shape& A, const mgfb_shape& B, float* d, int* st);
+// Penetrates::separation (collision.rs:404-425) for a batch: some[i] = 1 and sep[i] = distance for Some(d).
+int32_t mgfo_separation_batch(const mgfb_shape* a, const mgfb_shape* b, uint32_t n, float* sep, uint32_t* some) {
+    for (uint32_t i = 0; i < n; ++i) {
+        float d = 0.0f; int st = 0;
+        bool ok = sep_dispatch(a[i], b[i], &d, &st);
+        some[i] = ok ? 1u : (uint32_t)st; sep[i] = ok ? d : 0.0f;
     }
     return MGFB_OK;
 }
@@ -247,22 +258,43 @@ namespace {
 AABB to_aabb(const mgfb_shape& s) { return AABB{p3(s.p), p3(s.p + 3)}; }
 OBB to_obb(const mgfb_shape& s) { return OBB{p3(s.p), Quat{s.p[6], p3(s.p + 7)}, p3(s.p + 3)}; }
 template <class SA>
-bool gjk_with(const SA& a, const mgfb_shape& B, Contact* c, int* it) {
+bool gjk_with(const SA& a, const mgfb_shape& B, Contact* c, int* it, int* st) {
     switch (B.kind) {
-        case MGFB_SPHERE: return gjk_contact(a, to_sphere(B), c, it);
-        case MGFB_CAPSULE: return gjk_contact(a, to_capsule(B), c, it);
-        case MGFB_AABB: return gjk_contact(a, to_aabb(B), c, it);
-        case MGFB_OBB: return gjk_contact(a, to_obb(B), c, it);
+        case MGFB_SPHERE: return gjk_contact(a, to_sphere(B), c, it, st);
+        case MGFB_CAPSULE: return gjk_contact(a, to_capsule(B), c, it, st);
+        case MGFB_AABB: return gjk_contact(a, to_aabb(B), c, it, st);
+        case MGFB_OBB: return gjk_contact(a, to_obb(B), c, it, st);
         default: return false;
     }
 }
 }  // namespace
-static bool gjk_dispatch(const mgfb_shape& A, const mgfb_shape& B, Contact* c, int* it) {
+static bool gjk_dispatch(const mgfb_shape& A, const mgfb_shape& B, Contact* c, int* it, int* st) {
     switch (A.kind) {
-        case MGFB_SPHERE: return gjk_with(to_sphere(A), B, c, it);
-        case MGFB_CAPSULE: return gjk_with(to_capsule(A), B, c, it);
-        case MGFB_AABB: return gjk_with(to_aabb(A), B, c, it);
-        case MGFB_OBB: return gjk_with(to_obb(A), B, c, it);
+        case MGFB_SPHERE: return gjk_with(to_sphere(A), B, c, it, st);
+        case MGFB_CAPSULE: return gjk_with(to_capsule(A), B, c, it, st);
+        case MGFB_AABB: return gjk_with(to_aabb(A), B, c, it, st);
+        case MGFB_OBB: return gjk_with(to_obb(A), B, c, it, st);
+        default: return false;
+    }
+}
+namespace {
+template <class SA>
+bool sep_with(const SA& a, const mgfb_shape& B, float* d, int* st) {
+    switch (B.kind) {
+        case MGFB_SPHERE: return separation(a, to_sphere(B), d, st);
+        case MGFB_CAPSULE: return separation(a, to_capsule(B), d, st);
+        case MGFB_AABB: return separation(a, to_aabb(B), d, st);
+        case MGFB_OBB: return separation(a, to_obb(B), d, st);
+        default: return false;
+    }
+}
+}  // namespace
+static bool sep_dispatch(const mgfb_shape& A, const mgfb_shape& B, float* d, int* st) {
+    switch (A.kind) {
+        case MGFB_SPHERE: return sep_with(to_sphere(A), B, d, st);
+        case MGFB_CAPSULE: return sep_with(to_capsule(A), B, d, st);
+        case MGFB_AABB: return sep_with(to_aabb(A), B, d, st);
+        case MGFB_OBB: return sep_with(to_obb(A), B, d, st);
         default: return false;
     }
 }

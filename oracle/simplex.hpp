@@ -121,10 +121,16 @@ struct Simplex {
     void add_point(const SupportPoint& p) { points[state - 1] = p; }
 
     // simplex.rs:172-200
+    // The reference loops `loop { .. }` until one of the two exits fires; on some inputs (NaN, or a
+    // simplex that cycles between two supports) it never does.  Oracle and device both give up after
+    // GJK_MAX_STEPS and say so (`*converged = false`), instead of hanging.
+    static constexpr int GJK_MAX_STEPS = 4096;
     template <class Shape>
-    Vec3 closest_point_to_origin(const Shape& shape) {
+    Vec3 closest_point_to_origin(const Shape& shape, bool* converged = nullptr) {
         Vec3 prev_norm = v3(0, 0, 0);
-        for (;;) {
+        if (converged) *converged = true;
+        for (int step = 0;; ++step) {
+            if (step >= GJK_MAX_STEPS) { if (converged) *converged = false; return v3(0, 0, 0); }
             int next_state;
             Vec3 mn = min_norm(&next_state);
             if (magnitude2(mn) < COLLISION_EPSILON) {
@@ -226,11 +232,13 @@ struct Simplex {
 
 // collision.rs:404-425  Penetrates::separation; returns false for None.
 template <class A, class B>
-bool separation(const A& a, const B& b, float* out) {
+bool separation(const A& a, const B& b, float* out, int* status = nullptr) {
     Vec3 d = v3(1.0f, 0.0f, 0.0f);
     MinkowskiDiff<A, B> diff{&a, &b};
     Simplex simp = Simplex::from2(diff.support_pt(d), diff.support_pt(-d));
-    Vec3 min_dist = simp.closest_point_to_origin(diff);
+    bool ok = true;
+    Vec3 min_dist = simp.closest_point_to_origin(diff, &ok);
+    if (!ok) { if (status) *status = 3; return false; }
     float mag2 = magnitude2(min_dist);
     if (mag2 < COLLISION_EPSILON) return false;
     *out = sqrtf(mag2);
@@ -238,14 +246,19 @@ bool separation(const A& a, const B& b, float* out) {
 }
 // collision.rs:497-519  Contacts for Convex x Convex (discrete, t = 0)
 template <class A, class B>
-bool gjk_contact(const A& a, const B& b, Contact* out, int* epa_iters = nullptr) {
+bool gjk_contact(const A& a, const B& b, Contact* out, int* epa_iters = nullptr, int* status = nullptr) {
     Vec3 d = v3(0.0f, 1.0f, 0.0f);
     MinkowskiDiff<A, B> diff{&a, &b};
     Simplex simp = Simplex::from2(diff.support_pt(d), diff.support_pt(-d));
-    Vec3 min_dist = simp.closest_point_to_origin(diff);
+    bool ok = true;
+    Vec3 min_dist = simp.closest_point_to_origin(diff, &ok);
+    if (!ok) { if (status) *status = 3; return false; }
     float mag2 = magnitude2(min_dist);
     if (mag2 > COLLISION_EPSILON) return false;
-    *out = simp.compute_contact(a, b, epa_iters);
+    // `tris[closest_i]` panics in the reference when the closest-face search found nothing and slot 0
+    // is free (pool.rs:111 "unoccupied"): reported as status 4, never an abort across the C ABI.
+    try { *out = simp.compute_contact(a, b, epa_iters); }
+    catch (std::out_of_range&) { if (status) *status = 4; return false; }
     return true;
 }
 

@@ -63,8 +63,30 @@ def load():
     lib.mgfo_world_time_steps.argtypes = [_P, C.c_float, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
     lib.mgfo_gjk_batch.restype = C.c_int32
     lib.mgfo_gjk_batch.argtypes = [_P, _P, C.c_uint32, _P, _P, _P]
+    lib.mgfo_separation_batch.restype = C.c_int32
+    lib.mgfo_separation_batch.argtypes = [_P, _P, C.c_uint32, _P, _P]
     _lib = lib
     return lib
+
+
+def gjk_batch(a, b):
+    """Oracle of mgfb_gjk_batch: (contacts[n], hit[n], epa_iterations[n])."""
+    lib = load()
+    a = np.ascontiguousarray(a, dtype=L.SHAPE_DTYPE); b = np.ascontiguousarray(b, dtype=L.SHAPE_DTYPE)
+    n = len(a)
+    out = np.zeros(n, dtype=L.CONTACT_DTYPE); hit = np.zeros(n, np.uint32); iters = np.zeros(n, np.uint32)
+    assert lib.mgfo_gjk_batch(L.ptr(a), L.ptr(b), n, L.ptr(out), L.ptr(hit), L.ptr(iters)) == 0
+    return out, hit, iters
+
+
+def separation_batch(a, b):
+    """Oracle of mgfb_separation_batch: (distance[n], is_some[n])."""
+    lib = load()
+    a = np.ascontiguousarray(a, dtype=L.SHAPE_DTYPE); b = np.ascontiguousarray(b, dtype=L.SHAPE_DTYPE)
+    n = len(a)
+    sep = np.zeros(n, np.float32); some = np.zeros(n, np.uint32)
+    assert lib.mgfo_separation_batch(L.ptr(a), L.ptr(b), n, L.ptr(sep), L.ptr(some)) == 0
+    return sep, some
 
 
 def contacts_batch(pair_kind, recv, arg, want_local=False):
