@@ -174,6 +174,66 @@ def pile_xyz(nx, ny, nz, jitter=0.01, seed=1, rad=0.5, squeeze=0.98, floor_y=-10
             np.tile(np.array([0.0, -9.8, 0.0], np.float32), (n, 1)))
 
 
+def capsule_pile(nx, ny, nz, jitter=0.02, seed=1, floor_y=-10.0):
+    """capsules.rs:69-73 capsules (a = centre - (0.5,0,0), d = (1,0,0), r = 1) packed into a pile that
+    is already in contact: spacing 2.9 along the axis, 1.96 across, bottom layer on the floor."""
+    ii, jj, kk = np.meshgrid(np.arange(nx), np.arange(ny), np.arange(nz), indexing="ij")
+    pos = np.stack([(ii.ravel().astype(np.float32) - F(nx - 1) / F(2.0)) * F(2.9),
+                    F(floor_y + 1.0) + jj.ravel().astype(np.float32) * F(1.96),
+                    (kk.ravel().astype(np.float32) - F(nz - 1) / F(2.0)) * F(1.96)], axis=1).astype(np.float32)
+    n = len(pos)
+    if jitter:
+        u = lcg_uniform_fast(3 * n, seed).reshape(n, 3)
+        pos = (pos + (u * F(2.0) - F(1.0)) * F(jitter)).astype(np.float32)
+    shapes = np.zeros(n, dtype=L.SHAPE_DTYPE)
+    shapes["kind"] = L.CAPSULE
+    shapes["p"][:, 0:3] = pos + np.array([-0.5, 0.0, 0.0], np.float32)
+    shapes["p"][:, 3:6] = np.array([1.0, 0.0, 0.0], np.float32)
+    shapes["p"][:, 6] = 1.0
+    return (shapes, np.full(n, 1.0, np.float32), np.full(n, 0.3, np.float32), np.full(n, 0.6, np.float32),
+            np.tile(np.array([0.0, -9.8, 0.0], np.float32), (n, 1)))
+
+
+def config_c3(scale=1.0):
+    """BASELINE configs[2]: 50 000 capsules over a static 20 000-triangle mesh floor (Capsule x Triangle
+    narrowphase).  The floor is SURVEY 8(d)'s height field y = 0.5 sin(0.3x) cos(0.3z) - 10; the capsules
+    sit on it as a 50 x 20 x 50 pile so the capsule-triangle and capsule-capsule kernels work from step 0.
+    `scale` < 1 shrinks the body count (parity tests on small boxes)."""
+    nx, ny, nz = max(2, int(round(50 * scale))), max(2, int(round(20 * scale))), max(2, int(round(50 * scale)))
+    bodies = capsule_pile(nx, ny, nz)
+    size = max(2.9 * nx, 1.96 * nz) + 12.0
+    shapes = bodies[0]
+    shapes["p"][:, 1] += 0.6   # clear the crests of the height field
+    return bodies, heightfield_terrain(nq=100, size=size, y0=-10.0, amp=0.5, freq=0.3), 20
+
+
+def config_c5(scale=1.0):
+    """BASELINE configs[4] restated (RigidBodyVec holds single Components and Compound x Mesh has
+    no impl in the reference): a MIXED body set -- spheres r = 0.5 and capsules d = (1,0,0) r = 0.4
+    interleaved -- 200 000 bodies over a 200 000-triangle height field.  The GJK half of the config is the
+    separate static-pair batch (tests/gjk_cases.py)."""
+    nx, ny, nz = max(2, int(round(100 * scale))), max(2, int(round(20 * scale))), max(2, int(round(100 * scale)))
+    ii, jj, kk = np.meshgrid(np.arange(nx), np.arange(ny), np.arange(nz), indexing="ij")
+    pos = np.stack([(ii.ravel().astype(np.float32) - F(nx - 1) / F(2.0)) * F(1.38),
+                    F(-10.0 + 0.9) + jj.ravel().astype(np.float32) * F(0.88),
+                    (kk.ravel().astype(np.float32) - F(nz - 1) / F(2.0)) * F(0.88)], axis=1).astype(np.float32)
+    n = len(pos)
+    u = lcg_uniform_fast(3 * n, 5).reshape(n, 3)
+    pos = (pos + (u * F(2.0) - F(1.0)) * F(0.01)).astype(np.float32)
+    shapes = np.zeros(n, dtype=L.SHAPE_DTYPE)
+    is_cap = ((ii + jj + kk).ravel() % 2) == 1
+    shapes["kind"] = np.where(is_cap, L.CAPSULE, L.SPHERE)
+    shapes["p"][:, 0:3] = pos
+    shapes["p"][:, 3] = 0.5
+    shapes["p"][is_cap, 0] -= 0.5
+    shapes["p"][is_cap, 3:6] = np.array([1.0, 0.0, 0.0], np.float32)
+    shapes["p"][is_cap, 6] = 0.4
+    bodies = (shapes, np.full(n, 1.0, np.float32), np.full(n, 0.3, np.float32), np.full(n, 0.6, np.float32),
+              np.tile(np.array([0.0, -9.8, 0.0], np.float32), (n, 1)))
+    nq = max(4, int(round(316 * scale)))   # 2 * 316^2 = 199 712 triangles
+    return bodies, heightfield_terrain(nq=nq, size=max(1.38 * nx, 0.88 * nz) + 10.0, y0=-10.0, amp=0.5, freq=0.3), 20
+
+
 def tiled_pile(ntiles, tile=0, nx=50, ny=40, nz=50):
     """Tile `tile` of ONE pile of ntiles*nx x ny x nz spheres in one box, split along x (weak
     scaling: nx*ny*nz = 100 000 bodies per tile by default, the C2 body count).  Tiles abut at the
