@@ -173,6 +173,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="mgf_b200", choices=["mgf_b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--schedule", default="dataflow", choices=["dataflow", "phases"],
+                    help="solver schedule (include/mgfb.h mgfb_solver_schedule); tiled worlds always use phases")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "mgf_b200" else args.warmup
     rank = int(os.environ.get("RANK", "0")); local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -194,7 +196,7 @@ def main():
     dt = np.float32(1.0 / 60.0)
     if world == 1:
         bodies, terrain, iters = build_scene()
-        g = mgf_b200.World(device=local_rank)
+        g = mgf_b200.World(device=local_rank, solver_schedule=0 if args.schedule == "dataflow" else 1)
         g.add_bodies(*bodies); g.set_terrain(*terrain)
         workload = WORKLOAD
         parallelism = "single GPU"
@@ -279,7 +281,9 @@ def main():
     peak, peak_src = measured_peak()
     solve_s = sum(solve_ms) * 1e-3
     achieved = ALGO_BYTES_PER_CONSTRAINT_ITER * units / solve_s / 1e9
-    roofline = {"kernel": "k_solve (persistent cooperative sequential-impulse solver)", "bound": "hbm", "achieved": achieved, "peak": peak,
+    dataflow = world == 1 and args.schedule == "dataflow"
+    roofline = {"kernel": "k_solve_df (persistent sequential-impulse solver, per-body version counters, no grid barrier)" if dataflow
+                else "k_solve (persistent cooperative sequential-impulse solver, one grid barrier per colour)", "bound": "hbm", "achieved": achieved, "peak": peak,
                 "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": ALGO_BYTES_PER_CONSTRAINT_ITER * units / len(solve_ms),
                 "avg_launch_ms": sum(solve_ms) / len(solve_ms), "share_of_step": sum(solve_ms) / total_ms,

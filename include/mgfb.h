@@ -76,6 +76,13 @@ enum mgfb_pair_kind {
     MGFB_PAIR_KIND_COUNT = 12
 };
 
+/* How the device walks the constraint rows of Solver::solve (solver.rs:72-78).  Both produce the
+ * reference's sequential sweep over the same row order, bit for bit. */
+enum mgfb_solver_schedule {
+    MGFB_SCHEDULE_DATAFLOW = 0,  /* default: per-body version counters, a row runs as soon as both its bodies are ready */
+    MGFB_SCHEDULE_PHASES = 1     /* one grid-wide barrier per colour per iteration */
+};
+
 /* solver.rs:265-279 ContactConstraintParams, manifold.rs:27-39 PruningParams, world.rs:181 */
 typedef struct mgfb_config {
     int32_t device;                 /* CUDA device ordinal */
@@ -86,7 +93,8 @@ typedef struct mgfb_config {
     uint32_t initial_body_capacity; /* 0 = default */
     uint32_t max_cooperative_ctas;  /* 0 = one CTA per SM; lower it when several contexts must share one GPU */
     uint32_t tile_timeout_ms;       /* 0 = 20000: how long a tile waits for a neighbour before MGFB_ERR_TILE */
-    uint32_t reserved[2];
+    uint32_t solver_schedule;       /* mgfb_solver_schedule; coloured order only (as-given order and tiled worlds always use phases) */
+    uint32_t reserved;
 } mgfb_config;
 void mgfb_config_default(mgfb_config* cfg);
 

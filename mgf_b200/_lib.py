@@ -31,7 +31,10 @@ class Config(C.Structure):
     _fields_ = [("device", C.c_int32), ("penetration_slop", C.c_float), ("baumgarte", C.c_float),
                 ("persistent_threshold_sq", C.c_float), ("fat_margin", C.c_float),
                 ("initial_body_capacity", C.c_uint32), ("max_cooperative_ctas", C.c_uint32), ("tile_timeout_ms", C.c_uint32),
-                ("reserved", C.c_uint32 * 2)]
+                ("solver_schedule", C.c_uint32), ("reserved", C.c_uint32)]
+
+
+SCHEDULE_DATAFLOW, SCHEDULE_PHASES = 0, 1
 
 
 class Manifolds(C.Structure):
@@ -105,10 +108,11 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
-        raise RuntimeError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+    path = os.environ.get("MGFB_LIB", LIB_PATH)   # development builds (e.g. -DMGFB_DF_PROFILE); still a CUDA library, never a fallback
+    if not os.path.exists(path):
+        raise RuntimeError(f"{path} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
                            "(nvcc, sm_100a).  mgf_b200 has no CPU fallback.")
-    lib = C.CDLL(LIB_PATH)
+    lib = C.CDLL(path)
     for name, res, args in SYMBOLS:
         fn = getattr(lib, name)  # AttributeError if the ABI and the header disagree
         fn.restype = res

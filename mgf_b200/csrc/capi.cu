@@ -52,7 +52,9 @@ struct mgfb_ctx {
     Buf body_best, body_scratch /* mask[n] u64 + last[n] u32 */, group, group_count, group_start, phase_start, perm;
     unsigned group_cap = 0;
     // rows
-    Buf r_ab, r_n, r_t0, r_t1, r_ra, r_rb, r_imp, r_xra, r_xrb, r_xtm; unsigned row_cap = 0, xrow_cap = 0;
+    Buf r_ab, r_n, r_t0, r_t1, r_ra, r_rb, r_imp, r_xra, r_xrb, r_xtm, r_dep; unsigned row_cap = 0, xrow_cap = 0;
+    Buf body_deg, body_start, r_inc, r_next, r_cnt;   // dataflow solver: rows per body (CSR), successor links, signal counters
+    Buf sv;             // SolverVel[cap]: versioned v, omega of the dataflow solver (k_solve_df)
     // body grid
     Buf cell_count, cell_start, bg_ent, scan_sums; unsigned table = 0, ent_cap = 0;
     TerrainData terrain;
@@ -61,7 +63,8 @@ struct mgfb_ctx {
     // user-path staging
     Buf u_a, u_b, u_sc, u_sf, u_n, u_t, u_nc, u_la, u_lb;
     // cooperative grid sizes
-    int coop_order = 0, coop_solve = 0;
+    int coop_order = 0, coop_solve = 0, coop_df = 0;
+    unsigned df_threads = 512, df_backoff_ns = 0;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     // last step
     unsigned last_constraints = 0;
@@ -138,6 +141,9 @@ int32_t grow_bodies(mgfb_ctx* ctx, unsigned need) {
     TRY(ensure(ctx, ctx->gid, (size_t)nc * 4, true));
     TRY(ensure(ctx, ctx->body_best, (size_t)nc * 8, false, true));
     TRY(ensure(ctx, ctx->body_scratch, (size_t)nc * 12, false, true));
+    TRY(ensure(ctx, ctx->sv, (size_t)nc * sizeof(SolverVel)));
+    TRY(ensure(ctx, ctx->body_deg, (size_t)nc * 4)); TRY(ensure(ctx, ctx->body_start, ((size_t)nc + 1) * 4));
+    TRY(ensure(ctx, ctx->scan_sums, ((size_t)nc / SCAN_ITEMS + 2) * 4));
     ctx->cap = nc;
     return MGFB_OK;
 }
@@ -160,7 +166,8 @@ int32_t ensure_rows(mgfb_ctx* ctx, unsigned m, bool extras, unsigned groups) {
         unsigned rc = std::max(m, 1024u);
         TRY(ensure(ctx, ctx->r_ab, (size_t)rc * 8)); TRY(ensure(ctx, ctx->r_n, (size_t)rc * 16)); TRY(ensure(ctx, ctx->r_t0, (size_t)rc * 16));
         TRY(ensure(ctx, ctx->r_t1, (size_t)rc * 16)); TRY(ensure(ctx, ctx->r_ra, (size_t)rc * 16)); TRY(ensure(ctx, ctx->r_rb, (size_t)rc * 16));
-        TRY(ensure(ctx, ctx->r_imp, (size_t)rc * 4)); TRY(ensure(ctx, ctx->group, (size_t)rc * 4)); TRY(ensure(ctx, ctx->perm, (size_t)rc * 4));
+        TRY(ensure(ctx, ctx->r_imp, (size_t)rc * 4)); TRY(ensure(ctx, ctx->r_dep, (size_t)rc * 4)); TRY(ensure(ctx, ctx->r_inc, (size_t)rc * 8)); TRY(ensure(ctx, ctx->r_next, (size_t)rc * 8));
+        TRY(ensure(ctx, ctx->r_cnt, (size_t)rc * 4)); TRY(ensure(ctx, ctx->group, (size_t)rc * 4)); TRY(ensure(ctx, ctx->perm, (size_t)rc * 4));
         ctx->row_cap = rc;
     }
     if (extras && m > ctx->xrow_cap) {
@@ -277,14 +284,41 @@ int32_t enqueue_order_and_solve(mgfb_ctx* ctx, const OrderView& O, const Manifol
     k_group_scan<<<1, 1024, 0, ctx->stream>>>(gcount, gstart, pstart, c, gcap, tiled ? (unsigned)TILE_INTERIOR_COLOURS : 0xffffffffu);
     int g = grid_for(ctx, m_bound);
     k_scatter_rows<<<g, MGFB_THREADS, 0, ctx->stream>>>(O.group, gcount, gstart, perm, m_ptr, m_host, c);
+    // Schedule of the solve: dataflow (body version counters, no grid barrier) for coloured single-GPU
+    // solves; grid-barrier phases for as-given (level) order, tiled worlds, > 64 colours, or on request.
+    const bool dataflow = !as_given && !tiled && ctx->cfg.solver_schedule == MGFB_SCHEDULE_DATAFLOW;
+    unsigned* dep = dataflow ? ctx->r_dep.as<unsigned>() : nullptr;
+    unsigned* bstart = ctx->body_start.as<unsigned>(); unsigned* inc = ctx->r_inc.as<unsigned>();
+    const unsigned nb = M.user ? ctx->n : body_slots(ctx);
+    if (dataflow) {   // rows per body = number of colours at the body; CSR offsets for the successor links
+        k_body_deg<<<grid_for(ctx, nb), MGFB_THREADS, 0, ctx->stream>>>(O.body_mask, nb, ctx->body_deg.as<unsigned>(), c);
+        TRY(scan_u32(ctx, ctx->body_deg.as<unsigned>(), bstart, nb, ctx->scan_sums.as<unsigned>(), &c->df_links));
+        ctx->launches += 4;
+    }
     k_build_rows<<<g, MGFB_THREADS, 0, ctx->stream>>>(M, BI, perm, R, m_ptr, m_host, dt, ctx->cfg.baumgarte, ctx->cfg.penetration_slop, c,
-                                                      tiled ? ctx->edge_mark.as<unsigned char>() : nullptr, tiled ? ctx->n : 0xffffffffu);
+                                                      tiled ? ctx->edge_mark.as<unsigned char>() : nullptr, tiled ? ctx->n : 0xffffffffu,
+                                                      O.group, O.body_mask, dep, bstart, inc);
+    SolverVel* sv = ctx->sv.as<SolverVel>();
+    int2* nxt = ctx->r_next.as<int2>(); unsigned* cnt = ctx->r_cnt.as<unsigned>();
+    if (dataflow) {
+        k_df_init<<<g, MGFB_THREADS, 0, ctx->stream>>>(vel, sv, nb, R.ab, dep, bstart, inc, nxt, cnt, m_ptr, m_host, c);
+        ctx->launches += 1;
+    }
     CU(cudaGetLastError());
     if (time_solve) CU(cudaEventRecord(ctx->ev[2], ctx->stream));
+    if (dataflow) {
+        const unsigned* ps = pstart; unsigned it = iters; const unsigned* dp = dep; unsigned bo = ctx->df_backoff_ns;
+        const int2* nx = nxt;
+        void* args[] = {&R, &dp, &nx, &cnt, &vel, &sv, &ps, &it, &bo, &c};
+        void* fn = ctx->df_threads == 256 ? (void*)k_solve_df<256> : ctx->df_threads == 1024 ? (void*)k_solve_df<1024> : (void*)k_solve_df<512>;
+        CU(cudaLaunchCooperativeKernel(fn, dim3(ctx->coop_df), dim3(ctx->df_threads), args, 0, ctx->stream));
+        ctx->launches += 1;
+    }
     {
         const unsigned* ps = pstart; unsigned it = iters;
         TileLink T = ctx->link;
-        void* args[] = {&R, &vel, &ps, &it, &c, &T};
+        unsigned only_beyond = dataflow ? (unsigned)MGFB_DF_MAX_PHASES : 0u;   // after k_solve_df: only if it declined (> 64 colours)
+        void* args[] = {&R, &vel, &ps, &it, &c, &T, &only_beyond};
         void* fn = tiled ? (void*)k_solve<true> : (void*)k_solve<false>;
         CU(cudaLaunchCooperativeKernel(fn, dim3(ctx->coop_solve), dim3(MGFB_SOLVE_THREADS), args, 0, ctx->stream));
     }
@@ -478,6 +512,7 @@ int32_t mgfb_ctx_create(const mgfb_config* cfg, mgfb_ctx** out) {
                              (const void*)k_narrow_bodies<0, 1>, (const void*)k_narrow_bodies<1, 0>, (const void*)k_narrow_bodies<1, 1>,
                              (const void*)k_narrow_terrain<0>, (const void*)k_narrow_terrain<1>, (const void*)k_order, (const void*)k_group_scan,
                              (const void*)k_scatter_rows, (const void*)k_build_rows, (const void*)k_solve<false>, (const void*)k_solve<true>,
+                             (const void*)k_solve_df<256>, (const void*)k_solve_df<512>, (const void*)k_solve_df<1024>, (const void*)k_df_init, (const void*)k_body_deg,
                              (const void*)k_step_done, (const void*)k_pack_state, (const void*)k_set_velocity};
         cudaFuncAttributes fa;
         for (const void* f : fns) if ((e = cudaFuncGetAttributes(&fa, f)) != cudaSuccess) return bail(e, "cudaFuncGetAttributes");
@@ -486,6 +521,10 @@ int32_t mgfb_ctx_create(const mgfb_config* cfg, mgfb_ctx** out) {
     if (ctx->cfg.tile_timeout_ms) ctx->tile_timeout_ns = (unsigned long long)ctx->cfg.tile_timeout_ms * 1000000ULL;
     ctx->coop_order = coop_blocks(ctx, k_order, MGFB_THREADS, 2);
     ctx->coop_solve = std::min(coop_blocks(ctx, k_solve<false>, MGFB_SOLVE_THREADS, 1), coop_blocks(ctx, k_solve<true>, MGFB_SOLVE_THREADS, 1));
+    if (const char* e_ = getenv("MGFB_DF_THREADS")) { int t = atoi(e_); if (t == 256 || t == 512 || t == 1024) ctx->df_threads = (unsigned)t; }
+    if (const char* e_ = getenv("MGFB_DF_BACKOFF_NS")) ctx->df_backoff_ns = (unsigned)atoi(e_);
+    ctx->coop_df = ctx->df_threads == 256 ? coop_blocks(ctx, k_solve_df<256>, 256, 1) : ctx->df_threads == 1024 ? coop_blocks(ctx, k_solve_df<1024>, 1024, 1)
+                                                                                                              : coop_blocks(ctx, k_solve_df<512>, 512, 1);
     int32_t s = grow_bodies(ctx, std::max(ctx->cfg.initial_body_capacity, 1024u));
     if (s == MGFB_OK) s = ensure_rows(ctx, 1024, false, 4096);
     if (s != MGFB_OK) { g_create_err = ctx->err; delete ctx; return s; }
@@ -497,11 +536,22 @@ void mgfb_ctx_destroy(mgfb_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+#ifdef MGFB_DF_PROFILE
+    {
+        unsigned long long h[8];
+        cudaMemcpyFromSymbol(h, g_df_prof, sizeof(h));
+        double v = (double)std::max(1ULL, h[6]);
+        fprintf(stderr, "[df profile] warps=%llu visits=%llu per visit (cycles): fetch %.0f hint-poll %.0f version-poll %.0f compute+publish %.0f ; hint polls %.2f version polls %.2f\n",
+                h[7], h[6], h[0] / v, h[1] / v, h[2] / v, h[3] / v, h[4] / v, h[5] / v);
+        unsigned long long z[8] = {0};
+        cudaMemcpyToSymbol(g_df_prof, z, sizeof(z));
+    }
+#endif
     Buf* all[] = {&ctx->x, &ctx->q, &ctx->vel, &ctx->force, &ctx->torque, &ctx->imb, &ctx->col, &ctx->tight, &ctx->fat, &ctx->ctr,
                   &ctx->pair_list[0], &ctx->pair_list[1], &ctx->pair_list[2], &ctx->pair_list[3], &ctx->tpair_list[0], &ctx->tpair_list[1],
                   &ctx->c_a, &ctx->c_b, &ctx->c_face, &ctx->c_sub, &ctx->c_la, &ctx->c_lb, &ctx->c_nt, &ctx->body_best, &ctx->body_scratch,
                   &ctx->group, &ctx->group_count, &ctx->group_start, &ctx->perm, &ctx->r_ab, &ctx->r_n, &ctx->r_t0, &ctx->r_t1, &ctx->r_ra,
-                  &ctx->r_rb, &ctx->r_imp, &ctx->r_xra, &ctx->r_xrb, &ctx->r_xtm, &ctx->cell_count, &ctx->cell_start, &ctx->bg_ent,
+                  &ctx->r_rb, &ctx->r_imp, &ctx->r_xra, &ctx->r_xrb, &ctx->r_xtm, &ctx->r_dep, &ctx->sv, &ctx->body_deg, &ctx->body_start, &ctx->r_inc, &ctx->r_next, &ctx->r_cnt, &ctx->cell_count, &ctx->cell_start, &ctx->bg_ent,
                   &ctx->scan_sums, &ctx->u_a, &ctx->u_b, &ctx->u_sc, &ctx->u_sf, &ctx->u_n, &ctx->u_t, &ctx->u_nc, &ctx->u_la,
                   &ctx->u_lb, &ctx->stage, &ctx->terrain.verts, &ctx->terrain.faces, &ctx->terrain.boxes, &ctx->terrain.cell_count,
                   &ctx->terrain.cell_start, &ctx->terrain.ent_id, &ctx->terrain.ent_key, &ctx->terrain.max_bits,

@@ -678,12 +678,26 @@ __device__ __forceinline__ void contact_state(const BodyState& A, const BodyStat
 }
 __global__ void __launch_bounds__(MGFB_THREADS) k_build_rows(ManifoldInput M, BodyInfoView B, const unsigned* __restrict__ perm, ConstraintRows R,
                                                             const unsigned* m_ptr, unsigned m_host, float dt, float baumgarte, float slop, Counters* ctr,
-                                                            const unsigned char* __restrict__ edge_mark, unsigned n_own) {
+                                                            const unsigned char* __restrict__ edge_mark, unsigned n_own,
+                                                            const int* __restrict__ group, const unsigned long long* __restrict__ body_mask, unsigned* dep,
+                                                            const unsigned* __restrict__ body_start, unsigned* inc) {
     if (ctr->overflow | ctr->nan_bounds) return;
     const unsigned m = m_ptr ? *m_ptr : m_host;
     for (unsigned row = blockIdx.x * blockDim.x + threadIdx.x; row < m; row += gridDim.x * blockDim.x) {
         unsigned k = perm[row];
         int a = M.a[k], b = M.b[k];
+        if (dep) {
+            // dataflow schedule (k_solve_df): this row is the seq-th of deg rows at each of its bodies, in colour order
+            int g = group[k];
+            unsigned d = 0u;
+            if (g >= 0 && g < 64) {
+                unsigned long long below = (1ULL << g) - 1ULL;
+                // inc = the rows of every body in solve order (CSR over body_start): k_df_init links each row to its successors
+                if (a >= 0) { unsigned long long ma = body_mask[a]; unsigned sq = (unsigned)__popcll(ma & below); d |= sq | ((unsigned)__popcll(ma) << 8); inc[body_start[a] + sq] = row; }
+                if (b >= 0) { unsigned long long mb = body_mask[b]; unsigned sq = (unsigned)__popcll(mb & below); d |= (sq << 16) | ((unsigned)__popcll(mb) << 24); inc[body_start[b] + sq] = row; }
+            }
+            dep[row] = d;
+        }
         if (edge_mark && b >= 0 && (((unsigned)a >= n_own) != ((unsigned)b >= n_own))) {
             // boundary constraint: its owned body is updated here while the left neighbour may update
             // the bodies it holds as ghosts -- the two sets must not meet (tile too thin otherwise)
@@ -806,8 +820,9 @@ __device__ __forceinline__ void solve_row(const ConstraintRows& R, BodyVel* vel,
 // slots | boundary phases | ghost velocities back to the right neighbour  (see tile.cuh).
 template <bool TILED>
 __global__ void __launch_bounds__(MGFB_SOLVE_THREADS, 1) k_solve(ConstraintRows R, BodyVel* vel, const unsigned* __restrict__ phase_start,
-                                                                unsigned iters, Counters* ctr, TileLink T) {
+                                                                unsigned iters, Counters* ctr, TileLink T, unsigned only_beyond) {
     if (ctr->overflow | ctr->nan_bounds) return;
+    if (only_beyond && ctr->ngroups <= only_beyond) return;   // k_solve_df (dataflow schedule) took this step
     const unsigned P = ctr->n_phases;
     const unsigned Pint = TILED ? ctr->n_int_phases : P;
     if (!TILED && P == 0) return;
@@ -868,6 +883,211 @@ __global__ void __launch_bounds__(MGFB_SOLVE_THREADS, 1) k_solve(ConstraintRows 
     }
     if (TILED && T.has_left) tile_wait_cta(&T.mine->vel_from_left.flag, tile_seq(T.step, 1 + iters), T.timeout_ns, ctr);
 }
+// ---------------------------------------------------------------- Solver::solve, dataflow schedule
+// Same arithmetic and the same row order as k_solve, but NO grid barriers: every body carries a
+// version = the number of row updates applied to it so far, stored in the same 32-byte record
+// as its v and omega (SolverVel).  Row r at iteration `it` is the (seq + it*deg)-th update of
+// each of its bodies (seq = rank of the row's colour among the colours at that body, deg = the
+// body's number of rows), so it spins until both records show exactly that version, updates
+// them and publishes version+1 with the new velocities in ONE 32-byte store per body -- flag and
+// payload cannot be seen apart, so no fence is needed.  The sequential sweep over the rows in
+// row order is the unique execution these waits allow: the result is bit-identical to k_solve
+// and to the reference's loop over that order.  Progress: a warp takes warp-rows (32 rows of
+// one colour, never dependent on each other) in increasing (iteration, row) order, all warps
+// are co-resident (cooperative launch), so the smallest unfinished warp-row always has its
+// dependencies published.  Iterations pipeline: a body's rows of iteration it+1 start as soon
+// as ITS OWN iteration `it` is complete.
+struct __align__(32) SolverVel { float4 lo, hi; };   // v.xyz, version | omega.xyz, version
+__device__ __forceinline__ SolverVel ld_sv(const SolverVel* p) {
+    SolverVel r;
+    asm volatile("ld.relaxed.gpu.global.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(r.lo.x), "=f"(r.lo.y), "=f"(r.lo.z), "=f"(r.lo.w), "=f"(r.hi.x), "=f"(r.hi.y), "=f"(r.hi.z), "=f"(r.hi.w)
+                 : "l"(p) : "memory");
+    return r;
+}
+__device__ __forceinline__ void st_sv(SolverVel* p, V3 v, V3 w, unsigned ver) {
+    float fv = __uint_as_float(ver);
+    asm volatile("st.relaxed.gpu.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                 :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(fv), "f"(w.x), "f"(w.y), "f"(w.z), "f"(fv) : "memory");
+}
+__global__ void __launch_bounds__(MGFB_THREADS) k_body_deg(const unsigned long long* __restrict__ body_mask, unsigned n, unsigned* deg, Counters* ctr) {
+    if (ctr->overflow | ctr->nan_bounds) return;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) deg[i] = (unsigned)__popcll(body_mask[i]);
+}
+// Bodies: versioned copy of v, omega.  Rows: the successor of the row on each of its bodies (cyclic: the
+// body's last row is followed by its first row of the next iteration) and the row's signal counter,
+// which starts at the number of its bodies on which it is the FIRST row.
+__global__ void __launch_bounds__(MGFB_THREADS) k_df_init(const BodyVel* __restrict__ vel, SolverVel* sv, unsigned n, const int2* __restrict__ ab,
+                                                         const unsigned* __restrict__ dep, const unsigned* __restrict__ body_start,
+                                                         const unsigned* __restrict__ inc, int2* next, unsigned* cnt,
+                                                         const unsigned* m_ptr, unsigned m_host, Counters* ctr) {
+    if (ctr->overflow | ctr->nan_bounds) return;
+    const unsigned tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+    for (unsigned i = tid; i < n; i += nth) {
+        const float4* q = reinterpret_cast<const float4*>(vel + i);
+        float4 a = q[0], b = q[1];
+        st_sv(sv + i, mk3(a.x, a.y, a.z), mk3(a.w, b.x, b.y), 0u);
+    }
+    if (ctr->ngroups > 64u) return;   // k_solve takes this step
+    const unsigned m = m_ptr ? *m_ptr : m_host;
+    for (unsigned row = tid; row < m; row += nth) {
+        int2 p = ab[row]; unsigned d = dep[row];
+        unsigned seqA = d & 255u, degA = (d >> 8) & 255u, seqB = (d >> 16) & 255u, degB = d >> 24;
+        int2 nx = make_int2(-1, -1); unsigned c0 = 0u;
+        if (p.x >= 0) { nx.x = (int)inc[body_start[p.x] + (seqA + 1u == degA ? 0u : seqA + 1u)]; c0 += seqA == 0u; }
+        if (p.y >= 0) { nx.y = (int)inc[body_start[p.y] + (seqB + 1u == degB ? 0u : seqB + 1u)]; c0 += seqB == 0u; }
+        next[row] = nx; cnt[row] = c0;
+    }
+}
+__device__ __forceinline__ void load_inertia(const BodyVel* p, float* im, M3* I) {
+    const float4* q = reinterpret_cast<const float4*>(p);
+    float4 b = __ldcg(q + 1), c = __ldcg(q + 2), d = __ldcg(q + 3);
+    *im = b.z;
+    *I = mkm(mk3(b.w, c.x, c.y), mk3(c.z, c.w, d.x), mk3(d.y, d.z, d.w));
+}
+#ifdef MGFB_DF_PROFILE
+__device__ unsigned long long g_df_prof[8];   // cycles: fetch-issue, hint poll, version poll, compute+publish ; counts: hint polls, version polls, visits
+#define DF_T(x) long long x = clock64()
+#define DF_ACC(i, v) prof[i] += (unsigned long long)(v)
+#else
+#define DF_T(x)
+#define DF_ACC(i, v)
+#endif
+struct DfRow { RowData d; int2 next; unsigned dep, row; float imp; bool valid; };
+#define MGFB_DF_MAX_PHASES 64
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS, 1) k_solve_df(ConstraintRows R, const unsigned* __restrict__ dep, const int2* __restrict__ next, unsigned* cnt,
+                                                         BodyVel* vel, SolverVel* sv, const unsigned* __restrict__ phase_start, unsigned iters,
+                                                         unsigned backoff_ns, Counters* ctr) {
+    if (ctr->overflow | ctr->nan_bounds) return;
+    const unsigned P = ctr->n_phases;
+    if (P == 0 || ctr->ngroups > MGFB_DF_MAX_PHASES || iters == 0) return;   // > 64 colours: k_solve takes the step
+    __shared__ unsigned s_row0[MGFB_DF_MAX_PHASES + 1], s_wr0[MGFB_DF_MAX_PHASES + 1];
+    if (threadIdx.x == 0) {
+        unsigned w = 0;
+        for (unsigned p = 0; p < P; ++p) { unsigned r0 = phase_start[p], r1 = phase_start[p + 1]; s_row0[p] = r0; s_wr0[p] = w; w += (r1 - r0 + 31u) >> 5; }
+        s_row0[P] = phase_start[P]; s_wr0[P] = w;
+    }
+    __syncthreads();
+    const unsigned nwr = s_wr0[P];
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned gw = (threadIdx.x >> 5) * gridDim.x + blockIdx.x, nW = gridDim.x * (THREADS / 32);
+    if (gw >= nwr) return;
+    auto fetch = [&](unsigned wr, unsigned& p) {
+        DfRow f;
+        while (wr >= s_wr0[p + 1]) ++p;
+        unsigned row = s_row0[p] + ((wr - s_wr0[p]) << 5) + lane;
+        f.row = row;
+        f.valid = row < s_row0[p + 1];
+        if (f.valid) { f.d = load_row(R, row); f.dep = dep[row]; f.next = next[row]; f.imp = __ldcg(&R.impulse[row]); }
+        else { f.d.ab = make_int2(-1, -1); f.next = make_int2(-1, -1); f.dep = 0u; f.imp = 0.0f; }
+        return f;
+    };
+    unsigned p_next = 0, wr = gw, it = 0;
+#ifdef MGFB_DF_PROFILE
+    unsigned long long prof[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#endif
+    DfRow nxt = fetch(wr, p_next);
+    for (;;) {
+        DF_T(t0);
+        DfRow cur = nxt;
+        const unsigned row = cur.row;
+        // prefetch this warp's next warp-row (rows are immutable; its impulse was last written by this very thread)
+        unsigned wr_n = wr + nW, it_n = it;
+        if (wr_n >= nwr) { wr_n = gw; it_n = it + 1; p_next = 0; }
+        const bool more = it_n < iters;
+        const bool same_rows = (wr_n == wr);   // this warp owns one warp-row: its impulse is carried in registers
+        if (more) nxt = fetch(wr_n, p_next);
+        const int a = cur.d.ab.x, b = cur.d.ab.y;
+        const bool needA = cur.valid && a >= 0, needB = cur.valid && b >= 0;
+        const unsigned seqA = cur.dep & 255u, degA = (cur.dep >> 8) & 255u, seqB = (cur.dep >> 16) & 255u, degB = cur.dep >> 24;
+        const unsigned expA = seqA + it * degA, expB = seqB + it * degB;
+        float ima = 0.0f, imb = 0.0f; M3 IA = m_zero(), IB = m_zero();
+        if (needA) load_inertia(vel + a, &ima, &IA);
+        if (needB) load_inertia(vel + b, &imb, &IB);
+        SolverVel sa, sb;
+        sa.lo = sa.hi = sb.lo = sb.hi = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        bool okA = !needA, okB = !needB;
+        DF_T(t1); DF_ACC(0, t1 - t0);
+        // Cheap wait first: the predecessors of this row bump its signal counter (one coalesced 128-byte
+        // poll per warp instead of 64 scattered sectors).  The counter is only a HINT (relaxed, it may
+        // overtake the velocity store): the version check below is what admits the row.
+        {
+            const unsigned target = ((needA ? 1u : 0u) + (needB ? 1u : 0u)) * (it + 1u);
+            for (;;) {
+                unsigned c = 0xffffffffu;
+                if (cur.valid) asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(c) : "l"(cnt + row) : "memory");
+                DF_ACC(4, 1);
+                if (__all_sync(0xffffffffu, c >= target)) break;
+                if (backoff_ns) __nanosleep(backoff_ns);
+            }
+        }
+        DF_T(t2); DF_ACC(1, t2 - t1);
+        for (;;) {
+            if (!okA) { sa = ld_sv(sv + a); okA = __float_as_uint(sa.lo.w) == expA && __float_as_uint(sa.hi.w) == expA; }
+            if (!okB) { sb = ld_sv(sv + b); okB = __float_as_uint(sb.lo.w) == expB && __float_as_uint(sb.hi.w) == expB; }
+            DF_ACC(5, 1);
+            if (__all_sync(0xffffffffu, okA && okB)) break;
+            if (backoff_ns) __nanosleep(backoff_ns);
+        }
+        DF_T(t3); DF_ACC(2, t3 - t2);
+        if (cur.valid) {
+            V3 va = mk3(sa.lo.x, sa.lo.y, sa.lo.z), oa = mk3(sa.hi.x, sa.hi.y, sa.hi.z);
+            V3 vb = mk3(sb.lo.x, sb.lo.y, sb.lo.z), ob = mk3(sb.hi.x, sb.hi.y, sb.hi.z);
+            float4 n4 = cur.d.n, t04 = cur.d.t0, t14 = cur.d.t1, ra4 = cur.d.ra, rb4 = cur.d.rb;
+            V3 n = f4v(n4), t0 = f4v(t04), t1 = f4v(t14);
+            int nc = (int)fbits(rb4.w);
+            for (int c = 0; c < nc; ++c) {
+                V3 ra, rb; float bias, nmass, tm0, tm1, imp;
+                if (c == 0) { ra = f4v(ra4); rb = f4v(rb4); bias = n4.w; nmass = ra4.w; tm0 = t04.w; tm1 = t14.w; imp = cur.imp; }
+                else {
+                    unsigned e = row * 3 + (c - 1);
+                    float4 xa = R.xra[e], xb = R.xrb[e], xt = __ldcg(&R.xtm[e]);
+                    ra = f4v(xa); rb = f4v(xb); nmass = xa.w; bias = xb.w; tm0 = xt.x; tm1 = xt.y; imp = xt.z;
+                }
+                V3 dv = vb + cross3(ob, rb) - va - cross3(oa, ra);        // solver.rs:217-232, same stale dv for both tangents
+                float l0 = -dot3(dv, t0) * tm0;
+                apply_impulse(t0 * l0, ra, rb, ima, imb, IA, IB, va, oa, vb, ob);
+                float l1 = -dot3(dv, t1) * tm1;
+                apply_impulse(t1 * l1, ra, rb, ima, imb, IA, IB, va, oa, vb, ob);
+                V3 dv2 = vb + cross3(ob, rb) - va - cross3(oa, ra);       // solver.rs:234-247
+                float vn = dot3(dv2, n);
+                float lambda = nmass * (-vn + bias);
+                float prev = imp;
+                imp = fmaxf(prev + lambda, 0.0f);
+                lambda = imp - prev;
+                apply_impulse(n * lambda, ra, rb, ima, imb, IA, IB, va, oa, vb, ob);
+                if (c == 0) {
+                    if (same_rows) nxt.imp = imp;
+                    if (!same_rows || it + 1 == iters) __stcg(&R.impulse[row], imp);
+                }
+                else { unsigned e = row * 3 + (c - 1); __stcg(&R.xtm[e], make_float4(tm0, tm1, imp, 0.0f)); }
+            }
+            const bool last_it = it + 1 == iters;
+            if (needA) {
+                st_sv(sv + a, va, oa, expA + 1u);
+                const bool fin = last_it && seqA + 1u == degA;
+                if (fin) store_vel(vel + a, va, oa, ima, IA);   // the body's final update of the solve
+                else asm volatile("red.relaxed.gpu.global.add.u32 [%0], 1;" ::"l"(cnt + cur.next.x) : "memory");
+            }
+            if (needB) {
+                st_sv(sv + b, vb, ob, expB + 1u);
+                const bool fin = last_it && seqB + 1u == degB;
+                if (fin) store_vel(vel + b, vb, ob, imb, IB);
+                else asm volatile("red.relaxed.gpu.global.add.u32 [%0], 1;" ::"l"(cnt + cur.next.y) : "memory");
+            }
+        }
+        __syncwarp();
+        DF_T(t4); DF_ACC(3, t4 - t3); DF_ACC(6, 1);
+        if (!more) break;
+        wr = wr_n; it = it_n;
+    }
+#ifdef MGFB_DF_PROFILE
+    if (lane == 0) for (int i = 0; i < 7; ++i) atomicAdd(&g_df_prof[i], prof[i]);
+    if (lane == 0) atomicAdd(&g_df_prof[7], 1ULL);
+#endif
+}
+
 __global__ void k_step_done(Counters* ctr) {
     if (ctr->overflow | ctr->nan_bounds) return;
     ctr->steps_done++;

@@ -99,7 +99,7 @@ struct Counters {
     unsigned n_phases;       // non-empty groups (solver phases per iteration)
     unsigned n_int_phases;   // of which interior (before the boundary exchange); = n_phases when not tiled
     unsigned n_int_rows;     // constraints in interior phases
-    unsigned pad0;
+    unsigned df_links;       // dataflow solver: total (body, row) incidences = sum of rows per body
     // sticky until the host clears them
     unsigned overflow;       // bit0 pairs, bit1 tpairs, bit2 contacts, bit3 grid entries, bit4 groups, bit5 ghosts
     unsigned nan_bounds;     // AABB::combine assert (bounds.rs:125-127)

@@ -15,8 +15,19 @@ pytestmark = pytest.mark.gpu
 DT = np.float32(1.0 / 60.0)
 
 
+SCHEDULE = [L.SCHEDULE_DATAFLOW]
+
+
+@pytest.fixture(autouse=True, params=[L.SCHEDULE_DATAFLOW, L.SCHEDULE_PHASES], ids=["dataflow", "phases"])
+def _schedule(request):
+    """Every test runs under both solver schedules (include/mgfb.h mgfb_solver_schedule): body version
+    counters without grid barriers, and one grid barrier per colour."""
+    SCHEDULE[0] = request.param
+    yield
+
+
 def _pair(bodies, terrain):
-    g = mgf_b200.World(device=0)
+    g = mgf_b200.World(device=0, solver_schedule=SCHEDULE[0])
     o = oracle_lib.OracleWorld()
     for w in (g, o):
         w.add_bodies(*bodies)
