@@ -53,8 +53,9 @@ struct mgfb_ctx {
     unsigned group_cap = 0;
     // rows
     Buf r_ab, r_n, r_t0, r_t1, r_ra, r_rb, r_imp, r_xra, r_xrb, r_xtm, r_dep; unsigned row_cap = 0, xrow_cap = 0;
-    Buf body_deg, body_start, r_inc, r_next, r_cnt;   // dataflow solver: rows per body (CSR), successor links, signal counters
-    Buf sv;             // SolverVel[cap]: versioned v, omega of the dataflow solver (k_solve_df)
+    // dataflow solver (k_solve_df): rows per body (CSR), successor links, per-row inboxes and inertia
+    Buf body_deg, body_start, r_inc, r_next, r_in_a, r_in_b, r_ia;
+    unsigned df_epoch = 0;   // inbox tags of one solve are df_epoch + 1 .. df_epoch + iters + 1
     // body grid
     Buf cell_count, cell_start, bg_ent, scan_sums; unsigned table = 0, ent_cap = 0;
     TerrainData terrain;
@@ -64,7 +65,7 @@ struct mgfb_ctx {
     Buf u_a, u_b, u_sc, u_sf, u_n, u_t, u_nc, u_la, u_lb;
     // cooperative grid sizes
     int coop_order = 0, coop_solve = 0, coop_df = 0;
-    unsigned df_threads = 512, df_backoff_ns = 0;
+    unsigned df_threads = 256, df_backoff_ns = 0;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     // last step
     unsigned last_constraints = 0;
@@ -141,7 +142,6 @@ int32_t grow_bodies(mgfb_ctx* ctx, unsigned need) {
     TRY(ensure(ctx, ctx->gid, (size_t)nc * 4, true));
     TRY(ensure(ctx, ctx->body_best, (size_t)nc * 8, false, true));
     TRY(ensure(ctx, ctx->body_scratch, (size_t)nc * 12, false, true));
-    TRY(ensure(ctx, ctx->sv, (size_t)nc * sizeof(SolverVel)));
     TRY(ensure(ctx, ctx->body_deg, (size_t)nc * 4)); TRY(ensure(ctx, ctx->body_start, ((size_t)nc + 1) * 4));
     TRY(ensure(ctx, ctx->scan_sums, ((size_t)nc / SCAN_ITEMS + 2) * 4));
     ctx->cap = nc;
@@ -166,8 +166,11 @@ int32_t ensure_rows(mgfb_ctx* ctx, unsigned m, bool extras, unsigned groups) {
         unsigned rc = std::max(m, 1024u);
         TRY(ensure(ctx, ctx->r_ab, (size_t)rc * 8)); TRY(ensure(ctx, ctx->r_n, (size_t)rc * 16)); TRY(ensure(ctx, ctx->r_t0, (size_t)rc * 16));
         TRY(ensure(ctx, ctx->r_t1, (size_t)rc * 16)); TRY(ensure(ctx, ctx->r_ra, (size_t)rc * 16)); TRY(ensure(ctx, ctx->r_rb, (size_t)rc * 16));
-        TRY(ensure(ctx, ctx->r_imp, (size_t)rc * 4)); TRY(ensure(ctx, ctx->r_dep, (size_t)rc * 4)); TRY(ensure(ctx, ctx->r_inc, (size_t)rc * 8)); TRY(ensure(ctx, ctx->r_next, (size_t)rc * 8));
-        TRY(ensure(ctx, ctx->r_cnt, (size_t)rc * 4)); TRY(ensure(ctx, ctx->group, (size_t)rc * 4)); TRY(ensure(ctx, ctx->perm, (size_t)rc * 4));
+        TRY(ensure(ctx, ctx->r_imp, (size_t)rc * 4)); TRY(ensure(ctx, ctx->group, (size_t)rc * 4)); TRY(ensure(ctx, ctx->perm, (size_t)rc * 4));
+        TRY(ensure(ctx, ctx->r_dep, (size_t)rc * 4)); TRY(ensure(ctx, ctx->r_inc, (size_t)rc * 8)); TRY(ensure(ctx, ctx->r_next, (size_t)rc * 8));
+        TRY(ensure(ctx, ctx->r_ia, (size_t)rc * 80));
+        // inbox tags must never match by accident: zeroed when (re)allocated, epochs only grow
+        TRY(ensure(ctx, ctx->r_in_a, (size_t)rc * sizeof(Inbox), false, true)); TRY(ensure(ctx, ctx->r_in_b, (size_t)rc * sizeof(Inbox), false, true));
         ctx->row_cap = rc;
     }
     if (extras && m > ctx->xrow_cap) {
@@ -287,29 +290,34 @@ int32_t enqueue_order_and_solve(mgfb_ctx* ctx, const OrderView& O, const Manifol
     // Schedule of the solve: dataflow (body version counters, no grid barrier) for coloured single-GPU
     // solves; grid-barrier phases for as-given (level) order, tiled worlds, > 64 colours, or on request.
     const bool dataflow = !as_given && !tiled && ctx->cfg.solver_schedule == MGFB_SCHEDULE_DATAFLOW;
-    unsigned* dep = dataflow ? ctx->r_dep.as<unsigned>() : nullptr;
-    unsigned* bstart = ctx->body_start.as<unsigned>(); unsigned* inc = ctx->r_inc.as<unsigned>();
+    DfArrays D{};
     const unsigned nb = M.user ? ctx->n : body_slots(ctx);
     if (dataflow) {   // rows per body = number of colours at the body; CSR offsets for the successor links
+        D.in_a = ctx->r_in_a.as<Inbox>(); D.in_b = ctx->r_in_b.as<Inbox>(); D.ia = ctx->r_ia.as<float4>(); D.row_cap = ctx->row_cap;
+        D.next = ctx->r_next.as<unsigned>(); D.dep = ctx->r_dep.as<unsigned>(); D.body_start = ctx->body_start.as<unsigned>();
+        D.inc = ctx->r_inc.as<unsigned>();
         k_body_deg<<<grid_for(ctx, nb), MGFB_THREADS, 0, ctx->stream>>>(O.body_mask, nb, ctx->body_deg.as<unsigned>(), c);
-        TRY(scan_u32(ctx, ctx->body_deg.as<unsigned>(), bstart, nb, ctx->scan_sums.as<unsigned>(), &c->df_links));
+        TRY(scan_u32(ctx, ctx->body_deg.as<unsigned>(), ctx->body_start.as<unsigned>(), nb, ctx->scan_sums.as<unsigned>(), &c->df_links));
         ctx->launches += 4;
     }
     k_build_rows<<<g, MGFB_THREADS, 0, ctx->stream>>>(M, BI, perm, R, m_ptr, m_host, dt, ctx->cfg.baumgarte, ctx->cfg.penetration_slop, c,
                                                       tiled ? ctx->edge_mark.as<unsigned char>() : nullptr, tiled ? ctx->n : 0xffffffffu,
-                                                      O.group, O.body_mask, dep, bstart, inc);
-    SolverVel* sv = ctx->sv.as<SolverVel>();
-    int2* nxt = ctx->r_next.as<int2>(); unsigned* cnt = ctx->r_cnt.as<unsigned>();
+                                                      O.group, O.body_mask, D);
+    unsigned epoch = ctx->df_epoch;
     if (dataflow) {
-        k_df_init<<<g, MGFB_THREADS, 0, ctx->stream>>>(vel, sv, nb, R.ab, dep, bstart, inc, nxt, cnt, m_ptr, m_host, c);
+        if (ctx->df_epoch > 0xffffffffu - 2u * (iters + 2u)) {   // tag space exhausted (once per ~10^8 solves): start over from clean inboxes
+            CU(cudaMemsetAsync(ctx->r_in_a.p, 0, ctx->r_in_a.bytes, ctx->stream)); CU(cudaMemsetAsync(ctx->r_in_b.p, 0, ctx->r_in_b.bytes, ctx->stream));
+            ctx->df_epoch = epoch = 0;
+        }
+        ctx->df_epoch += iters + 2u;
+        k_df_init<<<g, MGFB_THREADS, 0, ctx->stream>>>(vel, nb, R.ab, D, epoch, m_ptr, m_host, c);
         ctx->launches += 1;
     }
     CU(cudaGetLastError());
     if (time_solve) CU(cudaEventRecord(ctx->ev[2], ctx->stream));
     if (dataflow) {
-        const unsigned* ps = pstart; unsigned it = iters; const unsigned* dp = dep; unsigned bo = ctx->df_backoff_ns;
-        const int2* nx = nxt;
-        void* args[] = {&R, &dp, &nx, &cnt, &vel, &sv, &ps, &it, &bo, &c};
+        const unsigned* ps = pstart; unsigned it = iters; unsigned bo = ctx->df_backoff_ns;
+        void* args[] = {&R, &D, &vel, &ps, &it, &epoch, &bo, &c};
         void* fn = ctx->df_threads == 256 ? (void*)k_solve_df<256> : ctx->df_threads == 1024 ? (void*)k_solve_df<1024> : (void*)k_solve_df<512>;
         CU(cudaLaunchCooperativeKernel(fn, dim3(ctx->coop_df), dim3(ctx->df_threads), args, 0, ctx->stream));
         ctx->launches += 1;
@@ -540,9 +548,9 @@ void mgfb_ctx_destroy(mgfb_ctx* ctx) {
     {
         unsigned long long h[8];
         cudaMemcpyFromSymbol(h, g_df_prof, sizeof(h));
-        double v = (double)std::max(1ULL, h[6]);
-        fprintf(stderr, "[df profile] warps=%llu visits=%llu per visit (cycles): fetch %.0f hint-poll %.0f version-poll %.0f compute+publish %.0f ; hint polls %.2f version polls %.2f\n",
-                h[7], h[6], h[0] / v, h[1] / v, h[2] / v, h[3] / v, h[4] / v, h[5] / v);
+        double v = (double)std::max(1ULL, h[4]);
+        fprintf(stderr, "[df profile] warps=%llu visits=%llu per visit (cycles): fetch %.0f inbox-poll %.0f compute+publish %.0f ; polls %.2f\n",
+                h[5], h[4], h[0] / v, h[1] / v, h[2] / v, h[3] / v);
         unsigned long long z[8] = {0};
         cudaMemcpyToSymbol(g_df_prof, z, sizeof(z));
     }
@@ -551,7 +559,7 @@ void mgfb_ctx_destroy(mgfb_ctx* ctx) {
                   &ctx->pair_list[0], &ctx->pair_list[1], &ctx->pair_list[2], &ctx->pair_list[3], &ctx->tpair_list[0], &ctx->tpair_list[1],
                   &ctx->c_a, &ctx->c_b, &ctx->c_face, &ctx->c_sub, &ctx->c_la, &ctx->c_lb, &ctx->c_nt, &ctx->body_best, &ctx->body_scratch,
                   &ctx->group, &ctx->group_count, &ctx->group_start, &ctx->perm, &ctx->r_ab, &ctx->r_n, &ctx->r_t0, &ctx->r_t1, &ctx->r_ra,
-                  &ctx->r_rb, &ctx->r_imp, &ctx->r_xra, &ctx->r_xrb, &ctx->r_xtm, &ctx->r_dep, &ctx->sv, &ctx->body_deg, &ctx->body_start, &ctx->r_inc, &ctx->r_next, &ctx->r_cnt, &ctx->cell_count, &ctx->cell_start, &ctx->bg_ent,
+                  &ctx->r_rb, &ctx->r_imp, &ctx->r_xra, &ctx->r_xrb, &ctx->r_xtm, &ctx->r_dep, &ctx->body_deg, &ctx->body_start, &ctx->r_inc, &ctx->r_next, &ctx->r_in_a, &ctx->r_in_b, &ctx->r_ia, &ctx->cell_count, &ctx->cell_start, &ctx->bg_ent,
                   &ctx->scan_sums, &ctx->u_a, &ctx->u_b, &ctx->u_sc, &ctx->u_sf, &ctx->u_n, &ctx->u_t, &ctx->u_nc, &ctx->u_la,
                   &ctx->u_lb, &ctx->stage, &ctx->terrain.verts, &ctx->terrain.faces, &ctx->terrain.boxes, &ctx->terrain.cell_count,
                   &ctx->terrain.cell_start, &ctx->terrain.ent_id, &ctx->terrain.ent_key, &ctx->terrain.max_bits,

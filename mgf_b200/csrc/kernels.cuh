@@ -632,6 +632,17 @@ __global__ void __launch_bounds__(MGFB_THREADS) k_scatter_rows(const int* __rest
 // ---------------------------------------------------------------- ContactConstraint::new
 // solver.rs:101-191.  Input manifolds come either from the step's ContactList (one contact,
 // tangents from compute_basis) or from user arrays (mgfb_solver_solve).
+// dataflow solver schedule (k_solve_df, below): per-row inboxes, row-resident inertia, successor links
+struct __align__(32) Inbox { float4 lo, hi; };   // v.xyz, tag | omega.xyz, tag
+struct DfArrays {
+    Inbox* in_a; Inbox* in_b;   // [row] inbox of the row's body a / body b
+    float4* ia;                 // [5][row_cap]: I_a (9 floats, columns), inv_mass_a, I_b (9), inv_mass_b
+    unsigned row_cap;
+    unsigned* next;             // [2][row_cap]: successor of the row on body a / b: row << 2 | wraps << 1 | side (0 = its a, 1 = its b)
+    unsigned* dep;              // [row] seq_a | deg_a << 8 | seq_b << 16 | deg_b << 24 (build-time scratch)
+    const unsigned* body_start; // [n+1] CSR offsets: sum of rows per body
+    unsigned* inc;              // [sum deg] rows of every body in solve order
+};
 struct ManifoldInput {
     const int* a; const int* b;
     const float4* la; const float4* lb; const float4* nt;   // step path (ContactList)
@@ -679,24 +690,23 @@ __device__ __forceinline__ void contact_state(const BodyState& A, const BodyStat
 __global__ void __launch_bounds__(MGFB_THREADS) k_build_rows(ManifoldInput M, BodyInfoView B, const unsigned* __restrict__ perm, ConstraintRows R,
                                                             const unsigned* m_ptr, unsigned m_host, float dt, float baumgarte, float slop, Counters* ctr,
                                                             const unsigned char* __restrict__ edge_mark, unsigned n_own,
-                                                            const int* __restrict__ group, const unsigned long long* __restrict__ body_mask, unsigned* dep,
-                                                            const unsigned* __restrict__ body_start, unsigned* inc) {
+                                                            const int* __restrict__ group, const unsigned long long* __restrict__ body_mask, DfArrays D) {
     if (ctr->overflow | ctr->nan_bounds) return;
     const unsigned m = m_ptr ? *m_ptr : m_host;
     for (unsigned row = blockIdx.x * blockDim.x + threadIdx.x; row < m; row += gridDim.x * blockDim.x) {
         unsigned k = perm[row];
         int a = M.a[k], b = M.b[k];
-        if (dep) {
+        if (D.dep) {
             // dataflow schedule (k_solve_df): this row is the seq-th of deg rows at each of its bodies, in colour order
             int g = group[k];
             unsigned d = 0u;
             if (g >= 0 && g < 64) {
                 unsigned long long below = (1ULL << g) - 1ULL;
                 // inc = the rows of every body in solve order (CSR over body_start): k_df_init links each row to its successors
-                if (a >= 0) { unsigned long long ma = body_mask[a]; unsigned sq = (unsigned)__popcll(ma & below); d |= sq | ((unsigned)__popcll(ma) << 8); inc[body_start[a] + sq] = row; }
-                if (b >= 0) { unsigned long long mb = body_mask[b]; unsigned sq = (unsigned)__popcll(mb & below); d |= (sq << 16) | ((unsigned)__popcll(mb) << 24); inc[body_start[b] + sq] = row; }
+                if (a >= 0) { unsigned long long ma = body_mask[a]; unsigned sq = (unsigned)__popcll(ma & below); d |= sq | ((unsigned)__popcll(ma) << 8); D.inc[D.body_start[a] + sq] = row; }
+                if (b >= 0) { unsigned long long mb = body_mask[b]; unsigned sq = (unsigned)__popcll(mb & below); d |= (sq << 16) | ((unsigned)__popcll(mb) << 24); D.inc[D.body_start[b] + sq] = row; }
             }
-            dep[row] = d;
+            D.dep[row] = d;
         }
         if (edge_mark && b >= 0 && (((unsigned)a >= n_own) != ((unsigned)b >= n_own))) {
             // boundary constraint: its owned body is updated here while the left neighbour may update
@@ -720,6 +730,14 @@ __global__ void __launch_bounds__(MGFB_THREADS) k_build_rows(ManifoldInput M, Bo
             V3 sc = mk3(M.static_center[3 * k], M.static_center[3 * k + 1], M.static_center[3 * k + 2]);
             A = a >= 0 ? load_body_info(B, a) : static_body_info(sc, M.static_friction[k]);
             Bs = b >= 0 ? load_body_info(B, b) : static_body_info(sc, M.static_friction[k]);
+        }
+        if (D.dep) {   // immutable during the solve: the dataflow solver streams them with the row instead of gathering BodyVel
+            const unsigned rc = D.row_cap;
+            D.ia[row] = make_float4(A.I.c0.x, A.I.c0.y, A.I.c0.z, A.I.c1.x);
+            D.ia[rc + row] = make_float4(A.I.c1.y, A.I.c1.z, A.I.c2.x, A.I.c2.y);
+            D.ia[2 * rc + row] = make_float4(A.I.c2.z, A.inv_mass, Bs.I.c0.x, Bs.I.c0.y);
+            D.ia[3 * rc + row] = make_float4(Bs.I.c0.z, Bs.I.c1.x, Bs.I.c1.y, Bs.I.c1.z);
+            D.ia[4 * rc + row] = make_float4(Bs.I.c2.x, Bs.I.c2.y, Bs.I.c2.z, Bs.inv_mass);
         }
         float restitution = fmaxf(A.rest, Bs.rest);   // solver.rs:125
         for (unsigned c = 0; c < nc; ++c) {
@@ -884,81 +902,84 @@ __global__ void __launch_bounds__(MGFB_SOLVE_THREADS, 1) k_solve(ConstraintRows 
     if (TILED && T.has_left) tile_wait_cta(&T.mine->vel_from_left.flag, tile_seq(T.step, 1 + iters), T.timeout_ns, ctr);
 }
 // ---------------------------------------------------------------- Solver::solve, dataflow schedule
-// Same arithmetic and the same row order as k_solve, but NO grid barriers: every body carries a
-// version = the number of row updates applied to it so far, stored in the same 32-byte record
-// as its v and omega (SolverVel).  Row r at iteration `it` is the (seq + it*deg)-th update of
-// each of its bodies (seq = rank of the row's colour among the colours at that body, deg = the
-// body's number of rows), so it spins until both records show exactly that version, updates
-// them and publishes version+1 with the new velocities in ONE 32-byte store per body -- flag and
-// payload cannot be seen apart, so no fence is needed.  The sequential sweep over the rows in
-// row order is the unique execution these waits allow: the result is bit-identical to k_solve
-// and to the reference's loop over that order.  Progress: a warp takes warp-rows (32 rows of
-// one colour, never dependent on each other) in increasing (iteration, row) order, all warps
+// Same arithmetic and the same row order as k_solve, but NO grid barriers and no gathers.  The
+// rows of one body form a chain in solve order (its colours ascending; the last row is followed
+// by the first row of the next iteration).  A row does not fetch its bodies' velocities: its
+// predecessor on each chain PUSHES them into the row's own inbox (one 32-byte record per side:
+// v, omega and a tag = epoch + iteration, written with ONE 32-byte store, so tag and payload
+// cannot be seen apart and no fence is needed).  A warp owns 32 consecutive rows of one colour
+// (never dependent on each other), polls their inboxes with two fully coalesced 1 KB loads until
+// every tag shows the current iteration, updates, and pushes the results to the successors'
+// inboxes.  World inverse inertia and inverse mass are immutable during the solve and are copied
+// into the row when it is built, so everything a row reads is a coalesced stream prefetched one
+// visit ahead.  The sequential sweep over the rows in row order is the unique execution these
+// waits allow: the result is bit-identical to k_solve and to the reference's loop over that
+// order.  Progress: a warp visits its warp-rows in increasing (iteration, row) order and all warps
 // are co-resident (cooperative launch), so the smallest unfinished warp-row always has its
-// dependencies published.  Iterations pipeline: a body's rows of iteration it+1 start as soon
-// as ITS OWN iteration `it` is complete.
-struct __align__(32) SolverVel { float4 lo, hi; };   // v.xyz, version | omega.xyz, version
-__device__ __forceinline__ SolverVel ld_sv(const SolverVel* p) {
-    SolverVel r;
+// inboxes filled.  Iterations pipeline: a body's rows of iteration it+1 start as soon as ITS
+// OWN iteration `it` is complete.
+__device__ __forceinline__ Inbox ld_inbox(const Inbox* p) {
+    Inbox r;
     asm volatile("ld.relaxed.gpu.global.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                  : "=f"(r.lo.x), "=f"(r.lo.y), "=f"(r.lo.z), "=f"(r.lo.w), "=f"(r.hi.x), "=f"(r.hi.y), "=f"(r.hi.z), "=f"(r.hi.w)
                  : "l"(p) : "memory");
     return r;
 }
-__device__ __forceinline__ void st_sv(SolverVel* p, V3 v, V3 w, unsigned ver) {
-    float fv = __uint_as_float(ver);
+__device__ __forceinline__ void st_inbox(Inbox* p, V3 v, V3 w, unsigned tag) {
+    float ft = __uint_as_float(tag);
     asm volatile("st.relaxed.gpu.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
-                 :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(fv), "f"(w.x), "f"(w.y), "f"(w.z), "f"(fv) : "memory");
+                 :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(ft), "f"(w.x), "f"(w.y), "f"(w.z), "f"(ft) : "memory");
 }
 __global__ void __launch_bounds__(MGFB_THREADS) k_body_deg(const unsigned long long* __restrict__ body_mask, unsigned n, unsigned* deg, Counters* ctr) {
     if (ctr->overflow | ctr->nan_bounds) return;
     for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) deg[i] = (unsigned)__popcll(body_mask[i]);
 }
-// Bodies: versioned copy of v, omega.  Rows: the successor of the row on each of its bodies (cyclic: the
-// body's last row is followed by its first row of the next iteration) and the row's signal counter,
-// which starts at the number of its bodies on which it is the FIRST row.
-__global__ void __launch_bounds__(MGFB_THREADS) k_df_init(const BodyVel* __restrict__ vel, SolverVel* sv, unsigned n, const int2* __restrict__ ab,
-                                                         const unsigned* __restrict__ dep, const unsigned* __restrict__ body_start,
-                                                         const unsigned* __restrict__ inc, int2* next, unsigned* cnt,
-                                                         const unsigned* m_ptr, unsigned m_host, Counters* ctr) {
+// Rows: successor links.  Bodies: v, omega into the inbox of the body's FIRST row, tagged for iteration 0.
+__global__ void __launch_bounds__(MGFB_THREADS) k_df_init(const BodyVel* __restrict__ vel, unsigned n, const int2* __restrict__ ab, DfArrays D,
+                                                         unsigned epoch, const unsigned* m_ptr, unsigned m_host, Counters* ctr) {
     if (ctr->overflow | ctr->nan_bounds) return;
+    if (ctr->ngroups > 64u) return;   // k_solve takes this step
     const unsigned tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
     for (unsigned i = tid; i < n; i += nth) {
+        unsigned s0 = D.body_start[i], s1 = D.body_start[i + 1];
+        if (s0 == s1) continue;
+        unsigned fr = D.inc[s0];
         const float4* q = reinterpret_cast<const float4*>(vel + i);
         float4 a = q[0], b = q[1];
-        st_sv(sv + i, mk3(a.x, a.y, a.z), mk3(a.w, b.x, b.y), 0u);
+        Inbox* dst = (ab[fr].x == (int)i) ? D.in_a + fr : D.in_b + fr;
+        st_inbox(dst, mk3(a.x, a.y, a.z), mk3(a.w, b.x, b.y), epoch + 1u);
     }
-    if (ctr->ngroups > 64u) return;   // k_solve takes this step
     const unsigned m = m_ptr ? *m_ptr : m_host;
     for (unsigned row = tid; row < m; row += nth) {
-        int2 p = ab[row]; unsigned d = dep[row];
+        int2 p = ab[row]; unsigned d = D.dep[row];
         unsigned seqA = d & 255u, degA = (d >> 8) & 255u, seqB = (d >> 16) & 255u, degB = d >> 24;
-        int2 nx = make_int2(-1, -1); unsigned c0 = 0u;
-        if (p.x >= 0) { nx.x = (int)inc[body_start[p.x] + (seqA + 1u == degA ? 0u : seqA + 1u)]; c0 += seqA == 0u; }
-        if (p.y >= 0) { nx.y = (int)inc[body_start[p.y] + (seqB + 1u == degB ? 0u : seqB + 1u)]; c0 += seqB == 0u; }
-        next[row] = nx; cnt[row] = c0;
+        unsigned na = 0xffffffffu, nb = 0xffffffffu;
+        if (p.x >= 0) {
+            bool wrap = seqA + 1u == degA;
+            unsigned nr = D.inc[D.body_start[p.x] + (wrap ? 0u : seqA + 1u)];
+            na = (nr << 2) | (wrap ? 2u : 0u) | (ab[nr].x == p.x ? 0u : 1u);
+        }
+        if (p.y >= 0) {
+            bool wrap = seqB + 1u == degB;
+            unsigned nr = D.inc[D.body_start[p.y] + (wrap ? 0u : seqB + 1u)];
+            nb = (nr << 2) | (wrap ? 2u : 0u) | (ab[nr].x == p.y ? 0u : 1u);
+        }
+        D.next[row] = na; D.next[D.row_cap + row] = nb;
     }
 }
-__device__ __forceinline__ void load_inertia(const BodyVel* p, float* im, M3* I) {
-    const float4* q = reinterpret_cast<const float4*>(p);
-    float4 b = __ldcg(q + 1), c = __ldcg(q + 2), d = __ldcg(q + 3);
-    *im = b.z;
-    *I = mkm(mk3(b.w, c.x, c.y), mk3(c.z, c.w, d.x), mk3(d.y, d.z, d.w));
-}
 #ifdef MGFB_DF_PROFILE
-__device__ unsigned long long g_df_prof[8];   // cycles: fetch-issue, hint poll, version poll, compute+publish ; counts: hint polls, version polls, visits
+__device__ unsigned long long g_df_prof[8];   // cycles: fetch, inbox poll, compute+publish ; counts: polls, visits, warps
 #define DF_T(x) long long x = clock64()
 #define DF_ACC(i, v) prof[i] += (unsigned long long)(v)
 #else
 #define DF_T(x)
 #define DF_ACC(i, v)
 #endif
-struct DfRow { RowData d; int2 next; unsigned dep, row; float imp; bool valid; };
+struct DfRow { RowData d; float4 i0, i1, i2, i3, i4; unsigned na, nb, row; float imp; bool valid; };
 #define MGFB_DF_MAX_PHASES 64
 template <int THREADS>
-__global__ void __launch_bounds__(THREADS, 1) k_solve_df(ConstraintRows R, const unsigned* __restrict__ dep, const int2* __restrict__ next, unsigned* cnt,
-                                                         BodyVel* vel, SolverVel* sv, const unsigned* __restrict__ phase_start, unsigned iters,
-                                                         unsigned backoff_ns, Counters* ctr) {
+__global__ void __launch_bounds__(THREADS, 1) k_solve_df(ConstraintRows R, DfArrays D, BodyVel* vel, const unsigned* __restrict__ phase_start,
+                                                         unsigned iters, unsigned epoch, unsigned backoff_ns, Counters* ctr) {
     if (ctr->overflow | ctr->nan_bounds) return;
     const unsigned P = ctr->n_phases;
     if (P == 0 || ctr->ngroups > MGFB_DF_MAX_PHASES || iters == 0) return;   // > 64 colours: k_solve takes the step
@@ -973,14 +994,22 @@ __global__ void __launch_bounds__(THREADS, 1) k_solve_df(ConstraintRows R, const
     const unsigned lane = threadIdx.x & 31u;
     const unsigned gw = (threadIdx.x >> 5) * gridDim.x + blockIdx.x, nW = gridDim.x * (THREADS / 32);
     if (gw >= nwr) return;
+    const unsigned rc = D.row_cap;
     auto fetch = [&](unsigned wr, unsigned& p) {
         DfRow f;
         while (wr >= s_wr0[p + 1]) ++p;
         unsigned row = s_row0[p] + ((wr - s_wr0[p]) << 5) + lane;
         f.row = row;
         f.valid = row < s_row0[p + 1];
-        if (f.valid) { f.d = load_row(R, row); f.dep = dep[row]; f.next = next[row]; f.imp = __ldcg(&R.impulse[row]); }
-        else { f.d.ab = make_int2(-1, -1); f.next = make_int2(-1, -1); f.dep = 0u; f.imp = 0.0f; }
+        if (f.valid) {
+            f.d = load_row(R, row);
+            f.i0 = D.ia[row]; f.i1 = D.ia[rc + row]; f.i2 = D.ia[2 * rc + row]; f.i3 = D.ia[3 * rc + row]; f.i4 = D.ia[4 * rc + row];
+            f.na = D.next[row]; f.nb = D.next[rc + row];
+            f.imp = __ldcg(&R.impulse[row]);
+        } else {
+            f.d.ab = make_int2(-1, -1); f.na = f.nb = 0xffffffffu; f.imp = 0.0f;
+            f.d.n = f.d.t0 = f.d.t1 = f.d.ra = f.d.rb = f.i0 = f.i1 = f.i2 = f.i3 = f.i4 = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        }
         return f;
     };
     unsigned p_next = 0, wr = gw, it = 0;
@@ -992,7 +1021,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_solve_df(ConstraintRows R, const
         DF_T(t0);
         DfRow cur = nxt;
         const unsigned row = cur.row;
-        // prefetch this warp's next warp-row (rows are immutable; its impulse was last written by this very thread)
+        // prefetch this warp's next warp-row (immutable but for its impulse, last written by this very thread)
         unsigned wr_n = wr + nW, it_n = it;
         if (wr_n >= nwr) { wr_n = gw; it_n = it + 1; p_next = 0; }
         const bool more = it_n < iters;
@@ -1000,40 +1029,26 @@ __global__ void __launch_bounds__(THREADS, 1) k_solve_df(ConstraintRows R, const
         if (more) nxt = fetch(wr_n, p_next);
         const int a = cur.d.ab.x, b = cur.d.ab.y;
         const bool needA = cur.valid && a >= 0, needB = cur.valid && b >= 0;
-        const unsigned seqA = cur.dep & 255u, degA = (cur.dep >> 8) & 255u, seqB = (cur.dep >> 16) & 255u, degB = cur.dep >> 24;
-        const unsigned expA = seqA + it * degA, expB = seqB + it * degB;
-        float ima = 0.0f, imb = 0.0f; M3 IA = m_zero(), IB = m_zero();
-        if (needA) load_inertia(vel + a, &ima, &IA);
-        if (needB) load_inertia(vel + b, &imb, &IB);
-        SolverVel sa, sb;
+        const unsigned tag = epoch + it + 1u;
+        Inbox sa, sb;
         sa.lo = sa.hi = sb.lo = sb.hi = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
         bool okA = !needA, okB = !needB;
         DF_T(t1); DF_ACC(0, t1 - t0);
-        // Cheap wait first: the predecessors of this row bump its signal counter (one coalesced 128-byte
-        // poll per warp instead of 64 scattered sectors).  The counter is only a HINT (relaxed, it may
-        // overtake the velocity store): the version check below is what admits the row.
-        {
-            const unsigned target = ((needA ? 1u : 0u) + (needB ? 1u : 0u)) * (it + 1u);
-            for (;;) {
-                unsigned c = 0xffffffffu;
-                if (cur.valid) asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(c) : "l"(cnt + row) : "memory");
-                DF_ACC(4, 1);
-                if (__all_sync(0xffffffffu, c >= target)) break;
-                if (backoff_ns) __nanosleep(backoff_ns);
-            }
-        }
-        DF_T(t2); DF_ACC(1, t2 - t1);
         for (;;) {
-            if (!okA) { sa = ld_sv(sv + a); okA = __float_as_uint(sa.lo.w) == expA && __float_as_uint(sa.hi.w) == expA; }
-            if (!okB) { sb = ld_sv(sv + b); okB = __float_as_uint(sb.lo.w) == expB && __float_as_uint(sb.hi.w) == expB; }
-            DF_ACC(5, 1);
+            if (!okA) { sa = ld_inbox(D.in_a + row); okA = __float_as_uint(sa.lo.w) == tag && __float_as_uint(sa.hi.w) == tag; }
+            if (!okB) { sb = ld_inbox(D.in_b + row); okB = __float_as_uint(sb.lo.w) == tag && __float_as_uint(sb.hi.w) == tag; }
+            DF_ACC(3, 1);
             if (__all_sync(0xffffffffu, okA && okB)) break;
             if (backoff_ns) __nanosleep(backoff_ns);
         }
-        DF_T(t3); DF_ACC(2, t3 - t2);
+        DF_T(t2); DF_ACC(1, t2 - t1);
         if (cur.valid) {
             V3 va = mk3(sa.lo.x, sa.lo.y, sa.lo.z), oa = mk3(sa.hi.x, sa.hi.y, sa.hi.z);
             V3 vb = mk3(sb.lo.x, sb.lo.y, sb.lo.z), ob = mk3(sb.hi.x, sb.hi.y, sb.hi.z);
+            const M3 IA = mkm(mk3(cur.i0.x, cur.i0.y, cur.i0.z), mk3(cur.i0.w, cur.i1.x, cur.i1.y), mk3(cur.i1.z, cur.i1.w, cur.i2.x));
+            const float ima = cur.i2.y;
+            const M3 IB = mkm(mk3(cur.i2.z, cur.i2.w, cur.i3.x), mk3(cur.i3.y, cur.i3.z, cur.i3.w), mk3(cur.i4.x, cur.i4.y, cur.i4.z));
+            const float imb = cur.i4.w;
             float4 n4 = cur.d.n, t04 = cur.d.t0, t14 = cur.d.t1, ra4 = cur.d.ra, rb4 = cur.d.rb;
             V3 n = f4v(n4), t0 = f4v(t04), t1 = f4v(t14);
             int nc = (int)fbits(rb4.w);
@@ -1065,26 +1080,24 @@ __global__ void __launch_bounds__(THREADS, 1) k_solve_df(ConstraintRows R, const
             }
             const bool last_it = it + 1 == iters;
             if (needA) {
-                st_sv(sv + a, va, oa, expA + 1u);
-                const bool fin = last_it && seqA + 1u == degA;
-                if (fin) store_vel(vel + a, va, oa, ima, IA);   // the body's final update of the solve
-                else asm volatile("red.relaxed.gpu.global.add.u32 [%0], 1;" ::"l"(cnt + cur.next.x) : "memory");
+                const unsigned nx = cur.na; const bool wrap = (nx & 2u) != 0u;
+                if (wrap && last_it) store_vel(vel + a, va, oa, ima, IA);   // the body's final update of the solve
+                else st_inbox(((nx & 1u) ? D.in_b : D.in_a) + (nx >> 2), va, oa, tag + (wrap ? 1u : 0u));
             }
             if (needB) {
-                st_sv(sv + b, vb, ob, expB + 1u);
-                const bool fin = last_it && seqB + 1u == degB;
-                if (fin) store_vel(vel + b, vb, ob, imb, IB);
-                else asm volatile("red.relaxed.gpu.global.add.u32 [%0], 1;" ::"l"(cnt + cur.next.y) : "memory");
+                const unsigned nx = cur.nb; const bool wrap = (nx & 2u) != 0u;
+                if (wrap && last_it) store_vel(vel + b, vb, ob, imb, IB);
+                else st_inbox(((nx & 1u) ? D.in_b : D.in_a) + (nx >> 2), vb, ob, tag + (wrap ? 1u : 0u));
             }
         }
         __syncwarp();
-        DF_T(t4); DF_ACC(3, t4 - t3); DF_ACC(6, 1);
+        DF_T(t3); DF_ACC(2, t3 - t2); DF_ACC(4, 1);
         if (!more) break;
         wr = wr_n; it = it_n;
     }
 #ifdef MGFB_DF_PROFILE
-    if (lane == 0) for (int i = 0; i < 7; ++i) atomicAdd(&g_df_prof[i], prof[i]);
-    if (lane == 0) atomicAdd(&g_df_prof[7], 1ULL);
+    if (lane == 0) for (int i = 0; i < 5; ++i) atomicAdd(&g_df_prof[i], prof[i]);
+    if (lane == 0) atomicAdd(&g_df_prof[5], 1ULL);
 #endif
 }
 
