@@ -80,7 +80,9 @@ enum mgfb_pair_kind {
  * reference's sequential sweep over the same row order, bit for bit. */
 enum mgfb_solver_schedule {
     MGFB_SCHEDULE_DATAFLOW = 0,  /* default: per-body version counters, a row runs as soon as both its bodies are ready */
-    MGFB_SCHEDULE_PHASES = 1     /* one grid-wide barrier per colour per iteration */
+    MGFB_SCHEDULE_PHASES = 1,    /* one grid-wide barrier per colour per iteration */
+    MGFB_SCHEDULE_PHASES_JP = 2  /* as PHASES, and the colouring itself by barrier-synchronised Jones-Plassmann rounds
+                                    instead of the chain (dataflow) colouring; same colours */
 };
 
 /* solver.rs:265-279 ContactConstraintParams, manifold.rs:27-39 PruningParams, world.rs:181 */

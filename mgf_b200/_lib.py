@@ -34,7 +34,7 @@ class Config(C.Structure):
                 ("solver_schedule", C.c_uint32), ("reserved", C.c_uint32)]
 
 
-SCHEDULE_DATAFLOW, SCHEDULE_PHASES = 0, 1
+SCHEDULE_DATAFLOW, SCHEDULE_PHASES, SCHEDULE_PHASES_JP = 0, 1, 2
 
 
 class Manifolds(C.Structure):

@@ -55,6 +55,7 @@ struct mgfb_ctx {
     Buf r_ab, r_n, r_t0, r_t1, r_ra, r_rb, r_imp, r_xra, r_xrb, r_xtm, r_dep; unsigned row_cap = 0, xrow_cap = 0;
     // dataflow solver (k_solve_df): rows per body (CSR), successor links, per-row inboxes and inertia
     Buf body_deg, body_start, r_inc, r_next, r_in_a, r_in_b, r_ia;
+    Buf c_key, c_csr, c_next, c_inbox;   // dataflow colouring (k_colour_df): keys, per-body constraint lists, chain links, mask inboxes
     unsigned df_epoch = 0;   // inbox tags of one solve are df_epoch + 1 .. df_epoch + iters + 1
     // body grid
     Buf cell_count, cell_start, bg_ent, scan_sums; unsigned table = 0, ent_cap = 0;
@@ -64,7 +65,7 @@ struct mgfb_ctx {
     // user-path staging
     Buf u_a, u_b, u_sc, u_sf, u_n, u_t, u_nc, u_la, u_lb;
     // cooperative grid sizes
-    int coop_order = 0, coop_solve = 0, coop_df = 0;
+    int coop_order = 0, coop_solve = 0, coop_df = 0, coop_colour = 0;
     unsigned df_threads = 256, df_backoff_ns = 0;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     // last step
@@ -169,6 +170,8 @@ int32_t ensure_rows(mgfb_ctx* ctx, unsigned m, bool extras, unsigned groups) {
         TRY(ensure(ctx, ctx->r_imp, (size_t)rc * 4)); TRY(ensure(ctx, ctx->group, (size_t)rc * 4)); TRY(ensure(ctx, ctx->perm, (size_t)rc * 4));
         TRY(ensure(ctx, ctx->r_dep, (size_t)rc * 4)); TRY(ensure(ctx, ctx->r_inc, (size_t)rc * 8)); TRY(ensure(ctx, ctx->r_next, (size_t)rc * 8));
         TRY(ensure(ctx, ctx->r_ia, (size_t)rc * 80));
+        TRY(ensure(ctx, ctx->c_key, (size_t)rc * 8)); TRY(ensure(ctx, ctx->c_csr, (size_t)rc * 8)); TRY(ensure(ctx, ctx->c_next, (size_t)rc * 8));
+        TRY(ensure(ctx, ctx->c_inbox, (size_t)rc * 16));
         // inbox tags must never match by accident: zeroed when (re)allocated, epochs only grow
         TRY(ensure(ctx, ctx->r_in_a, (size_t)rc * sizeof(Inbox), false, true)); TRY(ensure(ctx, ctx->r_in_b, (size_t)rc * sizeof(Inbox), false, true));
         ctx->row_cap = rc;
@@ -279,26 +282,41 @@ int32_t enqueue_order_and_solve(mgfb_ctx* ctx, const OrderView& O, const Manifol
     const bool tiled = ctx->tiled && !M.user;
     BodyVel* vel = ctx->vel.as<BodyVel>();
     unsigned gcap = ctx->group_cap;
+    const unsigned nb = M.user ? ctx->n : body_slots(ctx);
+    int g = grid_for(ctx, m_bound);
+    const bool colour_df = !as_given && ctx->cfg.solver_schedule != MGFB_SCHEDULE_PHASES_JP;
+    if (colour_df) {
+        // constraints per body -> CSR -> chains sorted by key -> colours travel down the chains (no grid barrier)
+        ColourView V{};
+        V.key = ctx->c_key.as<unsigned long long>(); V.deg = ctx->body_deg.as<unsigned>(); V.body_start = ctx->body_start.as<unsigned>();
+        V.csr = ctx->c_csr.as<unsigned>(); V.next = ctx->c_next.as<unsigned>(); V.inbox = ctx->c_inbox.as<unsigned long long>(); V.cap = ctx->row_cap;
+        CU(cudaMemsetAsync(V.deg, 0, (size_t)nb * 4, ctx->stream));
+        k_inc_count<<<g, MGFB_THREADS, 0, ctx->stream>>>(O, V, m_ptr, m_host, c);
+        TRY(scan_u32(ctx, V.deg, ctx->body_start.as<unsigned>(), nb, ctx->scan_sums.as<unsigned>(), &c->df_links));
+        k_inc_fill<<<g, MGFB_THREADS, 0, ctx->stream>>>(O, V, m_ptr, m_host, c);
+        k_inc_sort<<<grid_for(ctx, nb), MGFB_THREADS, 0, ctx->stream>>>(O, V, nb, c);
+        CU(cudaGetLastError());
+        OrderView Ov = O; unsigned mh = m_host; const unsigned* mp = m_ptr;
+        void* args[] = {&Ov, &V, &mp, &mh, &c};
+        CU(cudaLaunchCooperativeKernel((void*)k_colour_df, dim3(ctx->coop_colour), dim3(MGFB_THREADS), args, 0, ctx->stream));
+        ctx->launches += 7;
+    }
     {
         OrderView Ov = O; bool ag = as_given; unsigned mh = m_host; const unsigned* mp = m_ptr;
-        void* args[] = {&Ov, &mp, &mh, &ag, &c};
+        unsigned fallback_only = colour_df ? 1u : 0u; unsigned nbo = nb;
+        void* args[] = {&Ov, &mp, &mh, &ag, &c, &fallback_only, &nbo};
         CU(cudaLaunchCooperativeKernel((void*)k_order, dim3(ctx->coop_order), dim3(MGFB_THREADS), args, 0, ctx->stream));
     }
     k_group_scan<<<1, 1024, 0, ctx->stream>>>(gcount, gstart, pstart, c, gcap, tiled ? (unsigned)TILE_INTERIOR_COLOURS : 0xffffffffu);
-    int g = grid_for(ctx, m_bound);
     k_scatter_rows<<<g, MGFB_THREADS, 0, ctx->stream>>>(O.group, gcount, gstart, perm, m_ptr, m_host, c);
     // Schedule of the solve: dataflow (body version counters, no grid barrier) for coloured single-GPU
     // solves; grid-barrier phases for as-given (level) order, tiled worlds, > 64 colours, or on request.
-    const bool dataflow = !as_given && !tiled && ctx->cfg.solver_schedule == MGFB_SCHEDULE_DATAFLOW;
+    const bool dataflow = colour_df && !tiled && ctx->cfg.solver_schedule == MGFB_SCHEDULE_DATAFLOW;
     DfArrays D{};
-    const unsigned nb = M.user ? ctx->n : body_slots(ctx);
-    if (dataflow) {   // rows per body = number of colours at the body; CSR offsets for the successor links
+    if (dataflow) {   // rows per body = number of colours at the body; CSR offsets (already made by the colouring) for the successor links
         D.in_a = ctx->r_in_a.as<Inbox>(); D.in_b = ctx->r_in_b.as<Inbox>(); D.ia = ctx->r_ia.as<float4>(); D.row_cap = ctx->row_cap;
         D.next = ctx->r_next.as<unsigned>(); D.dep = ctx->r_dep.as<unsigned>(); D.body_start = ctx->body_start.as<unsigned>();
         D.inc = ctx->r_inc.as<unsigned>();
-        k_body_deg<<<grid_for(ctx, nb), MGFB_THREADS, 0, ctx->stream>>>(O.body_mask, nb, ctx->body_deg.as<unsigned>(), c);
-        TRY(scan_u32(ctx, ctx->body_deg.as<unsigned>(), ctx->body_start.as<unsigned>(), nb, ctx->scan_sums.as<unsigned>(), &c->df_links));
-        ctx->launches += 4;
     }
     k_build_rows<<<g, MGFB_THREADS, 0, ctx->stream>>>(M, BI, perm, R, m_ptr, m_host, dt, ctx->cfg.baumgarte, ctx->cfg.penetration_slop, c,
                                                       tiled ? ctx->edge_mark.as<unsigned char>() : nullptr, tiled ? ctx->n : 0xffffffffu,
@@ -520,7 +538,7 @@ int32_t mgfb_ctx_create(const mgfb_config* cfg, mgfb_ctx** out) {
                              (const void*)k_narrow_bodies<0, 1>, (const void*)k_narrow_bodies<1, 0>, (const void*)k_narrow_bodies<1, 1>,
                              (const void*)k_narrow_terrain<0>, (const void*)k_narrow_terrain<1>, (const void*)k_order, (const void*)k_group_scan,
                              (const void*)k_scatter_rows, (const void*)k_build_rows, (const void*)k_solve<false>, (const void*)k_solve<true>,
-                             (const void*)k_solve_df<256>, (const void*)k_solve_df<512>, (const void*)k_solve_df<1024>, (const void*)k_df_init, (const void*)k_body_deg,
+                             (const void*)k_solve_df<256>, (const void*)k_solve_df<512>, (const void*)k_solve_df<1024>, (const void*)k_df_init, (const void*)k_inc_count, (const void*)k_inc_fill, (const void*)k_inc_sort, (const void*)k_colour_df,
                              (const void*)k_step_done, (const void*)k_pack_state, (const void*)k_set_velocity};
         cudaFuncAttributes fa;
         for (const void* f : fns) if ((e = cudaFuncGetAttributes(&fa, f)) != cudaSuccess) return bail(e, "cudaFuncGetAttributes");
@@ -528,6 +546,7 @@ int32_t mgfb_ctx_create(const mgfb_config* cfg, mgfb_ctx** out) {
     ctx->max_ctas = (int)ctx->cfg.max_cooperative_ctas;
     if (ctx->cfg.tile_timeout_ms) ctx->tile_timeout_ns = (unsigned long long)ctx->cfg.tile_timeout_ms * 1000000ULL;
     ctx->coop_order = coop_blocks(ctx, k_order, MGFB_THREADS, 2);
+    ctx->coop_colour = coop_blocks(ctx, k_colour_df, MGFB_THREADS, 4);
     ctx->coop_solve = std::min(coop_blocks(ctx, k_solve<false>, MGFB_SOLVE_THREADS, 1), coop_blocks(ctx, k_solve<true>, MGFB_SOLVE_THREADS, 1));
     if (const char* e_ = getenv("MGFB_DF_THREADS")) { int t = atoi(e_); if (t == 256 || t == 512 || t == 1024) ctx->df_threads = (unsigned)t; }
     if (const char* e_ = getenv("MGFB_DF_BACKOFF_NS")) ctx->df_backoff_ns = (unsigned)atoi(e_);
@@ -559,7 +578,7 @@ void mgfb_ctx_destroy(mgfb_ctx* ctx) {
                   &ctx->pair_list[0], &ctx->pair_list[1], &ctx->pair_list[2], &ctx->pair_list[3], &ctx->tpair_list[0], &ctx->tpair_list[1],
                   &ctx->c_a, &ctx->c_b, &ctx->c_face, &ctx->c_sub, &ctx->c_la, &ctx->c_lb, &ctx->c_nt, &ctx->body_best, &ctx->body_scratch,
                   &ctx->group, &ctx->group_count, &ctx->group_start, &ctx->perm, &ctx->r_ab, &ctx->r_n, &ctx->r_t0, &ctx->r_t1, &ctx->r_ra,
-                  &ctx->r_rb, &ctx->r_imp, &ctx->r_xra, &ctx->r_xrb, &ctx->r_xtm, &ctx->r_dep, &ctx->body_deg, &ctx->body_start, &ctx->r_inc, &ctx->r_next, &ctx->r_in_a, &ctx->r_in_b, &ctx->r_ia, &ctx->cell_count, &ctx->cell_start, &ctx->bg_ent,
+                  &ctx->r_rb, &ctx->r_imp, &ctx->r_xra, &ctx->r_xrb, &ctx->r_xtm, &ctx->r_dep, &ctx->body_deg, &ctx->body_start, &ctx->r_inc, &ctx->r_next, &ctx->r_in_a, &ctx->r_in_b, &ctx->r_ia, &ctx->c_key, &ctx->c_csr, &ctx->c_next, &ctx->c_inbox, &ctx->cell_count, &ctx->cell_start, &ctx->bg_ent,
                   &ctx->scan_sums, &ctx->u_a, &ctx->u_b, &ctx->u_sc, &ctx->u_sf, &ctx->u_n, &ctx->u_t, &ctx->u_nc, &ctx->u_la,
                   &ctx->u_lb, &ctx->stage, &ctx->terrain.verts, &ctx->terrain.faces, &ctx->terrain.boxes, &ctx->terrain.cell_count,
                   &ctx->terrain.cell_start, &ctx->terrain.ent_id, &ctx->terrain.ent_key, &ctx->terrain.max_bits,

@@ -498,11 +498,17 @@ __device__ __forceinline__ unsigned long long order_key(const OrderView& O, unsi
     unsigned long long key = mix64(((unsigned long long)O.gid[a] << 32) | lo);
     return key ? key : 1ULL;
 }
-__global__ void __launch_bounds__(MGFB_THREADS) k_order(OrderView O, const unsigned* m_ptr, unsigned m_host, bool as_given, Counters* ctr) {
+__global__ void __launch_bounds__(MGFB_THREADS) k_order(OrderView O, const unsigned* m_ptr, unsigned m_host, bool as_given, Counters* ctr,
+                                                       unsigned fallback_only, unsigned nbodies) {
     if (ctr->overflow | ctr->nan_bounds) return;
+    if (fallback_only && !ctr->colour_fallback) return;   // k_colour_df coloured this step
     const unsigned m = m_ptr ? *m_ptr : m_host;
     const unsigned tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
     unsigned phase = 0;
+    if (fallback_only) {   // k_colour_df ran out of its 63 colours: start over from clean scratch
+        for (unsigned i = tid; i < nbodies; i += nth) { O.body_best[i] = 0ULL; O.body_mask[i] = 0ULL; O.body_last[i] = 0u; }
+        for (unsigned g = tid; g < O.gcap; g += nth) O.group_count[g] = 0u;
+    }
     for (unsigned k = tid; k < m; k += nth) __stcg(&O.group[k], -1);
     if (tid == 0) { ctr->remaining = m; ctr->ngroups = 0; ctr->rounds = 0; }
     grid_barrier(&ctr->bar, phase);
@@ -569,6 +575,135 @@ __global__ void __launch_bounds__(MGFB_THREADS) k_order(OrderView O, const unsig
         grid_barrier(&ctr->bar, phase);
     }
 }
+// ---------------------------------------------------------------- constraint colouring, dataflow
+// The same greedy edge colouring as k_order's coloured mode -- constraints in descending key
+// order, each taking the lowest colour free at both its bodies -- without grid barriers.  The
+// constraints of a body, sorted by key, form a chain; the body's colour mask travels down the
+// chain: a constraint that has received the masks of BOTH its bodies picks its colour and
+// pushes mask | colour to its successor on each chain (one 8-byte word: valid bit + 63 colour
+// bits, so flag and payload are one atomic store).  Steps: count constraints per body -> scan
+// -> fill the per-body lists (CSR) -> sort each short list by key and link it -> colour.
+struct ColourView {
+    unsigned long long* key;     // [m] priority (bijective hash of the constraint's identity)
+    unsigned* deg;               // [nbodies] constraints per body, consumed by the fill
+    const unsigned* body_start;  // [nbodies + 1]
+    unsigned* csr;               // [sum deg] constraints of every body, sorted by key descending
+    unsigned* next;              // [2][cap] successor on the chain of body a / body b: k << 1 | side, or 0xffffffff
+    unsigned long long* inbox;   // [2][cap] mask so far at body a / body b, bit 63 = valid
+    unsigned cap;
+};
+#define COLOUR_VALID (1ULL << 63)
+__global__ void __launch_bounds__(MGFB_THREADS) k_inc_count(OrderView O, ColourView V, const unsigned* m_ptr, unsigned m_host, Counters* ctr) {
+    if (ctr->overflow | ctr->nan_bounds) return;
+    const unsigned m = m_ptr ? *m_ptr : m_host;
+    for (unsigned k = blockIdx.x * blockDim.x + threadIdx.x; k < m; k += gridDim.x * blockDim.x) {
+        V.key[k] = order_key(O, k, false);
+        atomicAdd(&V.deg[O.a[k]], 1u);
+        int b = O.b[k];
+        if (b >= 0) atomicAdd(&V.deg[b], 1u);
+        V.inbox[k] = 0ULL; V.inbox[V.cap + k] = 0ULL;
+        V.next[k] = 0xffffffffu; V.next[V.cap + k] = 0xffffffffu;
+        O.group[k] = -1;
+    }
+}
+__global__ void __launch_bounds__(MGFB_THREADS) k_inc_fill(OrderView O, ColourView V, const unsigned* m_ptr, unsigned m_host, Counters* ctr) {
+    if (ctr->overflow | ctr->nan_bounds) return;
+    const unsigned m = m_ptr ? *m_ptr : m_host;
+    for (unsigned k = blockIdx.x * blockDim.x + threadIdx.x; k < m; k += gridDim.x * blockDim.x) {
+        int a = O.a[k], b = O.b[k];
+        V.csr[V.body_start[a] + (atomicSub(&V.deg[a], 1u) - 1u)] = k;
+        if (b >= 0) V.csr[V.body_start[b] + (atomicSub(&V.deg[b], 1u) - 1u)] = k;
+    }
+}
+// One thread per body: sort its constraints by key (descending), link the chain, seed the head's inbox.
+__global__ void __launch_bounds__(MGFB_THREADS) k_inc_sort(OrderView O, ColourView V, unsigned nbodies, Counters* ctr) {
+    if (ctr->overflow | ctr->nan_bounds) return;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < nbodies; i += gridDim.x * blockDim.x) {
+        const unsigned s0 = V.body_start[i], d = V.body_start[i + 1] - s0;
+        if (d == 0) continue;
+        unsigned* L = V.csr + s0;
+        if (d <= 16) {
+            unsigned kk[16]; unsigned long long ky[16];
+            for (unsigned j = 0; j < d; ++j) { kk[j] = L[j]; ky[j] = V.key[kk[j]]; }
+            for (unsigned j = 1; j < d; ++j) {
+                unsigned k = kk[j]; unsigned long long y = ky[j]; unsigned p = j;
+                while (p > 0 && ky[p - 1] < y) { kk[p] = kk[p - 1]; ky[p] = ky[p - 1]; --p; }
+                kk[p] = k; ky[p] = y;
+            }
+            for (unsigned j = 0; j < d; ++j) L[j] = kk[j];
+        } else {   // rare (a body touching > 16 others): in place
+            for (unsigned j = 1; j < d; ++j) {
+                unsigned k = L[j]; unsigned long long y = V.key[k]; unsigned p = j;
+                while (p > 0 && V.key[L[p - 1]] < y) { L[p] = L[p - 1]; --p; }
+                L[p] = k;
+            }
+        }
+        unsigned k = L[0]; unsigned side = O.a[k] == (int)i ? 0u : 1u;
+        V.inbox[side * V.cap + k] = COLOUR_VALID;
+        for (unsigned j = 0; j + 1 < d; ++j) {
+            unsigned kn = L[j + 1]; unsigned sn = O.a[kn] == (int)i ? 0u : 1u;
+            V.next[side * V.cap + k] = (kn << 1) | sn;
+            k = kn; side = sn;
+        }
+    }
+}
+__device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed_u64(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+// Persistent, all threads co-resident (cooperative launch).  A thread owns constraints tid, tid+nth, ...
+// and keeps sweeping the ones not yet coloured; it never blocks on one, so there is no ordering
+// requirement: the uncoloured constraint with the largest key always has both masks.
+__global__ void __launch_bounds__(MGFB_THREADS) k_colour_df(OrderView O, ColourView V, const unsigned* m_ptr, unsigned m_host, Counters* ctr) {
+    if (ctr->overflow | ctr->nan_bounds) return;
+    const unsigned m = m_ptr ? *m_ptr : m_host;
+    const unsigned tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+    if (tid >= m) return;
+    const unsigned mine = (m - tid + nth - 1) / nth;
+    unsigned left = mine, sweeps = 0;
+    unsigned long long done = 0ULL;   // first 64 of my constraints; beyond that group[] is re-read
+    while (left) {
+        unsigned j = 0;
+        for (unsigned k = tid; k < m; k += nth, ++j) {
+            if (j < 64 ? ((done >> j) & 1ULL) : (__ldcg(&O.group[k]) >= 0)) continue;
+            const int a = O.a[k], b = O.b[k];
+            unsigned long long ma = ld_relaxed_u64(V.inbox + k);
+            unsigned long long mb = b >= 0 ? ld_relaxed_u64(V.inbox + V.cap + k) : COLOUR_VALID;
+            if (!(ma & mb & COLOUR_VALID)) continue;
+            unsigned long long fr = ~(ma | mb);   // bit 63 is never free
+            if (O.n_own != 0xffffffffu) {
+                // tiled world: interior constraints take colours 0..31, boundary ones (a ghost endpoint) 32..62
+                bool boundary = (unsigned)a >= O.n_own || (b >= 0 && (unsigned)b >= O.n_own);
+                fr &= boundary ? 0x7FFFFFFF00000000ULL : 0x00000000FFFFFFFFULL;
+            }
+            unsigned g;
+            if (fr) g = (unsigned)__ffsll((long long)fr) - 1u;
+            else { atomicOr(&ctr->colour_fallback, 1u); g = 62u; }   // out of colours: k_order redoes the whole colouring
+            const unsigned long long bit = 1ULL << g;
+            const unsigned na = V.next[k], nb = V.next[V.cap + k];
+            if (na != 0xffffffffu) st_relaxed_u64(V.inbox + (na & 1u) * V.cap + (na >> 1), ma | bit);
+            else O.body_mask[a] = (ma | bit) & ~COLOUR_VALID;
+            if (b >= 0) {
+                if (nb != 0xffffffffu) st_relaxed_u64(V.inbox + (nb & 1u) * V.cap + (nb >> 1), mb | bit);
+                else O.body_mask[b] = (mb | bit) & ~COLOUR_VALID;
+            }
+            __stcg(&O.group[k], (int)g);
+            atomicAdd(&O.group_count[g], 1u);
+            if (j < 64) done |= 1ULL << j;
+            --left;
+        }
+        ++sweeps;
+    }
+    unsigned gmax = 0;   // ngroups = highest colour + 1 (recomputed per thread from its own constraints)
+    for (unsigned k = tid; k < m; k += nth) gmax = max(gmax, (unsigned)O.group[k] + 1u);
+    for (int o = 16; o > 0; o >>= 1) { gmax = max(gmax, __shfl_xor_sync(0xffffffffu, gmax, o)); sweeps = max(sweeps, __shfl_xor_sync(0xffffffffu, sweeps, o)); }
+    if ((threadIdx.x & 31) == 0) { atomicMax(&ctr->ngroups, gmax); atomicMax(&ctr->rounds, sweeps); }
+}
+
 // Exclusive scan of group_count[0..ngroups) into group_start (single block, chunked), then the
 // compact list of NON-EMPTY groups: phase p of the solver covers rows [phase_start[p],
 // phase_start[p+1]).  `split` = first boundary colour of a tiled world (else >= ngroups).

@@ -100,6 +100,8 @@ struct Counters {
     unsigned n_int_phases;   // of which interior (before the boundary exchange); = n_phases when not tiled
     unsigned n_int_rows;     // constraints in interior phases
     unsigned df_links;       // dataflow solver: total (body, row) incidences = sum of rows per body
+    unsigned colour_fallback; // k_colour_df ran out of colours: k_order (which stacks colours beyond 64) redoes the step's colouring
+    unsigned pad1;
     // sticky until the host clears them
     unsigned overflow;       // bit0 pairs, bit1 tpairs, bit2 contacts, bit3 grid entries, bit4 groups, bit5 ghosts
     unsigned nan_bounds;     // AABB::combine assert (bounds.rs:125-127)

@@ -18,7 +18,7 @@ DT = np.float32(1.0 / 60.0)
 SCHEDULE = [L.SCHEDULE_DATAFLOW]
 
 
-@pytest.fixture(autouse=True, params=[L.SCHEDULE_DATAFLOW, L.SCHEDULE_PHASES], ids=["dataflow", "phases"])
+@pytest.fixture(autouse=True, params=[L.SCHEDULE_DATAFLOW, L.SCHEDULE_PHASES, L.SCHEDULE_PHASES_JP], ids=["dataflow", "phases", "phases_jp"])
 def _schedule(request):
     """Every test runs under both solver schedules (include/mgfb.h mgfb_solver_schedule): body version
     counters without grid barriers, and one grid barrier per colour."""
