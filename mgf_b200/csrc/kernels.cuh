@@ -255,11 +255,17 @@ __global__ void __launch_bounds__(MGFB_THREADS) k_body_pairs_warp(const Box* __r
             int ki = col_kind(col[i]);
             int cx = cell_coord(tc.x, inv), cy = cell_coord(tc.y, inv), cz = cell_coord(tc.z, inv);
             unsigned e = 0, e1 = 0;
-            int x = 0, y = 0, z = 0;
-            if (lane < 27) {
-                x = cx + (int)(lane % 3) - 1; y = cy + (int)((lane / 3) % 3) - 1; z = cz + (int)(lane / 9) - 1;
-                unsigned h = cell_hash(cell_key(x, y, z), G.table_mask);
-                e = G.cell_start[h]; e1 = G.cell_start[h + 1];
+            {
+                // lanes 0..26: the 27 cells around the centre.  Two of them may hash to the same bucket: only the
+                // lowest such lane walks it.  Bodies of other cells in a bucket simply fail the exact overlap test
+                // (an overlapping pair is never more than one cell apart), so no per-entry cell check is needed.
+                unsigned h = 0xffffffffu - lane;   // lanes 27..31: unique dummies
+                if (lane < 27) {
+                    int x = cx + (int)(lane % 3) - 1, y = cy + (int)((lane / 3) % 3) - 1, z = cz + (int)(lane / 9) - 1;
+                    h = cell_hash(cell_key(x, y, z), G.table_mask);
+                }
+                unsigned same = __match_any_sync(0xffffffffu, h);
+                if (lane < 27 && (unsigned)__ffs((int)same) - 1u == lane) { e = G.cell_start[h]; e1 = G.cell_start[h + 1]; }
             }
             while (__any_sync(0xffffffffu, e < e1)) {
                 int kind = -1; unsigned j = 0;
@@ -268,9 +274,7 @@ __global__ void __launch_bounds__(MGFB_THREADS) k_body_pairs_warp(const Box* __r
                     ++e;
                     unsigned jw = __float_as_uint(a.w);
                     j = jw & 0x7fffffffu;
-                    // the bucket may also hold other cells (hash collisions): take only this cell's bodies
-                    if (__float_as_uint(b.w) < gi && !(ghost_i && j >= n_own) && cell_coord(a.x, inv) == x && cell_coord(a.y, inv) == y &&
-                        cell_coord(a.z, inv) == z && box_overlaps(tc, tr, mk3(a.x, a.y, a.z), mk3(b.x, b.y, b.z)))
+                    if (__float_as_uint(b.w) < gi && !(ghost_i && j >= n_own) && box_overlaps(tc, tr, mk3(a.x, a.y, a.z), mk3(b.x, b.y, b.z)))
                         kind = ki * 2 + (int)(jw >> 31);
                 }
                 unsigned m = __ballot_sync(0xffffffffu, kind >= 0);
@@ -292,8 +296,10 @@ __global__ void __launch_bounds__(MGFB_THREADS) k_body_pairs_warp(const Box* __r
                 }
                 if (kind >= 0) s_buf[w][cnt + __popc(m & ((1u << lane) - 1u))] = j | ((unsigned)kind << 30);
                 cnt += nh;
+                // hits per kind: body i has ONE kind, so only kinds 2*ki and 2*ki+1 can occur
+                unsigned n1 = __popc(__ballot_sync(0xffffffffu, kind == ki * 2 + 1));
 #pragma unroll
-                for (int k = 0; k < 4; ++k) kcnt[k] += __popc(__ballot_sync(0xffffffffu, kind == k));
+                for (int k = 0; k < 4; ++k) kcnt[k] += k == ki * 2 + 1 ? n1 : (k == ki * 2 ? nh - n1 : 0u);
             }
         }
         if (lane < 4) s_cnt[w][lane] = kcnt[lane];
@@ -658,50 +664,96 @@ __device__ __forceinline__ void st_relaxed_u64(unsigned long long* p, unsigned l
 // Persistent, all threads co-resident (cooperative launch).  A thread owns constraints tid, tid+nth, ...
 // and keeps sweeping the ones not yet coloured; it never blocks on one, so there is no ordering
 // requirement: the uncoloured constraint with the largest key always has both masks.
+#define COLOUR_CACHED 8   // constraints per thread whose endpoints and links live in registers
+__device__ __forceinline__ unsigned colour_one(const OrderView& O, const ColourView& V, unsigned k, int a, int b, unsigned na, unsigned nb,
+                                               unsigned long long ma, unsigned long long mb, Counters* ctr) {
+    unsigned long long fr = ~(ma | mb);   // bit 63 is never free
+    if (O.n_own != 0xffffffffu) {
+        // tiled world: interior constraints take colours 0..31, boundary ones (a ghost endpoint) 32..62
+        bool boundary = (unsigned)a >= O.n_own || (b >= 0 && (unsigned)b >= O.n_own);
+        fr &= boundary ? 0x7FFFFFFF00000000ULL : 0x00000000FFFFFFFFULL;
+    }
+    unsigned g;
+    if (fr) g = (unsigned)__ffsll((long long)fr) - 1u;
+    else { atomicOr(&ctr->colour_fallback, 1u); g = 62u; }   // out of colours: k_order redoes the whole colouring
+    const unsigned long long bit = 1ULL << g;
+    if (na != 0xffffffffu) st_relaxed_u64(V.inbox + (na & 1u) * V.cap + (na >> 1), ma | bit);
+    else O.body_mask[a] = (ma | bit) & ~COLOUR_VALID;
+    if (b >= 0) {
+        if (nb != 0xffffffffu) st_relaxed_u64(V.inbox + (nb & 1u) * V.cap + (nb >> 1), mb | bit);
+        else O.body_mask[b] = (mb | bit) & ~COLOUR_VALID;
+    }
+    __stcg(&O.group[k], (int)g);
+    return g;
+}
+// Persistent, all threads co-resident (cooperative launch).  A thread owns constraints tid, tid+nth, ...
+// and keeps sweeping the ones not yet coloured; it never blocks on one, so there is no ordering
+// requirement: the uncoloured constraint with the largest key always has both masks.  One sweep
+// over the (register-cached) first COLOUR_CACHED constraints is a single batch of independent
+// 8-byte L2 loads, so a colour travels one link of a chain per L2 round trip.
 __global__ void __launch_bounds__(MGFB_THREADS) k_colour_df(OrderView O, ColourView V, const unsigned* m_ptr, unsigned m_host, Counters* ctr) {
     if (ctr->overflow | ctr->nan_bounds) return;
     const unsigned m = m_ptr ? *m_ptr : m_host;
     const unsigned tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+    const unsigned wm = __ballot_sync(0xffffffffu, tid < m);   // the lanes of this warp that own constraints
     if (tid >= m) return;
     const unsigned mine = (m - tid + nth - 1) / nth;
-    unsigned left = mine, sweeps = 0;
-    unsigned long long done = 0ULL;   // first 64 of my constraints; beyond that group[] is re-read
+    int ca[COLOUR_CACHED], cb[COLOUR_CACHED]; unsigned cna[COLOUR_CACHED], cnb[COLOUR_CACHED];
+    unsigned pending = 0;   // bit j: cached constraint j not yet coloured
+#pragma unroll
+    for (int j = 0; j < COLOUR_CACHED; ++j) {
+        unsigned k = tid + (unsigned)j * nth;
+        ca[j] = 0; cb[j] = -1; cna[j] = cnb[j] = 0xffffffffu;
+        if (k < m) { ca[j] = O.a[k]; cb[j] = O.b[k]; cna[j] = V.next[k]; cnb[j] = V.next[V.cap + k]; pending |= 1u << j; }
+    }
+    unsigned left = mine, sweeps = 0, gmax = 0;
+    unsigned hist_g[COLOUR_CACHED];
     while (left) {
-        unsigned j = 0;
-        for (unsigned k = tid; k < m; k += nth, ++j) {
-            if (j < 64 ? ((done >> j) & 1ULL) : (__ldcg(&O.group[k]) >= 0)) continue;
+        unsigned long long ma[COLOUR_CACHED], mb[COLOUR_CACHED];
+#pragma unroll
+        for (int j = 0; j < COLOUR_CACHED; ++j) {
+            unsigned k = tid + (unsigned)j * nth;
+            ma[j] = mb[j] = 0ULL;
+            if ((pending >> j) & 1u) {
+                ma[j] = ld_relaxed_u64(V.inbox + k);
+                mb[j] = cb[j] >= 0 ? ld_relaxed_u64(V.inbox + V.cap + k) : COLOUR_VALID;
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < COLOUR_CACHED; ++j) {
+            if (((pending >> j) & 1u) && (ma[j] & mb[j] & COLOUR_VALID)) {
+                unsigned k = tid + (unsigned)j * nth;
+                unsigned g = colour_one(O, V, k, ca[j], cb[j], cna[j], cnb[j], ma[j], mb[j], ctr);
+                hist_g[j] = g; gmax = max(gmax, g + 1u);
+                pending &= ~(1u << j); --left;
+            }
+        }
+        // beyond the cached ones (more than COLOUR_CACHED x resident threads constraints): same sweep from global memory
+        for (unsigned k = tid + COLOUR_CACHED * nth; k < m; k += nth) {
+            if (__ldcg(&O.group[k]) >= 0) continue;
             const int a = O.a[k], b = O.b[k];
-            unsigned long long ma = ld_relaxed_u64(V.inbox + k);
-            unsigned long long mb = b >= 0 ? ld_relaxed_u64(V.inbox + V.cap + k) : COLOUR_VALID;
-            if (!(ma & mb & COLOUR_VALID)) continue;
-            unsigned long long fr = ~(ma | mb);   // bit 63 is never free
-            if (O.n_own != 0xffffffffu) {
-                // tiled world: interior constraints take colours 0..31, boundary ones (a ghost endpoint) 32..62
-                bool boundary = (unsigned)a >= O.n_own || (b >= 0 && (unsigned)b >= O.n_own);
-                fr &= boundary ? 0x7FFFFFFF00000000ULL : 0x00000000FFFFFFFFULL;
-            }
-            unsigned g;
-            if (fr) g = (unsigned)__ffsll((long long)fr) - 1u;
-            else { atomicOr(&ctr->colour_fallback, 1u); g = 62u; }   // out of colours: k_order redoes the whole colouring
-            const unsigned long long bit = 1ULL << g;
-            const unsigned na = V.next[k], nb = V.next[V.cap + k];
-            if (na != 0xffffffffu) st_relaxed_u64(V.inbox + (na & 1u) * V.cap + (na >> 1), ma | bit);
-            else O.body_mask[a] = (ma | bit) & ~COLOUR_VALID;
-            if (b >= 0) {
-                if (nb != 0xffffffffu) st_relaxed_u64(V.inbox + (nb & 1u) * V.cap + (nb >> 1), mb | bit);
-                else O.body_mask[b] = (mb | bit) & ~COLOUR_VALID;
-            }
-            __stcg(&O.group[k], (int)g);
-            atomicAdd(&O.group_count[g], 1u);
-            if (j < 64) done |= 1ULL << j;
+            unsigned long long xa = ld_relaxed_u64(V.inbox + k);
+            unsigned long long xb = b >= 0 ? ld_relaxed_u64(V.inbox + V.cap + k) : COLOUR_VALID;
+            if (!(xa & xb & COLOUR_VALID)) continue;
+            unsigned g = colour_one(O, V, k, a, b, V.next[k], V.next[V.cap + k], xa, xb, ctr);
+            atomicAdd(&O.group_count[g], 1u); gmax = max(gmax, g + 1u);
             --left;
         }
         ++sweeps;
     }
-    unsigned gmax = 0;   // ngroups = highest colour + 1 (recomputed per thread from its own constraints)
-    for (unsigned k = tid; k < m; k += nth) gmax = max(gmax, (unsigned)O.group[k] + 1u);
-    for (int o = 16; o > 0; o >>= 1) { gmax = max(gmax, __shfl_xor_sync(0xffffffffu, gmax, o)); sweeps = max(sweeps, __shfl_xor_sync(0xffffffffu, sweeps, o)); }
-    if ((threadIdx.x & 31) == 0) { atomicMax(&ctr->ngroups, gmax); atomicMax(&ctr->rounds, sweeps); }
+    // colour histogram: cached constraints are counted here, warp-aggregated per colour
+    __syncwarp(wm);
+#pragma unroll
+    for (int j = 0; j < COLOUR_CACHED; ++j) {
+        bool have = tid + (unsigned)j * nth < m;
+        unsigned act = __ballot_sync(wm, have);
+        if (have) {
+            unsigned peers = __match_any_sync(act, hist_g[j]);
+            if ((threadIdx.x & 31u) == (unsigned)__ffs((int)peers) - 1u) atomicAdd(&O.group_count[hist_g[j]], (unsigned)__popc(peers));
+        }
+    }
+    gmax = __reduce_max_sync(wm, gmax); sweeps = __reduce_max_sync(wm, sweeps);
+    if ((threadIdx.x & 31u) == (unsigned)__ffs((int)wm) - 1u) { atomicMax(&ctr->ngroups, gmax); atomicMax(&ctr->rounds, sweeps); }
 }
 
 // Exclusive scan of group_count[0..ngroups) into group_start (single block, chunked), then the
@@ -752,15 +804,27 @@ __global__ void __launch_bounds__(1024) k_group_scan(const unsigned* count, unsi
         ctr->n_phases = pcarry; ctr->n_int_phases = pint; ctr->n_int_rows = int_rows;
     }
 }
-// row = group_start[g] + (slot within the group); perm[row] = k
+// row = group_start[g] + (slot within the group); perm[row] = k.  Slots are claimed per CTA: a shared-memory
+// histogram of the tile's colours, one global atomic per colour per tile (a handful of colours hold all
+// constraints, so per-constraint global atomics would serialise on ~10 addresses).
 __global__ void __launch_bounds__(MGFB_THREADS) k_scatter_rows(const int* __restrict__ group, unsigned* group_count, const unsigned* __restrict__ group_start,
                                                               unsigned* perm, const unsigned* m_ptr, unsigned m_host, Counters* ctr) {
     if (ctr->overflow | ctr->nan_bounds) return;
+    __shared__ unsigned s_cnt[64], s_base[64];
     const unsigned m = m_ptr ? *m_ptr : m_host;
-    for (unsigned k = blockIdx.x * blockDim.x + threadIdx.x; k < m; k += gridDim.x * blockDim.x) {
-        int g = group[k];
-        unsigned row = group_start[g] + (atomicSub(&group_count[g], 1u) - 1u);
-        perm[row] = k;
+    for (unsigned base = blockIdx.x * blockDim.x; base < m; base += gridDim.x * blockDim.x) {
+        if (threadIdx.x < 64) s_cnt[threadIdx.x] = 0u;
+        __syncthreads();
+        unsigned k = base + threadIdx.x;
+        int g = k < m ? group[k] : -1;
+        unsigned local = 0;
+        if (g >= 0 && g < 64) local = atomicAdd(&s_cnt[g], 1u);
+        __syncthreads();
+        if (threadIdx.x < 64 && s_cnt[threadIdx.x]) s_base[threadIdx.x] = atomicSub(&group_count[threadIdx.x], s_cnt[threadIdx.x]) - s_cnt[threadIdx.x];
+        __syncthreads();
+        if (g >= 64) perm[group_start[g] + (atomicSub(&group_count[g], 1u) - 1u)] = k;   // colours stacked beyond the mask (k_order)
+        else if (g >= 0) perm[group_start[g] + s_base[g] + local] = k;
+        __syncthreads();
     }
 }
 
@@ -1064,10 +1128,6 @@ __device__ __forceinline__ void st_inbox(Inbox* p, V3 v, V3 w, unsigned tag) {
     float ft = __uint_as_float(tag);
     asm volatile("st.relaxed.gpu.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
                  :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(ft), "f"(w.x), "f"(w.y), "f"(w.z), "f"(ft) : "memory");
-}
-__global__ void __launch_bounds__(MGFB_THREADS) k_body_deg(const unsigned long long* __restrict__ body_mask, unsigned n, unsigned* deg, Counters* ctr) {
-    if (ctr->overflow | ctr->nan_bounds) return;
-    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) deg[i] = (unsigned)__popcll(body_mask[i]);
 }
 // Rows: successor links.  Bodies: v, omega into the inbox of the body's FIRST row, tagged for iteration 0.
 __global__ void __launch_bounds__(MGFB_THREADS) k_df_init(const BodyVel* __restrict__ vel, unsigned n, const int2* __restrict__ ab, DfArrays D,
