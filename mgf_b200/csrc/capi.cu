@@ -66,7 +66,6 @@ struct mgfb_ctx {
     Buf u_a, u_b, u_sc, u_sf, u_n, u_t, u_nc, u_la, u_lb;
     // cooperative grid sizes
     int coop_order = 0, coop_solve = 0, coop_df = 0, coop_colour = 0;
-    unsigned df_threads = 256, df_backoff_ns = 0;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     // last step
     unsigned last_constraints = 0;
@@ -75,6 +74,8 @@ struct mgfb_ctx {
     bool tile_exported = false, tiled = false;
     unsigned ghost_cap = 0;
     Buf edge_idx, edge_mark, ridx, mbox;
+    Buf edge_slot, tile_df;              // dataflow solve across tiles: [in_a | in_b | link_l | link_r] in ONE exported allocation
+    unsigned tile_row_cap = 0;           // row capacity frozen at export (the neighbours index my inboxes)
     TileLink link{};
     unsigned long long tile_step = 0;
     std::vector<void*> ipc_opened;
@@ -311,10 +312,11 @@ int32_t enqueue_order_and_solve(mgfb_ctx* ctx, const OrderView& O, const Manifol
     k_scatter_rows<<<g, MGFB_THREADS, 0, ctx->stream>>>(O.group, gcount, gstart, perm, m_ptr, m_host, c);
     // Schedule of the solve: dataflow (body version counters, no grid barrier) for coloured single-GPU
     // solves; grid-barrier phases for as-given (level) order, tiled worlds, > 64 colours, or on request.
-    const bool dataflow = colour_df && !tiled && ctx->cfg.solver_schedule == MGFB_SCHEDULE_DATAFLOW;
+    const bool dataflow = colour_df && ctx->cfg.solver_schedule == MGFB_SCHEDULE_DATAFLOW && (!tiled || m_bound <= ctx->tile_row_cap);
     DfArrays D{};
     if (dataflow) {   // rows per body = number of colours at the body; CSR offsets (already made by the colouring) for the successor links
         D.in_a = ctx->r_in_a.as<Inbox>(); D.in_b = ctx->r_in_b.as<Inbox>(); D.ia = ctx->r_ia.as<float4>(); D.row_cap = ctx->row_cap;
+        if (tiled) { D.in_a = ctx->tile_df.as<Inbox>(); D.in_b = D.in_a + ctx->tile_row_cap; }   // the inboxes the neighbours push into
         D.next = ctx->r_next.as<unsigned>(); D.dep = ctx->r_dep.as<unsigned>(); D.body_start = ctx->body_start.as<unsigned>();
         D.inc = ctx->r_inc.as<unsigned>();
     }
@@ -322,24 +324,41 @@ int32_t enqueue_order_and_solve(mgfb_ctx* ctx, const OrderView& O, const Manifol
                                                       tiled ? ctx->edge_mark.as<unsigned char>() : nullptr, tiled ? ctx->n : 0xffffffffu,
                                                       O.group, O.body_mask, D);
     unsigned epoch = ctx->df_epoch;
-    if (dataflow) {
-        if (ctx->df_epoch > 0xffffffffu - 2u * (iters + 2u)) {   // tag space exhausted (once per ~10^8 solves): start over from clean inboxes
+    TileLink TL = ctx->link;
+    if (dataflow && !tiled) {
+        if (ctx->df_epoch > 0x7fffffffu - 2u * (iters + 2u)) {   // tag space exhausted (once per ~10^8 solves): start over from clean inboxes
             CU(cudaMemsetAsync(ctx->r_in_a.p, 0, ctx->r_in_a.bytes, ctx->stream)); CU(cudaMemsetAsync(ctx->r_in_b.p, 0, ctx->r_in_b.bytes, ctx->stream));
             ctx->df_epoch = epoch = 0;
         }
         ctx->df_epoch += iters + 2u;
-        k_df_init<<<g, MGFB_THREADS, 0, ctx->stream>>>(vel, nb, R.ab, D, epoch, m_ptr, m_host, c);
+        k_df_init<false><<<g, MGFB_THREADS, 0, ctx->stream>>>(vel, nb, R.ab, D, epoch, m_ptr, m_host, c, TL);
         ctx->launches += 1;
+    }
+    if (dataflow && tiled) {
+        // every tile derives the same tags from the common step number (upper half of the tag space; the inboxes
+        // were cleared at step start whenever the 2^20-step cycle restarts)
+        epoch = 0x80000000u | (unsigned)((ctx->tile_step & 0xfffffULL) << 11);
+        k_tile_links_send<<<1, 1024, 0, ctx->stream>>>(TL, D, R.ab, c);
+        if (TL.has_left) k_tile_wait<<<1, 1, 0, ctx->stream>>>(&TL.mine->links_from_left.flag, TL.step, TL.timeout_ns, c);
+        if (TL.has_right) k_tile_wait<<<1, 1, 0, ctx->stream>>>(&TL.mine->links_from_right.flag, TL.step, TL.timeout_ns, c);
+        k_df_init<true><<<g, MGFB_THREADS, 0, ctx->stream>>>(vel, nb, R.ab, D, epoch, m_ptr, m_host, c, TL);
+        ctx->launches += 2 + (TL.has_left ? 1 : 0) + (TL.has_right ? 1 : 0);
     }
     CU(cudaGetLastError());
     if (time_solve) CU(cudaEventRecord(ctx->ev[2], ctx->stream));
     if (dataflow) {
-        const unsigned* ps = pstart; unsigned it = iters; unsigned bo = ctx->df_backoff_ns;
-        void* args[] = {&R, &D, &vel, &ps, &it, &epoch, &bo, &c};
-        void* fn = ctx->df_threads == 256 ? (void*)k_solve_df<256> : ctx->df_threads == 1024 ? (void*)k_solve_df<1024> : (void*)k_solve_df<512>;
-        CU(cudaLaunchCooperativeKernel(fn, dim3(ctx->coop_df), dim3(ctx->df_threads), args, 0, ctx->stream));
+        const unsigned* ps = pstart; unsigned it = iters;
+        void* args[] = {&R, &D, &vel, &ps, &it, &epoch, &c, &TL};
+        void* fn = tiled ? (void*)k_solve_df<true> : (void*)k_solve_df<false>;
+        CU(cudaLaunchCooperativeKernel(fn, dim3(ctx->coop_df), dim3(MGFB_DF_THREADS), args, 0, ctx->stream));
         ctx->launches += 1;
+        if (tiled) {   // my ghosts' final velocities are in their owner's records; wait for the same from the left tile
+            k_tile_solve_done<<<1, 1, 0, ctx->stream>>>(TL, c);
+            if (TL.has_left) k_tile_wait<<<1, 1, 0, ctx->stream>>>(&TL.mine->done_from_left.flag, TL.step, TL.timeout_ns, c);
+            ctx->launches += 1 + (TL.has_left ? 1 : 0);
+        }
     }
+    if (!(dataflow && tiled))
     {
         const unsigned* ps = pstart; unsigned it = iters;
         TileLink T = ctx->link;
@@ -349,7 +368,7 @@ int32_t enqueue_order_and_solve(mgfb_ctx* ctx, const OrderView& O, const Manifol
         CU(cudaLaunchCooperativeKernel(fn, dim3(ctx->coop_solve), dim3(MGFB_SOLVE_THREADS), args, 0, ctx->stream));
     }
     if (time_solve) CU(cudaEventRecord(ctx->ev[3], ctx->stream));
-    ctx->launches += 5;   // k_order, k_group_scan, k_scatter_rows, k_build_rows, k_solve
+    ctx->launches += 4 + ((dataflow && tiled) ? 0 : 1);   // k_order, k_group_scan, k_scatter_rows, k_build_rows (+ k_solve)
     return MGFB_OK;
 }
 
@@ -375,6 +394,7 @@ int32_t enqueue_step(mgfb_ctx* ctx, float dt, unsigned iters, bool from_integrat
         ctx->link.step = ctx->tile_step;
         const TileLink& T = ctx->link;
         CU(cudaMemsetAsync(ctx->edge_mark.p, 0, ctx->n, ctx->stream));
+        if ((ctx->tile_step & 0xfffffULL) == 0) CU(cudaMemsetAsync(ctx->tile_df.p, 0, (size_t)ctx->tile_row_cap * 2 * sizeof(Inbox), ctx->stream));
         k_integrate<true, true, true, true><<<gb, MGFB_THREADS, 0, ctx->stream>>>(B, n, dt, ctx->cfg.fat_margin, c);
         k_tile_publish<<<1, 1, 0, ctx->stream>>>(T, c);
         if (T.has_left) {
@@ -538,7 +558,8 @@ int32_t mgfb_ctx_create(const mgfb_config* cfg, mgfb_ctx** out) {
                              (const void*)k_narrow_bodies<0, 1>, (const void*)k_narrow_bodies<1, 0>, (const void*)k_narrow_bodies<1, 1>,
                              (const void*)k_narrow_terrain<0>, (const void*)k_narrow_terrain<1>, (const void*)k_order, (const void*)k_group_scan,
                              (const void*)k_scatter_rows, (const void*)k_build_rows, (const void*)k_solve<false>, (const void*)k_solve<true>,
-                             (const void*)k_solve_df<256>, (const void*)k_solve_df<512>, (const void*)k_solve_df<1024>, (const void*)k_df_init, (const void*)k_inc_count, (const void*)k_inc_fill, (const void*)k_inc_sort, (const void*)k_colour_df,
+                             (const void*)k_solve_df<false>, (const void*)k_solve_df<true>, (const void*)k_df_init<false>, (const void*)k_df_init<true>,
+                             (const void*)k_tile_links_send, (const void*)k_tile_solve_done, (const void*)k_inc_count, (const void*)k_inc_fill, (const void*)k_inc_sort, (const void*)k_colour_df,
                              (const void*)k_step_done, (const void*)k_pack_state, (const void*)k_set_velocity};
         cudaFuncAttributes fa;
         for (const void* f : fns) if ((e = cudaFuncGetAttributes(&fa, f)) != cudaSuccess) return bail(e, "cudaFuncGetAttributes");
@@ -548,10 +569,7 @@ int32_t mgfb_ctx_create(const mgfb_config* cfg, mgfb_ctx** out) {
     ctx->coop_order = coop_blocks(ctx, k_order, MGFB_THREADS, 2);
     ctx->coop_colour = coop_blocks(ctx, k_colour_df, MGFB_THREADS, 4);
     ctx->coop_solve = std::min(coop_blocks(ctx, k_solve<false>, MGFB_SOLVE_THREADS, 1), coop_blocks(ctx, k_solve<true>, MGFB_SOLVE_THREADS, 1));
-    if (const char* e_ = getenv("MGFB_DF_THREADS")) { int t = atoi(e_); if (t == 256 || t == 512 || t == 1024) ctx->df_threads = (unsigned)t; }
-    if (const char* e_ = getenv("MGFB_DF_BACKOFF_NS")) ctx->df_backoff_ns = (unsigned)atoi(e_);
-    ctx->coop_df = ctx->df_threads == 256 ? coop_blocks(ctx, k_solve_df<256>, 256, 1) : ctx->df_threads == 1024 ? coop_blocks(ctx, k_solve_df<1024>, 1024, 1)
-                                                                                                              : coop_blocks(ctx, k_solve_df<512>, 512, 1);
+    ctx->coop_df = std::min(coop_blocks(ctx, k_solve_df<false>, MGFB_DF_THREADS, 1), coop_blocks(ctx, k_solve_df<true>, MGFB_DF_THREADS, 1));
     int32_t s = grow_bodies(ctx, std::max(ctx->cfg.initial_body_capacity, 1024u));
     if (s == MGFB_OK) s = ensure_rows(ctx, 1024, false, 4096);
     if (s != MGFB_OK) { g_create_err = ctx->err; delete ctx; return s; }
@@ -582,7 +600,7 @@ void mgfb_ctx_destroy(mgfb_ctx* ctx) {
                   &ctx->scan_sums, &ctx->u_a, &ctx->u_b, &ctx->u_sc, &ctx->u_sf, &ctx->u_n, &ctx->u_t, &ctx->u_nc, &ctx->u_la,
                   &ctx->u_lb, &ctx->stage, &ctx->terrain.verts, &ctx->terrain.faces, &ctx->terrain.boxes, &ctx->terrain.cell_count,
                   &ctx->terrain.cell_start, &ctx->terrain.ent_id, &ctx->terrain.ent_key, &ctx->terrain.max_bits,
-                  &ctx->gid, &ctx->phase_start, &ctx->edge_idx, &ctx->edge_mark, &ctx->ridx, &ctx->mbox};
+                  &ctx->gid, &ctx->phase_start, &ctx->edge_idx, &ctx->edge_mark, &ctx->ridx, &ctx->mbox, &ctx->edge_slot, &ctx->tile_df};
     for (void* ptr : ctx->ipc_opened) cudaIpcCloseMemHandle(ptr);
     for (Buf* b : all) release(*b);
     if (ctx->h_ctr) cudaFreeHost(ctx->h_ctr);
@@ -1027,9 +1045,9 @@ namespace {
 struct TileDescRaw {           // what one tile tells the others (fits mgfb_tile_desc)
     uint64_t magic;
     int64_t pid;
-    int32_t device; uint32_t n_own, ghost_cap, pad;
-    void* ptr[10];             // x vel force torque col tight fat gid ridx mbox (valid inside the exporting process)
-    cudaIpcMemHandle_t ipc[10];
+    int32_t device; uint32_t n_own, ghost_cap, row_cap;
+    void* ptr[11];             // x vel force torque col tight fat gid ridx mbox tile_df (valid inside the exporting process)
+    cudaIpcMemHandle_t ipc[11];
 };
 static_assert(sizeof(TileDescRaw) <= sizeof(mgfb_tile_desc), "mgfb_tile_desc too small");
 const uint64_t TILE_MAGIC = 0x6d6766625f74696cULL;
@@ -1060,11 +1078,15 @@ int32_t mgfb_tile_export(mgfb_ctx* ctx, uint32_t ghost_capacity, mgfb_tile_desc*
     TRY(ensure_step_buffers(ctx, 2));
     TRY(ensure_grid(ctx, 2));
     TRY(ensure_rows(ctx, ctx->contact_cap, false, 4096));
+    ctx->tile_row_cap = ctx->row_cap;
+    TRY(ensure(ctx, ctx->edge_slot, (size_t)std::max(ctx->n, 1u) * 4, false, true));
+    TRY(ensure(ctx, ctx->tile_df, (size_t)ctx->tile_row_cap * 2 * sizeof(Inbox) + (size_t)ghost_capacity * 8, false, true));
     CU(cudaStreamSynchronize(ctx->stream));
     TileDescRaw d; std::memset(&d, 0, sizeof(d));
-    d.magic = TILE_MAGIC; d.pid = (int64_t)getpid(); d.device = ctx->device; d.n_own = ctx->n; d.ghost_cap = ghost_capacity;
-    void* ptrs[10] = {ctx->x.p, ctx->vel.p, ctx->force.p, ctx->torque.p, ctx->col.p, ctx->tight.p, ctx->fat.p, ctx->gid.p, ctx->ridx.p, ctx->mbox.p};
-    for (int k = 0; k < 10; ++k) { d.ptr[k] = ptrs[k]; CU(cudaIpcGetMemHandle(&d.ipc[k], ptrs[k])); }
+    d.magic = TILE_MAGIC; d.pid = (int64_t)getpid(); d.device = ctx->device; d.n_own = ctx->n; d.ghost_cap = ghost_capacity; d.row_cap = ctx->tile_row_cap;
+    void* ptrs[11] = {ctx->x.p, ctx->vel.p, ctx->force.p, ctx->torque.p, ctx->col.p, ctx->tight.p, ctx->fat.p, ctx->gid.p, ctx->ridx.p, ctx->mbox.p,
+                      ctx->tile_df.p};
+    for (int k = 0; k < 11; ++k) { d.ptr[k] = ptrs[k]; CU(cudaIpcGetMemHandle(&d.ipc[k], ptrs[k])); }
     std::memset(out, 0, sizeof(*out));
     std::memcpy(out, &d, sizeof(d));
     ctx->tile_exported = true;
@@ -1074,16 +1096,16 @@ int32_t mgfb_tile_export(mgfb_ctx* ctx, uint32_t ghost_capacity, mgfb_tile_desc*
 static int32_t tile_open_peer(mgfb_ctx* ctx, const mgfb_tile_desc* desc, TilePeer* P) {
     TileDescRaw d; std::memcpy(&d, desc, sizeof(d));
     if (d.magic != TILE_MAGIC) return fail(ctx, MGFB_ERR_INVALID_ARG, "not a tile descriptor");
-    void* p[10];
+    void* p[11];
     if (d.pid == (int64_t)getpid()) {   // a context of this very process: its pointers are ours already
         if (d.device != ctx->device) {
             cudaError_t e = cudaDeviceEnablePeerAccess(d.device, 0);
             if (e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
             else if (e != cudaSuccess) { ctx->err = std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(e); return MGFB_ERR_CUDA; }
         }
-        for (int k = 0; k < 10; ++k) p[k] = d.ptr[k];
+        for (int k = 0; k < 11; ++k) p[k] = d.ptr[k];
     } else {                            // another process: map its allocations over NVLink
-        for (int k = 0; k < 10; ++k) {
+        for (int k = 0; k < 11; ++k) {
             CU(cudaIpcOpenMemHandle(&p[k], d.ipc[k], cudaIpcMemLazyEnablePeerAccess));
             ctx->ipc_opened.push_back(p[k]);
         }
@@ -1091,6 +1113,8 @@ static int32_t tile_open_peer(mgfb_ctx* ctx, const mgfb_tile_desc* desc, TilePee
     P->x = (float4*)p[0]; P->vel = (BodyVel*)p[1]; P->force = (float4*)p[2]; P->torque = (float4*)p[3]; P->col = (Collider*)p[4];
     P->tight = (Box*)p[5]; P->fat = (Box*)p[6]; P->gid = (unsigned*)p[7]; P->ridx = (unsigned*)p[8]; P->mbox = (TileMailbox*)p[9];
     P->n_own = d.n_own; P->ghost_cap = d.ghost_cap;
+    P->in_a = (Inbox*)p[10]; P->in_b = P->in_a + d.row_cap;
+    P->link_l = reinterpret_cast<unsigned*>(P->in_b + d.row_cap); P->link_r = P->link_l + d.ghost_cap;
     return MGFB_OK;
 }
 
@@ -1105,6 +1129,8 @@ int32_t mgfb_tile_connect(mgfb_ctx* ctx, uint32_t rank, uint32_t nranks, const m
     if (T.has_right) TRY(tile_open_peer(ctx, &descs[rank + 1], &T.right));
     T.mine = ctx->mbox.as<TileMailbox>();
     T.edge_idx = ctx->edge_idx.as<unsigned>(); T.edge_mark = ctx->edge_mark.as<unsigned char>(); T.ridx = ctx->ridx.as<unsigned>();
+    T.edge_slot = ctx->edge_slot.as<unsigned>();
+    T.link_l = reinterpret_cast<unsigned*>(ctx->tile_df.as<Inbox>() + 2 * (size_t)ctx->tile_row_cap); T.link_r = T.link_l + ctx->ghost_cap;
     T.n_own = ctx->n; T.ghost_cap = ctx->ghost_cap; T.step = 0; T.timeout_ns = ctx->tile_timeout_ns;
     ctx->link = T;
     ctx->tile_step = 0;

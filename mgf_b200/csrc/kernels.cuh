@@ -832,7 +832,6 @@ __global__ void __launch_bounds__(MGFB_THREADS) k_scatter_rows(const int* __rest
 // solver.rs:101-191.  Input manifolds come either from the step's ContactList (one contact,
 // tangents from compute_basis) or from user arrays (mgfb_solver_solve).
 // dataflow solver schedule (k_solve_df, below): per-row inboxes, row-resident inertia, successor links
-struct __align__(32) Inbox { float4 lo, hi; };   // v.xyz, tag | omega.xyz, tag
 struct DfArrays {
     Inbox* in_a; Inbox* in_b;   // [row] inbox of the row's body a / body b
     float4* ia;                 // [5][row_cap]: I_a (9 floats, columns), inv_mass_a, I_b (9), inv_mass_b
@@ -1117,49 +1116,108 @@ __global__ void __launch_bounds__(MGFB_SOLVE_THREADS, 1) k_solve(ConstraintRows 
 // are co-resident (cooperative launch), so the smallest unfinished warp-row always has its
 // inboxes filled.  Iterations pipeline: a body's rows of iteration it+1 start as soon as ITS
 // OWN iteration `it` is complete.
+template <bool SYS>
 __device__ __forceinline__ Inbox ld_inbox(const Inbox* p) {
     Inbox r;
-    asm volatile("ld.relaxed.gpu.global.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                 : "=f"(r.lo.x), "=f"(r.lo.y), "=f"(r.lo.z), "=f"(r.lo.w), "=f"(r.hi.x), "=f"(r.hi.y), "=f"(r.hi.z), "=f"(r.hi.w)
-                 : "l"(p) : "memory");
+    if (SYS) asm volatile("ld.relaxed.sys.global.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(r.lo.x), "=f"(r.lo.y), "=f"(r.lo.z), "=f"(r.lo.w), "=f"(r.hi.x), "=f"(r.hi.y), "=f"(r.hi.z), "=f"(r.hi.w) : "l"(p) : "memory");
+    else asm volatile("ld.relaxed.gpu.global.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(r.lo.x), "=f"(r.lo.y), "=f"(r.lo.z), "=f"(r.lo.w), "=f"(r.hi.x), "=f"(r.hi.y), "=f"(r.hi.z), "=f"(r.hi.w) : "l"(p) : "memory");
     return r;
 }
+template <bool SYS>
 __device__ __forceinline__ void st_inbox(Inbox* p, V3 v, V3 w, unsigned tag) {
     float ft = __uint_as_float(tag);
-    asm volatile("st.relaxed.gpu.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+    if (SYS) asm volatile("st.relaxed.sys.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                 :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(ft), "f"(w.x), "f"(w.y), "f"(w.z), "f"(ft) : "memory");
+    else asm volatile("st.relaxed.gpu.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
                  :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(ft), "f"(w.x), "f"(w.y), "f"(w.z), "f"(ft) : "memory");
 }
+// Successor word of a row on one of its bodies: row << 4 | where << 2 | wraps << 1 | side.
+//   side   0 = the body is the successor's body a, 1 = its body b
+//   wraps  the successor runs in the NEXT iteration (this row is the last of the body's chain)
+//   where  0 = this tile, 1 = the left neighbour's rows, 2 = the right neighbour's rows (tiled world)
+#define DF_NONE 0xffffffffu
+#define DF_LEFT 1u
+#define DF_RIGHT 2u
+// Tiled world: for every ghost, tell its owner (right) the ghost's first boundary row here; for every edge
+// body, tell the left tile the body's first interior row here.  One CTA; flags after a system fence.
+__global__ void __launch_bounds__(1024) k_tile_links_send(TileLink T, DfArrays D, const int2* __restrict__ ab, Counters* ctr) {
+    if (ctr->overflow | ctr->nan_bounds | ctr->comm_error) return;
+    auto first_row = [&](unsigned body) {
+        unsigned s0 = D.body_start[body], s1 = D.body_start[body + 1];
+        if (s0 == s1) return DF_NONE;
+        unsigned fr = D.inc[s0];
+        return (fr << 1) | (ab[fr].x == (int)body ? 0u : 1u);
+    };
+    if (T.has_right) {
+        const unsigned n_ghost = ctr->n_total - T.n_own;
+        for (unsigned k = threadIdx.x; k < n_ghost; k += blockDim.x) T.right.link_l[k] = first_row(T.n_own + k);
+    }
+    if (T.has_left) {
+        const unsigned n_edge = min(ctr->n_edge, T.left.ghost_cap);
+        for (unsigned k = threadIdx.x; k < n_edge; k += blockDim.x) T.left.link_r[k] = first_row(T.edge_idx[k]);
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (T.has_right) st_release_sys_u64(&T.right.mbox->links_from_left.flag, T.step);
+        if (T.has_left) st_release_sys_u64(&T.left.mbox->links_from_right.flag, T.step);
+    }
+}
+__global__ void k_tile_solve_done(TileLink T, Counters* ctr) {
+    if (!T.has_right) return;
+    __threadfence_system();
+    st_release_sys_u64(&T.right.mbox->done_from_left.flag, T.step);
+}
 // Rows: successor links.  Bodies: v, omega into the inbox of the body's FIRST row, tagged for iteration 0.
+template <bool TILED>
 __global__ void __launch_bounds__(MGFB_THREADS) k_df_init(const BodyVel* __restrict__ vel, unsigned n, const int2* __restrict__ ab, DfArrays D,
-                                                         unsigned epoch, const unsigned* m_ptr, unsigned m_host, Counters* ctr) {
+                                                         unsigned epoch, const unsigned* m_ptr, unsigned m_host, Counters* ctr, TileLink T) {
     if (ctr->overflow | ctr->nan_bounds) return;
     if (ctr->ngroups > 64u) return;   // k_solve takes this step
+    if (TILED) n = ctr->n_total;
     const unsigned tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
     for (unsigned i = tid; i < n; i += nth) {
         unsigned s0 = D.body_start[i], s1 = D.body_start[i + 1];
         if (s0 == s1) continue;
+        // a ghost whose owner has rows of its own is seeded there: its chain reaches this tile through the boundary
+        if (TILED && i >= T.n_own && T.link_r[i - T.n_own] != DF_NONE) continue;
         unsigned fr = D.inc[s0];
         const float4* q = reinterpret_cast<const float4*>(vel + i);
         float4 a = q[0], b = q[1];
         Inbox* dst = (ab[fr].x == (int)i) ? D.in_a + fr : D.in_b + fr;
-        st_inbox(dst, mk3(a.x, a.y, a.z), mk3(a.w, b.x, b.y), epoch + 1u);
+        st_inbox<false>(dst, mk3(a.x, a.y, a.z), mk3(a.w, b.x, b.y), epoch + 1u);
     }
     const unsigned m = m_ptr ? *m_ptr : m_host;
     for (unsigned row = tid; row < m; row += nth) {
         int2 p = ab[row]; unsigned d = D.dep[row];
-        unsigned seqA = d & 255u, degA = (d >> 8) & 255u, seqB = (d >> 16) & 255u, degB = d >> 24;
-        unsigned na = 0xffffffffu, nb = 0xffffffffu;
-        if (p.x >= 0) {
-            bool wrap = seqA + 1u == degA;
-            unsigned nr = D.inc[D.body_start[p.x] + (wrap ? 0u : seqA + 1u)];
-            na = (nr << 2) | (wrap ? 2u : 0u) | (ab[nr].x == p.x ? 0u : 1u);
+        unsigned seq[2] = {d & 255u, (d >> 16) & 255u}, deg[2] = {(d >> 8) & 255u, d >> 24};
+        int body[2] = {p.x, p.y};
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+            unsigned nx = DF_NONE;
+            const int pb = body[s];
+            if (pb >= 0) {
+                const bool wrap = seq[s] + 1u == deg[s];
+                unsigned remote = DF_NONE;
+                if (TILED && wrap) {
+                    if ((unsigned)pb >= T.n_own) {   // ghost: after its last boundary row here, back to its owner's first row, next iteration
+                        unsigned l = T.link_r[(unsigned)pb - T.n_own];
+                        if (l != DF_NONE) remote = ((l >> 1) << 4) | (DF_RIGHT << 2) | 2u | (l & 1u);
+                    } else if (T.has_left && T.edge_mark[pb]) {   // edge body: after its last row here, on to its boundary rows on the left tile, same iteration
+                        unsigned l = T.link_l[T.edge_slot[pb]];
+                        if (l != DF_NONE) remote = ((l >> 1) << 4) | (DF_LEFT << 2) | (l & 1u);
+                    }
+                }
+                if (remote != DF_NONE) nx = remote;
+                else {
+                    unsigned nr = D.inc[D.body_start[pb] + (wrap ? 0u : seq[s] + 1u)];
+                    nx = (nr << 4) | (wrap ? 2u : 0u) | (ab[nr].x == pb ? 0u : 1u);
+                }
+            }
+            D.next[s * D.row_cap + row] = nx;
         }
-        if (p.y >= 0) {
-            bool wrap = seqB + 1u == degB;
-            unsigned nr = D.inc[D.body_start[p.y] + (wrap ? 0u : seqB + 1u)];
-            nb = (nr << 2) | (wrap ? 2u : 0u) | (ab[nr].x == p.y ? 0u : 1u);
-        }
-        D.next[row] = na; D.next[D.row_cap + row] = nb;
     }
 }
 #ifdef MGFB_DF_PROFILE
@@ -1172,10 +1230,12 @@ __device__ unsigned long long g_df_prof[8];   // cycles: fetch, inbox poll, comp
 #endif
 struct DfRow { RowData d; float4 i0, i1, i2, i3, i4; unsigned na, nb, row; float imp; bool valid; };
 #define MGFB_DF_MAX_PHASES 64
-template <int THREADS>
-__global__ void __launch_bounds__(THREADS, 1) k_solve_df(ConstraintRows R, DfArrays D, BodyVel* vel, const unsigned* __restrict__ phase_start,
-                                                         unsigned iters, unsigned epoch, unsigned backoff_ns, Counters* ctr) {
+#define MGFB_DF_THREADS 256
+template <bool TILED>
+__global__ void __launch_bounds__(MGFB_DF_THREADS, 1) k_solve_df(ConstraintRows R, DfArrays D, BodyVel* vel, const unsigned* __restrict__ phase_start,
+                                                                unsigned iters, unsigned epoch, Counters* ctr, TileLink T) {
     if (ctr->overflow | ctr->nan_bounds) return;
+    if (TILED && ctr->comm_error) return;
     const unsigned P = ctr->n_phases;
     if (P == 0 || ctr->ngroups > MGFB_DF_MAX_PHASES || iters == 0) return;   // > 64 colours: k_solve takes the step
     __shared__ unsigned s_row0[MGFB_DF_MAX_PHASES + 1], s_wr0[MGFB_DF_MAX_PHASES + 1];
@@ -1187,7 +1247,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_solve_df(ConstraintRows R, DfArr
     __syncthreads();
     const unsigned nwr = s_wr0[P];
     const unsigned lane = threadIdx.x & 31u;
-    const unsigned gw = (threadIdx.x >> 5) * gridDim.x + blockIdx.x, nW = gridDim.x * (THREADS / 32);
+    const unsigned gw = (threadIdx.x >> 5) * gridDim.x + blockIdx.x, nW = gridDim.x * (MGFB_DF_THREADS / 32);
     if (gw >= nwr) return;
     const unsigned rc = D.row_cap;
     auto fetch = [&](unsigned wr, unsigned& p) {
@@ -1202,10 +1262,26 @@ __global__ void __launch_bounds__(THREADS, 1) k_solve_df(ConstraintRows R, DfArr
             f.na = D.next[row]; f.nb = D.next[rc + row];
             f.imp = __ldcg(&R.impulse[row]);
         } else {
-            f.d.ab = make_int2(-1, -1); f.na = f.nb = 0xffffffffu; f.imp = 0.0f;
+            f.d.ab = make_int2(-1, -1); f.na = f.nb = DF_NONE; f.imp = 0.0f;
             f.d.n = f.d.t0 = f.d.t1 = f.d.ra = f.d.rb = f.i0 = f.i1 = f.i2 = f.i3 = f.i4 = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
         }
         return f;
+    };
+    // where a row's result goes: the successor's inbox (here or on a neighbour tile), or -- after the body's
+    // last row of the last iteration -- the body's record (on its owner, if the body is a ghost)
+    auto publish = [&](unsigned nx, int body, V3 v, V3 w, float im, const M3& I, unsigned tag, bool last_it) {
+        const bool wrap = (nx & 2u) != 0u;
+        if (wrap && last_it) {
+            BodyVel* dst = vel + body;
+            if (TILED && (unsigned)body >= T.n_own) dst = T.right.vel + T.ridx[(unsigned)body - T.n_own];
+            store_vel(dst, v, w, im, I);
+            return;
+        }
+        const unsigned where = TILED ? (nx >> 2) & 3u : 0u, side = nx & 1u, nr = nx >> 4;
+        Inbox* base = side ? D.in_b : D.in_a;
+        if (TILED && where == DF_LEFT) base = side ? T.left.in_b : T.left.in_a;
+        if (TILED && where == DF_RIGHT) base = side ? T.right.in_b : T.right.in_a;
+        st_inbox<TILED>(base + nr, v, w, tag + (wrap ? 1u : 0u));
     };
     unsigned p_next = 0, wr = gw, it = 0;
 #ifdef MGFB_DF_PROFILE
@@ -1229,12 +1305,22 @@ __global__ void __launch_bounds__(THREADS, 1) k_solve_df(ConstraintRows R, DfArr
         sa.lo = sa.hi = sb.lo = sb.hi = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
         bool okA = !needA, okB = !needB;
         DF_T(t1); DF_ACC(0, t1 - t0);
+        unsigned long long t_wait0 = 0; unsigned spins = 0;
         for (;;) {
-            if (!okA) { sa = ld_inbox(D.in_a + row); okA = __float_as_uint(sa.lo.w) == tag && __float_as_uint(sa.hi.w) == tag; }
-            if (!okB) { sb = ld_inbox(D.in_b + row); okB = __float_as_uint(sb.lo.w) == tag && __float_as_uint(sb.hi.w) == tag; }
+            if (!okA) { sa = ld_inbox<TILED>(D.in_a + row); okA = __float_as_uint(sa.lo.w) == tag && __float_as_uint(sa.hi.w) == tag; }
+            if (!okB) { sb = ld_inbox<TILED>(D.in_b + row); okB = __float_as_uint(sb.lo.w) == tag && __float_as_uint(sb.hi.w) == tag; }
             DF_ACC(3, 1);
             if (__all_sync(0xffffffffu, okA && okB)) break;
-            if (backoff_ns) __nanosleep(backoff_ns);
+            if (TILED && (++spins & 1023u) == 0u) {   // a dead or diverged neighbour must never hang the GPU
+                bool dead = false;
+                if (lane == 0) {
+                    unsigned long long now = globaltimer_ns();
+                    if (t_wait0 == 0) t_wait0 = now;
+                    if (*reinterpret_cast<volatile unsigned*>(&ctr->comm_error) & COMM_TIMEOUT) dead = true;
+                    else if (now - t_wait0 > T.timeout_ns) { atomicOr(&ctr->comm_error, (unsigned)COMM_TIMEOUT); dead = true; }
+                }
+                if (__shfl_sync(0xffffffffu, (int)dead, 0)) return;
+            }
         }
         DF_T(t2); DF_ACC(1, t2 - t1);
         if (cur.valid) {
@@ -1274,16 +1360,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_solve_df(ConstraintRows R, DfArr
                 else { unsigned e = row * 3 + (c - 1); __stcg(&R.xtm[e], make_float4(tm0, tm1, imp, 0.0f)); }
             }
             const bool last_it = it + 1 == iters;
-            if (needA) {
-                const unsigned nx = cur.na; const bool wrap = (nx & 2u) != 0u;
-                if (wrap && last_it) store_vel(vel + a, va, oa, ima, IA);   // the body's final update of the solve
-                else st_inbox(((nx & 1u) ? D.in_b : D.in_a) + (nx >> 2), va, oa, tag + (wrap ? 1u : 0u));
-            }
-            if (needB) {
-                const unsigned nx = cur.nb; const bool wrap = (nx & 2u) != 0u;
-                if (wrap && last_it) store_vel(vel + b, vb, ob, imb, IB);
-                else st_inbox(((nx & 1u) ? D.in_b : D.in_a) + (nx >> 2), vb, ob, tag + (wrap ? 1u : 0u));
-            }
+            if (needA) publish(cur.na, a, va, oa, ima, IA, tag, last_it);
+            if (needB) publish(cur.nb, b, vb, ob, imb, IB, tag, last_it);
         }
         __syncwarp();
         DF_T(t3); DF_ACC(2, t3 - t2); DF_ACC(4, 1);

@@ -113,6 +113,9 @@ struct Counters {
     unsigned long long acc_groups;
     unsigned long long acc_steps;
 };
+// One side of a row's inbox (dataflow solver, kernels.cuh): written by the row's predecessor with ONE 32-byte store.
+struct __align__(32) Inbox { float4 lo, hi; };   // v.xyz, tag | omega.xyz, tag
+
 enum { OVF_PAIRS = 1, OVF_TPAIRS = 2, OVF_CONTACTS = 4, OVF_GRID = 8, OVF_GROUPS = 16, OVF_GHOSTS = 32 };
 enum { COMM_TIMEOUT = 1, COMM_TILE_TOO_THIN = 2 };
 struct PairLists { int2* p[4]; };

@@ -27,6 +27,10 @@ struct TileMailbox {
     TileSlot ghosts;          // from the RIGHT neighbour: flag = step, u = number of ghosts written
     TileSlot vel_from_right;  // from the RIGHT neighbour: flag = V(step, 1 + it): edge velocities of iteration it are in my ghost slots
     TileSlot vel_from_left;   // from the LEFT neighbour: flag = V(step, 1): it may be sent velocities; V(step, 2 + it): my edge bodies hold its results
+    // dataflow solve (k_solve_df<true>): the chains of edge bodies run across the tile boundary
+    TileSlot links_from_left;   // flag = step: link_l[] holds, per edge slot, the first boundary row of that body on the left tile
+    TileSlot links_from_right;  // flag = step: link_r[] holds, per ghost slot, the first interior row of that body on its owner
+    TileSlot done_from_left;    // flag = step: the left tile's solver has finished (the final velocities of my edge bodies are in my records)
 };
 // A neighbour's arrays as mapped into this process.
 struct TilePeer {
@@ -34,6 +38,10 @@ struct TilePeer {
     unsigned* ridx;           // [ghost_cap] for each of ITS ghosts: the index of that body on the owner (me)
     TileMailbox* mbox;
     unsigned n_own, ghost_cap;
+    // dataflow solve: the neighbour's row inboxes and the link tables it reads
+    Inbox* in_a; Inbox* in_b;
+    unsigned* link_l;         // [ghost_cap] written by ITS left neighbour (me, if I am that)
+    unsigned* link_r;         // [ghost_cap] written by ITS right neighbour
 };
 struct TileLink {
     TilePeer left, right;
@@ -41,6 +49,9 @@ struct TileLink {
     unsigned* edge_idx;       // [n_edge] my bodies that are ghosts on the left neighbour, in ghost-slot order
     unsigned char* edge_mark; // [n_own] 1 = sent left this step
     unsigned* ridx;           // [ghost_cap] owner index of each of my ghosts (written by the right neighbour)
+    unsigned* edge_slot;      // [n_own] ghost slot on the left neighbour of each of my edge bodies (valid where edge_mark)
+    unsigned* link_l;         // [ghost_cap] mine, written by the left neighbour
+    unsigned* link_r;         // [ghost_cap] mine, written by the right neighbour
     unsigned n_own, ghost_cap;
     unsigned long long step;  // 1, 2, 3, ... the same on every rank
     unsigned long long timeout_ns;
@@ -119,6 +130,7 @@ __global__ void __launch_bounds__(256) k_ghost_send(BodyArrays B, TileLink T, Co
         if (k >= P.ghost_cap) { atomicOr(&ctr->overflow, (unsigned)OVF_GHOSTS); continue; }
         T.edge_idx[k] = i;
         T.edge_mark[i] = 1;
+        T.edge_slot[i] = k;
         unsigned d = P.n_own + k;
         P.x[d] = B.x[i];
         const float4* sv = reinterpret_cast<const float4*>(B.vel + i);

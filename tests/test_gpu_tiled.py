@@ -45,12 +45,23 @@ def _parallel(fns):
     return out
 
 
+SCHEDULE = [0]
+
+
+@pytest.fixture(autouse=True, params=[0, 1], ids=["dataflow", "phases"])
+def _schedule(request):
+    """Both solver schedules (include/mgfb.h mgfb_solver_schedule): body chains running across the tile
+    boundary through peer-memory inboxes, and the barrier-phased solve with explicit exchange phases."""
+    SCHEDULE[0] = request.param
+    yield
+
+
 def _make(bodies, terrain, ntiles, ctas):
     shapes = bodies[0]
     parts = tiling.slab_partition(tiling.shape_centres_x(shapes), ntiles)
     tiles = []
     for r in range(ntiles):
-        t = tiling.TiledWorld(r, ntiles, device=0, max_cooperative_ctas=ctas, tile_timeout_ms=4000)
+        t = tiling.TiledWorld(r, ntiles, device=0, max_cooperative_ctas=ctas, tile_timeout_ms=4000, solver_schedule=SCHEDULE[0])
         t.add_bodies(parts[r], *bodies)
         t.set_terrain(*terrain)
         tiles.append(t)
@@ -132,7 +143,7 @@ def test_tile_too_thin_is_reported():
     parts = tiling.slab_partition(tiling.shape_centres_x(shapes), 3)
     tiles = []
     for r in range(3):
-        t = tiling.TiledWorld(r, 3, device=0, max_cooperative_ctas=16, tile_timeout_ms=3000)
+        t = tiling.TiledWorld(r, 3, device=0, max_cooperative_ctas=16, tile_timeout_ms=3000, solver_schedule=SCHEDULE[0])
         t.add_bodies(parts[r], *bodies); t.set_terrain(*terrain); tiles.append(t)
     tiling.connect_local(tiles, ghost_capacity=256)
     codes = [None] * 3
