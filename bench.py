@@ -207,13 +207,15 @@ def main():
         from mgf_b200 import scenes, tiling
         bodies, ids, terrain = scenes.tiled_pile(world, rank)
         iters = 20
-        tw = tiling.TiledWorld(rank, world, device=local_rank)
+        tw = tiling.TiledWorld(rank, world, device=local_rank, solver_schedule=0 if args.schedule == "dataflow" else 1)
         tw.add_owned(ids, *bodies); tw.set_terrain(*terrain)
         tw.connect(tiling.all_gather_bytes, ghost_capacity=32768)
         g = tw.world
         workload = f"pile of {world} x 100000 spheres (50x40x50 lattice per tile, same radius/spacing/material as C2pile), one box"
-        parallelism = (f"{world} slabs along x, one per GPU; ghost bodies once per step and boundary velocities every solver "
-                       "iteration through NVLink peer memory inside the kernels")
+        parallelism = (f"{world} slabs along x, one per GPU; ghost bodies once per step through NVLink peer memory; "
+                       + ("solver: the constraint chains of boundary bodies continue on the neighbour GPU, every hand-over one 32-byte "
+                          "peer store from inside the solver kernel (no exchange phase, no grid barrier)" if args.schedule == "dataflow"
+                          else "boundary velocities every solver iteration through peer memory inside the barrier-phased solver kernel"))
     n = len(bodies[0])
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device="cuda")   # 256 MB > 126 MB L2
 
@@ -281,8 +283,8 @@ def main():
     peak, peak_src = measured_peak()
     solve_s = sum(solve_ms) * 1e-3
     achieved = ALGO_BYTES_PER_CONSTRAINT_ITER * units / solve_s / 1e9
-    dataflow = world == 1 and args.schedule == "dataflow"
-    roofline = {"kernel": "k_solve_df (persistent sequential-impulse solver, per-body version counters, no grid barrier)" if dataflow
+    dataflow = args.schedule == "dataflow"
+    roofline = {"kernel": "k_solve_df (persistent sequential-impulse solver; rows wait on per-row inboxes filled by their predecessors, no grid barrier)" if dataflow
                 else "k_solve (persistent cooperative sequential-impulse solver, one grid barrier per colour)", "bound": "hbm", "achieved": achieved, "peak": peak,
                 "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": ALGO_BYTES_PER_CONSTRAINT_ITER * units / len(solve_ms),

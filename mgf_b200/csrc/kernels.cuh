@@ -267,11 +267,30 @@ __global__ void __launch_bounds__(MGFB_THREADS) k_body_pairs_warp(const Box* __r
                 unsigned same = __match_any_sync(0xffffffffu, h);
                 if (lane < 27 && (unsigned)__ffs((int)same) - 1u == lane) { e = G.cell_start[h]; e1 = G.cell_start[h + 1]; }
             }
-            while (__any_sync(0xffffffffu, e < e1)) {
+            // Flatten the (at most 27) bucket ranges: lane l owns [e, e1); an inclusive warp scan of the lengths
+            // gives every candidate a global number t, and lane t%32 tests candidate t -- all 32 lanes busy
+            // whatever the spread of bucket sizes (the longest bucket no longer sets the trip count).
+            const unsigned len_l = e1 - e;
+            unsigned incl = len_l;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { unsigned y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= (unsigned)o) incl += y; }
+            const unsigned total = __shfl_sync(0xffffffffu, incl, 31);
+            for (unsigned t0 = 0; t0 < total; t0 += 32) {
+                const unsigned t = t0 + lane;
+                // owner of candidate t = first lane whose inclusive prefix exceeds t (binary search over the 32 prefixes)
+                unsigned lo = 0;
+#pragma unroll
+                for (int step = 16; step > 0; step >>= 1) {
+                    unsigned probe = __shfl_sync(0xffffffffu, incl, (int)(lo + step - 1));
+                    if (probe <= t) lo += step;
+                }
+                const unsigned src_incl = __shfl_sync(0xffffffffu, incl, (int)lo);
+                const unsigned src_len = __shfl_sync(0xffffffffu, len_l, (int)lo);
+                const unsigned src_e = __shfl_sync(0xffffffffu, e, (int)lo);
                 int kind = -1; unsigned j = 0;
-                if (e < e1) {
-                    float4 a = G.ent[2 * e], b = G.ent[2 * e + 1];
-                    ++e;
+                if (t < total) {
+                    const unsigned ee = src_e + (t - (src_incl - src_len));
+                    float4 a = G.ent[2 * ee], b = G.ent[2 * ee + 1];
                     unsigned jw = __float_as_uint(a.w);
                     j = jw & 0x7fffffffu;
                     if (__float_as_uint(b.w) < gi && !(ghost_i && j >= n_own) && box_overlaps(tc, tr, mk3(a.x, a.y, a.z), mk3(b.x, b.y, b.z)))
