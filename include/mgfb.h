@@ -95,7 +95,8 @@ typedef struct mgfb_config {
     uint32_t initial_body_capacity; /* 0 = default */
     uint32_t max_cooperative_ctas;  /* 0 = one CTA per SM; lower it when several contexts must share one GPU */
     uint32_t tile_timeout_ms;       /* 0 = 20000: how long a tile waits for a neighbour before MGFB_ERR_TILE */
-    uint32_t solver_schedule;       /* mgfb_solver_schedule; coloured order only (as-given order and tiled worlds always use phases) */
+    uint32_t solver_schedule;       /* mgfb_solver_schedule; coloured order only (as-given order always uses phases); every tile
+                                       of a tiled world must use the same value */
     uint32_t reserved;
 } mgfb_config;
 void mgfb_config_default(mgfb_config* cfg);
@@ -221,7 +222,7 @@ typedef struct mgfb_step_stats {
     float step_ms;                /* device time of the whole step */
     float solve_ms;               /* device time of the solve kernel alone */
     uint32_t overflow;            /* nonzero if a work list had to be regrown and the step rerun */
-    uint32_t colouring_rounds;    /* Jones-Plassmann rounds (diagnostic) */
+    uint32_t colouring_rounds;    /* sweeps of the chain colouring, or Jones-Plassmann rounds (diagnostic) */
     uint32_t ghosts;              /* tiled world: bodies received from the right neighbour this step */
     uint32_t boundary_constraints;/* tiled world: constraints between an owned body and a ghost */
     uint32_t phases;              /* non-empty groups = grid-wide phases per solver iteration */
@@ -252,8 +253,11 @@ int32_t mgfb_step_totals(mgfb_ctx* ctx, uint64_t* steps, uint64_t* constraints, 
  * Each GPU (one process per GPU, or one ctx per GPU) owns a slab of the bodies.  Once per step the
  * right neighbour's bodies that can touch this tile arrive as "ghosts" (written by the neighbour's
  * kernel straight into this ctx's body arrays over NVLink peer memory); constraints between an owned
- * body and a ghost are solved here, inside the same persistent solver kernel, with the ghost
- * velocities exchanged every iteration.  The executed constraint order is a valid sequential order
+ * body and a ghost are solved here, inside the same persistent solver kernel: with the default
+ * dataflow schedule the constraint chain of a boundary body simply continues on the neighbour GPU
+ * (each hand-over is one 32-byte peer store into the next constraint's inbox); with
+ * MGFB_SCHEDULE_PHASES the ghost velocities are exchanged once per iteration between barrier phases.
+ * The executed constraint order is a valid sequential order
  * (per iteration: every tile's interior constraints, then every tile's boundary constraints), exported
  * by mgfb_step_constraints with GLOBAL body ids so a caller (or the oracle) can replay it.
  *
