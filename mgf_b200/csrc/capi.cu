@@ -58,7 +58,7 @@ struct mgfb_ctx {
     Buf c_key, c_csr, c_next, c_inbox;   // dataflow colouring (k_colour_df): keys, per-body constraint lists, chain links, mask inboxes
     unsigned df_epoch = 0;   // inbox tags of one solve are df_epoch + 1 .. df_epoch + iters + 1
     // body grid
-    Buf cell_count, cell_start, bg_ent, scan_sums; unsigned table = 0, ent_cap = 0;
+    Buf cell_count, cell_start, bg_ent, scan_sums, scan_state; unsigned table = 0, ent_cap = 0;
     TerrainData terrain;
     Buf stage;          // packed state staging for get_state / set_velocity
     unsigned long long launches = 0;   // kernels launched since the last mgfb_step_totals(reset)
@@ -203,6 +203,15 @@ int32_t ensure_grid(mgfb_ctx* ctx, unsigned scale) {
     return MGFB_OK;
 }
 // exclusive scan of `in[0..n)` into out[0..n], out[n] = total (also stored at *total_dev if given)
+// single-pass scan (decoupled look-back) for the step path: one launch + one small memset
+int32_t scan_u32_lb(mgfb_ctx* ctx, const unsigned* in, unsigned* out, unsigned n, unsigned* total_dev) {
+    unsigned nb = (n + SCAN_ITEMS - 1) / SCAN_ITEMS;
+    TRY(ensure(ctx, ctx->scan_state, ((size_t)nb + 2) * 8));
+    CU(cudaMemsetAsync(ctx->scan_state.p, 0, ((size_t)nb + 1) * 8, ctx->stream));
+    k_scan_lookback<<<nb, 256, 0, ctx->stream>>>(in, n, out, ctx->scan_state.as<unsigned long long>(), total_dev);
+    CU(cudaGetLastError());
+    return MGFB_OK;
+}
 int32_t scan_u32(mgfb_ctx* ctx, const unsigned* in, unsigned* out, unsigned n, unsigned* sums, unsigned* total_dev) {
     unsigned nb = (n + SCAN_ITEMS - 1) / SCAN_ITEMS;
     k_scan_reduce<<<nb, 256, 0, ctx->stream>>>(in, n, sums);
@@ -293,14 +302,14 @@ int32_t enqueue_order_and_solve(mgfb_ctx* ctx, const OrderView& O, const Manifol
         V.csr = ctx->c_csr.as<unsigned>(); V.next = ctx->c_next.as<unsigned>(); V.inbox = ctx->c_inbox.as<unsigned long long>(); V.cap = ctx->row_cap;
         CU(cudaMemsetAsync(V.deg, 0, (size_t)nb * 4, ctx->stream));
         k_inc_count<<<g, MGFB_THREADS, 0, ctx->stream>>>(O, V, m_ptr, m_host, c);
-        TRY(scan_u32(ctx, V.deg, ctx->body_start.as<unsigned>(), nb, ctx->scan_sums.as<unsigned>(), &c->df_links));
+        TRY(scan_u32_lb(ctx, V.deg, ctx->body_start.as<unsigned>(), nb, &c->df_links));
         k_inc_fill<<<g, MGFB_THREADS, 0, ctx->stream>>>(O, V, m_ptr, m_host, c);
         k_inc_sort<<<grid_for(ctx, nb), MGFB_THREADS, 0, ctx->stream>>>(O, V, nb, c);
         CU(cudaGetLastError());
         OrderView Ov = O; unsigned mh = m_host; const unsigned* mp = m_ptr;
         void* args[] = {&Ov, &V, &mp, &mh, &c};
         CU(cudaLaunchCooperativeKernel((void*)k_colour_df, dim3(ctx->coop_colour), dim3(MGFB_THREADS), args, 0, ctx->stream));
-        ctx->launches += 7;
+        ctx->launches += 5;
     }
     {
         OrderView Ov = O; bool ag = as_given; unsigned mh = m_host; const unsigned* mp = m_ptr;
@@ -409,7 +418,7 @@ int32_t enqueue_step(mgfb_ctx* ctx, float dt, unsigned iters, bool from_integrat
     // broadphase over the stored fat boxes
     BodyGrid G = body_grid(ctx);
     k_bgrid_insert<false><<<gs, MGFB_THREADS, 0, ctx->stream>>>(B.fat, B.col, B.gid, G, c);
-    TRY(scan_u32(ctx, G.cell_count, G.cell_start, ctx->table, ctx->scan_sums.as<unsigned>(), &c->grid_entries));
+    TRY(scan_u32_lb(ctx, G.cell_count, G.cell_start, ctx->table, &c->grid_entries));
     k_bgrid_insert<true><<<gs, MGFB_THREADS, 0, ctx->stream>>>(B.fat, B.col, B.gid, G, c);
     PairLists PL; for (int k = 0; k < 4; ++k) PL.p[k] = ctx->pair_list[k].as<int2>();
     {
@@ -446,8 +455,8 @@ int32_t enqueue_step(mgfb_ctx* ctx, float dt, unsigned iters, bool from_integrat
     TRY(enqueue_order_and_solve(ctx, O, M, &c->contacts, 0, ctx->contact_cap, false, dt, iters, timed));
     k_step_done<<<1, 1, 0, ctx->stream>>>(c);
     CU(cudaGetLastError());
-    // k_integrate, 2x k_grid_insert, 3 scan kernels, k_body_pairs, k_step_done (+ terrain, narrowphase)
-    ctx->launches += 8 + (ctx->terrain.present ? 1 : 0) + (sph ? 1 : 0) + (sph && caps ? 2 : 0) + (caps ? 1 : 0) +
+    // k_integrate, 2x k_grid_insert, scan, k_body_pairs, k_step_done (+ terrain, narrowphase)
+    ctx->launches += 6 + (ctx->terrain.present ? 1 : 0) + (sph ? 1 : 0) + (sph && caps ? 2 : 0) + (caps ? 1 : 0) +
                      (ctx->terrain.present ? (sph ? 1 : 0) + (caps ? 1 : 0) : 0);
     return MGFB_OK;
 }
@@ -553,7 +562,7 @@ int32_t mgfb_ctx_create(const mgfb_config* cfg, mgfb_ctx** out) {
         const void* fns[] = {(const void*)k_integrate<true, true, true, false>, (const void*)k_integrate<true, true, true, true>,
                              (const void*)k_integrate<false, false, true, false>, (const void*)k_tile_publish, (const void*)k_tile_wait,
                              (const void*)k_ghost_send, (const void*)k_ghost_recv, (const void*)k_bgrid_insert<false>,
-                             (const void*)k_bgrid_insert<true>, (const void*)k_scan_reduce, (const void*)k_scan_sums, (const void*)k_scan_final,
+                             (const void*)k_bgrid_insert<true>, (const void*)k_scan_reduce, (const void*)k_scan_sums, (const void*)k_scan_final, (const void*)k_scan_lookback,
                              (const void*)k_body_pairs_warp, (const void*)k_terrain_pairs, (const void*)k_narrow_bodies<0, 0>,
                              (const void*)k_narrow_bodies<0, 1>, (const void*)k_narrow_bodies<1, 0>, (const void*)k_narrow_bodies<1, 1>,
                              (const void*)k_narrow_terrain<0>, (const void*)k_narrow_terrain<1>, (const void*)k_order, (const void*)k_group_scan,
@@ -597,7 +606,7 @@ void mgfb_ctx_destroy(mgfb_ctx* ctx) {
                   &ctx->c_a, &ctx->c_b, &ctx->c_face, &ctx->c_sub, &ctx->c_la, &ctx->c_lb, &ctx->c_nt, &ctx->body_best, &ctx->body_scratch,
                   &ctx->group, &ctx->group_count, &ctx->group_start, &ctx->perm, &ctx->r_ab, &ctx->r_n, &ctx->r_t0, &ctx->r_t1, &ctx->r_ra,
                   &ctx->r_rb, &ctx->r_imp, &ctx->r_xra, &ctx->r_xrb, &ctx->r_xtm, &ctx->r_dep, &ctx->body_deg, &ctx->body_start, &ctx->r_inc, &ctx->r_next, &ctx->r_in_a, &ctx->r_in_b, &ctx->r_ia, &ctx->c_key, &ctx->c_csr, &ctx->c_next, &ctx->c_inbox, &ctx->cell_count, &ctx->cell_start, &ctx->bg_ent,
-                  &ctx->scan_sums, &ctx->u_a, &ctx->u_b, &ctx->u_sc, &ctx->u_sf, &ctx->u_n, &ctx->u_t, &ctx->u_nc, &ctx->u_la,
+                  &ctx->scan_sums, &ctx->scan_state, &ctx->u_a, &ctx->u_b, &ctx->u_sc, &ctx->u_sf, &ctx->u_n, &ctx->u_t, &ctx->u_nc, &ctx->u_la,
                   &ctx->u_lb, &ctx->stage, &ctx->terrain.verts, &ctx->terrain.faces, &ctx->terrain.boxes, &ctx->terrain.cell_count,
                   &ctx->terrain.cell_start, &ctx->terrain.ent_id, &ctx->terrain.ent_key, &ctx->terrain.max_bits,
                   &ctx->gid, &ctx->phase_start, &ctx->edge_idx, &ctx->edge_mark, &ctx->ridx, &ctx->mbox, &ctx->edge_slot, &ctx->tile_df};

@@ -1422,8 +1422,51 @@ __global__ void __launch_bounds__(MGFB_THREADS) k_set_velocity(BodyArrays B, uns
     r->b.x = w[3 * i + 1]; r->b.y = w[3 * i + 2];
 }
 
-// ---------------------------------------------------------------- multi-block exclusive scan (u32)
+// ---------------------------------------------------------------- single-pass exclusive scan (u32)
+// Decoupled look-back: tiles of SCAN_ITEMS items take their number from an atomic ticket (so every
+// predecessor of a running tile is running or done), publish their aggregate, then their inclusive
+// prefix, in one 64-bit word (flag << 62 | value).  `state` = [ticket, pad, status[ntiles]] zeroed before
+// the launch.  out[n] = total (also *total_dev when given).
 #define SCAN_ITEMS 2048
+__global__ void __launch_bounds__(256) k_scan_lookback(const unsigned* __restrict__ in, unsigned n, unsigned* out, unsigned long long* state, unsigned* total_dev) {
+    __shared__ unsigned s_tile, s_excl, ws[8];
+    unsigned long long* status = state + 1;
+    if (threadIdx.x == 0) s_tile = atomicAdd(reinterpret_cast<unsigned*>(state), 1u);
+    __syncthreads();
+    const unsigned tile = s_tile, base = tile * SCAN_ITEMS + threadIdx.x * 8u;
+    unsigned v[8], sum = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { v[k] = base + k < n ? in[base + k] : 0u; sum += v[k]; }
+    unsigned x = sum;
+    for (int o = 1; o < 32; o <<= 1) { unsigned y = __shfl_up_sync(0xffffffffu, x, o); if ((threadIdx.x & 31) >= o) x += y; }
+    if ((threadIdx.x & 31) == 31) ws[threadIdx.x >> 5] = x;
+    __syncthreads();
+    unsigned woff = 0, agg = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) { if (w < (int)(threadIdx.x >> 5)) woff += ws[w]; agg += ws[w]; }
+    if (threadIdx.x == 0) {
+        unsigned excl = 0;
+        if (tile == 0) st_relaxed_u64(status, (2ULL << 62) | agg);
+        else {
+            st_relaxed_u64(status + tile, (1ULL << 62) | agg);
+            for (unsigned p = tile; p-- > 0;) {
+                unsigned long long st;
+                do { st = ld_relaxed_u64(status + p); } while ((st >> 62) == 0ULL);
+                excl += (unsigned)st;
+                if ((st >> 62) == 2ULL) break;
+            }
+            st_relaxed_u64(status + tile, (2ULL << 62) | (unsigned long long)(excl + agg));
+        }
+        s_excl = excl;
+        if ((unsigned long long)(tile + 1) * SCAN_ITEMS >= n) { out[n] = excl + agg; if (total_dev) *total_dev = excl + agg; }
+    }
+    __syncthreads();
+    unsigned run = s_excl + woff + x - sum;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { if (base + k < n) out[base + k] = run; run += v[k]; }
+}
+
+// ---------------------------------------------------------------- multi-block exclusive scan (u32), three passes (terrain build)
 __global__ void __launch_bounds__(256) k_scan_reduce(const unsigned* __restrict__ in, unsigned n, unsigned* block_sums) {
     __shared__ unsigned ws[8];
     unsigned base = blockIdx.x * SCAN_ITEMS, s = 0;
