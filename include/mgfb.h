@@ -149,6 +149,20 @@ int32_t mgfb_contacts_batch(mgfb_ctx* ctx, uint32_t pair_kind, const mgfb_shape*
                             uint32_t n, mgfb_contact* out /* n*2 */, mgfb_local_contact* out_local /* n*2 or NULL */,
                             uint32_t* counts /* n */);
 
+/* ---------------- ray casts: Intersects<RHS> for Particle (collision.rs:163-373) ---------------- */
+enum mgfb_particle_kind {
+    MGFB_RAY = 0,      /* geom.rs:341,818  Ray{p, d}:     6 floats p[3], d[3];  pos = p, dir = d,     DT = inf */
+    MGFB_SEGMENT = 1   /* geom.rs:349,842  Segment{a, b}: 6 floats a[3], b[3];  pos = a, dir = b - a, DT = 1   */
+};
+/* collision.rs:151 Intersection */
+typedef struct mgfb_intersection { float p[3]; float t; } mgfb_intersection;
+/* `particles[i].intersection(&shapes[i])` (Option<Intersection>): hit[i] = 1 and out[i] when Some.  Shapes: PLANE
+ * (collision.rs:169), TRIANGLE / RECTANGLE (:186, the plane hit must lie inside the face), AABB (:202), OBB (:238),
+ * SPHERE (:249), CAPSULE (:275), and Moving<Sphere> = a SPHERE with v != 0 (:361, the capsule its sweep covers).
+ * One thread per query, shapes of mixed kinds allowed (a warp diverges on the kind). */
+int32_t mgfb_intersections_batch(mgfb_ctx* ctx, uint32_t particle_kind, const float* particles /* n*6 */, const mgfb_shape* shapes /* n */,
+                                 uint32_t n, mgfb_intersection* out /* n */, uint32_t* hit /* n */);
+
 /* ---------------- discrete path: GJK + EPA (simplex.rs:172-553) ---------------- */
 /* `a[i].contacts(&b[i], cb)` for static convex pairs through the generic impl for Convex + Volumetric shapes
  * (collision.rs:497-519): GJK seeded along +-y (simplex.rs:172-200), then EPA (simplex.rs:456-553, at most

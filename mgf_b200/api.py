@@ -125,6 +125,18 @@ def separation_batch(ctx, a, b):
     return sep, status
 
 
+def intersections_batch(ctx, particle_kind, particles, shapes):
+    """`particles[i].intersection(&shapes[i])` (collision.rs:163-373).  particles: (n, 6) f32, Ray = (p, d),
+    Segment = (a, b).  Returns (intersections[n] {p, t}, hit[n])."""
+    particles = np.ascontiguousarray(particles, dtype=np.float32).reshape(-1, 6)
+    shapes = np.ascontiguousarray(shapes, dtype=L.SHAPE_DTYPE)
+    n = len(shapes)
+    assert len(particles) == n
+    out = np.zeros(n, dtype=L.INTERSECTION_DTYPE); hit = np.zeros(n, np.uint32)
+    ctx.check(ctx.lib.mgfb_intersections_batch(ctx.h, particle_kind, L.ptr(particles), L.ptr(shapes), n, L.ptr(out), L.ptr(hit)))
+    return out, hit
+
+
 def contacts_batch(ctx, pair_kind, recv, arg, want_local=False):
     """`recv[i].contacts(&arg[i], cb)` for a homogeneous batch (collision.rs:471).
 

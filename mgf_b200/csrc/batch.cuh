@@ -134,3 +134,78 @@ extern "C" int32_t mgfb_contacts_batch(mgfb_ctx* ctx, uint32_t pair_kind, const 
     release(dr); release(da); release(dout); release(dl); release(dc);
     return s;
 }
+
+// ---------------------------------------------------------------- ray casts (Intersects<RHS> for Particle)
+namespace {
+// collision.rs:163-373.  One thread per (particle, shape) query; Ray: DT = inf, Segment: DT = 1 and dir = b - a.
+__global__ void __launch_bounds__(128) k_intersections_batch(unsigned particle_kind, const float* __restrict__ particles,
+                                                             const mgfb_shape* __restrict__ shapes, unsigned n, mgfb_intersection* out, unsigned* hit) {
+    unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float* q = particles + 6 * (size_t)i;
+    const bool seg = particle_kind == MGFB_SEGMENT;
+    V3 p = mk3(q[0], q[1], q[2]), d = mk3(q[3], q[4], q[5]);
+    if (seg) d = d - p;   // geom.rs:848-850
+    const float DT = seg ? 1.0f : __builtin_huge_valf();
+    mgfb_shape S = shapes[i];
+    float t = 0.0f; V3 ip = zero3(); bool ok = false;
+    switch (S.kind) {
+        case MGFB_PLANE: ok = ray_plane(p, d, sh_plane(S), DT, &t, &ip); break;
+        case MGFB_TRIANGLE: { Tri tr = sh_tri(S); ok = ray_plane(p, d, tr.plane(), DT, &t, &ip) && tr.contains(ip); break; }      // collision.rs:186-200
+        case MGFB_RECTANGLE: { Rct rc = sh_rect(S); ok = ray_plane(p, d, rc.plane(), DT, &t, &ip) && rc.contains(ip); break; }
+        case MGFB_AABB: ok = ray_aabb(p, d, mk3(S.p[0], S.p[1], S.p[2]), mk3(S.p[3], S.p[4], S.p[5]), DT, &t, &ip); break;
+        case MGFB_OBB: {   // collision.rs:238-247: rotate the particle around the centre (geom.rs:829-836, :853-861), then the AABB test
+            V3 c = mk3(S.p[0], S.p[1], S.p[2]);
+            Q4 rot; rot.s = S.p[6]; rot.v = mk3(S.p[7], S.p[8], S.p[9]);
+            V3 rp = qrot(rot, p - c) + c, rd = qrot(rot, d);
+            if (seg) { V3 b = rp + rd; rd = b - rp; }
+            ok = ray_aabb(rp, rd, c, mk3(S.p[3], S.p[4], S.p[5]), DT, &t, &ip);
+            break;
+        }
+        case MGFB_SPHERE:
+            if (S.v[0] != 0.0f || S.v[1] != 0.0f || S.v[2] != 0.0f)   // Moving<Sphere>: the capsule its sweep covers (collision.rs:361-373)
+                ok = ray_capsule(p, d, mk3(S.p[0], S.p[1], S.p[2]), sh_vel(S), S.p[3], &t, &ip) && !(t > DT);
+            else ok = ray_sphere(p, d, mk3(S.p[0], S.p[1], S.p[2]), S.p[3], &t, &ip) && !(t > DT);
+            break;
+        case MGFB_CAPSULE: { Cap c = sh_capsule(S); ok = ray_capsule(p, d, c.a, c.d, c.r, &t, &ip) && !(t > DT); break; }
+        default: break;
+    }
+    hit[i] = ok ? 1u : 0u;
+    mgfb_intersection o;
+    o.p[0] = ok ? ip.x : 0.0f; o.p[1] = ok ? ip.y : 0.0f; o.p[2] = ok ? ip.z : 0.0f; o.t = ok ? t : 0.0f;
+    out[i] = o;
+}
+}  // namespace
+
+extern "C" int32_t mgfb_intersections_batch(mgfb_ctx* ctx, uint32_t particle_kind, const float* particles, const mgfb_shape* shapes, uint32_t n,
+                                            mgfb_intersection* out, uint32_t* hit) {
+    if (!ctx || (n && (!particles || !shapes || !out || !hit))) return fail(ctx, MGFB_ERR_INVALID_ARG, "null argument");
+    if (particle_kind > MGFB_SEGMENT) return fail(ctx, MGFB_ERR_INVALID_ARG, "particle kind must be MGFB_RAY or MGFB_SEGMENT");
+    if (n == 0) return MGFB_OK;
+    for (uint32_t i = 0; i < n; ++i) {
+        uint32_t k = shapes[i].kind;
+        if (k > MGFB_OBB) return fail(ctx, MGFB_ERR_INVALID_ARG, "unknown shape kind");
+        if ((k == MGFB_SPHERE && !(shapes[i].p[3] > 0.0f)) || (k == MGFB_CAPSULE && !(shapes[i].p[6] > 0.0f)))
+            return fail(ctx, MGFB_ERR_INVALID_ARG, "radius must be > 0 (geom.rs:300,328)");
+    }
+    CU(cudaSetDevice(ctx->device));
+    Buf dp, ds, dout, dh;
+    int32_t s = MGFB_OK;
+    auto body = [&]() -> int32_t {
+        TRY(ensure(ctx, dp, (size_t)n * 24)); TRY(ensure(ctx, ds, (size_t)n * sizeof(mgfb_shape)));
+        TRY(ensure(ctx, dout, (size_t)n * sizeof(mgfb_intersection))); TRY(ensure(ctx, dh, (size_t)n * 4));
+        CU(cudaMemcpyAsync(dp.p, particles, (size_t)n * 24, cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaMemcpyAsync(ds.p, shapes, (size_t)n * sizeof(mgfb_shape), cudaMemcpyHostToDevice, ctx->stream));
+        k_intersections_batch<<<(n + 127) / 128, 128, 0, ctx->stream>>>(particle_kind, dp.as<float>(), ds.as<mgfb_shape>(), n,
+                                                                        dout.as<mgfb_intersection>(), dh.as<unsigned>());
+        CU(cudaGetLastError());
+        CU(cudaMemcpyAsync(out, dout.p, (size_t)n * sizeof(mgfb_intersection), cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaMemcpyAsync(hit, dh.p, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        ctx->launches += 1;
+        return MGFB_OK;
+    };
+    s = body();
+    release(dp); release(ds); release(dout); release(dh);
+    return s;
+}

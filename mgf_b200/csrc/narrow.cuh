@@ -157,6 +157,37 @@ HD bool ray_capsule(V3 p, V3 d, V3 ca, V3 cd, float cr, float* tout, V3* pout) {
     return true;
 }
 
+// collision.rs:169-184
+HD bool ray_plane(V3 p, V3 d, Pln pl, float DT, float* tout, V3* pout) {
+    float denom = dot3(pl.n, d);
+    if (denom == 0.0f) return false;
+    float t = (pl.d - dot3(pl.n, p)) / denom;
+    if (t <= 0.0f || t > DT) return false;
+    *tout = t; *pout = p + d * t;
+    return true;
+}
+// collision.rs:202-236
+HD bool ray_aabb(V3 p, V3 d, V3 bc, V3 br, float DT, float* tout, V3* pout) {
+    float t_min = 0.0f, t_max = __builtin_huge_valf();
+    float ps[3] = {p.x, p.y, p.z}, ds[3] = {d.x, d.y, d.z}, cs[3] = {bc.x, bc.y, bc.z}, rs[3] = {br.x, br.y, br.z};
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        if (fabsf(ds[k]) < MGFB_EPS) {
+            if (fabsf(ps[k] - cs[k]) > rs[k]) return false;
+        } else {
+            float ood = 1.0f / ds[k];
+            float t1 = (cs[k] - rs[k] - ps[k]) * ood;
+            float t2 = (cs[k] + rs[k] - ps[k]) * ood;
+            if (t1 > t2) { t_min = fmaxf(t_min, t2); t_max = fminf(t_max, t1); }
+            else { t_min = fmaxf(t_min, t1); t_max = fminf(t_max, t2); }
+            if (t_min > t_max) return false;
+        }
+    }
+    if (t_min > DT) return false;
+    *tout = t_min; *pout = p + d * t_min;
+    return true;
+}
+
 // ---- Plane x Moving<Sphere> (collision.rs:521-553) ----
 HD bool plane_msphere(Pln pl, Sph s, V3 v, Hit* out) {
     float dist = dot3(pl.n, s.c) - pl.d;

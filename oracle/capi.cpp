@@ -26,6 +26,37 @@ void put_contact(mgfb_contact* o, const Contact& c) { put3(o->a, c.a); put3(o->b
 
 extern "C" {
 
+// Same contract as mgfb_intersections_batch (include/mgfb.h): Intersects<RHS> for Ray / Segment (collision.rs:163-373).
+int32_t mgfo_intersections_batch(uint32_t particle_kind, const float* particles, const mgfb_shape* shapes, uint32_t n,
+                                 mgfb_intersection* out, uint32_t* hit) {
+    for (uint32_t i = 0; i < n; ++i) {
+        const float* q = particles + 6 * i;
+        const bool seg = particle_kind == MGFB_SEGMENT;
+        // geom.rs:818-851: Ray{p, d}: pos = p, dir = d, DT = inf; Segment{a, b}: pos = a, dir = b - a, DT = 1
+        Ray r{p3(q), seg ? p3(q + 3) - p3(q) : p3(q + 3)};
+        const float DT = seg ? 1.0f : INF;
+        const mgfb_shape& S = shapes[i];
+        Intersection it{v3(0, 0, 0), 0.0f};
+        bool ok = false;
+        switch (S.kind) {
+            case MGFB_PLANE: ok = intersection(r, to_plane_s(S), &it, DT); break;
+            case MGFB_TRIANGLE: ok = intersection_poly(r, to_tri(S), &it, DT); break;
+            case MGFB_RECTANGLE: ok = intersection_poly(r, to_rect(S), &it, DT); break;
+            case MGFB_AABB: ok = intersection(r, AABB{p3(S.p), p3(S.p + 3)}, &it, DT); break;
+            case MGFB_OBB: ok = intersection(r, OBB{p3(S.p), Quat{S.p[6], p3(S.p + 7)}, p3(S.p + 3)}, &it, DT, seg); break;
+            case MGFB_SPHERE:   // Moving<Sphere> (v != 0) is the capsule swept by the sphere (collision.rs:361-373)
+                if (S.v[0] != 0.0f || S.v[1] != 0.0f || S.v[2] != 0.0f) ok = intersection(r, Capsule{p3(S.p), p3(S.v), S.p[3]}, &it, DT);
+                else ok = intersection(r, to_sphere(S), &it, DT);
+                break;
+            case MGFB_CAPSULE: ok = intersection(r, to_capsule(S), &it, DT); break;
+            default: return 1;
+        }
+        hit[i] = ok ? 1u : 0u;
+        if (ok) { put3(out[i].p, it.p); out[i].t = it.t; } else { out[i].p[0] = out[i].p[1] = out[i].p[2] = 0.0f; out[i].t = 0.0f; }
+    }
+    return 0;
+}
+
 // Same contract as mgfb_contacts_batch (include/mgfb.h).
 int32_t mgfo_contacts_batch(uint32_t pair_kind, const mgfb_shape* recv, const mgfb_shape* arg, uint32_t n, mgfb_contact* out,
                             mgfb_local_contact* out_local, uint32_t* counts) {

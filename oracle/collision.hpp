@@ -71,6 +71,21 @@ inline bool intersection(const Ray& r, const AABB& a, Intersection* out, float D
     *out = {p + d * t_min, t_min};
     return true;
 }
+// collision.rs:186-200: Particle x Polygon = plane hit that lies inside the face
+template <class Poly>
+inline bool intersection_poly(const Ray& r, const Poly& poly, Intersection* out, float DT = INF) {
+    Intersection i;
+    if (intersection(r, to_plane(poly), &i, DT) && contains(poly, i.p)) { *out = i; return true; }
+    return false;
+}
+// collision.rs:238-247 + geom.rs:829-836 (Ray) / :853-861 (Segment): rotate the particle around the box centre,
+// then the AABB test.  `segment`: the rotated direction is re-derived as b' - a' (geom.rs:856-858, :848-850).
+inline bool intersection(const Ray& r, const OBB& o, Intersection* out, float DT, bool segment) {
+    Vec3 p = rotate_vector(o.q, r.p - o.c) + o.c;
+    Vec3 d = rotate_vector(o.q, r.d);
+    if (segment) { Vec3 b = p + d; d = b - p; }
+    return intersection(Ray{p, d}, AABB{o.c, o.r}, out, DT);
+}
 // collision.rs:249-273
 inline bool intersection(const Ray& r, const Sphere& s, Intersection* out, float DT = INF) {
     Vec3 p = r.p, d = r.d;

@@ -30,6 +30,8 @@ def load():
     if not os.path.exists(SO) or any(os.path.getmtime(s) > os.path.getmtime(SO) for s in srcs):
         build()
     lib = C.CDLL(SO)
+    lib.mgfo_intersections_batch.restype = C.c_int32
+    lib.mgfo_intersections_batch.argtypes = [C.c_uint32, _P, _P, C.c_uint32, _P, _P]
     lib.mgfo_contacts_batch.restype = C.c_int32
     lib.mgfo_contacts_batch.argtypes = [C.c_uint32, _P, _P, C.c_uint32, _P, _P, _P]
     lib.mgfo_world_create.restype = _P
@@ -100,6 +102,17 @@ def contacts_batch(pair_kind, recv, arg, want_local=False):
     st = lib.mgfo_contacts_batch(pair_kind, L.ptr(recv), L.ptr(arg), n, L.ptr(out), L.ptr(loc), L.ptr(counts))
     assert st == 0
     return (out, counts, loc) if want_local else (out, counts)
+
+
+def intersections_batch(particle_kind, particles, shapes):
+    lib = load()
+    particles = np.ascontiguousarray(particles, dtype=np.float32).reshape(-1, 6)
+    shapes = np.ascontiguousarray(shapes, dtype=L.SHAPE_DTYPE)
+    n = len(shapes)
+    out = np.zeros(n, dtype=L.INTERSECTION_DTYPE); hit = np.zeros(n, np.uint32)
+    st = lib.mgfo_intersections_batch(particle_kind, L.ptr(particles), L.ptr(shapes), n, L.ptr(out), L.ptr(hit))
+    assert st == 0
+    return out, hit
 
 
 class OracleWorld:
