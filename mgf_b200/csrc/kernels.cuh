@@ -1249,7 +1249,9 @@ __device__ unsigned long long g_df_prof[8];   // cycles: fetch, inbox poll, comp
 #endif
 struct DfRow { RowData d; float4 i0, i1, i2, i3, i4; unsigned na, nb, row; float imp; bool valid; };
 #define MGFB_DF_MAX_PHASES 64
-#define MGFB_DF_THREADS 256
+#ifndef MGFB_DF_THREADS
+#define MGFB_DF_THREADS 384   /* 12 warps/SM: measured best at 100 k .. 500 k bodies (256: -3 %, 448 spills) */
+#endif
 template <bool TILED>
 __global__ void __launch_bounds__(MGFB_DF_THREADS, 1) k_solve_df(ConstraintRows R, DfArrays D, BodyVel* vel, const unsigned* __restrict__ phase_start,
                                                                 unsigned iters, unsigned epoch, Counters* ctr, TileLink T) {
