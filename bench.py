@@ -128,10 +128,11 @@ def run_reference(args, rank):
         workload = WORKLOAD
     else:   # the same one-box world the N-GPU arm tiles, whole, on one core
         from mgf_b200 import scenes
-        tiles = [scenes.tiled_pile(args.gpus, t) for t in range(args.gpus)]
+        tiles = [scenes.tiled_pile(args.gpus, t, nz=50 * args.bodies_per_gpu // 100000) for t in range(args.gpus)]
         bodies = tuple(np.concatenate([t[0][k] for t in tiles]) for k in range(5))
         terrain = tiles[0][2]; iters = 20
-        workload = f"pile of {args.gpus} x 100000 spheres (50x40x50 lattice per tile, same radius/spacing/material as C2pile), one box"
+        workload = (f"pile of {args.gpus} x {args.bodies_per_gpu} spheres (50x40x{50 * args.bodies_per_gpu // 100000} lattice per tile, same "
+                    "radius/spacing/material as C2pile), one box")
     w = oracle_lib.OracleWorld()
     w.add_bodies(*bodies); w.set_terrain(*terrain)
     dt = np.float32(1.0 / 60.0)
@@ -173,6 +174,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="mgf_b200", choices=["mgf_b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--bodies-per-gpu", type=int, default=100000,
+                    help="N > 1 only: 100000 (default, 50x40x50 per tile) or 250000 (50x40x125 per tile: 8 GPUs = the 2 M-sphere C4 scene)")
     ap.add_argument("--schedule", default="dataflow", choices=["dataflow", "phases"],
                     help="solver schedule (include/mgfb.h mgfb_solver_schedule); tiled worlds always use phases")
     args = ap.parse_args()
@@ -205,13 +208,14 @@ def main():
         # bodies and boundary velocities cross NVLink inside the kernels (csrc/tile.cuh); torch.distributed
         # only swaps the tiles' memory descriptors once, here.
         from mgf_b200 import scenes, tiling
-        bodies, ids, terrain = scenes.tiled_pile(world, rank)
+        nz = 50 * args.bodies_per_gpu // 100000
+        bodies, ids, terrain = scenes.tiled_pile(world, rank, nz=nz)
         iters = 20
         tw = tiling.TiledWorld(rank, world, device=local_rank, solver_schedule=0 if args.schedule == "dataflow" else 1)
         tw.add_owned(ids, *bodies); tw.set_terrain(*terrain)
-        tw.connect(tiling.all_gather_bytes, ghost_capacity=32768)
+        tw.connect(tiling.all_gather_bytes, ghost_capacity=32768 * max(1, nz // 50))
         g = tw.world
-        workload = f"pile of {world} x 100000 spheres (50x40x50 lattice per tile, same radius/spacing/material as C2pile), one box"
+        workload = f"pile of {world} x {len(bodies[0])} spheres (50x40x{nz} lattice per tile, same radius/spacing/material as C2pile), one box"
         parallelism = (f"{world} slabs along x, one per GPU; ghost bodies once per step through NVLink peer memory; "
                        + ("solver: the constraint chains of boundary bodies continue on the neighbour GPU, every hand-over one 32-byte "
                           "peer store from inside the solver kernel (no exchange phase, no grid barrier)" if args.schedule == "dataflow"
