@@ -163,6 +163,35 @@ typedef struct mgfb_intersection { float p[3]; float t; } mgfb_intersection;
 int32_t mgfb_intersections_batch(mgfb_ctx* ctx, uint32_t particle_kind, const float* particles /* n*6 */, const mgfb_shape* shapes /* n */,
                                  uint32_t n, mgfb_intersection* out /* n */, uint32_t* hit /* n */);
 
+/* ---------------- BVH<AABB, V> (src/bvh.rs:86-369), V = u32 ----------------
+ * The tree callers outside World::step use (ray picking, Compound, user code).  The reference grows it one insert
+ * at a time; here the leaf set lives on the device and the tree over it is rebuilt there (Morton order, implicit
+ * binary tree) before the first query after a change.  Preserved: WHICH leaves a query / raytrace reports (exactly
+ * the leaves whose own box passes the reference's test; the reference may additionally prune a leaf that merely
+ * touches, because its parents are rounded unions, bounds.rs:113-130).  Not preserved: the callback order (here
+ * ascending Morton order of the leaf centres, deterministic) and the numeric value of the indices insert returns
+ * (stable leaf handles, reused last-freed-first like pool.rs; the reference numbers its internal nodes too).
+ * Boxes are 6 floats: centre[3], half extents[3] (geom.rs:257 AABB{c, r}). */
+typedef struct mgfb_bvh mgfb_bvh;
+int32_t mgfb_bvh_create(mgfb_ctx* ctx, mgfb_bvh** out);                                   /* BVH::new        bvh.rs:88  */
+void mgfb_bvh_destroy(mgfb_bvh* bvh);
+/* BVH::insert(&key, value) -> index, n at a time (bvh.rs:125).  Half extents must be >= 0 (bounds.rs:125-127). */
+int32_t mgfb_bvh_insert(mgfb_bvh* bvh, const float* boxes /* n*6 */, const uint32_t* values /* n */, uint32_t n, uint32_t* indices /* n */);
+/* BVH::remove(index) (bvh.rs:225); an index that holds no leaf is MGFB_ERR_INVALID_ARG (the reference panics, pool.rs:100). */
+int32_t mgfb_bvh_remove(mgfb_bvh* bvh, const uint32_t* indices, uint32_t n);
+/* Index<usize> / get_leaf (bvh.rs:270, :483): the leaf's box and value; either output may be NULL. */
+int32_t mgfb_bvh_get(const mgfb_bvh* bvh, uint32_t index, float* box /* 6 */, uint32_t* value);
+int32_t mgfb_bvh_len(const mgfb_bvh* bvh, uint32_t* n);
+/* BVH::query(&arg, cb) for nq argument boxes (bvh.rs:283-310): values[offsets[q] .. offsets[q+1]) are the values of the
+ * leaves overlapping boxes[q] (AABB::overlaps, collision.rs:22-29, closed).  *total = all results; when it exceeds
+ * `capacity` nothing is written to `values` and the call returns MGFB_ERR_CAPACITY (offsets and *total are valid). */
+int32_t mgfb_bvh_query_batch(mgfb_bvh* bvh, const float* boxes /* nq*6 */, uint32_t nq, uint32_t* offsets /* nq+1 */, uint32_t* values,
+                             uint32_t capacity, uint32_t* total);
+/* BVH::raytrace(&arg, cb) for nq Rays / Segments (bvh.rs:340-369): every leaf whose box the particle intersects
+ * (collision.rs:202-236), with the Intersection the callback would receive. */
+int32_t mgfb_bvh_raytrace_batch(mgfb_bvh* bvh, uint32_t particle_kind, const float* particles /* nq*6 */, uint32_t nq, uint32_t* offsets /* nq+1 */,
+                                uint32_t* values, mgfb_intersection* hits, uint32_t capacity, uint32_t* total);
+
 /* ---------------- discrete path: GJK + EPA (simplex.rs:172-553) ---------------- */
 /* `a[i].contacts(&b[i], cb)` for static convex pairs through the generic impl for Convex + Volumetric shapes
  * (collision.rs:497-519): GJK seeded along +-y (simplex.rs:172-200), then EPA (simplex.rs:456-553, at most

@@ -96,6 +96,14 @@ SYMBOLS = [
     ("mgfb_step_totals", C.c_int32, [_P] + [C.POINTER(C.c_uint64)] * 5 + [C.c_int32]),
     ("mgfb_device_view_get", C.c_int32, [_P, C.POINTER(DeviceView)]),
     ("mgfb_intersections_batch", C.c_int32, [_P, C.c_uint32, _P, _P, C.c_uint32, _P, _P]),
+    ("mgfb_bvh_create", C.c_int32, [_P, C.POINTER(_P)]),
+    ("mgfb_bvh_destroy", None, [_P]),
+    ("mgfb_bvh_insert", C.c_int32, [_P, _P, _P, C.c_uint32, _P]),
+    ("mgfb_bvh_remove", C.c_int32, [_P, _P, C.c_uint32]),
+    ("mgfb_bvh_get", C.c_int32, [_P, C.c_uint32, _P, C.POINTER(C.c_uint32)]),
+    ("mgfb_bvh_len", C.c_int32, [_P, C.POINTER(C.c_uint32)]),
+    ("mgfb_bvh_query_batch", C.c_int32, [_P, _P, C.c_uint32, _P, _P, C.c_uint32, C.POINTER(C.c_uint32)]),
+    ("mgfb_bvh_raytrace_batch", C.c_int32, [_P, C.c_uint32, _P, C.c_uint32, _P, _P, _P, C.c_uint32, C.POINTER(C.c_uint32)]),
     ("mgfb_gjk_batch", C.c_int32, [_P, _P, _P, C.c_uint32, _P, _P, _P]),
     ("mgfb_separation_batch", C.c_int32, [_P, _P, _P, C.c_uint32, _P, _P]),
     ("mgfb_bodies_set_gid", C.c_int32, [_P, C.c_uint32, C.c_uint32, _P]),

@@ -152,6 +152,79 @@ def contacts_batch(ctx, pair_kind, recv, arg, want_local=False):
     return (out, counts, loc) if want_local else (out, counts)
 
 
+class BVH:
+    """src/bvh.rs BVH<AABB, u32>: insert / remove / get / len / query / raytrace, batched (include/mgfb.h).
+    Boxes are (n, 6) f32 rows (centre, half extents)."""
+
+    def __init__(self, ctx):
+        self.ctx = ctx
+        h = C.c_void_p()
+        ctx.check(ctx.lib.mgfb_bvh_create(ctx.h, C.byref(h)))
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None) and getattr(self.ctx, "h", None):
+            self.ctx.lib.mgfb_bvh_destroy(self.h)
+        self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:   # noqa: BLE001
+            pass
+
+    def __len__(self):
+        n = C.c_uint32()
+        self.ctx.check(self.ctx.lib.mgfb_bvh_len(self.h, C.byref(n)))
+        return n.value
+
+    def insert(self, boxes, values):
+        boxes = np.ascontiguousarray(boxes, dtype=np.float32).reshape(-1, 6)
+        values = np.ascontiguousarray(values, dtype=np.uint32).reshape(-1)
+        assert len(values) == len(boxes)
+        idx = np.zeros(len(boxes), np.uint32)
+        self.ctx.check(self.ctx.lib.mgfb_bvh_insert(self.h, L.ptr(boxes), L.ptr(values), len(boxes), L.ptr(idx)))
+        return idx
+
+    def remove(self, indices):
+        indices = np.ascontiguousarray(indices, dtype=np.uint32).reshape(-1)
+        self.ctx.check(self.ctx.lib.mgfb_bvh_remove(self.h, L.ptr(indices), len(indices)))
+
+    def get(self, index):
+        box = np.zeros(6, np.float32); val = C.c_uint32()
+        self.ctx.check(self.ctx.lib.mgfb_bvh_get(self.h, int(index), L.ptr(box), C.byref(val)))
+        return box, val.value
+
+    def _batch(self, call, nq, want_hits):
+        offsets = np.zeros(nq + 1, np.uint32); total = C.c_uint32()
+        cap = max(1024, 16 * nq)
+        for _ in range(2):
+            values = np.zeros(cap, np.uint32)
+            hits = np.zeros(cap, dtype=L.INTERSECTION_DTYPE) if want_hits else None
+            st = call(offsets, values, hits, cap, total)
+            if st == L.ERR_CAPACITY and total.value > cap:
+                cap = total.value
+                continue
+            self.ctx.check(st)
+            break
+        n = total.value
+        return (offsets, values[:n], hits[:n]) if want_hits else (offsets, values[:n])
+
+    def query(self, boxes):
+        """BVH::query for every row of `boxes`: (offsets[nq+1], values) -- CSR of the overlapping leaves' values."""
+        boxes = np.ascontiguousarray(boxes, dtype=np.float32).reshape(-1, 6)
+        lib = self.ctx.lib
+        return self._batch(lambda off, val, hits, cap, tot: lib.mgfb_bvh_query_batch(self.h, L.ptr(boxes), len(boxes), L.ptr(off), L.ptr(val), cap,
+                                                                                       C.byref(tot)), len(boxes), False)
+
+    def raytrace(self, particle_kind, particles):
+        """BVH::raytrace for every Ray / Segment: (offsets[nq+1], values, intersections)."""
+        particles = np.ascontiguousarray(particles, dtype=np.float32).reshape(-1, 6)
+        lib = self.ctx.lib
+        return self._batch(lambda off, val, hits, cap, tot: lib.mgfb_bvh_raytrace_batch(self.h, particle_kind, L.ptr(particles), len(particles), L.ptr(off),
+                                                                                          L.ptr(val), L.ptr(hits), cap, C.byref(tot)), len(particles), True)
+
+
 class World:
     """mgf_demo/world.rs World restricted to the physics: bodies + terrain + step."""
 

@@ -1157,3 +1157,4 @@ int32_t mgfb_device_view_get(mgfb_ctx* ctx, mgfb_device_view* out) {
 
 #include "batch.cuh"
 #include "gjk.cuh"
+#include "bvh.cuh"

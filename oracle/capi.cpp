@@ -26,6 +26,30 @@ void put_contact(mgfb_contact* o, const Contact& c) { put3(o->a, c.a); put3(o->b
 
 extern "C" {
 
+// ---- BVH<AABB, u32> exactly as src/bvh.rs builds it (incremental insert / remove / balance): the checker of mgfb_bvh_*
+void* mgfo_bvh_create() { return new BVH<uint32_t>(); }
+void mgfo_bvh_destroy(void* h) { delete static_cast<BVH<uint32_t>*>(h); }
+uint32_t mgfo_bvh_insert(void* h, const float* box, uint32_t value) {
+    return (uint32_t)static_cast<BVH<uint32_t>*>(h)->insert(AABB{p3(box), p3(box + 3)}, value);
+}
+void mgfo_bvh_remove(void* h, uint32_t index) { static_cast<BVH<uint32_t>*>(h)->remove(index); }
+// values in the reference's DFS callback order; returns the number of callbacks (may exceed cap)
+uint32_t mgfo_bvh_query(void* h, const float* box, uint32_t* out, uint32_t cap) {
+    uint32_t n = 0;
+    static_cast<BVH<uint32_t>*>(h)->query(AABB{p3(box), p3(box + 3)}, [&](const uint32_t& v) { if (n < cap) out[n] = v; ++n; });
+    return n;
+}
+uint32_t mgfo_bvh_raytrace(void* h, uint32_t particle_kind, const float* q, uint32_t* out, mgfb_intersection* hits, uint32_t cap) {
+    const bool seg = particle_kind == MGFB_SEGMENT;
+    Ray r{p3(q), seg ? p3(q + 3) - p3(q) : p3(q + 3)};
+    uint32_t n = 0;
+    static_cast<BVH<uint32_t>*>(h)->raytrace(r, [&](const uint32_t& v, const Intersection& it) {
+        if (n < cap) { out[n] = v; put3(hits[n].p, it.p); hits[n].t = it.t; }
+        ++n;
+    }, seg ? 1.0f : INF);
+    return n;
+}
+
 // Same contract as mgfb_intersections_batch (include/mgfb.h): Intersects<RHS> for Ray / Segment (collision.rs:163-373).
 int32_t mgfo_intersections_batch(uint32_t particle_kind, const float* particles, const mgfb_shape* shapes, uint32_t n,
                                  mgfb_intersection* out, uint32_t* hit) {

@@ -30,6 +30,12 @@ def load():
     if not os.path.exists(SO) or any(os.path.getmtime(s) > os.path.getmtime(SO) for s in srcs):
         build()
     lib = C.CDLL(SO)
+    lib.mgfo_bvh_create.restype = _P; lib.mgfo_bvh_create.argtypes = []
+    lib.mgfo_bvh_destroy.restype = None; lib.mgfo_bvh_destroy.argtypes = [_P]
+    lib.mgfo_bvh_insert.restype = C.c_uint32; lib.mgfo_bvh_insert.argtypes = [_P, _P, C.c_uint32]
+    lib.mgfo_bvh_remove.restype = None; lib.mgfo_bvh_remove.argtypes = [_P, C.c_uint32]
+    lib.mgfo_bvh_query.restype = C.c_uint32; lib.mgfo_bvh_query.argtypes = [_P, _P, _P, C.c_uint32]
+    lib.mgfo_bvh_raytrace.restype = C.c_uint32; lib.mgfo_bvh_raytrace.argtypes = [_P, C.c_uint32, _P, _P, _P, C.c_uint32]
     lib.mgfo_intersections_batch.restype = C.c_int32
     lib.mgfo_intersections_batch.argtypes = [C.c_uint32, _P, _P, C.c_uint32, _P, _P]
     lib.mgfo_contacts_batch.restype = C.c_int32
@@ -113,6 +119,40 @@ def intersections_batch(particle_kind, particles, shapes):
     st = lib.mgfo_intersections_batch(particle_kind, L.ptr(particles), L.ptr(shapes), n, L.ptr(out), L.ptr(hit))
     assert st == 0
     return out, hit
+
+
+class OracleBVH:
+    """src/bvh.rs BVH<AABB, u32> on the CPU restatement (incremental insert / remove / balance)."""
+
+    def __init__(self):
+        self.lib = load()
+        self.h = self.lib.mgfo_bvh_create()
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.lib.mgfo_bvh_destroy(self.h)
+            self.h = None
+
+    def insert(self, box, value):
+        box = np.ascontiguousarray(box, dtype=np.float32)
+        return self.lib.mgfo_bvh_insert(self.h, L.ptr(box), int(value))
+
+    def remove(self, index):
+        self.lib.mgfo_bvh_remove(self.h, int(index))
+
+    def query(self, box, cap=65536):
+        box = np.ascontiguousarray(box, dtype=np.float32)
+        out = np.zeros(cap, np.uint32)
+        n = self.lib.mgfo_bvh_query(self.h, L.ptr(box), L.ptr(out), cap)
+        assert n <= cap
+        return out[:n]
+
+    def raytrace(self, kind, particle, cap=65536):
+        particle = np.ascontiguousarray(particle, dtype=np.float32)
+        out = np.zeros(cap, np.uint32); hits = np.zeros(cap, dtype=L.INTERSECTION_DTYPE)
+        n = self.lib.mgfo_bvh_raytrace(self.h, kind, L.ptr(particle), L.ptr(out), L.ptr(hits), cap)
+        assert n <= cap
+        return out[:n], hits[:n]
 
 
 class OracleWorld:
