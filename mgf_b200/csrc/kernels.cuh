@@ -1128,8 +1128,9 @@ __global__ void __launch_bounds__(MGFB_SOLVE_THREADS, 1) k_solve(ConstraintRows 
 // (never dependent on each other), polls their inboxes with two fully coalesced 1 KB loads until
 // every tag shows the current iteration, updates, and pushes the results to the successors'
 // inboxes.  World inverse inertia and inverse mass are immutable during the solve and are copied
-// into the row when it is built, so everything a row reads is a coalesced stream prefetched one
-// visit ahead.  The sequential sweep over the rows in row order is the unique execution these
+// into the row when it is built, so everything a row reads is a coalesced stream, loaded at the
+// start of the visit together with the first look at the inboxes (no register prefetch: measured
+// faster, the freed registers buy more resident warps).  The sequential sweep over the rows in row order is the unique execution these
 // waits allow: the result is bit-identical to k_solve and to the reference's loop over that
 // order.  Progress: a warp visits its warp-rows in increasing (iteration, row) order and all warps
 // are co-resident (cooperative launch), so the smallest unfinished warp-row always has its
@@ -1250,7 +1251,7 @@ __device__ unsigned long long g_df_prof[8];   // cycles: fetch, inbox poll, comp
 struct DfRow { RowData d; float4 i0, i1, i2, i3, i4; unsigned na, nb, row; float imp; bool valid; };
 #define MGFB_DF_MAX_PHASES 64
 #ifndef MGFB_DF_THREADS
-#define MGFB_DF_THREADS 384   /* 12 warps/SM: measured best at 100 k .. 500 k bodies (256: -3 %, 448 spills) */
+#define MGFB_DF_THREADS 320   /* 10 warps/SM: measured best at 100 k .. 500 k bodies (256: +20 %, 384: +6 % solve time) */
 #endif
 template <bool TILED>
 __global__ void __launch_bounds__(MGFB_DF_THREADS, 1) k_solve_df(ConstraintRows R, DfArrays D, BodyVel* vel, const unsigned* __restrict__ phase_start,
@@ -1308,17 +1309,19 @@ __global__ void __launch_bounds__(MGFB_DF_THREADS, 1) k_solve_df(ConstraintRows 
 #ifdef MGFB_DF_PROFILE
     unsigned long long prof[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 #endif
-    DfRow nxt = fetch(wr, p_next);
+    float carried_imp = 0.0f; bool have_carried = false;
     for (;;) {
         DF_T(t0);
-        DfRow cur = nxt;
+        // no register prefetch: the row is loaded at the start of its visit, together with the first look at its
+        // inboxes (both are L2 round trips, and most visits wait for an input anyway) -- 48 registers less per
+        // thread, so more warps per SM hide each other's latency
+        DfRow cur = fetch(wr, p_next);
+        if (have_carried) cur.imp = carried_imp;
         const unsigned row = cur.row;
-        // prefetch this warp's next warp-row (immutable but for its impulse, last written by this very thread)
         unsigned wr_n = wr + nW, it_n = it;
         if (wr_n >= nwr) { wr_n = gw; it_n = it + 1; p_next = 0; }
         const bool more = it_n < iters;
         const bool same_rows = (wr_n == wr);   // this warp owns one warp-row: its impulse is carried in registers
-        if (more) nxt = fetch(wr_n, p_next);
         const int a = cur.d.ab.x, b = cur.d.ab.y;
         const bool needA = cur.valid && a >= 0, needB = cur.valid && b >= 0;
         const unsigned tag = epoch + it + 1u;
@@ -1375,7 +1378,7 @@ __global__ void __launch_bounds__(MGFB_DF_THREADS, 1) k_solve_df(ConstraintRows 
                 lambda = imp - prev;
                 apply_impulse(n * lambda, ra, rb, ima, imb, IA, IB, va, oa, vb, ob);
                 if (c == 0) {
-                    if (same_rows) nxt.imp = imp;
+                    if (same_rows) { carried_imp = imp; have_carried = true; }
                     if (!same_rows || it + 1 == iters) __stcg(&R.impulse[row], imp);
                 }
                 else { unsigned e = row * 3 + (c - 1); __stcg(&R.xtm[e], make_float4(tm0, tm1, imp, 0.0f)); }
