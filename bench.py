@@ -292,14 +292,14 @@ def main():
                 else "k_solve (persistent cooperative sequential-impulse solver, one grid barrier per colour)", "bound": "hbm", "achieved": achieved, "peak": peak,
                 "unit": "GB/s", "frac": achieved / peak,
                 # dram__bytes_read.sum + dram__bytes_write.sum of one k_solve_df launch of this workload, `ncu --set full`
-                # (profiles/r01_v3_k_solve_df_raw.csv; ncu starts every replay pass from a flushed L2)
-                "traffic": 308.1e6 if (dataflow and world == 1) else None, "traffic_unit": "bytes per launch (ncu, cold L2)",
+                # (profiles/r01_v4_k_solve_df_raw.csv; ncu starts every replay pass from a flushed L2)
+                "traffic": 145.2e6 if (dataflow and world == 1) else None, "traffic_unit": "bytes per launch (ncu, cold L2)",
                 "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": ALGO_BYTES_PER_CONSTRAINT_ITER * units / len(solve_ms),
                 "avg_launch_ms": sum(solve_ms) / len(solve_ms), "share_of_step": sum(solve_ms) / total_ms,
                 "note": "268 B per constraint-iteration x constraints x 20 iterations per launch; the rows (~70 MB) are "
                         "L2-resident, so the kernel is bound by the latency of its 180 chain hand-overs, not by HBM bytes "
-                        "(profiles/r01_summary_v3.md)"}
+                        "(profiles/r01_summary_v4.md)"}
 
     # ---- CPU baseline (rank 0, N=1): bounded sample of the same workload on the oracle
     cpu = None
