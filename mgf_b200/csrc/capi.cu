@@ -576,7 +576,7 @@ int32_t mgfb_ctx_create(const mgfb_config* cfg, mgfb_ctx** out) {
     ctx->max_ctas = (int)ctx->cfg.max_cooperative_ctas;
     if (ctx->cfg.tile_timeout_ms) ctx->tile_timeout_ns = (unsigned long long)ctx->cfg.tile_timeout_ms * 1000000ULL;
     ctx->coop_order = coop_blocks(ctx, k_order, MGFB_THREADS, 2);
-    ctx->coop_colour = coop_blocks(ctx, k_colour_df, MGFB_THREADS, 4);
+    ctx->coop_colour = coop_blocks(ctx, k_colour_df, MGFB_THREADS, 8);
     ctx->coop_solve = std::min(coop_blocks(ctx, k_solve<false>, MGFB_SOLVE_THREADS, 1), coop_blocks(ctx, k_solve<true>, MGFB_SOLVE_THREADS, 1));
     ctx->coop_df = std::min(coop_blocks(ctx, k_solve_df<false>, MGFB_DF_THREADS, 1), coop_blocks(ctx, k_solve_df<true>, MGFB_DF_THREADS, 1));
     int32_t s = grow_bodies(ctx, std::max(ctx->cfg.initial_body_capacity, 1024u));

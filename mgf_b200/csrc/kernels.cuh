@@ -683,7 +683,12 @@ __device__ __forceinline__ void st_relaxed_u64(unsigned long long* p, unsigned l
 // Persistent, all threads co-resident (cooperative launch).  A thread owns constraints tid, tid+nth, ...
 // and keeps sweeping the ones not yet coloured; it never blocks on one, so there is no ordering
 // requirement: the uncoloured constraint with the largest key always has both masks.
-#define COLOUR_CACHED 8   // constraints per thread whose endpoints and links live in registers
+#ifndef COLOUR_CACHED
+#define COLOUR_CACHED 4   // constraints per thread whose endpoints and links live in registers (4 x 4 CTAs/SM measured best)
+#endif
+#ifndef COLOUR_CTAS
+#define COLOUR_CTAS 4     // resident CTAs per SM the register budget is sized for
+#endif
 __device__ __forceinline__ unsigned colour_one(const OrderView& O, const ColourView& V, unsigned k, int a, int b, unsigned na, unsigned nb,
                                                unsigned long long ma, unsigned long long mb, Counters* ctr) {
     unsigned long long fr = ~(ma | mb);   // bit 63 is never free
@@ -710,7 +715,7 @@ __device__ __forceinline__ unsigned colour_one(const OrderView& O, const ColourV
 // requirement: the uncoloured constraint with the largest key always has both masks.  One sweep
 // over the (register-cached) first COLOUR_CACHED constraints is a single batch of independent
 // 8-byte L2 loads, so a colour travels one link of a chain per L2 round trip.
-__global__ void __launch_bounds__(MGFB_THREADS) k_colour_df(OrderView O, ColourView V, const unsigned* m_ptr, unsigned m_host, Counters* ctr) {
+__global__ void __launch_bounds__(MGFB_THREADS, COLOUR_CTAS) k_colour_df(OrderView O, ColourView V, const unsigned* m_ptr, unsigned m_host, Counters* ctr) {
     if (ctr->overflow | ctr->nan_bounds) return;
     const unsigned m = m_ptr ? *m_ptr : m_host;
     const unsigned tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
@@ -1279,7 +1284,8 @@ __global__ void __launch_bounds__(MGFB_DF_THREADS, 1) k_solve_df(ConstraintRows 
         f.row = row;
         f.valid = row < s_row0[p + 1];
         if (f.valid) {
-            f.d = load_row(R, row);
+            f.d.ab = make_int2(0, 0);   // not streamed: the links say which sides exist, the body index is only needed for the final store
+            f.d.n = R.n[row]; f.d.t0 = R.t0[row]; f.d.t1 = R.t1[row]; f.d.ra = R.ra[row]; f.d.rb = R.rb[row];
             f.i0 = D.ia[row]; f.i1 = D.ia[rc + row]; f.i2 = D.ia[2 * rc + row]; f.i3 = D.ia[3 * rc + row]; f.i4 = D.ia[4 * rc + row];
             f.na = D.next[row]; f.nb = D.next[rc + row];
             f.imp = __ldcg(&R.impulse[row]);
@@ -1322,8 +1328,7 @@ __global__ void __launch_bounds__(MGFB_DF_THREADS, 1) k_solve_df(ConstraintRows 
         if (wr_n >= nwr) { wr_n = gw; it_n = it + 1; p_next = 0; }
         const bool more = it_n < iters;
         const bool same_rows = (wr_n == wr);   // this warp owns one warp-row: its impulse is carried in registers
-        const int a = cur.d.ab.x, b = cur.d.ab.y;
-        const bool needA = cur.valid && a >= 0, needB = cur.valid && b >= 0;
+        const bool needA = cur.valid && cur.na != DF_NONE, needB = cur.valid && cur.nb != DF_NONE;
         const unsigned tag = epoch + it + 1u;
         Inbox sa, sb;
         sa.lo = sa.hi = sb.lo = sb.hi = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
@@ -1384,6 +1389,8 @@ __global__ void __launch_bounds__(MGFB_DF_THREADS, 1) k_solve_df(ConstraintRows 
                 else { unsigned e = row * 3 + (c - 1); __stcg(&R.xtm[e], make_float4(tm0, tm1, imp, 0.0f)); }
             }
             const bool last_it = it + 1 == iters;
+            int a = 0, b = 0;
+            if (last_it) { int2 ab = R.ab[row]; a = ab.x; b = ab.y; }
             if (needA) publish(cur.na, a, va, oa, ima, IA, tag, last_it);
             if (needB) publish(cur.nb, b, vb, ob, imb, IB, tag, last_it);
         }
