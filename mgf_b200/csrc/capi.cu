@@ -359,7 +359,9 @@ int32_t enqueue_order_and_solve(mgfb_ctx* ctx, const OrderView& O, const Manifol
         const unsigned* ps = pstart; unsigned it = iters;
         void* args[] = {&R, &D, &vel, &ps, &it, &epoch, &c, &TL};
         void* fn = tiled ? (void*)k_solve_df<true> : (void*)k_solve_df<false>;
-        CU(cudaLaunchCooperativeKernel(fn, dim3(ctx->coop_df), dim3(MGFB_DF_THREADS), args, 0, ctx->stream));
+        // rows of the previous solve decide the block size (the count of THIS step is still on the device)
+        const unsigned threads = ctx->last_constraints > MGFB_DF_LARGE_ROWS ? MGFB_DF_THREADS_LARGE : MGFB_DF_THREADS_SMALL;
+        CU(cudaLaunchCooperativeKernel(fn, dim3(ctx->coop_df), dim3(threads), args, 0, ctx->stream));
         ctx->launches += 1;
         if (tiled) {   // my ghosts' final velocities are in their owner's records; wait for the same from the left tile
             k_tile_solve_done<<<1, 1, 0, ctx->stream>>>(TL, c);
@@ -578,7 +580,7 @@ int32_t mgfb_ctx_create(const mgfb_config* cfg, mgfb_ctx** out) {
     ctx->coop_order = coop_blocks(ctx, k_order, MGFB_THREADS, 2);
     ctx->coop_colour = coop_blocks(ctx, k_colour_df, MGFB_THREADS, 8);
     ctx->coop_solve = std::min(coop_blocks(ctx, k_solve<false>, MGFB_SOLVE_THREADS, 1), coop_blocks(ctx, k_solve<true>, MGFB_SOLVE_THREADS, 1));
-    ctx->coop_df = std::min(coop_blocks(ctx, k_solve_df<false>, MGFB_DF_THREADS, 1), coop_blocks(ctx, k_solve_df<true>, MGFB_DF_THREADS, 1));
+    ctx->coop_df = std::min(coop_blocks(ctx, k_solve_df<false>, MGFB_DF_THREADS_LARGE, 1), coop_blocks(ctx, k_solve_df<true>, MGFB_DF_THREADS_LARGE, 1));
     int32_t s = grow_bodies(ctx, std::max(ctx->cfg.initial_body_capacity, 1024u));
     if (s == MGFB_OK) s = ensure_rows(ctx, 1024, false, 4096);
     if (s != MGFB_OK) { g_create_err = ctx->err; delete ctx; return s; }

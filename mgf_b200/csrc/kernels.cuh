@@ -1255,11 +1255,13 @@ __device__ unsigned long long g_df_prof[8];   // cycles: fetch, inbox poll, comp
 #endif
 struct DfRow { RowData d; float4 i0, i1, i2, i3, i4; unsigned na, nb, row; float imp; bool valid; };
 #define MGFB_DF_MAX_PHASES 64
-#ifndef MGFB_DF_THREADS
-#define MGFB_DF_THREADS 320   /* 10 warps/SM: measured best at 100 k .. 500 k bodies (256: +20 %, 384: +6 % solve time) */
-#endif
+// Block size is chosen at launch: 10 warps/SM measured best while the rows are L2-resident (100 k .. 300 k bodies;
+// 256: +20 %, 384: +6 % solve time), 16 warps/SM once they stream from HBM (> ~1 M rows).
+#define MGFB_DF_THREADS_SMALL 320
+#define MGFB_DF_THREADS_LARGE 512
+#define MGFB_DF_LARGE_ROWS 1000000u
 template <bool TILED>
-__global__ void __launch_bounds__(MGFB_DF_THREADS, 1) k_solve_df(ConstraintRows R, DfArrays D, BodyVel* vel, const unsigned* __restrict__ phase_start,
+__global__ void __launch_bounds__(MGFB_DF_THREADS_LARGE, 1) k_solve_df(ConstraintRows R, DfArrays D, BodyVel* vel, const unsigned* __restrict__ phase_start,
                                                                 unsigned iters, unsigned epoch, Counters* ctr, TileLink T) {
     if (ctr->overflow | ctr->nan_bounds) return;
     if (TILED && ctr->comm_error) return;
@@ -1274,7 +1276,7 @@ __global__ void __launch_bounds__(MGFB_DF_THREADS, 1) k_solve_df(ConstraintRows 
     __syncthreads();
     const unsigned nwr = s_wr0[P];
     const unsigned lane = threadIdx.x & 31u;
-    const unsigned gw = (threadIdx.x >> 5) * gridDim.x + blockIdx.x, nW = gridDim.x * (MGFB_DF_THREADS / 32);
+    const unsigned gw = (threadIdx.x >> 5) * gridDim.x + blockIdx.x, nW = gridDim.x * (blockDim.x >> 5);
     if (gw >= nwr) return;
     const unsigned rc = D.row_cap;
     auto fetch = [&](unsigned wr, unsigned& p) {
