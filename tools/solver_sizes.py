@@ -1,6 +1,7 @@
 """Dev aid: solver time vs problem size for both schedules (not part of the bench contract)."""
-import sys, numpy as np
-sys.path.insert(0, '.')
+import os, sys, numpy as np
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
 import torch, mgf_b200
 from mgf_b200 import scenes
 sizes = ((8, 0), (20, 0), (46, 2664), (80, 0)) if len(sys.argv) < 2 else [(int(a), 0) for a in sys.argv[1:]]
