@@ -258,30 +258,52 @@ def main():
         total_ms_max, units_all, pairs_all = total_ms, units, npairs
     value = units_all / (total_ms_max * 1e-3)
 
-    # ---- end to end: public API with host buffers; pinned H2D (v, omega) + D2H (x, q, v, omega) per step
+    # ---- end to end: public API with host buffers; every step: pinned H2D of that step's inputs (v, omega) and D2H of its
+    # result (x, q, v, omega).  One GPU: the pipelined step API (mgfb_step_enqueue / mgfb_step_wait: the transfers of step
+    # k overlap the kernels of step k+1, two output buffer sets); tiled worlds step in lock-step with their neighbours and
+    # use the synchronous calls.
     pin = lambda shape: torch.empty(shape, dtype=torch.float32, pin_memory=True).numpy()
-    hx, hq, hv, hw = pin((n, 3)), pin((n, 4)), pin((n, 3)), pin((n, 3))
+    hv, hw = pin((n, 3)), pin((n, 3))
+    outs = [(pin((n, 3)), pin((n, 4)), pin((n, 3)), pin((n, 3))) for _ in range(2)]
+    # one GPU: the per-step inputs are external velocity increments (zero here, so the e2e loop steps the SAME world the
+    # device-timed loop stepped); tiled worlds: the synchronous calls overwrite the velocities with the host's copy
     _, _, v0, w0 = g.state()
-    hv[:] = v0; hw[:] = w0
+    if world == 1:
+        hv[:] = 0.0; hw[:] = 0.0
+    else:
+        hv[:] = v0; hw[:] = w0
     from mgf_b200 import _lib as L
     lib, h = g.ctx.lib, g.ctx.h
-    barrier()
-    e2e_units = 0.0
-    t0 = time.perf_counter()
     import ctypes as C
     st = L.StepStats()
-    for _ in range(args.steps):
-        g.ctx.check(lib.mgfb_bodies_set_velocity(h, 0, n, L.ptr(hv), L.ptr(hw)))            # H2D
-        g.ctx.check(lib.mgfb_step(h, dt, iters, C.byref(st)))
-        g.ctx.check(lib.mgfb_bodies_get_state(h, 0, n, L.ptr(hx), L.ptr(hq), L.ptr(hv), L.ptr(hw)))   # D2H
-        e2e_units += st.constraints * iters
+    barrier()
+    e2e_units = 0.0; e2e_dev_ms = 0.0
+    t0 = time.perf_counter()
+    if world == 1:
+        for k in range(args.steps):
+            hx, hq, ov, ow = outs[k & 1]
+            g.ctx.check(lib.mgfb_step_enqueue(h, dt, iters, L.INPUT_ADD, L.ptr(hv), L.ptr(hw), L.ptr(hx), L.ptr(hq), L.ptr(ov), L.ptr(ow)))   # H2D + step + D2H queued
+            if k > 0:
+                g.ctx.check(lib.mgfb_step_wait(h, C.byref(st)))   # step k-1's state is in outs[(k-1) & 1]
+                e2e_units += st.constraints * iters; e2e_dev_ms += st.step_ms
+        g.ctx.check(lib.mgfb_step_wait(h, C.byref(st)))
+        e2e_units += st.constraints * iters; e2e_dev_ms += st.step_ms
+        e2e_api = "mgfb_step_enqueue / mgfb_step_wait (pipelined, 2 steps in flight)"
+    else:
+        hx, hq, ov, ow = outs[0]
+        for _ in range(args.steps):
+            g.ctx.check(lib.mgfb_bodies_set_velocity(h, 0, n, L.ptr(hv), L.ptr(hw)))            # H2D
+            g.ctx.check(lib.mgfb_step(h, dt, iters, C.byref(st)))
+            g.ctx.check(lib.mgfb_bodies_get_state(h, 0, n, L.ptr(hx), L.ptr(hq), L.ptr(ov), L.ptr(ow)))   # D2H
+            e2e_units += st.constraints * iters; e2e_dev_ms += st.step_ms
+        e2e_api = "mgfb_bodies_set_velocity + mgfb_step + mgfb_bodies_get_state (synchronous)"
     barrier()
     e2e_s = time.perf_counter() - t0
     if world > 1:
         t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64); dist.all_reduce(t, op=dist.ReduceOp.MAX); e2e_s = t.item()
         u = torch.tensor([e2e_units], device="cuda", dtype=torch.float64); dist.all_reduce(u, op=dist.ReduceOp.SUM); e2e_units = u.item()
     e2e_val = e2e_units / e2e_s
-    assert np.isfinite(hx).all()
+    assert np.isfinite(outs[0][0]).all() and np.isfinite(outs[(args.steps - 1) & 1][0]).all()
 
     # ---- roofline of the dominant kernel (k_solve), live CUDA-event durations
     peak, peak_src = measured_peak()
@@ -330,7 +352,8 @@ def main():
             "solver_only_constraint_iters_per_second": units / solve_s,
             "roofline": roofline, "cpu_baseline": cpu,
             "e2e": {"value": e2e_val, "unit": "constraint-iters/s", "h2d_bytes_per_step": n * 24, "d2h_bytes_per_step": n * 52,
-                    "ms_per_step": 1e3 * e2e_s / args.steps},
+                    "ms_per_step": 1e3 * e2e_s / args.steps, "api": e2e_api,
+                    "device_ms_per_step": e2e_dev_ms / args.steps, "constraints_per_step": e2e_units / iters / args.steps / max(world, 1)},
             "gpu_launches": tot["kernel_launches"], "clocks": clocks, "wall_s_timed_region": t_wall,
         }
         print(json.dumps(line), flush=True)

@@ -279,6 +279,21 @@ int32_t mgfb_step(mgfb_ctx* ctx, float dt, uint32_t iters, mgfb_step_stats* stat
 /* Enqueue `nsteps` steps with no host synchronisation in between (stats of the last one). */
 int32_t mgfb_step_n(mgfb_ctx* ctx, float dt, uint32_t iters, uint32_t nsteps, mgfb_step_stats* stats);
 
+/* Pipelined World::step for callers that move state across PCIe every step (rendering, logging, a host-side
+ * controller).  mgfb_step_enqueue queues  [v_in, omega_in -> device]  ->  the step  ->  [x, q, v, omega -> host]
+ * and returns at once; mgfb_step_wait blocks until the OLDEST queued step's outputs are in the caller's buffers
+ * and returns its stats.  Up to two steps may be in flight: the transfers of step k (separate copy streams, both
+ * directions) overlap the kernels of step k+1.  Same kernels and bit-identical results as mgfb_step.
+ * v_in/omega_in (n*3 each, both or neither) are applied before the step: MGFB_INPUT_SET overwrites the velocities
+ * (ConstrainedSet::set, physics.rs:304), MGFB_INPUT_ADD adds to them (what `bodies.v[i] += dv` on the pub fields does
+ * between two steps of the reference: external impulses).  Any output pointer may be NULL.  Host buffers must be page-locked and must not be touched until the
+ * matching wait returns.  Work lists are sized once (16 pairs / 16 contacts per body): an overflow is reported by
+ * the wait as MGFB_ERR_CAPACITY (call mgfb_step, which regrows, to continue).  Not available on tiled worlds. */
+enum mgfb_input_mode { MGFB_INPUT_SET = 0, MGFB_INPUT_ADD = 1 };
+int32_t mgfb_step_enqueue(mgfb_ctx* ctx, float dt, uint32_t iters, uint32_t input_mode, const float* v_in, const float* omega_in,
+                          float* x_out, float* q_out, float* v_out, float* omega_out);
+int32_t mgfb_step_wait(mgfb_ctx* ctx, mgfb_step_stats* stats /* may be NULL */);
+
 /* Identity of the constraints of the most recent step, in the order they were solved:
  * body_a = i, body_b = j (< i) or -1 for terrain, face = terrain face index, sub = k-th contact
  * of that (body, face) pair.  Arrays hold stats.constraints entries; any may be NULL. */

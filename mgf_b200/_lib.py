@@ -25,6 +25,7 @@ SHAPE_DTYPE = np.dtype([("kind", "<u4"), ("p", "<f4", (12,)), ("v", "<f4", (3,))
 CONTACT_DTYPE = np.dtype([("a", "<f4", (3,)), ("b", "<f4", (3,)), ("n", "<f4", (3,)), ("t", "<f4")])
 INTERSECTION_DTYPE = np.dtype([("p", "<f4", (3,)), ("t", "<f4")])   # collision.rs:151 Intersection
 RAY, SEGMENT = 0, 1
+INPUT_SET, INPUT_ADD = 0, 1
 LOCAL_CONTACT_DTYPE = np.dtype([("local_a", "<f4", (3,)), ("local_b", "<f4", (3,)), ("global", CONTACT_DTYPE)])
 assert SHAPE_DTYPE.itemsize == 64 and CONTACT_DTYPE.itemsize == 40 and LOCAL_CONTACT_DTYPE.itemsize == 64
 
@@ -92,6 +93,8 @@ SYMBOLS = [
     ("mgfb_solver_solve", C.c_int32, [_P, C.POINTER(Manifolds), C.c_float, C.c_uint32, C.c_uint32, _P, _P, C.POINTER(SolveStats)]),
     ("mgfb_step", C.c_int32, [_P, C.c_float, C.c_uint32, C.POINTER(StepStats)]),
     ("mgfb_step_n", C.c_int32, [_P, C.c_float, C.c_uint32, C.c_uint32, C.POINTER(StepStats)]),
+    ("mgfb_step_enqueue", C.c_int32, [_P, C.c_float, C.c_uint32, C.c_uint32, _P, _P, _P, _P, _P, _P]),
+    ("mgfb_step_wait", C.c_int32, [_P, C.POINTER(StepStats)]),
     ("mgfb_step_constraints", C.c_int32, [_P, C.c_uint32, _P, _P, _P, _P, _P, C.POINTER(C.c_uint32)]),
     ("mgfb_step_totals", C.c_int32, [_P] + [C.POINTER(C.c_uint64)] * 5 + [C.c_int32]),
     ("mgfb_device_view_get", C.c_int32, [_P, C.POINTER(DeviceView)]),

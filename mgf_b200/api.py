@@ -292,6 +292,20 @@ class World:
         self.ctx.check(self.lib.mgfb_step_n(self.ctx.h, dt, iters, nsteps, C.byref(st)))
         return st.as_dict()
 
+    # -- pipelined step: transfers of step k overlap the kernels of step k+1 (mgfb_step_enqueue / mgfb_step_wait)
+    def step_enqueue(self, dt, iters=20, v_in=None, omega_in=None, x_out=None, q_out=None, v_out=None, omega_out=None, add=False):
+        """Queue [v_in, omega_in -> device] -> step -> [state -> host] and return at once.  All arrays must be
+        C-contiguous float32 in PAGE-LOCKED memory and stay untouched until the matching step_wait().  add=True: the
+        inputs are ADDED to the velocities (external impulses) instead of replacing them."""
+        self.ctx.check(self.lib.mgfb_step_enqueue(self.ctx.h, dt, iters, L.INPUT_ADD if add else L.INPUT_SET, L.ptr(v_in), L.ptr(omega_in), L.ptr(x_out), L.ptr(q_out),
+                                                  L.ptr(v_out), L.ptr(omega_out)))
+
+    def step_wait(self):
+        """Block until the oldest queued step's outputs are in the host buffers; returns its stats."""
+        st = L.StepStats()
+        self.ctx.check(self.lib.mgfb_step_wait(self.ctx.h, C.byref(st)))
+        return st.as_dict()
+
     # -- one world tiled across GPUs (mgfb.h "one world tiled across GPUs"; driver in tiling.py)
     def set_gid(self, gids, first=0):
         gids = np.ascontiguousarray(gids, dtype=np.uint32)

@@ -67,6 +67,10 @@ struct mgfb_ctx {
     // cooperative grid sizes
     int coop_order = 0, coop_solve = 0, coop_df = 0, coop_colour = 0;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t* cur_ev = nullptr;        // the four timing events of the step being enqueued (ev, or a pipeline slot's)
+    struct PipeSlot* pipe = nullptr;     // mgfb_step_enqueue / mgfb_step_wait (pipeline.cuh)
+    cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
+    unsigned pipe_head = 0, pipe_inflight = 0;
     // last step
     unsigned last_constraints = 0;
     bool have_step = false;
@@ -354,7 +358,7 @@ int32_t enqueue_order_and_solve(mgfb_ctx* ctx, const OrderView& O, const Manifol
         ctx->launches += 2 + (TL.has_left ? 1 : 0) + (TL.has_right ? 1 : 0);
     }
     CU(cudaGetLastError());
-    if (time_solve) CU(cudaEventRecord(ctx->ev[2], ctx->stream));
+    if (time_solve) CU(cudaEventRecord(ctx->cur_ev[2], ctx->stream));
     if (dataflow) {
         const unsigned* ps = pstart; unsigned it = iters;
         void* args[] = {&R, &D, &vel, &ps, &it, &epoch, &c, &TL};
@@ -378,7 +382,7 @@ int32_t enqueue_order_and_solve(mgfb_ctx* ctx, const OrderView& O, const Manifol
         void* fn = tiled ? (void*)k_solve<true> : (void*)k_solve<false>;
         CU(cudaLaunchCooperativeKernel(fn, dim3(ctx->coop_solve), dim3(MGFB_SOLVE_THREADS), args, 0, ctx->stream));
     }
-    if (time_solve) CU(cudaEventRecord(ctx->ev[3], ctx->stream));
+    if (time_solve) CU(cudaEventRecord(ctx->cur_ev[3], ctx->stream));
     ctx->launches += 4 + ((dataflow && tiled) ? 0 : 1);   // k_order, k_group_scan, k_scatter_rows, k_build_rows (+ k_solve)
     return MGFB_OK;
 }
@@ -514,6 +518,8 @@ M3 capsule_tensor(V3 a, V3 d, float r, float m) {
 
 }  // namespace
 
+void pipe_destroy(mgfb_ctx* ctx);   // pipeline.cuh
+
 // ============================================================================ C ABI
 extern "C" {
 
@@ -553,6 +559,7 @@ int32_t mgfb_ctx_create(const mgfb_config* cfg, mgfb_ctx** out) {
     if (!prop.cooperativeLaunch) return bail(cudaErrorNotSupported, "device lacks cooperative launch");
     if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "cudaStreamCreate");
     for (auto& ev : ctx->ev) if ((e = cudaEventCreate(&ev)) != cudaSuccess) return bail(e, "cudaEventCreate");
+    ctx->cur_ev = ctx->ev;
     if ((e = cudaMallocHost(&ctx->h_ctr, sizeof(Counters))) != cudaSuccess) return bail(e, "cudaMallocHost");
     if ((e = cudaMalloc(&ctx->ctr.p, sizeof(Counters))) != cudaSuccess) return bail(e, "cudaMalloc");
     ctx->ctr.bytes = sizeof(Counters);
@@ -571,7 +578,7 @@ int32_t mgfb_ctx_create(const mgfb_config* cfg, mgfb_ctx** out) {
                              (const void*)k_scatter_rows, (const void*)k_build_rows, (const void*)k_solve<false>, (const void*)k_solve<true>,
                              (const void*)k_solve_df<false>, (const void*)k_solve_df<true>, (const void*)k_df_init<false>, (const void*)k_df_init<true>,
                              (const void*)k_tile_links_send, (const void*)k_tile_solve_done, (const void*)k_inc_count, (const void*)k_inc_fill, (const void*)k_inc_sort, (const void*)k_colour_df,
-                             (const void*)k_step_done, (const void*)k_pack_state, (const void*)k_set_velocity};
+                             (const void*)k_step_done, (const void*)k_pack_state, (const void*)k_set_velocity<false>, (const void*)k_set_velocity<true>};
         cudaFuncAttributes fa;
         for (const void* f : fns) if ((e = cudaFuncGetAttributes(&fa, f)) != cudaSuccess) return bail(e, "cudaFuncGetAttributes");
     }
@@ -612,6 +619,7 @@ void mgfb_ctx_destroy(mgfb_ctx* ctx) {
                   &ctx->u_lb, &ctx->stage, &ctx->terrain.verts, &ctx->terrain.faces, &ctx->terrain.boxes, &ctx->terrain.cell_count,
                   &ctx->terrain.cell_start, &ctx->terrain.ent_id, &ctx->terrain.ent_key, &ctx->terrain.max_bits,
                   &ctx->gid, &ctx->phase_start, &ctx->edge_idx, &ctx->edge_mark, &ctx->ridx, &ctx->mbox, &ctx->edge_slot, &ctx->tile_df};
+    pipe_destroy(ctx);
     for (void* ptr : ctx->ipc_opened) cudaIpcCloseMemHandle(ptr);
     for (Buf* b : all) release(*b);
     if (ctx->h_ctr) cudaFreeHost(ctx->h_ctr);
@@ -730,7 +738,7 @@ int32_t mgfb_bodies_set_velocity(mgfb_ctx* ctx, uint32_t first, uint32_t n, cons
     float* sv = ctx->stage.as<float>(); float* sw = sv + (size_t)3 * n;
     CU(cudaMemcpyAsync(sv, v, (size_t)n * 12, cudaMemcpyHostToDevice, ctx->stream));
     CU(cudaMemcpyAsync(sw, omega, (size_t)n * 12, cudaMemcpyHostToDevice, ctx->stream));
-    k_set_velocity<<<(n + MGFB_THREADS - 1) / MGFB_THREADS, MGFB_THREADS, 0, ctx->stream>>>(body_arrays(ctx), first, n, sv, sw);
+    k_set_velocity<false><<<(n + MGFB_THREADS - 1) / MGFB_THREADS, MGFB_THREADS, 0, ctx->stream>>>(body_arrays(ctx), first, n, sv, sw);
     CU(cudaGetLastError());
     ctx->launches += 1;
     CU(cudaStreamSynchronize(ctx->stream));
@@ -841,8 +849,10 @@ int32_t mgfb_terrain_set(mgfb_ctx* ctx, const float* verts, uint32_t nverts, con
     return MGFB_OK;
 }
 
-static void fill_step_stats(mgfb_ctx* ctx, mgfb_step_stats* st, unsigned iters, bool timed, unsigned overflowed) {
-    const Counters& h = *ctx->h_ctr;
+static void fill_step_stats(mgfb_ctx* ctx, mgfb_step_stats* st, unsigned iters, bool timed, unsigned overflowed, const Counters* hc = nullptr,
+                            cudaEvent_t* evs = nullptr) {
+    const Counters& h = hc ? *hc : *ctx->h_ctr;
+    if (!evs) evs = ctx->ev;
     std::memset(st, 0, sizeof(*st));
     st->bodies = ctx->n;
     st->candidate_pairs = h.pairs[0] + h.pairs[1] + h.pairs[2] + h.pairs[3];
@@ -858,8 +868,8 @@ static void fill_step_stats(mgfb_ctx* ctx, mgfb_step_stats* st, unsigned iters, 
     st->boundary_constraints = h.contacts - h.n_int_rows;
     st->phases = h.n_phases;
     if (timed) {
-        cudaEventElapsedTime(&st->step_ms, ctx->ev[0], ctx->ev[1]);
-        cudaEventElapsedTime(&st->solve_ms, ctx->ev[2], ctx->ev[3]);
+        cudaEventElapsedTime(&st->step_ms, evs[0], evs[1]);
+        cudaEventElapsedTime(&st->solve_ms, evs[2], evs[3]);
     }
 }
 
@@ -1160,3 +1170,4 @@ int32_t mgfb_device_view_get(mgfb_ctx* ctx, mgfb_device_view* out) {
 #include "batch.cuh"
 #include "gjk.cuh"
 #include "bvh.cuh"
+#include "pipeline.cuh"

@@ -1428,12 +1428,20 @@ __global__ void __launch_bounds__(MGFB_THREADS) k_pack_state(BodyArrays B, unsig
         if (w) { w[3 * i] = r.a.w; w[3 * i + 1] = r.b.x; w[3 * i + 2] = r.b.y; }
     }
 }
+// ADD: v += v_in, omega += omega_in (what `bodies.v[i] += dv` between steps does on the CPU); else overwrite (ConstrainedSet::set)
+template <bool ADD = false>
 __global__ void __launch_bounds__(MGFB_THREADS) k_set_velocity(BodyArrays B, unsigned first, unsigned n, const float* v, const float* w) {
     unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     BodyVel* r = B.vel + first + i;
-    r->a = make_float4(v[3 * i], v[3 * i + 1], v[3 * i + 2], w[3 * i]);
-    r->b.x = w[3 * i + 1]; r->b.y = w[3 * i + 2];
+    if (ADD) {
+        float4 a = r->a;
+        r->a = make_float4(a.x + v[3 * i], a.y + v[3 * i + 1], a.z + v[3 * i + 2], a.w + w[3 * i]);
+        r->b.x = r->b.x + w[3 * i + 1]; r->b.y = r->b.y + w[3 * i + 2];
+    } else {
+        r->a = make_float4(v[3 * i], v[3 * i + 1], v[3 * i + 2], w[3 * i]);
+        r->b.x = w[3 * i + 1]; r->b.y = w[3 * i + 2];
+    }
 }
 
 // ---------------------------------------------------------------- single-pass exclusive scan (u32)

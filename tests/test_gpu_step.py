@@ -256,3 +256,53 @@ def test_work_list_overflow_regrows_and_stays_exact():
     perm = np.array([index[k] for k in zip(ga.tolist(), gb.tolist(), gf.tolist(), gs.tolist())], dtype=np.uint32)
     o.solve_order(perm, 2)
     _assert_state_equal(g, o, "after overflow")
+
+
+def test_pipelined_step_equals_synchronous_step_bit_for_bit():
+    """mgfb_step_enqueue / mgfb_step_wait (transfers of step k overlap the kernels of step k+1) must deliver, step by
+    step, exactly what set_velocity + step + get_state deliver."""
+    import torch
+    shapes, mass, rest, fric, force = scenes.balls_scene(num=6, jitter=0.2, seed=3)
+    shapes["p"][:, 1] -= 24.0
+    bodies = (shapes, mass, rest, fric, force)
+    terrain = scenes.box_terrain(4.0, 10.0, 4.0)
+    n = len(shapes)
+    a = mgf_b200.World(device=0, solver_schedule=SCHEDULE[0]); b = mgf_b200.World(device=0, solver_schedule=SCHEDULE[0])
+    for w in (a, b):
+        w.add_bodies(*bodies); w.set_terrain(*terrain)
+        w.step(DT, 10, nsteps=60)          # into the contact-rich phase
+    pin = lambda shape: torch.empty(shape, dtype=torch.float32, pin_memory=True).numpy()
+    rng = np.random.default_rng(1)
+    nsteps = 12
+    vin = [pin((n, 3)) for _ in range(nsteps)]; win = [pin((n, 3)) for _ in range(nsteps)]
+    outs = [tuple(pin(s) for s in ((n, 3), (n, 4), (n, 3), (n, 3))) for _ in range(nsteps)]
+    _, _, v0, w0 = a.state()
+    for k in range(nsteps):
+        vin[k][:] = v0 + rng.uniform(-0.05, 0.05, (n, 3)).astype(np.float32); win[k][:] = w0
+    ref = []
+    for k in range(nsteps):
+        a.set_velocity(0, vin[k], win[k])
+        sa = a.step(DT, 10)
+        ref.append((sa["constraints"], [x.copy() for x in a.state()]))
+    stats = []
+    for k in range(nsteps):
+        b.step_enqueue(DT, 10, vin[k], win[k], *outs[k])
+        if k > 0:
+            stats.append(b.step_wait())
+    stats.append(b.step_wait())
+    with pytest.raises(mgf_b200.MgfbError):
+        b.step_wait()                       # nothing in flight
+    assert sum(c for c, _ in ref) > 1000
+    for k in range(nsteps):
+        assert stats[k]["constraints"] == ref[k][0]
+        for name, got, want in zip("x q v omega".split(), outs[k], ref[k][1]):
+            assert np.array_equal(_bits(got), _bits(want)), f"step {k}: {name} differs"
+    _assert_same = [np.array_equal(_bits(x), _bits(y)) for x, y in zip(a.state(), b.state())]
+    assert all(_assert_same)
+    # MGFB_INPUT_ADD: the inputs are added (external impulses); the synchronous twin adds on the host
+    dv = pin((n, 3)); dw = pin((n, 3))
+    dv[:] = rng.uniform(-0.02, 0.02, (n, 3)).astype(np.float32); dw[:] = 0.0
+    _, _, va, wa = a.state()
+    a.set_velocity(0, (va + dv).astype(np.float32), (wa + dw).astype(np.float32)); a.step(DT, 10)
+    b.step_enqueue(DT, 10, dv, dw, *outs[0], add=True); b.step_wait()
+    assert all(np.array_equal(_bits(x), _bits(y)) for x, y in zip(a.state(), b.state()))
