@@ -266,7 +266,7 @@ def main():
     hv, hw = pin((n, 3)), pin((n, 3))
     outs = [(pin((n, 3)), pin((n, 4)), pin((n, 3)), pin((n, 3))) for _ in range(2)]
     # one GPU: the per-step inputs are external velocity increments (zero here, so the e2e loop steps the SAME world the
-    # device-timed loop stepped); tiled worlds: the synchronous calls overwrite the velocities with the host's copy
+    # device-timed loop stepped); tiled worlds: the synchronous calls write back the velocities read the step before
     _, _, v0, w0 = g.state()
     if world == 1:
         hv[:] = 0.0; hw[:] = 0.0
@@ -291,8 +291,9 @@ def main():
         e2e_api = "mgfb_step_enqueue / mgfb_step_wait (pipelined, 2 steps in flight)"
     else:
         hx, hq, ov, ow = outs[0]
+        ov[:] = hv; ow[:] = hw
         for _ in range(args.steps):
-            g.ctx.check(lib.mgfb_bodies_set_velocity(h, 0, n, L.ptr(hv), L.ptr(hw)))            # H2D
+            g.ctx.check(lib.mgfb_bodies_set_velocity(h, 0, n, L.ptr(ov), L.ptr(ow)))            # H2D: the velocities read back last step (neutral)
             g.ctx.check(lib.mgfb_step(h, dt, iters, C.byref(st)))
             g.ctx.check(lib.mgfb_bodies_get_state(h, 0, n, L.ptr(hx), L.ptr(hq), L.ptr(ov), L.ptr(ow)))   # D2H
             e2e_units += st.constraints * iters; e2e_dev_ms += st.step_ms
