@@ -259,19 +259,14 @@ def main():
     value = units_all / (total_ms_max * 1e-3)
 
     # ---- end to end: public API with host buffers; every step: pinned H2D of that step's inputs (v, omega) and D2H of its
-    # result (x, q, v, omega).  One GPU: the pipelined step API (mgfb_step_enqueue / mgfb_step_wait: the transfers of step
-    # k overlap the kernels of step k+1, two output buffer sets); tiled worlds step in lock-step with their neighbours and
-    # use the synchronous calls.
+    # result (x, q, v, omega), through the pipelined step API (mgfb_step_enqueue / mgfb_step_wait: the transfers of step
+    # k overlap the kernels of step k+1, two output buffer sets); on a tiled world every rank runs the same sequence.
     pin = lambda shape: torch.empty(shape, dtype=torch.float32, pin_memory=True).numpy()
     hv, hw = pin((n, 3)), pin((n, 3))
     outs = [(pin((n, 3)), pin((n, 4)), pin((n, 3)), pin((n, 3))) for _ in range(2)]
-    # one GPU: the per-step inputs are external velocity increments (zero here, so the e2e loop steps the SAME world the
-    # device-timed loop stepped); tiled worlds: the synchronous calls write back the velocities read the step before
-    _, _, v0, w0 = g.state()
-    if world == 1:
-        hv[:] = 0.0; hw[:] = 0.0
-    else:
-        hv[:] = v0; hw[:] = w0
+    # the per-step inputs are external velocity increments (zero here, so the e2e loop steps the SAME world the
+    # device-timed loop stepped)
+    hv[:] = 0.0; hw[:] = 0.0
     from mgf_b200 import _lib as L
     lib, h = g.ctx.lib, g.ctx.h
     import ctypes as C
@@ -279,25 +274,15 @@ def main():
     barrier()
     e2e_units = 0.0; e2e_dev_ms = 0.0
     t0 = time.perf_counter()
-    if world == 1:
-        for k in range(args.steps):
-            hx, hq, ov, ow = outs[k & 1]
-            g.ctx.check(lib.mgfb_step_enqueue(h, dt, iters, L.INPUT_ADD, L.ptr(hv), L.ptr(hw), L.ptr(hx), L.ptr(hq), L.ptr(ov), L.ptr(ow)))   # H2D + step + D2H queued
-            if k > 0:
-                g.ctx.check(lib.mgfb_step_wait(h, C.byref(st)))   # step k-1's state is in outs[(k-1) & 1]
-                e2e_units += st.constraints * iters; e2e_dev_ms += st.step_ms
-        g.ctx.check(lib.mgfb_step_wait(h, C.byref(st)))
-        e2e_units += st.constraints * iters; e2e_dev_ms += st.step_ms
-        e2e_api = "mgfb_step_enqueue / mgfb_step_wait (pipelined, 2 steps in flight)"
-    else:
-        hx, hq, ov, ow = outs[0]
-        ov[:] = hv; ow[:] = hw
-        for _ in range(args.steps):
-            g.ctx.check(lib.mgfb_bodies_set_velocity(h, 0, n, L.ptr(ov), L.ptr(ow)))            # H2D: the velocities read back last step (neutral)
-            g.ctx.check(lib.mgfb_step(h, dt, iters, C.byref(st)))
-            g.ctx.check(lib.mgfb_bodies_get_state(h, 0, n, L.ptr(hx), L.ptr(hq), L.ptr(ov), L.ptr(ow)))   # D2H
+    for k in range(args.steps):
+        hx, hq, ov, ow = outs[k & 1]
+        g.ctx.check(lib.mgfb_step_enqueue(h, dt, iters, L.INPUT_ADD, L.ptr(hv), L.ptr(hw), L.ptr(hx), L.ptr(hq), L.ptr(ov), L.ptr(ow)))   # H2D + step + D2H queued
+        if k > 0:
+            g.ctx.check(lib.mgfb_step_wait(h, C.byref(st)))   # step k-1's state is in outs[(k-1) & 1]
             e2e_units += st.constraints * iters; e2e_dev_ms += st.step_ms
-        e2e_api = "mgfb_bodies_set_velocity + mgfb_step + mgfb_bodies_get_state (synchronous)"
+    g.ctx.check(lib.mgfb_step_wait(h, C.byref(st)))
+    e2e_units += st.constraints * iters; e2e_dev_ms += st.step_ms
+    e2e_api = "mgfb_step_enqueue / mgfb_step_wait (pipelined, 2 steps in flight)"
     barrier()
     e2e_s = time.perf_counter() - t0
     if world > 1:

@@ -288,7 +288,8 @@ int32_t mgfb_step_n(mgfb_ctx* ctx, float dt, uint32_t iters, uint32_t nsteps, mg
  * (ConstrainedSet::set, physics.rs:304), MGFB_INPUT_ADD adds to them (what `bodies.v[i] += dv` on the pub fields does
  * between two steps of the reference: external impulses).  Any output pointer may be NULL.  Host buffers must be page-locked and must not be touched until the
  * matching wait returns.  Work lists are sized once (16 pairs / 16 contacts per body): an overflow is reported by
- * the wait as MGFB_ERR_CAPACITY (call mgfb_step, which regrows, to continue).  Not available on tiled worlds. */
+ * the wait as MGFB_ERR_CAPACITY (call mgfb_step, which regrows, to continue).  On a tiled world every rank must
+ * enqueue and wait the same sequence of steps. */
 enum mgfb_input_mode { MGFB_INPUT_SET = 0, MGFB_INPUT_ADD = 1 };
 int32_t mgfb_step_enqueue(mgfb_ctx* ctx, float dt, uint32_t iters, uint32_t input_mode, const float* v_in, const float* omega_in,
                           float* x_out, float* q_out, float* v_out, float* omega_out);

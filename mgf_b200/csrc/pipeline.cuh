@@ -2,7 +2,8 @@
 // a host-side controller): mgfb_step_enqueue queues  [H2D v, omega] -> step -> [pack x, q, v, omega -> D2H]
 // and returns at once; mgfb_step_wait blocks until the OLDEST queued step's outputs are in the caller's
 // buffers.  Two steps may be in flight, so the PCIe transfers of step k (separate copy streams, both
-// directions at once) overlap the kernels of step k+1.  Same kernels, same results as mgfb_step.
+// directions at once) overlap the kernels of step k+1.  Same kernels, same results as mgfb_step.  On a tiled
+// world every rank enqueues and waits the same sequence (the tiles meet on the device, as with mgfb_step_n).
 // Included at the end of capi.cu.
 #pragma once
 
@@ -56,7 +57,6 @@ int32_t mgfb_step_enqueue(mgfb_ctx* ctx, float dt, uint32_t iters, uint32_t inpu
     if (!(dt > 0.0f)) return fail(ctx, MGFB_ERR_INVALID_ARG, "dt must be > 0");
     if ((v_in == nullptr) != (omega_in == nullptr)) return fail(ctx, MGFB_ERR_INVALID_ARG, "v_in and omega_in go together");
     if (input_mode > MGFB_INPUT_ADD) return fail(ctx, MGFB_ERR_INVALID_ARG, "unknown input mode");
-    if (ctx->tiled) return fail(ctx, MGFB_ERR_STATE, "a tiled world steps in lock-step with its neighbours: use mgfb_step");
     if (ctx->n == 0) return fail(ctx, MGFB_ERR_STATE, "no bodies");
     if (ctx->pipe_inflight >= 2) return fail(ctx, MGFB_ERR_STATE, "two steps are in flight: mgfb_step_wait first");
     CU(cudaSetDevice(ctx->device));
@@ -112,6 +112,12 @@ int32_t mgfb_step_wait(mgfb_ctx* ctx, mgfb_step_stats* stats) {
     CU(cudaEventSynchronize(s.ev_out));
     ctx->pipe_head++; ctx->pipe_inflight--;
     const Counters& h = *s.h_ctr;
+    if (ctx->tiled && !(h.nan_bounds | h.overflow) && h.comm_error) {   // same reports as mgfb_step_n
+        while (ctx->pipe_inflight) { cudaEventSynchronize(ctx->pipe[ctx->pipe_head & 1u].ev_out); ctx->pipe_head++; ctx->pipe_inflight--; }
+        if (h.comm_error & COMM_TILE_TOO_THIN)
+            return fail(ctx, MGFB_ERR_TILE, "tile too thin: a body is a ghost on the left neighbour and touches a ghost from the right (or reaches two tiles away); use fewer, wider tiles");
+        return fail(ctx, MGFB_ERR_TILE, "neighbour tile did not answer within the time limit");
+    }
     if (h.nan_bounds | h.overflow) {
         // every later kernel returned early on the sticky flag: drain what is queued, then report
         while (ctx->pipe_inflight) { cudaEventSynchronize(ctx->pipe[ctx->pipe_head & 1u].ev_out); ctx->pipe_head++; ctx->pipe_inflight--; }
