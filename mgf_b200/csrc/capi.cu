@@ -70,6 +70,8 @@ struct mgfb_ctx {
     cudaEvent_t* cur_ev = nullptr;        // the four timing events of the step being enqueued (ev, or a pipeline slot's)
     struct PipeSlot* pipe = nullptr;     // mgfb_step_enqueue / mgfb_step_wait (pipeline.cuh)
     cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
+    cudaStream_t s_aux = nullptr;         // the terrain half of the broad/narrowphase runs beside the body half
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     unsigned pipe_head = 0, pipe_inflight = 0;
     // last step
     unsigned last_constraints = 0;
@@ -421,6 +423,7 @@ int32_t enqueue_step(mgfb_ctx* ctx, float dt, unsigned iters, bool from_integrat
         ctx->launches += 2 + (T.has_left ? 2 : 0) + (T.has_right ? 1 : 0);
     }
     int gs = grid_for(ctx, slots);
+    if (ctx->terrain.present) CU(cudaEventRecord(ctx->ev_fork, ctx->stream));   // tight boxes are final: the terrain half may start
     // broadphase over the stored fat boxes
     BodyGrid G = body_grid(ctx);
     k_bgrid_insert<false><<<gs, MGFB_THREADS, 0, ctx->stream>>>(B.fat, B.col, B.gid, G, c);
@@ -434,24 +437,27 @@ int32_t enqueue_step(mgfb_ctx* ctx, float dt, unsigned iters, bool from_integrat
     }
     ContactList L = contact_list(ctx);
     TerrainView T{};
-    if (ctx->terrain.present) {
-        T = terrain_view(ctx);
-        PairLists TL; for (int k = 0; k < 4; ++k) TL.p[k] = k < 2 ? ctx->tpair_list[k].as<int2>() : nullptr;
-        k_terrain_pairs<<<gb, MGFB_THREADS, 0, ctx->stream>>>(B.tight, B.col, n, T, TL, ctx->tpair_cap, c);
-    }
-    // narrowphase, one specialisation per shape pair
     bool caps = ctx->n_capsules > 0, sph = ctx->n_capsules < ctx->n;
     int gp = grid_for(ctx, (size_t)slots * 4);
+    if (ctx->terrain.present) {
+        // body x terrain (mesh query + its narrowphase) shares nothing with body x body but the contact list's cursor:
+        // it runs on a side stream beside the body grid / pair sweep / body narrowphase and joins before the colouring
+        T = terrain_view(ctx);
+        PairLists TL; for (int k = 0; k < 4; ++k) TL.p[k] = k < 2 ? ctx->tpair_list[k].as<int2>() : nullptr;
+        CU(cudaStreamWaitEvent(ctx->s_aux, ctx->ev_fork, 0));
+        k_terrain_pairs<<<gb, MGFB_THREADS, 0, ctx->s_aux>>>(B.tight, B.col, n, T, TL, ctx->tpair_cap, c);
+        if (sph) k_narrow_terrain<0><<<gp, MGFB_THREADS, 0, ctx->s_aux>>>(B.col, ctx->tpair_list[0].as<int2>(), T, L, ctx->contact_cap, c);
+        if (caps) k_narrow_terrain<1><<<gp, MGFB_THREADS, 0, ctx->s_aux>>>(B.col, ctx->tpair_list[1].as<int2>(), T, L, ctx->contact_cap, c);
+        CU(cudaEventRecord(ctx->ev_join, ctx->s_aux));
+    }
+    // narrowphase, one specialisation per shape pair
     if (sph) k_narrow_bodies<0, 0><<<gp, MGFB_THREADS, 0, ctx->stream>>>(B.col, PL.p[0], L, ctx->contact_cap, c);
     if (sph && caps) {
         k_narrow_bodies<0, 1><<<gp, MGFB_THREADS, 0, ctx->stream>>>(B.col, PL.p[1], L, ctx->contact_cap, c);
         k_narrow_bodies<1, 0><<<gp, MGFB_THREADS, 0, ctx->stream>>>(B.col, PL.p[2], L, ctx->contact_cap, c);
     }
     if (caps) k_narrow_bodies<1, 1><<<gp, MGFB_THREADS, 0, ctx->stream>>>(B.col, PL.p[3], L, ctx->contact_cap, c);
-    if (ctx->terrain.present) {
-        if (sph) k_narrow_terrain<0><<<gp, MGFB_THREADS, 0, ctx->stream>>>(B.col, ctx->tpair_list[0].as<int2>(), T, L, ctx->contact_cap, c);
-        if (caps) k_narrow_terrain<1><<<gp, MGFB_THREADS, 0, ctx->stream>>>(B.col, ctx->tpair_list[1].as<int2>(), T, L, ctx->contact_cap, c);
-    }
+    if (ctx->terrain.present) CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
     CU(cudaGetLastError());
     // constraints: colour, build rows in solve order, solve
     OrderView O = order_view(ctx, L.a, L.b, L.face, L.sub);
@@ -560,6 +566,9 @@ int32_t mgfb_ctx_create(const mgfb_config* cfg, mgfb_ctx** out) {
     if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "cudaStreamCreate");
     for (auto& ev : ctx->ev) if ((e = cudaEventCreate(&ev)) != cudaSuccess) return bail(e, "cudaEventCreate");
     ctx->cur_ev = ctx->ev;
+    if ((e = cudaStreamCreateWithFlags(&ctx->s_aux, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "cudaStreamCreate");
+    if ((e = cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming)) != cudaSuccess) return bail(e, "cudaEventCreate");
+    if ((e = cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming)) != cudaSuccess) return bail(e, "cudaEventCreate");
     if ((e = cudaMallocHost(&ctx->h_ctr, sizeof(Counters))) != cudaSuccess) return bail(e, "cudaMallocHost");
     if ((e = cudaMalloc(&ctx->ctr.p, sizeof(Counters))) != cudaSuccess) return bail(e, "cudaMalloc");
     ctx->ctr.bytes = sizeof(Counters);
@@ -624,6 +633,9 @@ void mgfb_ctx_destroy(mgfb_ctx* ctx) {
     for (Buf* b : all) release(*b);
     if (ctx->h_ctr) cudaFreeHost(ctx->h_ctr);
     for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
+    if (ctx->s_aux) cudaStreamDestroy(ctx->s_aux);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
