@@ -327,7 +327,8 @@ int32_t enqueue_order_and_solve(mgfb_ctx* ctx, const OrderView& O, const Manifol
     k_scatter_rows<<<g, MGFB_THREADS, 0, ctx->stream>>>(O.group, gcount, gstart, perm, m_ptr, m_host, c);
     // Schedule of the solve: dataflow (body version counters, no grid barrier) for coloured single-GPU
     // solves; grid-barrier phases for as-given (level) order, tiled worlds, > 64 colours, or on request.
-    const bool dataflow = colour_df && ctx->cfg.solver_schedule == MGFB_SCHEDULE_DATAFLOW && (!tiled || m_bound <= ctx->tile_row_cap);
+    // (a tiled world derives its inbox tags from the common step number: 2048 tags per step)
+    const bool dataflow = colour_df && ctx->cfg.solver_schedule == MGFB_SCHEDULE_DATAFLOW && (!tiled || (m_bound <= ctx->tile_row_cap && iters < 2000u));
     DfArrays D{};
     if (dataflow) {   // rows per body = number of colours at the body; CSR offsets (already made by the colouring) for the successor links
         D.in_a = ctx->r_in_a.as<Inbox>(); D.in_b = ctx->r_in_b.as<Inbox>(); D.ia = ctx->r_ia.as<float4>(); D.row_cap = ctx->row_cap;
