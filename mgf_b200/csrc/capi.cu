@@ -432,7 +432,7 @@ int32_t enqueue_step(mgfb_ctx* ctx, float dt, unsigned iters, bool from_integrat
     k_bgrid_insert<true><<<gs, MGFB_THREADS, 0, ctx->stream>>>(B.fat, B.col, B.gid, G, c);
     PairLists PL; for (int k = 0; k < 4; ++k) PL.p[k] = ctx->pair_list[k].as<int2>();
     {
-        int gw = std::max(1, std::min((int)((slots + BP_WARPS - 1) / BP_WARPS), ctx->num_sms * 8));
+        int gw = std::max(1, std::min((int)((slots + BP_WARPS * BP_PER - 1) / (BP_WARPS * BP_PER)), ctx->num_sms * 8));
         if (ctx->max_ctas) gw = std::min(gw, ctx->max_ctas * 4);
         k_body_pairs_warp<<<gw, MGFB_THREADS, 0, ctx->stream>>>(B.tight, B.col, B.gid, tiled ? n : 0xffffffffu, G, PL, ctx->pair_cap, c);
     }

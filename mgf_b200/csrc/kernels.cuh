@@ -216,12 +216,15 @@ __global__ void __launch_bounds__(MGFB_THREADS) k_bgrid_insert(const Box* __rest
 // a tiled world bodies >= n_own are ghosts: they take part as i or as j, never both.
 #define BP_WARPS (MGFB_THREADS / 32)
 #define BP_BUF 128
-__device__ __forceinline__ void bp_flush_warp(unsigned* buf, unsigned cnt, unsigned i, const unsigned base[4], PairLists lists, unsigned cap,
-                                              Counters* ctr, unsigned lane) {
-    // buf entries: j | kind << 30.  base[k]: where this warp's kind-k entries start in list k.
+#define BP_PER 4     // bodies per warp between two CTA-wide reservations (3 CTA barriers per 32 bodies instead of per 8)
+__device__ __forceinline__ void bp_flush_warp(unsigned* buf, const unsigned char* sub, unsigned cnt, unsigned i0, const unsigned base[4], PairLists lists,
+                                              unsigned cap, Counters* ctr, unsigned lane) {
+    // buf entries: j | kind << 30, sub[e] = which of the warp's BP_PER bodies (body i0 + sub * BP_WARPS).  base[k]: where this
+    // warp's kind-k entries start in list k.
     unsigned run[4] = {0, 0, 0, 0};
     for (unsigned s0 = 0; s0 < cnt; s0 += 32) {
         unsigned e = s0 + lane < cnt ? buf[s0 + lane] : 0xffffffffu;
+        const unsigned i = i0 + (s0 + lane < cnt ? (unsigned)sub[s0 + lane] : 0u) * BP_WARPS;
         int kind = e == 0xffffffffu ? -1 : (int)(e >> 30);
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
@@ -238,15 +241,17 @@ __device__ __forceinline__ void bp_flush_warp(unsigned* buf, unsigned cnt, unsig
 __global__ void __launch_bounds__(MGFB_THREADS) k_body_pairs_warp(const Box* __restrict__ tight, const Collider* __restrict__ col, const unsigned* __restrict__ gid,
                                                                  unsigned n_own, BodyGrid G, PairLists lists, unsigned cap, Counters* ctr) {
     __shared__ unsigned s_buf[BP_WARPS][BP_BUF];
+    __shared__ unsigned char s_sub[BP_WARPS][BP_BUF];
     __shared__ unsigned s_cnt[BP_WARPS][4];     // per warp, per kind
     __shared__ unsigned s_base[BP_WARPS][4];
     if (ctr->overflow | ctr->nan_bounds) return;
     const float inv = grid_inv_cell(ctr);
     const unsigned n = ctr->n_total;
     const unsigned lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
-    for (unsigned batch = blockIdx.x * BP_WARPS; batch < n; batch += gridDim.x * BP_WARPS) {   // uniform per block
-        const unsigned i = batch + w;
+    for (unsigned batch = blockIdx.x * (BP_WARPS * BP_PER); batch < n; batch += gridDim.x * (BP_WARPS * BP_PER)) {   // uniform per block
         unsigned cnt = 0, kcnt[4] = {0, 0, 0, 0};
+        for (unsigned sub = 0; sub < BP_PER; ++sub) {
+        const unsigned i = batch + sub * BP_WARPS + w;
         if (i < n) {   // (world.rs:256 skips body 0: it has no j < i)
             const unsigned gi = gid[i];
             const bool ghost_i = i >= n_own;
@@ -309,17 +314,18 @@ __global__ void __launch_bounds__(MGFB_THREADS) k_body_pairs_warp(const Box* __r
                         kcnt[k] = 0;
                     }
                     __syncwarp();
-                    bp_flush_warp(s_buf[w], cnt, i, base, lists, cap, ctr, lane);
+                    bp_flush_warp(s_buf[w], s_sub[w], cnt, batch + w, base, lists, cap, ctr, lane);
                     __syncwarp();
                     cnt = 0;
                 }
-                if (kind >= 0) s_buf[w][cnt + __popc(m & ((1u << lane) - 1u))] = j | ((unsigned)kind << 30);
+                if (kind >= 0) { unsigned slot = cnt + __popc(m & ((1u << lane) - 1u)); s_buf[w][slot] = j | ((unsigned)kind << 30); s_sub[w][slot] = (unsigned char)sub; }
                 cnt += nh;
                 // hits per kind: body i has ONE kind, so only kinds 2*ki and 2*ki+1 can occur
                 unsigned n1 = __popc(__ballot_sync(0xffffffffu, kind == ki * 2 + 1));
 #pragma unroll
                 for (int k = 0; k < 4; ++k) kcnt[k] += k == ki * 2 + 1 ? n1 : (k == ki * 2 ? nh - n1 : 0u);
             }
+        }
         }
         if (lane < 4) s_cnt[w][lane] = kcnt[lane];
         __syncthreads();
@@ -332,7 +338,7 @@ __global__ void __launch_bounds__(MGFB_THREADS) k_body_pairs_warp(const Box* __r
         __syncthreads();
         if (cnt) {
             unsigned base[4] = {s_base[w][0], s_base[w][1], s_base[w][2], s_base[w][3]};
-            bp_flush_warp(s_buf[w], cnt, i, base, lists, cap, ctr, lane);
+            bp_flush_warp(s_buf[w], s_sub[w], cnt, batch + w, base, lists, cap, ctr, lane);
         }
         __syncthreads();
     }
@@ -647,7 +653,20 @@ __global__ void __launch_bounds__(MGFB_THREADS) k_inc_sort(OrderView O, ColourVi
         const unsigned s0 = V.body_start[i], d = V.body_start[i + 1] - s0;
         if (d == 0) continue;
         unsigned* L = V.csr + s0;
-        if (d <= 16) {
+        if (d <= 8) {   // the common case: rank by counting, all in registers (keys are unique and non-zero)
+            unsigned kk[8]; unsigned long long ky[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { kk[j] = 0u; ky[j] = 0ULL; if ((unsigned)j < d) { kk[j] = L[j]; ky[j] = V.key[kk[j]]; } }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                if ((unsigned)j < d) {
+                    unsigned rank = 0;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) rank += ky[i] > ky[j] ? 1u : 0u;
+                    L[rank] = kk[j];
+                }
+            }
+        } else if (d <= 16) {
             unsigned kk[16]; unsigned long long ky[16];
             for (unsigned j = 0; j < d; ++j) { kk[j] = L[j]; ky[j] = V.key[kk[j]]; }
             for (unsigned j = 1; j < d; ++j) {
