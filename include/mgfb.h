@@ -82,7 +82,8 @@ enum mgfb_solver_schedule {
     MGFB_SCHEDULE_DATAFLOW = 0,  /* default: per-body version counters, a row runs as soon as both its bodies are ready */
     MGFB_SCHEDULE_PHASES = 1,    /* one grid-wide barrier per colour per iteration */
     MGFB_SCHEDULE_PHASES_JP = 2  /* as PHASES, and the colouring itself by barrier-synchronised Jones-Plassmann rounds
-                                    instead of the chain (dataflow) colouring; same colours */
+                                    (priorities = identity hash only) instead of the chain colouring (priorities =
+                                    geometric class, then hash): a different, equally valid proper colouring */
 };
 
 /* solver.rs:265-279 ContactConstraintParams, manifold.rs:27-39 PruningParams, world.rs:181 */

@@ -271,6 +271,7 @@ OrderView order_view(const mgfb_ctx* ctx, const int* a, const int* b, const uint
     O.body_last = reinterpret_cast<unsigned*>(ctx->body_scratch.as<unsigned long long>() + ctx->cap);
     O.group = ctx->group.as<int>(); O.group_count = ctx->group_count.as<unsigned>(); O.gcap = ctx->group_cap;
     O.gid = ctx->gid.as<unsigned>(); O.n_own = ctx->tiled ? ctx->n : 0xffffffffu;
+    O.x = face ? ctx->x.as<float4>() : nullptr; O.col = face ? ctx->col.as<Collider>() : nullptr;   // step path only: caller-built manifolds carry no geometry
     return O;
 }
 Counters* dctr(const mgfb_ctx* ctx) { return ctx->ctr.as<Counters>(); }

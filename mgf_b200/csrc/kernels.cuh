@@ -518,6 +518,7 @@ struct OrderView {
     unsigned* group_count;             // [gcap]
     unsigned gcap;
     const unsigned* gid;               // global body ids: priorities do not depend on the tiling
+    const float4* x; const Collider* col;   // body positions / colliders for the geometric priority classes (NULL: hash only)
     unsigned n_own;                    // tiled world: bodies >= n_own are ghosts; 0xffffffff otherwise
 };
 #define TILE_INTERIOR_COLOURS 32
@@ -614,6 +615,31 @@ __global__ void __launch_bounds__(MGFB_THREADS) k_order(OrderView O, const unsig
 // pushes mask | colour to its successor on each chain (one 8-byte word: valid bit + 63 colour
 // bits, so flag and payload are one atomic store).  Steps: count constraints per body -> scan
 // -> fill the per-body lists (CSR) -> sort each short list by key and link it -> colour.
+// Priority of a constraint in the chain colouring: a geometric CLASS in the top bits, the identity hash below.
+// Greedy colouring takes constraints class by class: body-body contacts by the dominant axis of the centre
+// offset and the parity of floor(midpoint / (r_a + r_b)) along it, terrain contacts last.  In a stacked or
+// settled pile the contacts of one class are (nearly) disjoint -- along a row of touching bodies they alternate
+// parity -- so a class costs about one colour: 7 colours instead of 10 at C2 (the maximum degree is 7), and the
+// chains the colours travel down are 7-10 links deep instead of ~26.  On irregular piles it is neutral (+-1 colour).
+// Depends only on the two bodies' state, which ghosts copy exactly: the same key on every tile.
+__device__ __forceinline__ unsigned long long chain_key(const OrderView& O, unsigned k) {
+    unsigned long long h = order_key(O, k, false);
+    if (!O.x) return h;
+    const int a = O.a[k], b = O.b[k];
+    unsigned cls = 6u;
+    if (b >= 0) {
+        float4 xa = O.x[a], xb = O.x[b];
+        float dx = xa.x - xb.x, dy = xa.y - xb.y, dz = xa.z - xb.z;
+        float ax = fabsf(dx), ay = fabsf(dy), az = fabsf(dz);
+        unsigned axis = (ay > ax) ? ((az > ay) ? 2u : 1u) : ((az > ax) ? 2u : 0u);
+        float mid = axis == 0u ? (xa.x + xb.x) * 0.5f : (axis == 1u ? (xa.y + xb.y) * 0.5f : (xa.z + xb.z) * 0.5f);
+        float scale = O.col[a].p0.w + O.col[b].p0.w;
+        float q = floorf(mid / scale);
+        unsigned par = (fabsf(q) < 1.0e9f) ? ((unsigned)(long long)q & 1u) : 0u;
+        cls = axis * 2u + par;
+    }
+    return ((unsigned long long)(7u - cls) << 61) | (h >> 3);
+}
 struct ColourView {
     unsigned long long* key;     // [m] priority (bijective hash of the constraint's identity)
     unsigned* deg;               // [nbodies] constraints per body, consumed by the fill
@@ -628,7 +654,7 @@ __global__ void __launch_bounds__(MGFB_THREADS) k_inc_count(OrderView O, ColourV
     if (ctr->overflow | ctr->nan_bounds) return;
     const unsigned m = m_ptr ? *m_ptr : m_host;
     for (unsigned k = blockIdx.x * blockDim.x + threadIdx.x; k < m; k += gridDim.x * blockDim.x) {
-        V.key[k] = order_key(O, k, false);
+        V.key[k] = chain_key(O, k);
         atomicAdd(&V.deg[O.a[k]], 1u);
         int b = O.b[k];
         if (b >= 0) atomicAdd(&V.deg[b], 1u);
@@ -662,7 +688,7 @@ __global__ void __launch_bounds__(MGFB_THREADS) k_inc_sort(OrderView O, ColourVi
                 if ((unsigned)j < d) {
                     unsigned rank = 0;
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) rank += ky[i] > ky[j] ? 1u : 0u;
+                    for (int i = 0; i < 8; ++i) rank += (ky[i] > ky[j] || (ky[i] == ky[j] && kk[i] > kk[j])) ? 1u : 0u;   // (61 hash bits can tie: break by index)
                     L[rank] = kk[j];
                 }
             }
@@ -671,14 +697,14 @@ __global__ void __launch_bounds__(MGFB_THREADS) k_inc_sort(OrderView O, ColourVi
             for (unsigned j = 0; j < d; ++j) { kk[j] = L[j]; ky[j] = V.key[kk[j]]; }
             for (unsigned j = 1; j < d; ++j) {
                 unsigned k = kk[j]; unsigned long long y = ky[j]; unsigned p = j;
-                while (p > 0 && ky[p - 1] < y) { kk[p] = kk[p - 1]; ky[p] = ky[p - 1]; --p; }
+                while (p > 0 && (ky[p - 1] < y || (ky[p - 1] == y && kk[p - 1] < k))) { kk[p] = kk[p - 1]; ky[p] = ky[p - 1]; --p; }
                 kk[p] = k; ky[p] = y;
             }
             for (unsigned j = 0; j < d; ++j) L[j] = kk[j];
         } else {   // rare (a body touching > 16 others): in place
             for (unsigned j = 1; j < d; ++j) {
                 unsigned k = L[j]; unsigned long long y = V.key[k]; unsigned p = j;
-                while (p > 0 && V.key[L[p - 1]] < y) { L[p] = L[p - 1]; --p; }
+                while (p > 0 && (V.key[L[p - 1]] < y || (V.key[L[p - 1]] == y && L[p - 1] < k))) { L[p] = L[p - 1]; --p; }
                 L[p] = k;
             }
         }
