@@ -617,7 +617,8 @@ __global__ void __launch_bounds__(MGFB_THREADS) k_order(OrderView O, const unsig
 // -> fill the per-body lists (CSR) -> sort each short list by key and link it -> colour.
 // Priority of a constraint in the chain colouring: a geometric CLASS in the top bits, the identity hash below.
 // Greedy colouring takes constraints class by class: body-body contacts by the dominant axis of the centre
-// offset and the parity of floor(midpoint / (r_a + r_b)) along it, terrain contacts last.  In a stacked or
+// offset and the parity of round(x_lower / diameter_lower) along it (the lower body's place in a row of touching
+// bodies), terrain contacts last.  In a stacked or
 // settled pile the contacts of one class are (nearly) disjoint -- along a row of touching bodies they alternate
 // parity -- so a class costs about one colour: 7 colours instead of 10 at C2 (the maximum degree is 7), and the
 // chains the colours travel down are 7-10 links deep instead of ~26.  On irregular piles it is neutral (+-1 colour).
@@ -632,9 +633,10 @@ __device__ __forceinline__ unsigned long long chain_key(const OrderView& O, unsi
         float dx = xa.x - xb.x, dy = xa.y - xb.y, dz = xa.z - xb.z;
         float ax = fabsf(dx), ay = fabsf(dy), az = fabsf(dz);
         unsigned axis = (ay > ax) ? ((az > ay) ? 2u : 1u) : ((az > ax) ? 2u : 0u);
-        float mid = axis == 0u ? (xa.x + xb.x) * 0.5f : (axis == 1u ? (xa.y + xb.y) * 0.5f : (xa.z + xb.z) * 0.5f);
-        float scale = O.col[a].p0.w + O.col[b].p0.w;
-        float q = floorf(mid / scale);
+        // parity of the LOWER body's place in a row of touching bodies along that axis: round(x_lo / diameter_lo)
+        float ca = axis == 0u ? xa.x : (axis == 1u ? xa.y : xa.z), cb = axis == 0u ? xb.x : (axis == 1u ? xb.y : xb.z);
+        const bool lo_a = ca < cb;
+        float q = floorf((lo_a ? ca : cb) / (2.0f * (lo_a ? O.col[a].p0.w : O.col[b].p0.w)) + 0.5f);
         unsigned par = (fabsf(q) < 1.0e9f) ? ((unsigned)(long long)q & 1u) : 0u;
         cls = axis * 2u + par;
     }
