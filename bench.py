@@ -7,23 +7,33 @@ workload below with 20 solver iterations; `value` is whole-job constraint-iterat
 all inputs resident in HBM, timed on the device with CUDA events (the library's own events
 on its launching stream), L2 flushed between timed steps; `e2e` is the same metric through
 the public API with host buffers (pinned H2D of velocities + D2H of the full body state every
-step, wall clock).  `roofline` is for the dominant kernel (k_solve), `cpu_baseline` is the
-oracle (a C++ port of the reference: the Rust reference cannot be built here) on one core.
+step, wall clock).  `roofline` is for the dominant kernel (the solver), `kernels` gives the
+other phases of the step against their own algorithmic bytes, `cpu_baseline` is the oracle
+(a C++ port of the reference: the Rust reference cannot be built here) on one core.
 
 `--impl reference` times that CPU port alone on the same workload (bounded sample).
 
-Workload "C2pile": BASELINE.json configs[1] body set (100 000 spheres r=0.5, balls.rs lattice
-46^3 + 2664, LCG jitter +-0.01 seed 1, box 160x160x40, restitution 0.3, friction 0.6, g=-9.8,
-dt=1/60, 20 iterations) arranged as a pile already in contact (lattice spacing squeezed to
-0.98*2r, bottom layer on the floor) so that the ~295 k contact constraints per step of the
-settled pile exist from step 0 in BOTH arms; the free-fall variant needs ~600 steps (10 min of
-CPU time) before its first dense contact.
+Workloads (`--workload`, default C2settled at N=1):
+  C2settled  BASELINE.json configs[1] as BASELINE.md section 2 writes it: 100 000 spheres r=0.5 dropped from
+             the balls.rs lattice (46^3 + 2664, spacing 1.25, LCG jitter +-0.01 seed 1) into the 160x160x40
+             box, restitution 0.3, friction 0.6, g=-9.8, dt=1/60, 20 iterations; the timed window starts at
+             step 600 (the disordered pile).  Steps 0..599 are run ONCE on the GPU; the state at step 600
+             (x, q, v, omega, colliders, stored fat boxes) is a snapshot that BOTH arms load, so the GPU and
+             the CPU port time the same steps 600.. on identical inputs (tests/test_gpu_configs.py lock-steps
+             them bit for bit from that snapshot).
+  C2pile     the same body set squeezed into a lattice pile already in contact (round 1's workload: the
+             solver's best case, kept for comparison).
+  C1         BASELINE configs[0]: 512 spheres in the demo box, 10 iterations, window from step 400.
+  C3         BASELINE configs[2]: 50 000 capsules on a 20 000-triangle mesh floor (Capsule x Triangle).
+  C5         BASELINE configs[4] restated: 200 000 mixed sphere/capsule bodies on a 200 000-triangle mesh.
+At N=1 with no --workload the line also carries short runs of the other workloads under `other_workloads`.
 """
 import argparse
 import json
 import os
 import subprocess
 import sys
+import tempfile
 import threading
 import time
 
@@ -31,7 +41,16 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 ALGO_BYTES_PER_CONSTRAINT_ITER = 268.0   # 216 B read + 52 B written
-WORKLOAD = "C2pile"
+# name: (scene, pre-roll steps run once on the GPU before the window, description)
+WORKLOADS = {
+    "C2settled": ("C2", 600, "C2settled: 100000 spheres dropped into the 160x160x40 box (balls.rs lattice 46^3+2664, jitter 0.01), window from step 600"),
+    "C2pile": ("C2pile", 0, "C2pile: the C2 body set as a squeezed lattice pile already in contact, window from step 0"),
+    "C1": ("C1", 400, "C1: 512 spheres in the demo box (balls.rs n=8), 10 iterations, window from step 400"),
+    "C3": ("C3", 60, "C3: 50000 capsules on a 20000-triangle height-field floor, window from step 60"),
+    "C5": ("C5", 60, "C5: 200000 mixed sphere/capsule bodies on a 199712-triangle height field, window from step 60"),
+}
+DEFAULT_WORKLOAD = "C2settled"
+DT = 1.0 / 60.0
 
 
 def measured_peak():
@@ -110,11 +129,74 @@ class ClockSampler:
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.smax, "reasons": reasons, "samples": len(sm)}
 
 
-def build_scene():
+# ------------------------------------------------------------------------------------------ workloads
+def build_scene(name):
+    """(bodies, terrain, iters) of a workload's scene at step 0 (host-side generators, mgf_b200/scenes.py)."""
     from mgf_b200 import scenes
-    return scenes.build_config(WORKLOAD)
+    scene = WORKLOADS[name][0]
+    if scene == "C3":
+        return scenes.config_c3()
+    if scene == "C5":
+        return scenes.config_c5()
+    return scenes.build_config(scene)
 
 
+def config_of(name, nbodies, iters):
+    """The `config` object: the same keys and values in both arms."""
+    return {"workload": WORKLOADS[name][2], "bodies": int(nbodies), "solver_iterations": int(iters), "dt": DT,
+            "window_first_step": WORKLOADS[name][1]}
+
+
+def snapshot_path(name):
+    return os.path.join(tempfile.gettempdir(), f"mgfb_bench_snapshot_{name}_{WORKLOADS[name][1]}.npz")
+
+
+def save_snapshot(name, snap):
+    import numpy as np
+    tmp = snapshot_path(name) + f".{os.getpid()}.tmp.npz"
+    np.savez(tmp, **snap)
+    os.replace(tmp, snapshot_path(name))
+
+
+def load_snapshot(name):
+    import numpy as np
+    p = snapshot_path(name)
+    if not os.path.exists(p):
+        return None
+    with np.load(p) as z:
+        return {k: z[k] for k in z.files}
+
+
+def gpu_preroll(name, device=0):
+    """Steps 0..window_first_step-1 on the GPU (once); returns the world, positioned at the window's first step,
+    its scene and the snapshot of that state."""
+    import numpy as np
+    import mgf_b200
+    bodies, terrain, iters = build_scene(name)
+    g = mgf_b200.World(device=device)
+    g.add_bodies(*bodies); g.set_terrain(*terrain)
+    pre = WORKLOADS[name][1]
+    if pre:
+        g.step(np.float32(DT), iters, nsteps=pre)
+    return g, bodies, terrain, iters, g.snapshot()
+
+
+def reference_snapshot(name):
+    """The window's initial state for the CPU arm: the cached snapshot, else made by a GPU pre-roll in a CHILD process
+    (this process never loads the CUDA library), else -- no GPU -- by pre-rolling on the CPU port itself."""
+    if WORKLOADS[name][1] == 0:
+        return None, "step 0 of the scene (no pre-roll)"
+    snap = load_snapshot(name)
+    if snap is not None:
+        return snap, "snapshot of the GPU pre-roll (cached by an earlier bench.py run on this box)"
+    r = subprocess.run([sys.executable, os.path.abspath(__file__), "--make-snapshot", name], capture_output=True, text=True)
+    snap = load_snapshot(name)
+    if r.returncode == 0 and snap is not None:
+        return snap, "snapshot of a GPU pre-roll run in a child process (inputs only; the timed region is CPU-only)"
+    return "cpu", "pre-rolled on the CPU port itself (no GPU available for the pre-roll)"
+
+
+# ------------------------------------------------------------------------------------------ reference arm
 def run_reference(args, rank):
     """CPU arm: the oracle port of the reference, single thread (mgf is single-threaded and its
     Gauss-Seidel sweep is inherently serial, solver.rs:73-77)."""
@@ -123,19 +205,25 @@ def run_reference(args, rank):
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import numpy as np
     import oracle_lib   # bench.py's reference arm is one of the two places allowed to execute oracle/
+    dt = np.float32(DT)
     if args.gpus == 1:
-        bodies, terrain, iters = build_scene()
-        workload = WORKLOAD
+        name = args.workload or DEFAULT_WORKLOAD
+        bodies, terrain, iters = build_scene(name)
+        config = config_of(name, len(bodies[0]), iters)
+        snap, how = reference_snapshot(name)
     else:   # the same one-box world the N-GPU arm tiles, whole, on one core
         from mgf_b200 import scenes
         tiles = [scenes.tiled_pile(args.gpus, t, nz=50 * args.bodies_per_gpu // 100000) for t in range(args.gpus)]
         bodies = tuple(np.concatenate([t[0][k] for t in tiles]) for k in range(5))
         terrain = tiles[0][2]; iters = 20
-        workload = (f"pile of {args.gpus} x {args.bodies_per_gpu} spheres (50x40x{50 * args.bodies_per_gpu // 100000} lattice per tile, same "
-                    "radius/spacing/material as C2pile), one box")
+        config = tiled_config(args.gpus, args.bodies_per_gpu, iters)
+        snap, how = None, "step 0 of the scene (no pre-roll)"
     w = oracle_lib.OracleWorld()
     w.add_bodies(*bodies); w.set_terrain(*terrain)
-    dt = np.float32(1.0 / 60.0)
+    if isinstance(snap, dict):
+        w.restore(snap)
+    elif snap == "cpu":
+        w.step(dt, iters, WORKLOADS[name][1])
     budget_s = 150.0
     t_start = time.time()
     warm = 0
@@ -154,11 +242,11 @@ def run_reference(args, rank):
         "impl": "reference", "metric": "contact_constraint_iterations_per_second", "value": val, "unit": "constraint-iters/s",
         "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": 1e3 * sec / steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload, "bodies": len(bodies[0]), "solver_iterations": iters, "dt": 1.0 / 60.0,
-                   "constraints_per_step": ci / iters / steps, "candidate_pairs_per_step": pairs / steps},
+        "config": config,
+        "work": {"constraints_per_step": ci / iters / steps, "candidate_pairs_per_step": pairs / steps, "initial_state": how},
         "narrowphase_pairs_per_second": pairs / sec,
         "cpu_baseline": {"value": val, "unit": "constraint-iters/s", "cores": 1, "kind": "port",
-                         "sample": f"{steps} full World::step of {workload} after {warm} warm-up steps, C++ port of the reference "
+                         "sample": f"{steps} full World::step of the workload after {warm} warm-up steps, C++ port of the reference "
                                    "(oracle/), g++ -O2 -ffp-contract=off, whole step timed like balls.rs:107-109; host has "
                                    f"{os.cpu_count()} cores, 1 used (reference is single-threaded)"},
         "e2e": {"value": val, "unit": "constraint-iters/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -167,18 +255,101 @@ def run_reference(args, rank):
     print(json.dumps(line), flush=True)
 
 
+def tiled_config(world, bodies_per_gpu, iters):
+    nz = 50 * bodies_per_gpu // 100000
+    return {"workload": f"pile of {world} x {bodies_per_gpu} spheres (50x40x{nz} lattice per tile, same radius/spacing/material as C2pile), one box",
+            "bodies": world * bodies_per_gpu, "solver_iterations": iters, "dt": DT, "window_first_step": 0}
+
+
+# ------------------------------------------------------------------------------------------ GPU arm helpers
+def time_steps_device(g, torch, flush, dt, iters, nsteps):
+    """nsteps World::steps, each timed by the library's CUDA events on its stream, L2 flushed in between."""
+    rows = []
+    for _ in range(nsteps):
+        flush.fill_(1.0); torch.cuda.synchronize()
+        rows.append(g.step(dt, iters))
+    return rows
+
+
+def phase_rooflines(g, torch, flush, dt, iters, nsteps, peak):
+    """Per-phase device time (mgfb_step_profile: an event between the phases) against each phase's ALGORITHMIC bytes
+    (SURVEY.md section 8d): integrate 272 B/body; narrowphase 64 B (SxS), 72 (SxCap / CapxS), 88 (CapxCap), 72 (TrixS),
+    84 (TrixCap) per candidate pair + 64 B per LocalContact; ContactConstraint::new 2x84 + 64 read + 100 written per
+    constraint; solver 268 B per constraint-iteration."""
+    acc = {}; n = 0
+    for _ in range(nsteps):
+        flush.fill_(1.0); torch.cuda.synchronize()
+        st, pr = g.step_profile(dt, iters)
+        n += 1
+        pb = pr["pairs"]; tp = pr["terrain_pairs"]
+        bytes_ = {
+            "integrate": 272.0 * st["bodies"],
+            "body_grid": None, "pair_sweep": None, "colouring": None,
+            "narrow_bodies": 64.0 * pb[0] + 72.0 * (pb[1] + pb[2]) + 88.0 * pb[3] + 64.0 * pr["body_contacts"],
+            "terrain": 72.0 * tp[0] + 84.0 * tp[1] + 64.0 * pr["terrain_contacts"],
+            "build_rows": (2 * 84.0 + 64.0 + 100.0) * st["constraints"],
+            "solve": ALGO_BYTES_PER_CONSTRAINT_ITER * st["constraints"] * iters,
+        }
+        units = {"integrate": st["bodies"], "body_grid": st["bodies"], "pair_sweep": sum(pb), "narrow_bodies": sum(pb), "terrain": sum(tp),
+                 "colouring": st["constraints"], "build_rows": st["constraints"], "solve": st["constraints"] * iters}
+        for k in bytes_:
+            a = acc.setdefault(k, {"ms": 0.0, "bytes": 0.0, "units": 0.0, "has_bytes": bytes_[k] is not None})
+            a["ms"] += pr[k]; a["bytes"] += bytes_[k] or 0.0; a["units"] += units[k]
+    out = {}
+    unit_names = {"integrate": "bodies", "body_grid": "bodies", "pair_sweep": "candidate pairs", "narrow_bodies": "candidate pairs",
+                  "terrain": "(body, face) candidates", "colouring": "constraints", "build_rows": "constraints", "solve": "constraint-iterations"}
+    for k, a in acc.items():
+        ms = a["ms"] / n
+        row = {"ms": ms, "units_per_step": a["units"] / n, "unit": unit_names[k],
+               "units_per_second": (a["units"] / n) / (ms * 1e-3) if ms > 0 else None}
+        if a["has_bytes"] and ms > 0:
+            gbs = a["bytes"] / n / (ms * 1e-3) / 1e9
+            row.update({"algorithmic_bytes_per_step": a["bytes"] / n, "achieved_gbs": gbs, "frac_of_hbm_peak": gbs / peak})
+        out[k] = row
+    return out
+
+
+def short_run(name, torch, flush, device, peak):
+    """A secondary workload: pre-roll, 3 warm-up + 10 timed steps, device-timed, no CPU arm."""
+    import numpy as np
+    dt = np.float32(DT)
+    g, bodies, terrain, iters, snap = gpu_preroll(name, device)
+    g.step(dt, iters, nsteps=3)
+    rows = time_steps_device(g, torch, flush, dt, iters, 10)
+    ms = sum(r["step_ms"] for r in rows); sms = sum(r["solve_ms"] for r in rows)
+    cons = sum(r["constraints"] for r in rows); prs = sum(r["candidate_pairs"] + r["terrain_candidates"] for r in rows)
+    phases = phase_rooflines(g, torch, flush, dt, iters, 4, peak)
+    out = {"config": config_of(name, len(bodies[0]), iters), "value": cons * iters / (ms * 1e-3), "unit": "constraint-iters/s",
+           "ms_per_step": ms / len(rows), "solve_ms": sms / len(rows), "constraints_per_step": cons / len(rows),
+           "candidate_pairs_per_step": prs / len(rows), "narrowphase_pairs_per_second": prs / (ms * 1e-3),
+           "colours": sum(r["phases"] for r in rows) / len(rows),
+           "solver_frac_of_hbm_peak": ALGO_BYTES_PER_CONSTRAINT_ITER * cons * iters / (sms * 1e-3) / 1e9 / peak if sms > 0 else None,
+           "kernels": {k: {kk: v[kk] for kk in ("ms", "units_per_second", "unit", "frac_of_hbm_peak") if kk in v} for k, v in phases.items()}}
+    g.ctx.close()
+    return out
+
+
+# ------------------------------------------------------------------------------------------ main
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="mgf_b200", choices=["mgf_b200", "reference"])
+    ap.add_argument("--workload", default=None, choices=sorted(WORKLOADS),
+                    help=f"N = 1 only; default {DEFAULT_WORKLOAD} (plus short runs of the others under other_workloads)")
+    ap.add_argument("--make-snapshot", default=None, choices=sorted(WORKLOADS), help="internal: GPU pre-roll of a workload, cached for the reference arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-other-workloads", action="store_true")
     ap.add_argument("--bodies-per-gpu", type=int, default=100000,
                     help="N > 1 only: 100000 (default, 50x40x50 per tile) or 250000 (50x40x125 per tile: 8 GPUs = the 2 M-sphere C4 scene)")
     ap.add_argument("--schedule", default="dataflow", choices=["dataflow", "phases"],
-                    help="solver schedule (include/mgfb.h mgfb_solver_schedule); tiled worlds always use phases")
+                    help="solver schedule (include/mgfb.h mgfb_solver_schedule)")
     args = ap.parse_args()
+    if args.make_snapshot:
+        g, _, _, _, snap = gpu_preroll(args.make_snapshot)
+        save_snapshot(args.make_snapshot, snap)
+        return
     args.warmup = max(args.warmup, 3) if args.impl == "mgf_b200" else args.warmup
     rank = int(os.environ.get("RANK", "0")); local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -196,12 +367,21 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     import mgf_b200
 
-    dt = np.float32(1.0 / 60.0)
+    dt = np.float32(DT)
+    snap = None
+    initial_state = "step 0 of the scene (no pre-roll)"
     if world == 1:
-        bodies, terrain, iters = build_scene()
-        g = mgf_b200.World(device=local_rank, solver_schedule=0 if args.schedule == "dataflow" else 1)
-        g.add_bodies(*bodies); g.set_terrain(*terrain)
-        workload = WORKLOAD
+        name = args.workload or DEFAULT_WORKLOAD
+        g, bodies, terrain, iters, snap = gpu_preroll(name, local_rank)
+        if WORKLOADS[name][1]:
+            save_snapshot(name, snap)
+            initial_state = (f"steps 0..{WORKLOADS[name][1] - 1} run once on the GPU; the snapshot of that state (x, q, v, omega, colliders, stored fat "
+                             "boxes) is what the CPU arm loads too")
+        if args.schedule != "dataflow":
+            g.ctx.close()
+            g = mgf_b200.World(device=local_rank, solver_schedule=1)
+            g.add_bodies(*bodies); g.set_terrain(*terrain); g.restore(snap)
+        config = config_of(name, len(bodies[0]), iters)
         parallelism = "single GPU"
     else:
         # ONE world of `world` x 100 000 spheres in one box, one slab per GPU (weak scaling).  Ghost
@@ -215,7 +395,7 @@ def main():
         tw.add_owned(ids, *bodies); tw.set_terrain(*terrain)
         tw.connect(tiling.all_gather_bytes, ghost_capacity=32768 * max(1, nz // 50))
         g = tw.world
-        workload = f"pile of {world} x {len(bodies[0])} spheres (50x40x{nz} lattice per tile, same radius/spacing/material as C2pile), one box"
+        config = tiled_config(world, args.bodies_per_gpu, iters)
         parallelism = (f"{world} slabs along x, one per GPU; ghost bodies once per step through NVLink peer memory; "
                        + ("solver: the constraint chains of boundary bodies continue on the neighbour GPU, every hand-over one 32-byte "
                           "peer store from inside the solver kernel (no exchange phase, no grid barrier)" if args.schedule == "dataflow"
@@ -237,18 +417,15 @@ def main():
     # ---- timed: K steps, device time from the library's CUDA events, L2 flushed between steps
     barrier()
     mark0 = sampler.mark()
-    step_ms = []; solve_ms = []; cons = []; pairs = []; groups = []; ghosts = []; bcons = []
     t_wall0 = time.perf_counter()
-    for _ in range(args.steps):
-        flush.fill_(1.0); torch.cuda.synchronize()
-        st = g.step(dt, iters)
-        step_ms.append(st["step_ms"]); solve_ms.append(st["solve_ms"]); cons.append(st["constraints"])
-        pairs.append(st["candidate_pairs"] + st["terrain_candidates"]); groups.append(st["phases"])
-        ghosts.append(st["ghosts"]); bcons.append(st["boundary_constraints"])
+    rows = time_steps_device(g, torch, flush, dt, iters, args.steps)
     barrier()
     t_wall = time.perf_counter() - t_wall0
     clocks = sampler.stop(mark0, sampler.mark())
     tot = g.totals(reset=True)
+    step_ms = [r["step_ms"] for r in rows]; solve_ms = [r["solve_ms"] for r in rows]; cons = [r["constraints"] for r in rows]
+    pairs = [r["candidate_pairs"] + r["terrain_candidates"] for r in rows]; groups = [r["phases"] for r in rows]
+    ghosts = [r["ghosts"] for r in rows]; bcons = [r["boundary_constraints"] for r in rows]
     total_ms = float(sum(step_ms)); units = float(sum(cons)) * iters; npairs = float(sum(pairs))
     if world > 1:
         t = torch.tensor([total_ms], device="cuda", dtype=torch.float64); dist.all_reduce(t, op=dist.ReduceOp.MAX); total_ms_max = t.item()
@@ -261,6 +438,9 @@ def main():
     # ---- end to end: public API with host buffers; every step: pinned H2D of that step's inputs (v, omega) and D2H of its
     # result (x, q, v, omega), through the pipelined step API (mgfb_step_enqueue / mgfb_step_wait: the transfers of step
     # k overlap the kernels of step k+1, two output buffer sets); on a tiled world every rank runs the same sequence.
+    if snap is not None:
+        g.restore(snap)      # the e2e loop walks the same window again
+        g.step(dt, iters, nsteps=args.warmup)
     pin = lambda shape: torch.empty(shape, dtype=torch.float32, pin_memory=True).numpy()
     hv, hw = pin((n, 3)), pin((n, 3))
     outs = [(pin((n, 3)), pin((n, 4)), pin((n, 3)), pin((n, 3))) for _ in range(2)]
@@ -271,6 +451,7 @@ def main():
     lib, h = g.ctx.lib, g.ctx.h
     import ctypes as C
     st = L.StepStats()
+    g.totals(reset=True)
     barrier()
     e2e_units = 0.0; e2e_dev_ms = 0.0
     t0 = time.perf_counter()
@@ -285,13 +466,14 @@ def main():
     e2e_api = "mgfb_step_enqueue / mgfb_step_wait (pipelined, 2 steps in flight)"
     barrier()
     e2e_s = time.perf_counter() - t0
+    tot_e2e = g.totals(reset=True)
     if world > 1:
         t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64); dist.all_reduce(t, op=dist.ReduceOp.MAX); e2e_s = t.item()
         u = torch.tensor([e2e_units], device="cuda", dtype=torch.float64); dist.all_reduce(u, op=dist.ReduceOp.SUM); e2e_units = u.item()
     e2e_val = e2e_units / e2e_s
     assert np.isfinite(outs[0][0]).all() and np.isfinite(outs[(args.steps - 1) & 1][0]).all()
 
-    # ---- roofline of the dominant kernel (k_solve), live CUDA-event durations
+    # ---- roofline of the dominant kernel (the solver), live CUDA-event durations
     peak, peak_src = measured_peak()
     solve_s = sum(solve_ms) * 1e-3
     achieved = ALGO_BYTES_PER_CONSTRAINT_ITER * units / solve_s / 1e9
@@ -299,52 +481,76 @@ def main():
     roofline = {"kernel": "k_solve_df (persistent sequential-impulse solver; rows wait on per-row inboxes filled by their predecessors, no grid barrier)" if dataflow
                 else "k_solve (persistent cooperative sequential-impulse solver, one grid barrier per colour)", "bound": "hbm", "achieved": achieved, "peak": peak,
                 "unit": "GB/s", "frac": achieved / peak,
-                # dram__bytes_read.sum + dram__bytes_write.sum of one k_solve_df launch of this workload, `ncu --set full`
-                # (profiles/r01_v4_k_solve_df_raw.csv; ncu starts every replay pass from a flushed L2)
-                "traffic": 145.2e6 if (dataflow and world == 1) else None, "traffic_unit": "bytes per launch (ncu, cold L2)",
+                # dram__bytes_read.sum + dram__bytes_write.sum of one solver launch, `ncu --set full` (profiles/; ncu starts every replay
+                # pass from a flushed L2); null until this round's capture of this workload is in profiles/
+                "traffic": NCU_TRAFFIC.get((config["workload"].split(":")[0], dataflow and world == 1)), "traffic_unit": "bytes per launch (ncu, cold L2)",
+                "l2_throughput_frac_ncu": NCU_L2_FRAC.get((config["workload"].split(":")[0], dataflow and world == 1)),
                 "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": ALGO_BYTES_PER_CONSTRAINT_ITER * units / len(solve_ms),
                 "avg_launch_ms": sum(solve_ms) / len(solve_ms), "share_of_step": sum(solve_ms) / total_ms,
-                "note": "268 B per constraint-iteration x constraints x 20 iterations per launch; the rows (~70 MB) are "
-                        "L2-resident, so the kernel is bound by the latency of its 180 chain hand-overs, not by HBM bytes "
-                        "(profiles/r01_summary_v4.md)"}
+                "colours_per_iteration": sum(groups) / len(groups),
+                "note": "268 B per constraint-iteration x constraints x 20 iterations per launch.  The rows are L2-resident at this size, so "
+                        "`achieved` is ALGORITHMIC bytes served mostly from L2, not DRAM traffic: the kernel is bound by the latency of "
+                        "its chain hand-overs (colours x iterations), see profiles/ and DESIGN.md section 4"}
 
+    kernels = None; others = None; cpu = None
+    if world == 1:
+        # ---- the other phases of the step against their own algorithmic bytes (a separate, event-instrumented pass)
+        if snap is not None:
+            g.restore(snap); g.step(dt, iters, nsteps=args.warmup)
+        kernels = phase_rooflines(g, torch, flush, dt, iters, 8, peak)
     # ---- CPU baseline (rank 0, N=1): bounded sample of the same workload on the oracle
-    cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         sys.path.insert(0, os.path.join(ROOT, "tests"))
         import oracle_lib
         o = oracle_lib.OracleWorld()
         o.add_bodies(*bodies); o.set_terrain(*terrain)
-        o.step(dt, iters, min(args.warmup, 3))
-        sec, ci, pr = o.time_steps(dt, iters, 8)
+        if WORKLOADS[name][1]:
+            o.restore(snap)
+        ncpu = 8 if n > 10000 else 200
+        o.step(dt, iters, 2)
+        sec, ci, pr = o.time_steps(dt, iters, ncpu)
         cpu = {"value": ci / sec, "unit": "constraint-iters/s", "cores": 1, "kind": "port",
-               "pairs_per_second": pr / sec, "ms_per_step": 1e3 * sec / 8,
-               "sample": f"8 full World::step of {WORKLOAD} after {min(args.warmup, 3)} warm-up steps on the C++ port of the reference "
+               "pairs_per_second": pr / sec, "ms_per_step": 1e3 * sec / ncpu,
+               "sample": f"{ncpu} full World::step of the workload (from the same snapshot) after 2 warm-up steps on the C++ port of the reference "
                          f"(the Rust reference cannot be built: no rustc); 1 of {os.cpu_count()} host cores (reference is single-threaded)"}
+    if world == 1 and args.workload is None and not args.no_other_workloads:
+        g.ctx.close()
+        others = {}
+        for other in WORKLOADS:
+            if other != name:
+                others[other] = short_run(other, torch, flush, local_rank, peak)
 
     if rank == 0:
         line = {
             "metric": "contact_constraint_iterations_per_second", "value": value, "unit": "constraint-iters/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms_max / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload, "bodies_per_gpu": n, "solver_iterations": iters, "dt": 1.0 / 60.0,
-                       "constraints_per_step": units_all / iters / args.steps, "candidate_pairs_per_step": pairs_all / args.steps,
-                       "colour_groups": sum(groups) / len(groups), "l2": "flushed between timed steps (256 MB write)",
-                       "parallelism": parallelism,
-                       "rank0_ghosts_per_step": sum(ghosts) / len(ghosts), "rank0_boundary_constraints_per_step": sum(bcons) / len(bcons),
-                       "arithmetic": "--fmad=false, IEEE div/sqrt: bit-exact vs the CPU port"},
+            "config": config,
+            "work": {"constraints_per_step": units_all / iters / args.steps, "candidate_pairs_per_step": pairs_all / args.steps,
+                     "colour_groups": sum(groups) / len(groups), "l2": "flushed between timed steps (256 MB write)",
+                     "parallelism": parallelism, "bodies_per_gpu": n,
+                     "rank0_ghosts_per_step": sum(ghosts) / len(ghosts), "rank0_boundary_constraints_per_step": sum(bcons) / len(bcons),
+                     "arithmetic": "--fmad=false, IEEE div/sqrt: bit-exact vs the CPU port",
+                     "initial_state": initial_state},
             "narrowphase_pairs_per_second": pairs_all / (total_ms_max * 1e-3),
             "solver_only_constraint_iters_per_second": units / solve_s,
-            "roofline": roofline, "cpu_baseline": cpu,
+            "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu,
             "e2e": {"value": e2e_val, "unit": "constraint-iters/s", "h2d_bytes_per_step": n * 24, "d2h_bytes_per_step": n * 52,
                     "ms_per_step": 1e3 * e2e_s / args.steps, "api": e2e_api,
-                    "device_ms_per_step": e2e_dev_ms / args.steps, "constraints_per_step": e2e_units / iters / args.steps / max(world, 1)},
+                    "device_ms_per_step": e2e_dev_ms / args.steps, "constraints_per_step": e2e_units / iters / args.steps / max(world, 1),
+                    "gpu_launches": tot_e2e["kernel_launches"]},
             "gpu_launches": tot["kernel_launches"], "clocks": clocks, "wall_s_timed_region": t_wall,
+            "other_workloads": others,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+# ncu `--set full` captures of one solver launch (profiles/): (workload, dataflow single GPU) -> DRAM bytes, L2 throughput fraction
+NCU_TRAFFIC = {("C2pile", True): 145.2e6}
+NCU_L2_FRAC = {("C2pile", True): 0.32}
 
 
 if __name__ == "__main__":

@@ -129,6 +129,18 @@ int32_t mgfb_bodies_set_velocity(mgfb_ctx* ctx, uint32_t first, uint32_t n, cons
 int32_t mgfb_bodies_get_colliders(mgfb_ctx* ctx, uint32_t first, uint32_t n, mgfb_shape* out);
 /* world inverse inertia (physics.rs:152,232), 9 floats column-major per body. */
 int32_t mgfb_bodies_get_inv_moment(mgfb_ctx* ctx, uint32_t first, uint32_t n, float* out /* n*9 */);
+/* The stored fat AABB of each body in the demo world's body BVH (world.rs:180-181, refreshed lazily at :235-238;
+ * `bvh[bvh_ids[i]]`, bvh.rs:483): centre[3], half extents[3] per body. */
+int32_t mgfb_bodies_get_fat_bounds(mgfb_ctx* ctx, uint32_t first, uint32_t n, float* boxes /* n*6 */);
+/* Writes the pub fields x, q, collider (physics.rs:142-154), the velocities (ConstrainedSet::set, physics.rs:306) and the
+ * stored fat AABBs of bodies first..first+n: together with get_state / get_colliders / get_fat_bounds this saves and
+ * restores a world bit for bit (checkpoint, or loading one state into two implementations).  Any pointer may be NULL
+ * (that field is kept).  A collider keeps its Component kind and radius (MGFB_ERR_INVALID_ARG otherwise); colliders[i].v is
+ * Moving.1, the displacement complete_motion adds next (physics.rs:262-269).  The world inverse inertia follows q
+ * (physics.rs:231-232). */
+int32_t mgfb_bodies_set_state(mgfb_ctx* ctx, uint32_t first, uint32_t n, const float* x /* n*3 */, const float* q /* n*4 */,
+                              const float* v /* n*3 */, const float* omega /* n*3 */, const mgfb_shape* colliders /* n */,
+                              const float* fat_boxes /* n*6 */);
 /* RigidBodyVec::integrate (physics.rs:222-253) */
 int32_t mgfb_integrate(mgfb_ctx* ctx, float dt);
 /* RigidBodyVec::complete_motion (physics.rs:262-269) */
@@ -280,17 +292,42 @@ int32_t mgfb_step(mgfb_ctx* ctx, float dt, uint32_t iters, mgfb_step_stats* stat
 /* Enqueue `nsteps` steps with no host synchronisation in between (stats of the last one). */
 int32_t mgfb_step_n(mgfb_ctx* ctx, float dt, uint32_t iters, uint32_t nsteps, mgfb_step_stats* stats);
 
+/* One step with a CUDA event between its phases: where the step's device time goes (diagnostic; the events cost a few
+ * microseconds, so mgfb_step's own step_ms is the number to quote).  MGFB_PHASE_TERRAIN runs on a
+ * side stream beside BODY_GRID..NARROW_BODIES and is timed there. */
+enum mgfb_phase {
+    MGFB_PHASE_INTEGRATE = 0,      /* complete_motion + integrate + swept / fat AABBs (physics.rs:222-269, world.rs:235-238)  */
+    MGFB_PHASE_BODY_GRID = 1,      /* broadphase index over the stored fat boxes (replaces the incremental tree, bvh.rs)       */
+    MGFB_PHASE_PAIR_SWEEP = 2,     /* BVH::query + j < i filter (world.rs:261-268)                                            */
+    MGFB_PHASE_NARROW_BODIES = 3,  /* Moving<Component> x Moving<Component> LocalContacts (compound.rs:192-207)               */
+    MGFB_PHASE_TERRAIN = 4,        /* Mesh::contacts: mesh query + Polygon x Moving<Sphere|Capsule> (mesh.rs:115-139)         */
+    MGFB_PHASE_COLOURING = 5,      /* solve order: chain colouring, group scan, row scatter                                   */
+    MGFB_PHASE_BUILD_ROWS = 6,     /* ContactConstraint::new (solver.rs:101-191)                                              */
+    MGFB_PHASE_SOLVE = 7,          /* Solver::solve (solver.rs:72-78)                                                         */
+    MGFB_PHASE_COUNT = 8
+};
+typedef struct mgfb_phase_profile {
+    float phase_ms[8];          /* indexed by mgfb_phase */
+    uint32_t pairs[4];          /* body-pair candidates per shape pair: [receiver kind * 2 + argument kind], 0 = sphere, 1 = capsule */
+    uint32_t terrain_pairs[2];  /* (body, face) candidates per body kind */
+    uint32_t body_contacts;     /* LocalContacts emitted by the body-body narrowphase */
+    uint32_t terrain_contacts;  /* LocalContacts emitted by the terrain narrowphase */
+} mgfb_phase_profile;
+int32_t mgfb_step_profile(mgfb_ctx* ctx, float dt, uint32_t iters, mgfb_step_stats* stats /* may be NULL */, mgfb_phase_profile* out);
+
 /* Pipelined World::step for callers that move state across PCIe every step (rendering, logging, a host-side
  * controller).  mgfb_step_enqueue queues  [v_in, omega_in -> device]  ->  the step  ->  [x, q, v, omega -> host]
  * and returns at once; mgfb_step_wait blocks until the OLDEST queued step's outputs are in the caller's buffers
- * and returns its stats.  Up to two steps may be in flight: the transfers of step k (separate copy streams, both
- * directions) overlap the kernels of step k+1.  Same kernels and bit-identical results as mgfb_step.
+ * and returns its stats.  Up to four steps may be in flight: the transfers of step k (separate copy streams, both
+ * directions) overlap the kernels of the steps behind it.  Same kernels and bit-identical results as mgfb_step.
  * v_in/omega_in (n*3 each, both or neither) are applied before the step: MGFB_INPUT_SET overwrites the velocities
  * (ConstrainedSet::set, physics.rs:304), MGFB_INPUT_ADD adds to them (what `bodies.v[i] += dv` on the pub fields does
  * between two steps of the reference: external impulses).  Any output pointer may be NULL.  Host buffers must be page-locked and must not be touched until the
- * matching wait returns.  Work lists are sized once (16 pairs / 16 contacts per body): an overflow is reported by
- * the wait as MGFB_ERR_CAPACITY (call mgfb_step, which regrows, to continue).  On a tiled world every rank must
- * enqueue and wait the same sequence of steps. */
+ * matching wait returns.  Work lists are sized once (16 pairs / 16 contacts per body); when a step overflows one all the
+ * same, its mgfb_step_wait drains the pipeline, regrows the lists, re-runs that step from after its integration and
+ * re-queues the younger steps whole (stats.overflow != 0 tells; results are unchanged).  Only a TILED world cannot regrow
+ * (its neighbours hold pointers into the lists): there the wait returns MGFB_ERR_CAPACITY.  On a tiled world every rank
+ * must enqueue and wait the same sequence of steps. */
 enum mgfb_input_mode { MGFB_INPUT_SET = 0, MGFB_INPUT_ADD = 1 };
 int32_t mgfb_step_enqueue(mgfb_ctx* ctx, float dt, uint32_t iters, uint32_t input_mode, const float* v_in, const float* omega_in,
                           float* x_out, float* q_out, float* v_out, float* omega_out);
@@ -337,6 +374,14 @@ typedef struct mgfb_tile_desc { uint64_t opaque[112]; } mgfb_tile_desc;   /* 896
 int32_t mgfb_tile_export(mgfb_ctx* ctx, uint32_t ghost_capacity, mgfb_tile_desc* out);
 /* descs[0..nranks) in tile order along x; maps the neighbours' memory (rank-1, rank+1). */
 int32_t mgfb_tile_connect(mgfb_ctx* ctx, uint32_t rank, uint32_t nranks, const mgfb_tile_desc* descs);
+
+/* The dataflow solver hands velocities from one constraint row to the next with single 32-byte stores (payload + tag in one
+ * sector) instead of flag + fence; that such a store is never observed half-written is checked, not assumed: at
+ * mgfb_ctx_create on local memory and at mgfb_tile_connect across each NVLink peer mapping (writers overwrite records while
+ * readers on other SMs poll them).  A torn read makes the context fall back to MGFB_SCHEDULE_PHASES (tiled: MGFB_ERR_TILE
+ * asking for that schedule).  This call runs `rounds` more rounds of the local test (0 = none) and returns the totals so
+ * far: *torn must be 0; *observed counts distinct whole records the readers saw. */
+int32_t mgfb_selftest_handover(mgfb_ctx* ctx, uint32_t rounds, uint32_t* torn, uint32_t* observed);
 
 /* Device-resident staging used by multi-GPU drivers and benchmarks: raw device pointers to the
  * SoA body arrays (for NCCL send/recv issued by the host plumbing).  See DESIGN.md. */

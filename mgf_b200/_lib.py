@@ -26,6 +26,7 @@ CONTACT_DTYPE = np.dtype([("a", "<f4", (3,)), ("b", "<f4", (3,)), ("n", "<f4", (
 INTERSECTION_DTYPE = np.dtype([("p", "<f4", (3,)), ("t", "<f4")])   # collision.rs:151 Intersection
 RAY, SEGMENT = 0, 1
 INPUT_SET, INPUT_ADD = 0, 1
+PHASES = ("integrate", "body_grid", "pair_sweep", "narrow_bodies", "terrain", "colouring", "build_rows", "solve")   # enum mgfb_phase
 LOCAL_CONTACT_DTYPE = np.dtype([("local_a", "<f4", (3,)), ("local_b", "<f4", (3,)), ("global", CONTACT_DTYPE)])
 assert SHAPE_DTYPE.itemsize == 64 and CONTACT_DTYPE.itemsize == 40 and LOCAL_CONTACT_DTYPE.itemsize == 64
 
@@ -62,6 +63,11 @@ class StepStats(C.Structure):
         return {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}
 
 
+class PhaseProfile(C.Structure):
+    _fields_ = [("phase_ms", C.c_float * 8), ("pairs", C.c_uint32 * 4), ("terrain_pairs", C.c_uint32 * 2),
+                ("body_contacts", C.c_uint32), ("terrain_contacts", C.c_uint32)]
+
+
 class TileDesc(C.Structure):
     _fields_ = [("opaque", C.c_uint64 * 112)]
 
@@ -86,6 +92,8 @@ SYMBOLS = [
     ("mgfb_bodies_set_velocity", C.c_int32, [_P, C.c_uint32, C.c_uint32, _P, _P]),
     ("mgfb_bodies_get_colliders", C.c_int32, [_P, C.c_uint32, C.c_uint32, _P]),
     ("mgfb_bodies_get_inv_moment", C.c_int32, [_P, C.c_uint32, C.c_uint32, _P]),
+    ("mgfb_bodies_get_fat_bounds", C.c_int32, [_P, C.c_uint32, C.c_uint32, _P]),
+    ("mgfb_bodies_set_state", C.c_int32, [_P, C.c_uint32, C.c_uint32, _P, _P, _P, _P, _P, _P]),
     ("mgfb_integrate", C.c_int32, [_P, C.c_float]),
     ("mgfb_complete_motion", C.c_int32, [_P]),
     ("mgfb_terrain_set", C.c_int32, [_P, _P, C.c_uint32, _P, C.c_uint32, _P]),
@@ -93,6 +101,7 @@ SYMBOLS = [
     ("mgfb_solver_solve", C.c_int32, [_P, C.POINTER(Manifolds), C.c_float, C.c_uint32, C.c_uint32, _P, _P, C.POINTER(SolveStats)]),
     ("mgfb_step", C.c_int32, [_P, C.c_float, C.c_uint32, C.POINTER(StepStats)]),
     ("mgfb_step_n", C.c_int32, [_P, C.c_float, C.c_uint32, C.c_uint32, C.POINTER(StepStats)]),
+    ("mgfb_step_profile", C.c_int32, [_P, C.c_float, C.c_uint32, C.POINTER(StepStats), C.POINTER(PhaseProfile)]),
     ("mgfb_step_enqueue", C.c_int32, [_P, C.c_float, C.c_uint32, C.c_uint32, _P, _P, _P, _P, _P, _P]),
     ("mgfb_step_wait", C.c_int32, [_P, C.POINTER(StepStats)]),
     ("mgfb_step_constraints", C.c_int32, [_P, C.c_uint32, _P, _P, _P, _P, _P, C.POINTER(C.c_uint32)]),
@@ -112,6 +121,7 @@ SYMBOLS = [
     ("mgfb_bodies_set_gid", C.c_int32, [_P, C.c_uint32, C.c_uint32, _P]),
     ("mgfb_tile_export", C.c_int32, [_P, C.c_uint32, C.POINTER(TileDesc)]),
     ("mgfb_tile_connect", C.c_int32, [_P, C.c_uint32, C.c_uint32, _P]),
+    ("mgfb_selftest_handover", C.c_int32, [_P, C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
 ]
 
 _lib = None

@@ -72,6 +72,12 @@ class Context:
         self.h = h
         self.cfg = c
 
+    def selftest_handover(self, rounds=0):
+        """(torn, observed) 32-byte hand-overs seen by the self-tests so far (+ `rounds` more local rounds); torn must be 0."""
+        t = C.c_uint32(); o = C.c_uint32()
+        self.check(self.lib.mgfb_selftest_handover(self.h, rounds, C.byref(t), C.byref(o)))
+        return t.value, o.value
+
     def check(self, st):
         if st != L.OK:
             raise MgfbError(st, (self.lib.mgfb_last_error(self.h) or b"").decode())
@@ -280,6 +286,31 @@ class World:
         self.ctx.check(self.lib.mgfb_bodies_get_inv_moment(self.ctx.h, first, n, L.ptr(out)))
         return out
 
+    def fat_bounds(self, first=0, n=None):
+        """Stored fat AABBs of the body BVH (world.rs:180, 235-238): (n, 6) = centre, half extents."""
+        n = len(self) - first if n is None else n
+        out = np.zeros((n, 6), np.float32)
+        self.ctx.check(self.lib.mgfb_bodies_get_fat_bounds(self.ctx.h, first, n, L.ptr(out)))
+        return out
+
+    def set_state(self, first=0, x=None, q=None, v=None, omega=None, colliders=None, fat=None):
+        """Write the pub fields x, q, collider, the velocities and the stored fat boxes (mgfb_bodies_set_state)."""
+        arrs = [None if a is None else np.ascontiguousarray(a, dtype=np.float32) for a in (x, q, v, omega)]
+        col = None if colliders is None else np.ascontiguousarray(colliders, dtype=L.SHAPE_DTYPE)
+        fb = None if fat is None else np.ascontiguousarray(fat, dtype=np.float32)
+        ns = {len(a) for a in (*arrs, col, fb) if a is not None}
+        assert len(ns) == 1, "all given arrays must describe the same bodies"
+        self.ctx.check(self.lib.mgfb_bodies_set_state(self.ctx.h, first, ns.pop(), *[L.ptr(a) for a in arrs], L.ptr(col), L.ptr(fb)))
+
+    def snapshot(self):
+        """Everything World::step carries from one step to the next: x, q, v, omega, collider (incl. the pending
+        displacement complete_motion adds), stored fat boxes.  restore() of it continues bit-identically."""
+        x, q, v, w = self.state()
+        return dict(x=x, q=q, v=v, omega=w, colliders=self.colliders(), fat=self.fat_bounds())
+
+    def restore(self, snap):
+        self.set_state(0, snap["x"], snap["q"], snap["v"], snap["omega"], snap["colliders"], snap["fat"])
+
     def integrate(self, dt):
         self.ctx.check(self.lib.mgfb_integrate(self.ctx.h, dt))
 
@@ -291,6 +322,14 @@ class World:
         st = L.StepStats()
         self.ctx.check(self.lib.mgfb_step_n(self.ctx.h, dt, iters, nsteps, C.byref(st)))
         return st.as_dict()
+
+    def step_profile(self, dt, iters=20):
+        """One step with events between its phases: (stats, {phase name: device ms, + per-kind pair / contact counts})."""
+        st = L.StepStats(); pr = L.PhaseProfile()
+        self.ctx.check(self.lib.mgfb_step_profile(self.ctx.h, dt, iters, C.byref(st), C.byref(pr)))
+        d = dict(zip(L.PHASES, list(pr.phase_ms)))
+        d.update(pairs=list(pr.pairs), terrain_pairs=list(pr.terrain_pairs), body_contacts=pr.body_contacts, terrain_contacts=pr.terrain_contacts)
+        return st.as_dict(), d
 
     # -- pipelined step: transfers of step k overlap the kernels of step k+1 (mgfb_step_enqueue / mgfb_step_wait)
     def step_enqueue(self, dt, iters=20, v_in=None, omega_in=None, x_out=None, q_out=None, v_out=None, omega_out=None, add=False):

@@ -295,13 +295,21 @@ int32_t mgfb_bvh_insert(mgfb_bvh* b, const float* boxes, const uint32_t* values,
 int32_t mgfb_bvh_remove(mgfb_bvh* b, const uint32_t* indices, uint32_t n) {
     if (!b || (n && !indices)) return MGFB_ERR_INVALID_ARG;
     mgfb_ctx* ctx = b->ctx;
-    for (uint32_t i = 0; i < n; ++i)   // pool.rs:100-113 panics on a free or out-of-range slot
-        if (indices[i] >= b->alive.size() || !b->alive[indices[i]]) return fail(ctx, MGFB_ERR_INVALID_ARG, "no leaf at that index");
+    // validate EVERYTHING before touching anything (pool.rs:100-113 panics on a free or out-of-range slot; a slot named twice
+    // would be removed twice): alive[] doubles as the mark, 2 = named in this call
+    int32_t bad = MGFB_OK;
+    uint32_t marked = 0;
+    for (; marked < n; ++marked) {
+        const uint32_t s = indices[marked];
+        if (s >= b->alive.size() || !b->alive[s]) { bad = fail(ctx, MGFB_ERR_INVALID_ARG, "no leaf at that index"); break; }
+        if (b->alive[s] == 2) { bad = fail(ctx, MGFB_ERR_INVALID_ARG, "leaf removed twice in one call"); break; }
+        b->alive[s] = 2;
+    }
+    if (bad != MGFB_OK) { for (uint32_t i = 0; i < marked; ++i) b->alive[indices[i]] = 1; return bad; }   // nothing was changed
     CU(cudaSetDevice(ctx->device));
     const float4 dead = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
     for (uint32_t i = 0; i < n; ++i) {
         unsigned s = indices[i];
-        if (!b->alive[s]) return fail(ctx, MGFB_ERR_INVALID_ARG, "leaf removed twice in one call");
         b->alive[s] = 0; b->free_list.push_back(s);
         CU(cudaMemcpyAsync(b->d_r.as<float4>() + s, &dead, 16, cudaMemcpyHostToDevice, ctx->stream));
     }

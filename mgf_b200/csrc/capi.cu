@@ -13,6 +13,8 @@
 
 using namespace mgfb;
 
+#define MGFB_PIPE_DEPTH 4   // steps mgfb_step_enqueue may have in flight
+
 namespace {
 
 struct Buf {
@@ -72,7 +74,7 @@ struct mgfb_ctx {
     cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
     cudaStream_t s_aux = nullptr;         // the terrain half of the broad/narrowphase runs beside the body half
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
-    unsigned pipe_head = 0, pipe_inflight = 0;
+    unsigned pipe_head = 0, pipe_inflight = 0, pipe_scale = 2;
     // last step
     unsigned last_constraints = 0;
     bool have_step = false;
@@ -87,6 +89,11 @@ struct mgfb_ctx {
     std::vector<void*> ipc_opened;
     int max_ctas = 0;                    // cfg.reserved[0]: cap on cooperative grids (two tiles sharing one GPU in tests)
     unsigned long long tile_timeout_ns = 20000000000ULL;
+    // mgfb_step_profile: events between the phases of one step (prof_ev[k] = start of phase k; [8] = end; [9],[10] = terrain side stream)
+    // selftest.cuh: torn / whole 32-byte hand-overs seen so far (create-time local test + connect-time peer tests + on request)
+    unsigned handover_torn = 0, handover_observed = 0;
+    bool prof_on = false;
+    cudaEvent_t prof_ev[11] = {};
 };
 
 namespace {
@@ -101,6 +108,7 @@ namespace {
     } while (0)
 #define TRY(call) do { int32_t _s = (call); if (_s != MGFB_OK) return _s; } while (0)
 
+#define PROF(id) do { if (ctx->prof_on) CU(cudaEventRecord(ctx->prof_ev[id], ctx->stream)); } while (0)
 int32_t fail(mgfb_ctx* ctx, int32_t code, const char* msg) { if (ctx) ctx->err = msg; return code; }
 
 // (re)allocate to at least `bytes`, optionally keeping the old contents
@@ -302,6 +310,7 @@ int32_t enqueue_order_and_solve(mgfb_ctx* ctx, const OrderView& O, const Manifol
     const unsigned nb = M.user ? ctx->n : body_slots(ctx);
     int g = grid_for(ctx, m_bound);
     const bool colour_df = !as_given && ctx->cfg.solver_schedule != MGFB_SCHEDULE_PHASES_JP;
+    PROF(MGFB_PHASE_COLOURING);
     if (colour_df) {
         // constraints per body -> CSR -> chains sorted by key -> colours travel down the chains (no grid barrier)
         ColourView V{};
@@ -337,6 +346,7 @@ int32_t enqueue_order_and_solve(mgfb_ctx* ctx, const OrderView& O, const Manifol
         D.next = ctx->r_next.as<unsigned>(); D.dep = ctx->r_dep.as<unsigned>(); D.body_start = ctx->body_start.as<unsigned>();
         D.inc = ctx->r_inc.as<unsigned>();
     }
+    PROF(MGFB_PHASE_BUILD_ROWS);
     k_build_rows<<<g, MGFB_THREADS, 0, ctx->stream>>>(M, BI, perm, R, m_ptr, m_host, dt, ctx->cfg.baumgarte, ctx->cfg.penetration_slop, c,
                                                       tiled ? ctx->edge_mark.as<unsigned char>() : nullptr, tiled ? ctx->n : 0xffffffffu,
                                                       O.group, O.body_mask, D);
@@ -363,6 +373,7 @@ int32_t enqueue_order_and_solve(mgfb_ctx* ctx, const OrderView& O, const Manifol
     }
     CU(cudaGetLastError());
     if (time_solve) CU(cudaEventRecord(ctx->cur_ev[2], ctx->stream));
+    PROF(MGFB_PHASE_SOLVE);
     if (dataflow) {
         const unsigned* ps = pstart; unsigned it = iters;
         void* args[] = {&R, &D, &vel, &ps, &it, &epoch, &c, &TL};
@@ -387,6 +398,7 @@ int32_t enqueue_order_and_solve(mgfb_ctx* ctx, const OrderView& O, const Manifol
         CU(cudaLaunchCooperativeKernel(fn, dim3(ctx->coop_solve), dim3(MGFB_SOLVE_THREADS), args, 0, ctx->stream));
     }
     if (time_solve) CU(cudaEventRecord(ctx->cur_ev[3], ctx->stream));
+    PROF(MGFB_PHASE_COUNT);
     ctx->launches += 4 + ((dataflow && tiled) ? 0 : 1);   // k_order, k_group_scan, k_scatter_rows, k_build_rows (+ k_solve)
     return MGFB_OK;
 }
@@ -404,6 +416,7 @@ int32_t enqueue_step(mgfb_ctx* ctx, float dt, unsigned iters, bool from_integrat
     int gb = grid_for(ctx, n);
     const bool tiled = ctx->tiled;
     const unsigned slots = body_slots(ctx);   // upper bound of n_total (device-resident: own + this step's ghosts)
+    PROF(MGFB_PHASE_INTEGRATE);
     if (!tiled) {
         if (from_integrate) k_integrate<true, true, true><<<gb, MGFB_THREADS, 0, ctx->stream>>>(B, n, dt, ctx->cfg.fat_margin, c);
         else k_integrate<false, false, true><<<gb, MGFB_THREADS, 0, ctx->stream>>>(B, n, dt, ctx->cfg.fat_margin, c);
@@ -427,11 +440,13 @@ int32_t enqueue_step(mgfb_ctx* ctx, float dt, unsigned iters, bool from_integrat
     int gs = grid_for(ctx, slots);
     if (ctx->terrain.present) CU(cudaEventRecord(ctx->ev_fork, ctx->stream));   // tight boxes are final: the terrain half may start
     // broadphase over the stored fat boxes
+    PROF(MGFB_PHASE_BODY_GRID);
     BodyGrid G = body_grid(ctx);
     k_bgrid_insert<false><<<gs, MGFB_THREADS, 0, ctx->stream>>>(B.fat, B.col, B.gid, G, c);
     TRY(scan_u32_lb(ctx, G.cell_count, G.cell_start, ctx->table, &c->grid_entries));
     k_bgrid_insert<true><<<gs, MGFB_THREADS, 0, ctx->stream>>>(B.fat, B.col, B.gid, G, c);
     PairLists PL; for (int k = 0; k < 4; ++k) PL.p[k] = ctx->pair_list[k].as<int2>();
+    PROF(MGFB_PHASE_PAIR_SWEEP);
     {
         int gw = std::max(1, std::min((int)((slots + BP_WARPS * BP_PER - 1) / (BP_WARPS * BP_PER)), ctx->num_sms * 8));
         if (ctx->max_ctas) gw = std::min(gw, ctx->max_ctas * 4);
@@ -447,12 +462,15 @@ int32_t enqueue_step(mgfb_ctx* ctx, float dt, unsigned iters, bool from_integrat
         T = terrain_view(ctx);
         PairLists TL; for (int k = 0; k < 4; ++k) TL.p[k] = k < 2 ? ctx->tpair_list[k].as<int2>() : nullptr;
         CU(cudaStreamWaitEvent(ctx->s_aux, ctx->ev_fork, 0));
+        if (ctx->prof_on) CU(cudaEventRecord(ctx->prof_ev[9], ctx->s_aux));
         k_terrain_pairs<<<gb, MGFB_THREADS, 0, ctx->s_aux>>>(B.tight, B.col, n, T, TL, ctx->tpair_cap, c);
         if (sph) k_narrow_terrain<0><<<gp, MGFB_THREADS, 0, ctx->s_aux>>>(B.col, ctx->tpair_list[0].as<int2>(), T, L, ctx->contact_cap, c);
         if (caps) k_narrow_terrain<1><<<gp, MGFB_THREADS, 0, ctx->s_aux>>>(B.col, ctx->tpair_list[1].as<int2>(), T, L, ctx->contact_cap, c);
+        if (ctx->prof_on) CU(cudaEventRecord(ctx->prof_ev[10], ctx->s_aux));
         CU(cudaEventRecord(ctx->ev_join, ctx->s_aux));
     }
     // narrowphase, one specialisation per shape pair
+    PROF(MGFB_PHASE_NARROW_BODIES);
     if (sph) k_narrow_bodies<0, 0><<<gp, MGFB_THREADS, 0, ctx->stream>>>(B.col, PL.p[0], L, ctx->contact_cap, c);
     if (sph && caps) {
         k_narrow_bodies<0, 1><<<gp, MGFB_THREADS, 0, ctx->stream>>>(B.col, PL.p[1], L, ctx->contact_cap, c);
@@ -527,6 +545,8 @@ M3 capsule_tensor(V3 a, V3 d, float r, float m) {
 }  // namespace
 
 void pipe_destroy(mgfb_ctx* ctx);   // pipeline.cuh
+namespace { int32_t local_handover_selftest(mgfb_ctx* ctx, unsigned rounds, unsigned* torn, unsigned* observed);
+            int32_t run_handover_selftest(mgfb_ctx* ctx, Inbox* box, bool sys, unsigned rounds, unsigned* torn, unsigned* observed); }   // selftest.cuh
 
 // ============================================================================ C ABI
 extern "C" {
@@ -589,7 +609,7 @@ int32_t mgfb_ctx_create(const mgfb_config* cfg, mgfb_ctx** out) {
                              (const void*)k_scatter_rows, (const void*)k_build_rows, (const void*)k_solve<false>, (const void*)k_solve<true>,
                              (const void*)k_solve_df<false>, (const void*)k_solve_df<true>, (const void*)k_df_init<false>, (const void*)k_df_init<true>,
                              (const void*)k_tile_links_send, (const void*)k_tile_solve_done, (const void*)k_inc_count, (const void*)k_inc_fill, (const void*)k_inc_sort, (const void*)k_colour_df,
-                             (const void*)k_step_done, (const void*)k_pack_state, (const void*)k_set_velocity<false>, (const void*)k_set_velocity<true>};
+                             (const void*)k_step_done, (const void*)k_pack_state, (const void*)k_set_velocity<false>, (const void*)k_set_velocity<true>, (const void*)k_set_state};
         cudaFuncAttributes fa;
         for (const void* f : fns) if ((e = cudaFuncGetAttributes(&fa, f)) != cudaSuccess) return bail(e, "cudaFuncGetAttributes");
     }
@@ -601,6 +621,11 @@ int32_t mgfb_ctx_create(const mgfb_config* cfg, mgfb_ctx** out) {
     ctx->coop_df = std::min(coop_blocks(ctx, k_solve_df<false>, MGFB_DF_THREADS_LARGE, 1), coop_blocks(ctx, k_solve_df<true>, MGFB_DF_THREADS_LARGE, 1));
     int32_t s = grow_bodies(ctx, std::max(ctx->cfg.initial_body_capacity, 1024u));
     if (s == MGFB_OK) s = ensure_rows(ctx, 1024, false, 4096);
+    // the dataflow solver's hand-over is one 32-byte store: check that this device delivers it whole (selftest.cuh)
+    if (s == MGFB_OK && ctx->cfg.solver_schedule == MGFB_SCHEDULE_DATAFLOW) {
+        s = local_handover_selftest(ctx, 512, nullptr, nullptr);
+        if (s == MGFB_OK && ctx->handover_torn) ctx->cfg.solver_schedule = MGFB_SCHEDULE_PHASES;
+    }
     if (s != MGFB_OK) { g_create_err = ctx->err; delete ctx; return s; }
     *out = ctx;
     return MGFB_OK;
@@ -635,6 +660,7 @@ void mgfb_ctx_destroy(mgfb_ctx* ctx) {
     for (Buf* b : all) release(*b);
     if (ctx->h_ctr) cudaFreeHost(ctx->h_ctr);
     for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
+    for (auto& e : ctx->prof_ev) if (e) cudaEventDestroy(e);
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
     if (ctx->s_aux) cudaStreamDestroy(ctx->s_aux);
@@ -752,7 +778,7 @@ int32_t mgfb_bodies_set_velocity(mgfb_ctx* ctx, uint32_t first, uint32_t n, cons
     float* sv = ctx->stage.as<float>(); float* sw = sv + (size_t)3 * n;
     CU(cudaMemcpyAsync(sv, v, (size_t)n * 12, cudaMemcpyHostToDevice, ctx->stream));
     CU(cudaMemcpyAsync(sw, omega, (size_t)n * 12, cudaMemcpyHostToDevice, ctx->stream));
-    k_set_velocity<false><<<(n + MGFB_THREADS - 1) / MGFB_THREADS, MGFB_THREADS, 0, ctx->stream>>>(body_arrays(ctx), first, n, sv, sw);
+    k_set_velocity<false><<<(n + MGFB_THREADS - 1) / MGFB_THREADS, MGFB_THREADS, 0, ctx->stream>>>(body_arrays(ctx), first, n, sv, sw, nullptr);
     CU(cudaGetLastError());
     ctx->launches += 1;
     CU(cudaStreamSynchronize(ctx->stream));
@@ -789,6 +815,59 @@ int32_t mgfb_bodies_get_inv_moment(mgfb_ctx* ctx, uint32_t first, uint32_t n, fl
         float* o = out + 9 * i;
         o[0] = I.c0.x; o[1] = I.c0.y; o[2] = I.c0.z; o[3] = I.c1.x; o[4] = I.c1.y; o[5] = I.c1.z; o[6] = I.c2.x; o[7] = I.c2.y; o[8] = I.c2.z;
     }
+    return MGFB_OK;
+}
+
+int32_t mgfb_bodies_get_fat_bounds(mgfb_ctx* ctx, uint32_t first, uint32_t n, float* boxes) {
+    if (!ctx || (uint64_t)first + n > ctx->n || !boxes) return fail(ctx, MGFB_ERR_INVALID_ARG, "bad arguments");
+    if (n == 0) return MGFB_OK;
+    CU(cudaSetDevice(ctx->device));
+    std::vector<Box> hb(n);
+    CU(cudaMemcpyAsync(hb.data(), ctx->fat.as<Box>() + first, (size_t)n * sizeof(Box), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    for (uint32_t i = 0; i < n; ++i) {
+        float* o = boxes + 6 * i;
+        o[0] = hb[i].c.x; o[1] = hb[i].c.y; o[2] = hb[i].c.z; o[3] = hb[i].r.x; o[4] = hb[i].r.y; o[5] = hb[i].r.z;
+    }
+    return MGFB_OK;
+}
+
+int32_t mgfb_bodies_set_state(mgfb_ctx* ctx, uint32_t first, uint32_t n, const float* x, const float* q, const float* v, const float* omega,
+                              const mgfb_shape* colliders, const float* fat_boxes) {
+    if (!ctx || (uint64_t)first + n > ctx->n) return fail(ctx, MGFB_ERR_INVALID_ARG, "body range out of bounds");
+    if (n == 0) return MGFB_OK;
+    if (ctx->pipe_inflight) return fail(ctx, MGFB_ERR_STATE, "steps are in flight: mgfb_step_wait first");
+    CU(cudaSetDevice(ctx->device));
+    std::vector<float> hc;
+    if (colliders) {
+        std::vector<Collider> cur(n);
+        CU(cudaMemcpyAsync(cur.data(), ctx->col.as<Collider>() + first, (size_t)n * sizeof(Collider), cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        hc.resize((size_t)n * 9);
+        for (uint32_t i = 0; i < n; ++i) {
+            const mgfb_shape& s = colliders[i];
+            if ((int)s.kind != col_kind(cur[i])) return fail(ctx, MGFB_ERR_INVALID_ARG, "a collider cannot change its Component kind (physics.rs:153 constructor)");
+            const float r_new = s.kind == MGFB_SPHERE ? s.p[3] : s.p[6];
+            if (r_new != cur[i].p0.w) return fail(ctx, MGFB_ERR_INVALID_ARG, "a collider cannot change its radius (the inertia tensor was built for it, physics.rs:212)");
+            float* c = hc.data() + 9 * (size_t)i;
+            c[0] = s.p[0]; c[1] = s.p[1]; c[2] = s.p[2];
+            c[3] = s.kind == MGFB_CAPSULE ? s.p[3] : 0.0f; c[4] = s.kind == MGFB_CAPSULE ? s.p[4] : 0.0f; c[5] = s.kind == MGFB_CAPSULE ? s.p[5] : 0.0f;
+            c[6] = s.v[0]; c[7] = s.v[1]; c[8] = s.v[2];
+        }
+    }
+    if (fat_boxes) for (uint32_t i = 0; i < n; ++i) for (int k = 3; k < 6; ++k)
+        if (!(fat_boxes[6 * (size_t)i + k] >= 0.0f)) return fail(ctx, MGFB_ERR_NAN_BOUNDS, "AABB half extent must be >= 0 (bounds.rs:125)");
+    TRY(ensure(ctx, ctx->stage, (size_t)n * 28 * 4));
+    float* sx = ctx->stage.as<float>(); float* sq = sx + (size_t)3 * n; float* sv = sq + (size_t)4 * n; float* sw = sv + (size_t)3 * n;
+    float* sc = sw + (size_t)3 * n; float* sf = sc + (size_t)9 * n;
+    auto up = [&](float* dst, const float* src, size_t per) { return src ? cudaMemcpyAsync(dst, src, (size_t)n * per * 4, cudaMemcpyHostToDevice, ctx->stream) : cudaSuccess; };
+    CU(up(sx, x, 3)); CU(up(sq, q, 4)); CU(up(sv, v, 3)); CU(up(sw, omega, 3)); CU(up(sc, colliders ? hc.data() : nullptr, 9)); CU(up(sf, fat_boxes, 6));
+    k_set_state<<<(n + MGFB_THREADS - 1) / MGFB_THREADS, MGFB_THREADS, 0, ctx->stream>>>(body_arrays(ctx), first, n, x ? sx : nullptr, q ? sq : nullptr,
+                                                                                          v ? sv : nullptr, omega ? sw : nullptr, colliders ? sc : nullptr,
+                                                                                          fat_boxes ? sf : nullptr);
+    CU(cudaGetLastError());
+    ctx->launches += 1;
+    CU(cudaStreamSynchronize(ctx->stream));
     return MGFB_OK;
 }
 
@@ -941,6 +1020,31 @@ int32_t mgfb_step_n(mgfb_ctx* ctx, float dt, uint32_t iters, uint32_t nsteps, mg
 }
 
 int32_t mgfb_step(mgfb_ctx* ctx, float dt, uint32_t iters, mgfb_step_stats* stats) { return mgfb_step_n(ctx, dt, iters, 1, stats); }
+
+int32_t mgfb_step_profile(mgfb_ctx* ctx, float dt, uint32_t iters, mgfb_step_stats* stats, mgfb_phase_profile* out) {
+    if (!ctx || !out) return MGFB_ERR_INVALID_ARG;
+    std::memset(out, 0, sizeof(*out));
+    float* phase_ms = out->phase_ms;
+    if (ctx->pipe_inflight) return fail(ctx, MGFB_ERR_STATE, "steps are in flight: mgfb_step_wait first");
+    CU(cudaSetDevice(ctx->device));
+    for (auto& e : ctx->prof_ev) if (!e) CU(cudaEventCreate(&e));
+    ctx->prof_on = true;
+    int32_t st = mgfb_step_n(ctx, dt, iters, 1, stats);
+    ctx->prof_on = false;
+    TRY(st);
+    for (int k = 0; k < MGFB_PHASE_COUNT; ++k) phase_ms[k] = 0.0f;
+    if (ctx->n == 0) return MGFB_OK;
+    // phase k runs from mark k to the next mark on the main stream (the terrain half has its own pair on the side stream)
+    const int order[] = {MGFB_PHASE_INTEGRATE, MGFB_PHASE_BODY_GRID, MGFB_PHASE_PAIR_SWEEP, MGFB_PHASE_NARROW_BODIES, MGFB_PHASE_COLOURING,
+                         MGFB_PHASE_BUILD_ROWS, MGFB_PHASE_SOLVE, MGFB_PHASE_COUNT};
+    for (int k = 0; k + 1 < 8; ++k) CU(cudaEventElapsedTime(&phase_ms[order[k]], ctx->prof_ev[order[k]], ctx->prof_ev[order[k + 1]]));
+    if (ctx->terrain.present) CU(cudaEventElapsedTime(&phase_ms[MGFB_PHASE_TERRAIN], ctx->prof_ev[9], ctx->prof_ev[10]));
+    const Counters& h = *ctx->h_ctr;
+    for (int k = 0; k < 4; ++k) out->pairs[k] = h.pairs[k];
+    out->terrain_pairs[0] = h.tpairs[0]; out->terrain_pairs[1] = h.tpairs[1];
+    out->terrain_contacts = h.tcontacts; out->body_contacts = h.contacts - h.tcontacts;
+    return MGFB_OK;
+}
 
 int32_t mgfb_step_constraints(mgfb_ctx* ctx, uint32_t capacity, uint32_t* body_a, int32_t* body_b, uint32_t* face, uint32_t* sub,
                               uint32_t* colour, uint32_t* count) {
@@ -1115,7 +1219,8 @@ int32_t mgfb_tile_export(mgfb_ctx* ctx, uint32_t ghost_capacity, mgfb_tile_desc*
     TRY(ensure_rows(ctx, ctx->contact_cap, false, 4096));
     ctx->tile_row_cap = ctx->row_cap;
     TRY(ensure(ctx, ctx->edge_slot, (size_t)std::max(ctx->n, 1u) * 4, false, true));
-    TRY(ensure(ctx, ctx->tile_df, (size_t)ctx->tile_row_cap * 2 * sizeof(Inbox) + (size_t)ghost_capacity * 8, false, true));
+    // [in_a | in_b | link_l | link_r | pad to 32 B | 2 x hand-over self-test scratch (written by the left / right neighbour)]
+    TRY(ensure(ctx, ctx->tile_df, (size_t)ctx->tile_row_cap * 2 * sizeof(Inbox) + (((size_t)ghost_capacity * 8 + 31) & ~(size_t)31) + 2 * (size_t)SELFTEST_PAIRS * 32 * sizeof(Inbox), false, true));
     CU(cudaStreamSynchronize(ctx->stream));
     TileDescRaw d; std::memset(&d, 0, sizeof(d));
     d.magic = TILE_MAGIC; d.pid = (int64_t)getpid(); d.device = ctx->device; d.n_own = ctx->n; d.ghost_cap = ghost_capacity; d.row_cap = ctx->tile_row_cap;
@@ -1148,8 +1253,12 @@ static int32_t tile_open_peer(mgfb_ctx* ctx, const mgfb_tile_desc* desc, TilePee
     P->x = (float4*)p[0]; P->vel = (BodyVel*)p[1]; P->force = (float4*)p[2]; P->torque = (float4*)p[3]; P->col = (Collider*)p[4];
     P->tight = (Box*)p[5]; P->fat = (Box*)p[6]; P->gid = (unsigned*)p[7]; P->ridx = (unsigned*)p[8]; P->mbox = (TileMailbox*)p[9];
     P->n_own = d.n_own; P->ghost_cap = d.ghost_cap;
+    // the link tables of the dataflow solve are indexed by a NEIGHBOUR's ghost slots: one common capacity, or a nearly full
+    // ghost set would run past them
+    if (d.ghost_cap != ctx->ghost_cap) return fail(ctx, MGFB_ERR_INVALID_ARG, "every tile must export the same ghost_capacity");
     P->in_a = (Inbox*)p[10]; P->in_b = P->in_a + d.row_cap;
     P->link_l = reinterpret_cast<unsigned*>(P->in_b + d.row_cap); P->link_r = P->link_l + d.ghost_cap;
+    P->selftest = reinterpret_cast<Inbox*>(reinterpret_cast<char*>(P->link_l) + (((size_t)d.ghost_cap * 8 + 31) & ~(size_t)31));
     return MGFB_OK;
 }
 
@@ -1169,6 +1278,13 @@ int32_t mgfb_tile_connect(mgfb_ctx* ctx, uint32_t rank, uint32_t nranks, const m
     T.n_own = ctx->n; T.ghost_cap = ctx->ghost_cap; T.step = 0; T.timeout_ns = ctx->tile_timeout_ns;
     ctx->link = T;
     ctx->tile_step = 0;
+    // hand-overs cross the tile boundary as 32-byte peer stores: check each neighbour link delivers them whole (selftest.cuh);
+    // every tile must end up with the same schedule, so the verdict is also part of what the caller's next collective carries
+    if (ctx->cfg.solver_schedule == MGFB_SCHEDULE_DATAFLOW) {
+        if (T.has_left) TRY(run_handover_selftest(ctx, T.left.selftest + SELFTEST_PAIRS * 32, true, 256, nullptr, nullptr));   // its "from the right" half
+        if (T.has_right) TRY(run_handover_selftest(ctx, T.right.selftest, true, 256, nullptr, nullptr));                        // its "from the left" half
+        if (ctx->handover_torn) return fail(ctx, MGFB_ERR_TILE, "a 32-byte peer store was observed torn on this interconnect: create every tile with MGFB_SCHEDULE_PHASES");
+    }
     ctx->tiled = true;
     return MGFB_OK;
 }
@@ -1185,3 +1301,4 @@ int32_t mgfb_device_view_get(mgfb_ctx* ctx, mgfb_device_view* out) {
 #include "gjk.cuh"
 #include "bvh.cuh"
 #include "pipeline.cuh"
+#include "selftest.cuh"

@@ -1477,7 +1477,8 @@ __global__ void __launch_bounds__(MGFB_THREADS) k_pack_state(BodyArrays B, unsig
 }
 // ADD: v += v_in, omega += omega_in (what `bodies.v[i] += dv` between steps does on the CPU); else overwrite (ConstrainedSet::set)
 template <bool ADD = false>
-__global__ void __launch_bounds__(MGFB_THREADS) k_set_velocity(BodyArrays B, unsigned first, unsigned n, const float* v, const float* w) {
+__global__ void __launch_bounds__(MGFB_THREADS) k_set_velocity(BodyArrays B, unsigned first, unsigned n, const float* v, const float* w, const Counters* ctr) {
+    if (ctr && (ctr->overflow | ctr->nan_bounds)) return;   // a queued step of a poisoned pipeline: it will be re-queued whole
     unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     BodyVel* r = B.vel + first + i;
@@ -1488,6 +1489,41 @@ __global__ void __launch_bounds__(MGFB_THREADS) k_set_velocity(BodyArrays B, uns
     } else {
         r->a = make_float4(v[3 * i], v[3 * i + 1], v[3 * i + 2], w[3 * i]);
         r->b.x = w[3 * i + 1]; r->b.y = w[3 * i + 2];
+    }
+}
+
+// Restores saved state (mgfb_bodies_set_state): the pub fields x, q, collider (physics.rs:142-154), v, omega and the stored
+// fat box of the world's body BVH (world.rs:180).  The world inverse inertia follows q like in integrate (physics.rs:231-232).
+// Staged arrays are packed f32; any may be NULL (field kept).  col: 9 floats per body = p0.xyz|r is kept| d.xyz | delta.xyz:
+//   [0..3) centre (sphere) / a (capsule), [3..6) d (capsule), [6..9) Moving.1
+__global__ void __launch_bounds__(MGFB_THREADS) k_set_state(BodyArrays B, unsigned first, unsigned n, const float* x, const float* q, const float* v,
+                                                           const float* w, const float* col, const float* fat) {
+    unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    unsigned b = first + i;
+    if (x) B.x[b] = make_float4(x[3 * i], x[3 * i + 1], x[3 * i + 2], 0.0f);
+    BodyVel r = B.vel[b];
+    if (q) {
+        B.q[b] = make_float4(q[4 * i], q[4 * i + 1], q[4 * i + 2], q[4 * i + 3]);
+        Q4 qi = mkq(q[4 * i], mk3(q[4 * i + 1], q[4 * i + 2], q[4 * i + 3]));
+        M3 R = m_from_q(qi);
+        M3 Ib = mkm(f4v(B.imb[3 * b]), f4v(B.imb[3 * b + 1]), f4v(B.imb[3 * b + 2]));
+        vel_set_inertia(r, mmul(mmul(R, Ib), mtrans(R)));
+    }
+    if (v) { r.a.x = v[3 * i]; r.a.y = v[3 * i + 1]; r.a.z = v[3 * i + 2]; }
+    if (w) { r.a.w = w[3 * i]; r.b.x = w[3 * i + 1]; r.b.y = w[3 * i + 2]; }
+    if (q || v || w) B.vel[b] = r;
+    if (col) {
+        Collider k = B.col[b];
+        const float* c = col + 9 * i;
+        k.p0 = make_float4(c[0], c[1], c[2], k.p0.w);
+        if (col_kind(k) != 0) k.p1 = make_float4(c[3], c[4], c[5], k.p1.w);
+        k.v = make_float4(c[6], c[7], c[8], k.v.w);
+        B.col[b] = k;
+    }
+    if (fat) {
+        Box f; f.c = make_float4(fat[6 * i], fat[6 * i + 1], fat[6 * i + 2], 0.0f); f.r = make_float4(fat[6 * i + 3], fat[6 * i + 4], fat[6 * i + 5], 0.0f);
+        B.fat[b] = f;
     }
 }
 

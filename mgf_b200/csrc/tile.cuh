@@ -20,6 +20,8 @@
 
 namespace mgfb {
 
+#define SELFTEST_PAIRS 16u   // writer/reader CTA pairs of the hand-over self-test (selftest.cuh)
+
 // Lives in each rank's own memory; only the neighbours write to it (each field has one writer).
 struct __align__(32) TileSlot { unsigned long long flag; unsigned u; float f; unsigned pad[4]; };
 struct TileMailbox {
@@ -42,6 +44,7 @@ struct TilePeer {
     Inbox* in_a; Inbox* in_b;
     unsigned* link_l;         // [ghost_cap] written by ITS left neighbour (me, if I am that)
     unsigned* link_r;         // [ghost_cap] written by ITS right neighbour
+    Inbox* selftest;          // 2 x SELFTEST_PAIRS x 32 scratch records: hand-over self-test of the link (selftest.cuh)
 };
 struct TileLink {
     TilePeer left, right;

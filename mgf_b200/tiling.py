@@ -86,6 +86,9 @@ class TiledWorld:
         return self.desc
 
     def connect(self, gather=all_gather_bytes, ghost_capacity=None):
+        if self.desc is None and ghost_capacity is None:
+            # one capacity for every tile (mgfb_tile_connect insists): the largest of the ranks' own defaults
+            ghost_capacity = max(int(c) for c in gather(str(max(4096, len(self.ids) // 2)).encode()))
         descs = gather(self.desc or self.export(ghost_capacity))
         assert len(descs) == self.nranks
         self.world.tile_connect(self.rank, descs)
@@ -105,6 +108,8 @@ class TiledWorld:
 
 def connect_local(tiles, ghost_capacity=None):
     """Wire tiles that live in ONE process (tests; several GPUs driven by one host thread each)."""
+    if ghost_capacity is None:
+        ghost_capacity = max(max(4096, len(t.ids) // 2) for t in tiles)   # one capacity for every tile
     descs = [t.export(ghost_capacity) for t in tiles]
     for t in tiles:
         t.world.tile_connect(t.rank, descs)

@@ -183,6 +183,44 @@ void mgfo_world_get_inv_moment(const mgfo_world* h, float* out) {
     const RigidBodyVec& b = h->w.bodies;
     for (size_t i = 0; i < b.len(); ++i) for (int c = 0; c < 3; ++c) put3(out + 9 * i + 3 * c, b.inv_moment[i].c[c]);
 }
+// Checkpoint support (the checker of mgfb_bodies_get_fat_bounds / mgfb_bodies_set_state): the stored fat boxes are the
+// leaves bvh[bvh_ids[i]] (world.rs:180, 235-238).
+void mgfo_world_get_fat_bounds(const mgfo_world* h, float* out) {
+    const World& w = h->w;
+    for (size_t i = 0; i < w.bodies.len(); ++i) { const AABB& b = w.bvh[w.bvh_ids[i]]; put3(out + 6 * i, b.c); put3(out + 6 * i + 3, b.r); }
+}
+// Overwrites the pub fields x, q, collider (physics.rs:142-154), v, omega, and rebuilds the body BVH from the given fat
+// boxes, inserted in body order like add_body does (world.rs:180-182).  inv_moment follows q as in integrate
+// (physics.rs:231-232).  Any pointer may be NULL.
+int32_t mgfo_world_set_state(mgfo_world* h, const float* x, const float* q, const float* v, const float* omega, const mgfb_shape* colliders,
+                             const float* fat) {
+    World& w = h->w;
+    RigidBodyVec& b = w.bodies;
+    for (size_t i = 0; i < b.len(); ++i) {
+        if (x) b.x[i] = p3(x + 3 * i);
+        if (q) {
+            b.q[i] = Quat{q[4 * i], p3(q + 4 * i + 1)};
+            Mat3 r = mat3_from_quat(b.q[i]);
+            b.inv_moment[i] = r * b.inv_moment_body[i] * transpose(r);
+        }
+        if (v) b.v[i] = p3(v + 3 * i);
+        if (omega) b.omega[i] = p3(omega + 3 * i);
+        if (colliders) {
+            const mgfb_shape& s = colliders[i];
+            MovingComponent& m = b.collider[i];
+            if ((s.kind == MGFB_SPHERE) != (m.g.kind == Component::SPHERE)) return MGFB_ERR_INVALID_ARG;
+            if (s.kind == MGFB_SPHERE) m.g.s.c = p3(s.p); else { m.g.c.a = p3(s.p); m.g.c.d = p3(s.p + 3); }
+            m.v = p3(s.v);
+        }
+    }
+    if (fat) {
+        try {
+            w.bvh.clear();   // a fresh BVH::new, then the inserts add_body makes (world.rs:180-182)
+            for (size_t i = 0; i < b.len(); ++i) w.bvh_ids[i] = w.bvh.insert(AABB{p3(fat + 6 * i), p3(fat + 6 * i + 3)}, i);
+        } catch (NanBounds&) { return MGFB_ERR_NAN_BOUNDS; }
+    }
+    return MGFB_OK;
+}
 void mgfo_world_integrate(mgfo_world* h, float dt) { h->w.bodies.integrate(dt); }
 void mgfo_world_complete_motion(mgfo_world* h) { h->w.bodies.complete_motion(); }
 

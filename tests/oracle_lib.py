@@ -53,6 +53,9 @@ def load():
     lib.mgfo_world_set_velocity.argtypes = [_P, C.c_uint32, C.c_uint32, _P, _P]
     lib.mgfo_world_get_colliders.argtypes = [_P, _P]
     lib.mgfo_world_get_inv_moment.argtypes = [_P, _P]
+    lib.mgfo_world_get_fat_bounds.argtypes = [_P, _P]
+    lib.mgfo_world_set_state.restype = C.c_int32
+    lib.mgfo_world_set_state.argtypes = [_P, _P, _P, _P, _P, _P, _P]
     lib.mgfo_world_integrate.argtypes = [_P, C.c_float]
     lib.mgfo_world_complete_motion.argtypes = [_P]
     lib.mgfo_world_step.restype = C.c_int32
@@ -205,6 +208,24 @@ class OracleWorld:
         out = np.zeros((len(self), 9), np.float32)
         self.lib.mgfo_world_get_inv_moment(self.h, L.ptr(out))
         return out
+
+    def fat_bounds(self):
+        out = np.zeros((len(self), 6), np.float32)
+        self.lib.mgfo_world_get_fat_bounds(self.h, L.ptr(out))
+        return out
+
+    def snapshot(self):
+        x, q, v, w = self.state()
+        return dict(x=x, q=q, v=v, omega=w, colliders=self.colliders(), fat=self.fat_bounds())
+
+    def restore(self, snap):
+        """Load a state saved by snapshot() -- of this oracle or of mgf_b200.World (same layout)."""
+        f = lambda a: np.ascontiguousarray(a, dtype=np.float32)
+        col = np.ascontiguousarray(snap["colliders"], dtype=L.SHAPE_DTYPE)
+        assert len(col) == len(self)
+        st = self.lib.mgfo_world_set_state(self.h, L.ptr(f(snap["x"])), L.ptr(f(snap["q"])), L.ptr(f(snap["v"])), L.ptr(f(snap["omega"])),
+                                           L.ptr(col), L.ptr(f(snap["fat"])))
+        assert st == 0, st
 
     def integrate(self, dt):
         self.lib.mgfo_world_integrate(self.h, dt)

@@ -100,3 +100,25 @@ def test_bvh_empty_and_capacity(ctx):
     offsets = np.zeros(2, np.uint32); values = np.zeros(3, np.uint32); total = C.c_uint32()
     st = ctx.lib.mgfb_bvh_query_batch(g.h, L.ptr(big), 1, L.ptr(offsets), L.ptr(values), 3, C.byref(total))
     assert st == L.ERR_CAPACITY and total.value == 10
+
+
+def test_remove_rejects_bad_batches_without_changing_anything(ctx):
+    """A batch naming a free slot, an out-of-range slot or the same slot twice is refused BEFORE anything is removed."""
+    import mgf_b200
+    from mgf_b200 import _lib as L
+    rng = np.random.default_rng(11)
+    boxes = np.concatenate([rng.uniform(-5, 5, (64, 3)), rng.uniform(0.1, 1.0, (64, 3))], axis=1).astype(np.float32)
+    t = mgf_b200.BVH(ctx)
+    idx = t.insert(boxes, np.arange(64, dtype=np.uint32))
+    everything = np.array([[0, 0, 0, 100, 100, 100]], np.float32)
+    before = sorted(t.query(everything)[1].tolist())
+    for bad in ([idx[3], idx[7], idx[3]], [idx[1], 10 ** 6], ):
+        with pytest.raises(mgf_b200.MgfbError) as e:
+            t.remove(np.array(bad, dtype=np.uint32))
+        assert e.value.code == L.ERR_INVALID_ARG
+        assert len(t) == 64 and sorted(t.query(everything)[1].tolist()) == before
+    t.remove(np.array([idx[3], idx[7]], dtype=np.uint32))
+    assert len(t) == 62 and sorted(t.query(everything)[1].tolist()) == [v for v in before if v not in (3, 7)]
+    with pytest.raises(mgf_b200.MgfbError):
+        t.remove(np.array([idx[3]], dtype=np.uint32))      # already free
+    assert len(t) == 62

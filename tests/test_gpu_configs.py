@@ -48,6 +48,20 @@ def test_c2_100k_spheres_full_size():
     assert total > 800000
 
 
+def test_c2_settled_window_full_size_from_snapshot():
+    """BASELINE.md's C2 as written: 100 000 spheres dropped from the balls.rs lattice into the 160 x 160 box; the window
+    the benchmark times starts at step 600 (the disordered pile).  The GPU runs the 600 steps, its state is loaded into the
+    oracle (snapshot = x, q, v, omega, colliders, stored fat boxes) and the two are lock-stepped from there."""
+    bodies, terrain, iters = scenes.build_config("C2")
+    g, o = _pair(bodies, terrain)
+    g.step(DT, iters, nsteps=600)
+    snap = g.snapshot()
+    assert np.isfinite(snap["x"]).all() and snap["x"][:, 1].min() > -10.6
+    o.restore(snap)
+    total = _lockstep_full(g, o, iters, 3, "C2 settled window (steps 600..602)")
+    assert total > 300000, total
+
+
 def test_c3_50k_capsules_on_20k_triangle_mesh_full_size():
     bodies, terrain, iters = scenes.config_c3()
     assert len(bodies[0]) == 50000 and len(terrain[1]) == 20000

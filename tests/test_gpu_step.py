@@ -306,3 +306,84 @@ def test_pipelined_step_equals_synchronous_step_bit_for_bit():
     a.set_velocity(0, (va + dv).astype(np.float32), (wa + dw).astype(np.float32)); a.step(DT, 10)
     b.step_enqueue(DT, 10, dv, dw, *outs[0], add=True); b.step_wait()
     assert all(np.array_equal(_bits(x), _bits(y)) for x, y in zip(a.state(), b.state()))
+
+
+def test_snapshot_restore_into_gpu_and_oracle_continues_bit_identically():
+    """mgfb_bodies_get_fat_bounds / mgfb_bodies_set_state: a world stepped on the GPU, saved, and loaded into (a) a fresh
+    GPU world and (b) the oracle continues bit-identically in all three (the benchmark's settled window relies on it)."""
+    shapes, mass, rest, fric, force = scenes.balls_scene(num=6, jitter=0.2, seed=5)
+    shapes["p"][:, 1] -= 24.0
+    bodies = (shapes, mass, rest, fric, force)
+    terrain = scenes.box_terrain(4.0, 10.0, 4.0)
+    g, o = _pair(bodies, terrain)
+    g.step(DT, 20, nsteps=90)
+    snap = g.snapshot()
+    assert np.abs(snap["omega"]).max() > 0 and np.abs(snap["colliders"]["v"]).max() > 0
+    g2, _ = _pair(bodies, terrain)
+    g2.restore(snap); o.restore(snap)
+    for k, v in g2.snapshot().items():
+        assert np.array_equal(np.ascontiguousarray(v).view(np.uint8), np.ascontiguousarray(snap[k]).view(np.uint8)), k
+    for k, v in o.snapshot().items():
+        assert np.array_equal(np.ascontiguousarray(v).view(np.uint8), np.ascontiguousarray(snap[k]).view(np.uint8)), k
+    assert np.array_equal(_bits(g.inv_moment()), _bits(g2.inv_moment()))
+    total = _lockstep(g2, o, 20, 8, "restored world")
+    assert total > 1500
+    g.step(DT, 20, nsteps=8)
+    for a, b in zip(g.state(), g2.state()):
+        assert np.array_equal(_bits(a), _bits(b))
+    # error behaviour: a collider cannot change kind or radius; negative half extents are the reference's bounds.rs:125 assert
+    bad = snap["colliders"].copy(); bad["p"][0, 3] = 0.7
+    with pytest.raises(mgf_b200.MgfbError) as e:
+        g2.set_state(0, colliders=bad)
+    assert e.value.code == L.ERR_INVALID_ARG
+    fat = snap["fat"].copy(); fat[3, 4] = -1.0
+    with pytest.raises(mgf_b200.MgfbError) as e:
+        g2.set_state(0, fat=fat)
+    assert e.value.code == L.ERR_NAN_BOUNDS
+
+
+def test_pipelined_overflow_regrows_requeues_and_stays_exact():
+    """A pipelined step that overflows a work list (dense blob: ~500 pairs per body against 16 slots) while younger steps
+    are queued behind it: mgfb_step_wait regrows, re-runs the step from after its integration and re-queues the younger
+    steps whole (their ADDed velocity inputs must be applied exactly once).  Same bits as the synchronous calls."""
+    import torch
+    rng = np.random.default_rng(3)
+    n = 1500
+    shapes = np.zeros(n, dtype=L.SHAPE_DTYPE)
+    shapes["kind"] = L.SPHERE
+    shapes["p"][:, 0:3] = rng.uniform(-1.2, 1.2, (n, 3)); shapes["p"][:, 3] = 0.5
+    bodies = (shapes, np.ones(n, np.float32), np.full(n, 0.3, np.float32), np.full(n, 0.6, np.float32), np.zeros((n, 3), np.float32))
+    a = mgf_b200.World(device=0, solver_schedule=SCHEDULE[0]); b = mgf_b200.World(device=0, solver_schedule=SCHEDULE[0])
+    a.add_bodies(*bodies); b.add_bodies(*bodies)
+    pin = lambda shape: torch.empty(shape, dtype=torch.float32, pin_memory=True).numpy()
+    nsteps = 3
+    vin = [pin((n, 3)) for _ in range(nsteps)]; win = [pin((n, 3)) for _ in range(nsteps)]
+    outs = [tuple(pin(s) for s in ((n, 3), (n, 4), (n, 3), (n, 3))) for _ in range(nsteps)]
+    for k in range(nsteps):
+        vin[k][:] = rng.uniform(-0.05, 0.05, (n, 3)).astype(np.float32); win[k][:] = rng.uniform(-0.05, 0.05, (n, 3)).astype(np.float32)
+    ref = []
+    for k in range(nsteps):
+        _, _, v, w = a.state()
+        a.set_velocity(0, v + vin[k], w + win[k])
+        sa = a.step(DT, 2)
+        ref.append((sa["constraints"], [x.copy() for x in a.state()]))
+    for k in range(nsteps):
+        b.step_enqueue(DT, 2, vin[k], win[k], *outs[k], add=True)       # all three in flight
+    stats = [b.step_wait() for _ in range(nsteps)]
+    assert stats[0]["overflow"] != 0 and stats[1]["overflow"] == 0
+    for k in range(nsteps):
+        assert stats[k]["constraints"] == ref[k][0], (k, stats[k]["constraints"], ref[k][0])
+        for got, want in zip(outs[k], ref[k][1]):
+            assert np.array_equal(_bits(got), _bits(want)), f"pipelined step {k} differs from the synchronous step"
+    for x, y in zip(a.state(), b.state()):
+        assert np.array_equal(_bits(x), _bits(y))
+
+
+def test_handover_selftest_sees_no_torn_record():
+    """The 32-byte hand-over store of the dataflow solver is checked at context creation (selftest.cuh); run it harder here:
+    writers overwrite records 20 000 times while readers on other SMs poll -- every record read must be whole."""
+    with mgf_b200.Context(device=0) as c:
+        torn, seen = c.selftest_handover(20000)
+        assert torn == 0
+        assert seen > 16 * 32       # the readers did watch the records change
+        assert c.cfg.solver_schedule == L.SCHEDULE_DATAFLOW
