@@ -1,0 +1,9 @@
+#!/bin/bash
+# GPU session 1: correctness of the new solver kernel, A/B timings, per-visit profile
+mkdir -p gpurun_out
+{
+echo "=== quick parity (df2 default)"; timeout 600 python -m pytest tests/test_gpu_step.py -x -q -m gpu -k "c1 or jittered or snapshot or pipelined or handover or capsules" 2>&1 | tail -15
+echo "=== A/B"; timeout 600 python tools/solver_ab.py C2pile C2settled 2>&1 | tail -20
+echo "=== per-visit profile, C2settled"; MGFB_LIB=$PWD/mgf_b200/lib/libmgfb_prof.so MGFB_AB="1:0,2:10,2:12,2:14" MGFB_AB_STEPS=4 timeout 300 python tools/solver_ab.py C2settled 2>&1 | tail -20
+} > gpurun_out/run1.log 2>&1
+tail -60 gpurun_out/run1.log
