@@ -282,7 +282,7 @@ typedef struct mgfb_step_stats {
     uint32_t ghosts;              /* tiled world: bodies received from the right neighbour this step */
     uint32_t boundary_constraints;/* tiled world: constraints between an owned body and a ghost */
     uint32_t phases;              /* non-empty groups = grid-wide phases per solver iteration */
-    uint32_t local_handover_permille; /* dataflow solver: share of the row-to-row hand-overs that stayed inside one SM's shared memory */
+    uint32_t reserved;
 } mgfb_step_stats;
 
 /* One World::step(dt) with `iters` solver iterations (the demo hard-codes 20, world.rs:293).

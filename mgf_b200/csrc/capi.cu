@@ -5,13 +5,11 @@
 #include <unistd.h>
 #include <algorithm>
 #include <cstdio>
-#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
 #include "../../include/mgfb.h"
 #include "kernels.cuh"
-#include "solve_local.cuh"
 
 using namespace mgfb;
 
@@ -70,11 +68,6 @@ struct mgfb_ctx {
     Buf u_a, u_b, u_sc, u_sf, u_n, u_t, u_nc, u_la, u_lb;
     // cooperative grid sizes
     int coop_order = 0, coop_solve = 0, coop_df = 0, coop_colour = 0;
-    int df_kernel = 3, df2_warps = 12;   // 3: k_solve_loc (SM-local hand-overs, solve_local.cuh)
-    // SM-local solver: body -> home CTA partition (refreshed every few steps) and the (CTA, colour)-major row layout
-    Buf part_key, part_key2, part_val, part_val2, part_tmp, part_w, part_wpre, part_bb, home, loc_hist, loc_seg, loc_slot, loc_flags, loc_owned, loc_cross, loc_cta;
-    size_t part_tmp_bytes = 0; unsigned part_n = 0, part_age = 0xffffffffu, part_every = 8;
-    //   // development knobs (env MGFB_DF_KERNEL = 1: k_solve_df, 2: k_solve_df2; MGFB_DF_WARPS)
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t* cur_ev = nullptr;        // the four timing events of the step being enqueued (ev, or a pipeline slot's)
     struct PipeSlot* pipe = nullptr;     // mgfb_step_enqueue / mgfb_step_wait (pipeline.cuh)
@@ -167,9 +160,6 @@ int32_t grow_bodies(mgfb_ctx* ctx, unsigned need) {
     TRY(ensure(ctx, ctx->body_scratch, (size_t)nc * 12, false, true));
     TRY(ensure(ctx, ctx->body_deg, (size_t)nc * 4)); TRY(ensure(ctx, ctx->body_start, ((size_t)nc + 1) * 4));
     TRY(ensure(ctx, ctx->scan_sums, ((size_t)nc / SCAN_ITEMS + 2) * 4));
-    TRY(ensure(ctx, ctx->home, (size_t)nc * 2, false, true)); TRY(ensure(ctx, ctx->loc_owned, (size_t)nc * 4, false, true));
-    TRY(ensure(ctx, ctx->loc_cross, (size_t)nc * 4, false, true));
-    ctx->part_age = 0xffffffffu;   // new bodies: partition again
     ctx->cap = nc;
     return MGFB_OK;
 }
@@ -197,7 +187,6 @@ int32_t ensure_rows(mgfb_ctx* ctx, unsigned m, bool extras, unsigned groups) {
         TRY(ensure(ctx, ctx->r_ia, (size_t)rc * 80));
         TRY(ensure(ctx, ctx->c_key, (size_t)rc * 8)); TRY(ensure(ctx, ctx->c_csr, (size_t)rc * 8)); TRY(ensure(ctx, ctx->c_next, (size_t)rc * 8));
         TRY(ensure(ctx, ctx->c_inbox, (size_t)rc * 16));
-        TRY(ensure(ctx, ctx->loc_slot, (size_t)rc * 4)); TRY(ensure(ctx, ctx->loc_flags, (size_t)rc * 4)); TRY(ensure(ctx, ctx->loc_cta, (size_t)rc * 2));
         // inbox tags must never match by accident: zeroed when (re)allocated, epochs only grow
         TRY(ensure(ctx, ctx->r_in_a, (size_t)rc * sizeof(Inbox), false, true)); TRY(ensure(ctx, ctx->r_in_b, (size_t)rc * sizeof(Inbox), false, true));
         ctx->row_cap = rc;
@@ -304,35 +293,6 @@ int coop_blocks(const mgfb_ctx* ctx, K kernel, int threads, int max_per_sm) {
     return ctx->max_ctas ? std::min(blocks, ctx->max_ctas) : blocks;
 }
 
-// SM-local solver: which CTA is home to each body (solve_local.cuh).  Bodies along a Morton curve, cut into coop_df chunks of
-// equal weight (1 + rows the body was home to in the last step).  All on the stream, no host round trip.
-int32_t refresh_partition(mgfb_ctx* ctx) {
-    const unsigned n = ctx->n, G = (unsigned)ctx->coop_df;
-    const size_t cap = ctx->cap;
-    TRY(ensure(ctx, ctx->part_key, cap * 4)); TRY(ensure(ctx, ctx->part_key2, cap * 4)); TRY(ensure(ctx, ctx->part_val, cap * 4)); TRY(ensure(ctx, ctx->part_val2, cap * 4));
-    TRY(ensure(ctx, ctx->part_w, cap * 4)); TRY(ensure(ctx, ctx->part_wpre, (cap + 1) * 4)); TRY(ensure(ctx, ctx->part_bb, 32));
-    TRY(ensure(ctx, ctx->loc_hist, (size_t)G * LOC_SEGS * 4)); TRY(ensure(ctx, ctx->loc_seg, ((size_t)G * LOC_SEGS + 1) * 4));
-    size_t tmp = 0;
-    CU(cub::DeviceRadixSort::SortPairs(nullptr, tmp, ctx->part_key.as<unsigned>(), ctx->part_key2.as<unsigned>(), ctx->part_val.as<unsigned>(),
-                                       ctx->part_val2.as<unsigned>(), (int)cap, 0, 30, ctx->stream));
-    TRY(ensure(ctx, ctx->part_tmp, std::max<size_t>(tmp, 16)));
-    tmp = ctx->part_tmp.bytes;
-    unsigned* bb = ctx->part_bb.as<unsigned>();
-    CU(cudaMemsetAsync(bb, 0xff, 12, ctx->stream)); CU(cudaMemsetAsync(bb + 3, 0, 12, ctx->stream));
-    const int gb = grid_for(ctx, n), nb1 = (int)((n + MGFB_THREADS - 1) / MGFB_THREADS);
-    k_part_bbox<<<gb, MGFB_THREADS, 0, ctx->stream>>>(ctx->x.as<float4>(), n, bb);
-    k_part_keys<<<nb1, MGFB_THREADS, 0, ctx->stream>>>(ctx->x.as<float4>(), n, bb, ctx->part_key.as<unsigned>(), ctx->part_val.as<unsigned>());
-    CU(cub::DeviceRadixSort::SortPairs(ctx->part_tmp.p, tmp, ctx->part_key.as<unsigned>(), ctx->part_key2.as<unsigned>(), ctx->part_val.as<unsigned>(),
-                                       ctx->part_val2.as<unsigned>(), (int)n, 0, 30, ctx->stream));
-    k_part_weights<<<nb1, MGFB_THREADS, 0, ctx->stream>>>(ctx->part_val2.as<unsigned>(), ctx->part_n == n ? ctx->loc_owned.as<unsigned>() : nullptr, n, ctx->part_w.as<unsigned>());
-    TRY(scan_u32_lb(ctx, ctx->part_w.as<unsigned>(), ctx->part_wpre.as<unsigned>(), n, nullptr));
-    k_part_assign<<<nb1, MGFB_THREADS, 0, ctx->stream>>>(ctx->part_val2.as<unsigned>(), ctx->part_wpre.as<unsigned>(), n, G, ctx->home.as<unsigned short>());
-    CU(cudaGetLastError());
-    ctx->launches += 8;   // bbox, keys, sort (~3 kernels), weights, scan, assign
-    ctx->part_n = n; ctx->part_age = 0;
-    return MGFB_OK;
-}
-
 // order -> scan -> scatter -> build -> solve, for `m` constraints counted on the device
 // (m_ptr) or known on the host (m_host).
 int32_t enqueue_order_and_solve(mgfb_ctx* ctx, const OrderView& O, const ManifoldInput& M, const unsigned* m_ptr, unsigned m_host,
@@ -351,20 +311,12 @@ int32_t enqueue_order_and_solve(mgfb_ctx* ctx, const OrderView& O, const Manifol
     int g = grid_for(ctx, m_bound);
     const bool colour_df = !as_given && ctx->cfg.solver_schedule != MGFB_SCHEDULE_PHASES_JP;
     PROF(MGFB_PHASE_COLOURING);
-    // SM-local hand-overs (solve_local.cuh): single-GPU step path with the dataflow schedule; rows laid out (CTA, colour)-major
-    const bool local = colour_df && ctx->cfg.solver_schedule == MGFB_SCHEDULE_DATAFLOW && !tiled && !M.user && ctx->df_kernel == 3 && m_ptr;
     if (colour_df) {
         // constraints per body -> CSR -> chains sorted by key -> colours travel down the chains (no grid barrier)
         ColourView V{};
         V.key = ctx->c_key.as<unsigned long long>(); V.deg = ctx->body_deg.as<unsigned>(); V.body_start = ctx->body_start.as<unsigned>();
         V.csr = ctx->c_csr.as<unsigned>(); V.next = ctx->c_next.as<unsigned>(); V.inbox = ctx->c_inbox.as<unsigned long long>(); V.cap = ctx->row_cap;
         CU(cudaMemsetAsync(V.deg, 0, (size_t)nb * 4, ctx->stream));
-        if (local) {
-            V.home = ctx->home.as<unsigned short>(); V.cross = ctx->loc_cross.as<unsigned>(); V.cta = ctx->loc_cta.as<unsigned short>();
-            V.seg_hist = ctx->loc_hist.as<unsigned>(); V.seg_slot = ctx->loc_slot.as<unsigned>();
-            CU(cudaMemsetAsync(V.cross, 0, (size_t)nb * 4, ctx->stream));
-            CU(cudaMemsetAsync(V.seg_hist, 0, (size_t)ctx->coop_df * LOC_SEGS * 4, ctx->stream));
-        }
         k_inc_count<<<g, MGFB_THREADS, 0, ctx->stream>>>(O, V, m_ptr, m_host, c);
         TRY(scan_u32_lb(ctx, V.deg, ctx->body_start.as<unsigned>(), nb, &c->df_links));
         k_inc_fill<<<g, MGFB_THREADS, 0, ctx->stream>>>(O, V, m_ptr, m_host, c);
@@ -382,17 +334,7 @@ int32_t enqueue_order_and_solve(mgfb_ctx* ctx, const OrderView& O, const Manifol
         CU(cudaLaunchCooperativeKernel((void*)k_order, dim3(ctx->coop_order), dim3(MGFB_THREADS), args, 0, ctx->stream));
     }
     k_group_scan<<<1, 1024, 0, ctx->stream>>>(gcount, gstart, pstart, c, gcap, tiled ? (unsigned)TILE_INTERIOR_COLOURS : 0xffffffffu);
-    LocalView LV{};
-    if (local) {
-        LV.home = ctx->home.as<unsigned short>(); LV.hist = ctx->loc_hist.as<unsigned>(); LV.seg_start = ctx->loc_seg.as<unsigned>();
-        LV.slot = ctx->loc_slot.as<unsigned>(); LV.flags = ctx->loc_flags.as<unsigned>(); LV.owned = ctx->loc_owned.as<unsigned>(); LV.G = (unsigned)ctx->coop_df;
-        LV.cta = ctx->loc_cta.as<unsigned short>();
-        CU(cudaMemsetAsync(LV.owned, 0, (size_t)ctx->cap * 4, ctx->stream));
-        TRY(scan_u32_lb(ctx, LV.hist, LV.seg_start, LV.G * LOC_SEGS, nullptr));
-        k_loc_scatter<<<g, MGFB_THREADS, 0, ctx->stream>>>(O.a, O.b, O.group, LV, perm, m_ptr, c);
-        ctx->launches += 2;
-    }
-    k_scatter_rows<<<g, MGFB_THREADS, 0, ctx->stream>>>(O.group, gcount, gstart, perm, m_ptr, m_host, c, local ? (unsigned)LOC_COLOURS : 0u);
+    k_scatter_rows<<<g, MGFB_THREADS, 0, ctx->stream>>>(O.group, gcount, gstart, perm, m_ptr, m_host, c);
     // Schedule of the solve: dataflow (body version counters, no grid barrier) for coloured single-GPU
     // solves; grid-barrier phases for as-given (level) order, tiled worlds, > 64 colours, or on request.
     // (a tiled world derives its inbox tags from the common step number: 2048 tags per step)
@@ -410,16 +352,6 @@ int32_t enqueue_order_and_solve(mgfb_ctx* ctx, const OrderView& O, const Manifol
                                                       O.group, O.body_mask, D);
     unsigned epoch = ctx->df_epoch;
     TileLink TL = ctx->link;
-    if (local) {
-        if (ctx->df_epoch > 0x7fffffffu - 2u * (iters + 2u)) {
-            CU(cudaMemsetAsync(ctx->r_in_a.p, 0, ctx->r_in_a.bytes, ctx->stream)); CU(cudaMemsetAsync(ctx->r_in_b.p, 0, ctx->r_in_b.bytes, ctx->stream));
-            ctx->df_epoch = epoch = 0;
-        }
-        ctx->df_epoch += iters + 2u;
-        CU(cudaMemsetAsync(LV.flags, 0, (size_t)ctx->row_cap * 4, ctx->stream));
-        k_loc_init<<<g, MGFB_THREADS, 0, ctx->stream>>>(vel, nb, R.ab, D, LV, epoch, m_ptr, c);
-        ctx->launches += 1;
-    } else
     if (dataflow && !tiled) {
         if (ctx->df_epoch > 0x7fffffffu - 2u * (iters + 2u)) {   // tag space exhausted (once per ~10^8 solves): start over from clean inboxes
             CU(cudaMemsetAsync(ctx->r_in_a.p, 0, ctx->r_in_a.bytes, ctx->stream)); CU(cudaMemsetAsync(ctx->r_in_b.p, 0, ctx->r_in_b.bytes, ctx->stream));
@@ -445,18 +377,10 @@ int32_t enqueue_order_and_solve(mgfb_ctx* ctx, const OrderView& O, const Manifol
     if (dataflow) {
         const unsigned* ps = pstart; unsigned it = iters;
         void* args[] = {&R, &D, &vel, &ps, &it, &epoch, &c, &TL};
-        if (local) {
-            void* largs[] = {&R, &D, &LV, &vel, &it, &epoch, &c};
-            CU(cudaLaunchCooperativeKernel((void*)k_solve_loc, dim3(ctx->coop_df), dim3(LOC_THREADS), largs, (size_t)LOC_SMEM_BYTES, ctx->stream));
-        } else if (ctx->df_kernel >= 2) {
-            void* fn = tiled ? (void*)k_solve_df2<true> : (void*)k_solve_df2<false>;
-            CU(cudaLaunchCooperativeKernel(fn, dim3(ctx->coop_df), dim3(ctx->df2_warps * 32), args, (size_t)ctx->df2_warps * DF2_WARP_BYTES, ctx->stream));
-        } else {
-            void* fn = tiled ? (void*)k_solve_df<true> : (void*)k_solve_df<false>;
-            // rows of the previous solve decide the block size (the count of THIS step is still on the device)
-            const unsigned threads = ctx->last_constraints > MGFB_DF_LARGE_ROWS ? MGFB_DF_THREADS_LARGE : MGFB_DF_THREADS_SMALL;
-            CU(cudaLaunchCooperativeKernel(fn, dim3(ctx->coop_df), dim3(threads), args, 0, ctx->stream));
-        }
+        void* fn = tiled ? (void*)k_solve_df<true> : (void*)k_solve_df<false>;
+        // rows of the previous solve decide the block size (the count of THIS step is still on the device)
+        const unsigned threads = ctx->last_constraints > MGFB_DF_LARGE_ROWS ? MGFB_DF_THREADS_LARGE : MGFB_DF_THREADS_SMALL;
+        CU(cudaLaunchCooperativeKernel(fn, dim3(ctx->coop_df), dim3(threads), args, 0, ctx->stream));
         ctx->launches += 1;
         if (tiled) {   // my ghosts' final velocities are in their owner's records; wait for the same from the left tile
             k_tile_solve_done<<<1, 1, 0, ctx->stream>>>(TL, c);
@@ -468,7 +392,7 @@ int32_t enqueue_order_and_solve(mgfb_ctx* ctx, const OrderView& O, const Manifol
     {
         const unsigned* ps = pstart; unsigned it = iters;
         TileLink T = ctx->link;
-        unsigned only_beyond = dataflow ? (unsigned)MGFB_DF_MAX_PHASES | (local ? 0x80000000u : 0u) : 0u;   // after a dataflow kernel: only if it declined
+        unsigned only_beyond = dataflow ? (unsigned)MGFB_DF_MAX_PHASES : 0u;   // after k_solve_df: only if it declined (> 64 colours)
         void* args[] = {&R, &vel, &ps, &it, &c, &T, &only_beyond};
         void* fn = tiled ? (void*)k_solve<true> : (void*)k_solve<false>;
         CU(cudaLaunchCooperativeKernel(fn, dim3(ctx->coop_solve), dim3(MGFB_SOLVE_THREADS), args, 0, ctx->stream));
@@ -491,10 +415,6 @@ int32_t enqueue_step(mgfb_ctx* ctx, float dt, unsigned iters, bool from_integrat
     CU(cudaMemsetAsync(ctx->cell_count.p, 0, (size_t)ctx->table * 4, ctx->stream));
     int gb = grid_for(ctx, n);
     const bool tiled = ctx->tiled;
-    if (!tiled && ctx->df_kernel == 3 && ctx->cfg.solver_schedule == MGFB_SCHEDULE_DATAFLOW) {
-        if (ctx->part_n != n || ctx->part_age >= ctx->part_every) TRY(refresh_partition(ctx));
-        ctx->part_age++;
-    }
     const unsigned slots = body_slots(ctx);   // upper bound of n_total (device-resident: own + this step's ghosts)
     PROF(MGFB_PHASE_INTEGRATE);
     if (!tiled) {
@@ -687,8 +607,7 @@ int32_t mgfb_ctx_create(const mgfb_config* cfg, mgfb_ctx** out) {
                              (const void*)k_narrow_bodies<0, 1>, (const void*)k_narrow_bodies<1, 0>, (const void*)k_narrow_bodies<1, 1>,
                              (const void*)k_narrow_terrain<0>, (const void*)k_narrow_terrain<1>, (const void*)k_order, (const void*)k_group_scan,
                              (const void*)k_scatter_rows, (const void*)k_build_rows, (const void*)k_solve<false>, (const void*)k_solve<true>,
-                             (const void*)k_solve_df<false>, (const void*)k_solve_df<true>, (const void*)k_solve_df2<false>, (const void*)k_solve_df2<true>, (const void*)k_solve_loc, (const void*)k_loc_init, (const void*)k_loc_scatter,
-                             (const void*)k_part_bbox, (const void*)k_part_keys, (const void*)k_part_weights, (const void*)k_part_assign, (const void*)k_df_init<false>, (const void*)k_df_init<true>,
+                             (const void*)k_solve_df<false>, (const void*)k_solve_df<true>, (const void*)k_df_init<false>, (const void*)k_df_init<true>,
                              (const void*)k_tile_links_send, (const void*)k_tile_solve_done, (const void*)k_inc_count, (const void*)k_inc_fill, (const void*)k_inc_sort, (const void*)k_colour_df,
                              (const void*)k_step_done, (const void*)k_pack_state, (const void*)k_set_velocity<false>, (const void*)k_set_velocity<true>, (const void*)k_set_state};
         cudaFuncAttributes fa;
@@ -700,21 +619,6 @@ int32_t mgfb_ctx_create(const mgfb_config* cfg, mgfb_ctx** out) {
     ctx->coop_colour = coop_blocks(ctx, k_colour_df, MGFB_THREADS, 8);
     ctx->coop_solve = std::min(coop_blocks(ctx, k_solve<false>, MGFB_SOLVE_THREADS, 1), coop_blocks(ctx, k_solve<true>, MGFB_SOLVE_THREADS, 1));
     ctx->coop_df = std::min(coop_blocks(ctx, k_solve_df<false>, MGFB_DF_THREADS_LARGE, 1), coop_blocks(ctx, k_solve_df<true>, MGFB_DF_THREADS_LARGE, 1));
-    if (const char* e = getenv("MGFB_DF_KERNEL")) ctx->df_kernel = std::max(1, std::min(atoi(e), 3));
-    if (const char* e = getenv("MGFB_PART_EVERY")) ctx->part_every = (unsigned)std::max(1, atoi(e));
-    if (const char* e = getenv("MGFB_DF_WARPS")) ctx->df2_warps = std::max(1, std::min(atoi(e), MGFB_DF_THREADS_LARGE / 32));
-    ctx->df2_warps = std::min<int>(ctx->df2_warps, (int)((prop.sharedMemPerBlockOptin - 1024) / DF2_WARP_BYTES));
-    {
-        const int dyn = ctx->df2_warps * DF2_WARP_BYTES;
-        if ((e = cudaFuncSetAttribute(k_solve_df2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn)) != cudaSuccess) return bail(e, "cudaFuncSetAttribute");
-        if ((e = cudaFuncSetAttribute(k_solve_df2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn)) != cudaSuccess) return bail(e, "cudaFuncSetAttribute");
-        if ((e = cudaFuncSetAttribute(k_solve_loc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LOC_SMEM_BYTES)) != cudaSuccess) return bail(e, "cudaFuncSetAttribute");
-        int per_sm = 0;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_solve_loc, LOC_THREADS, LOC_SMEM_BYTES);
-        if (per_sm < 1) return bail(cudaErrorLaunchOutOfResources, "k_solve_loc does not fit one CTA per SM");
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_solve_df2<true>, ctx->df2_warps * 32, dyn);
-        if (per_sm < 1) return bail(cudaErrorLaunchOutOfResources, "k_solve_df2 does not fit one CTA per SM");
-    }
     int32_t s = grow_bodies(ctx, std::max(ctx->cfg.initial_body_capacity, 1024u));
     if (s == MGFB_OK) s = ensure_rows(ctx, 1024, false, 4096);
     // the dataflow solver's hand-over is one 32-byte store: check that this device delivers it whole (selftest.cuh)
@@ -740,16 +644,6 @@ void mgfb_ctx_destroy(mgfb_ctx* ctx) {
                 h[5], h[4], h[0] / v, h[1] / v, h[2] / v, h[3] / v);
         unsigned long long z[8] = {0};
         cudaMemcpyToSymbol(g_df_prof, z, sizeof(z));
-        cudaMemcpyFromSymbol(h, g_df2_prof, sizeof(h));
-        v = (double)std::max(1ULL, h[0]);
-        fprintf(stderr, "[df2 profile] warps=%llu visits=%llu inputs-in-prefetch %.1f%% polls/visit %.2f ; cycles per visit: copy-wait %.0f poll %.0f compute+publish+prefetch %.0f\n",
-                h[6], h[0], 100.0 * h[1] / v, h[2] / v, h[3] / v, h[4] / v, h[5] / v);
-        cudaMemcpyToSymbol(g_df2_prof, z, sizeof(z));
-        cudaMemcpyFromSymbol(h, g_loc_prof, sizeof(h));
-        v = (double)std::max(1ULL, h[0]);
-        fprintf(stderr, "[loc profile] warps=%llu visits=%llu polls/visit %.2f ; cycles per visit: fetch %.0f poll %.0f compute+publish %.0f\n",
-                h[5], h[0], h[1] / v, h[2] / v, h[3] / v, h[4] / v);
-        cudaMemcpyToSymbol(g_loc_prof, z, sizeof(z));
     }
 #endif
     Buf* all[] = {&ctx->x, &ctx->q, &ctx->vel, &ctx->force, &ctx->torque, &ctx->imb, &ctx->col, &ctx->tight, &ctx->fat, &ctx->ctr,
@@ -760,8 +654,6 @@ void mgfb_ctx_destroy(mgfb_ctx* ctx) {
                   &ctx->scan_sums, &ctx->scan_state, &ctx->u_a, &ctx->u_b, &ctx->u_sc, &ctx->u_sf, &ctx->u_n, &ctx->u_t, &ctx->u_nc, &ctx->u_la,
                   &ctx->u_lb, &ctx->stage, &ctx->terrain.verts, &ctx->terrain.faces, &ctx->terrain.boxes, &ctx->terrain.cell_count,
                   &ctx->terrain.cell_start, &ctx->terrain.ent_id, &ctx->terrain.ent_key, &ctx->terrain.max_bits,
-                  &ctx->part_key, &ctx->part_key2, &ctx->part_val, &ctx->part_val2, &ctx->part_tmp, &ctx->part_w, &ctx->part_wpre, &ctx->part_bb, &ctx->home,
-                  &ctx->loc_hist, &ctx->loc_seg, &ctx->loc_slot, &ctx->loc_flags, &ctx->loc_owned, &ctx->loc_cross, &ctx->loc_cta,
                   &ctx->gid, &ctx->phase_start, &ctx->edge_idx, &ctx->edge_mark, &ctx->ridx, &ctx->mbox, &ctx->edge_slot, &ctx->tile_df};
     pipe_destroy(ctx);
     for (void* ptr : ctx->ipc_opened) cudaIpcCloseMemHandle(ptr);
@@ -976,7 +868,6 @@ int32_t mgfb_bodies_set_state(mgfb_ctx* ctx, uint32_t first, uint32_t n, const f
     CU(cudaGetLastError());
     ctx->launches += 1;
     CU(cudaStreamSynchronize(ctx->stream));
-    if (x) ctx->part_age = 0xffffffffu;   // bodies moved: the SM-local solver re-partitions
     return MGFB_OK;
 }
 
@@ -1069,7 +960,6 @@ static void fill_step_stats(mgfb_ctx* ctx, mgfb_step_stats* st, unsigned iters, 
     st->ghosts = h.n_total - ctx->n;
     st->boundary_constraints = h.contacts - h.n_int_rows;
     st->phases = h.n_phases;
-    st->local_handover_permille = (h.loc_edges + h.glob_edges) ? (uint32_t)((1000ull * h.loc_edges) / (h.loc_edges + h.glob_edges)) : 0u;
     if (timed) {
         cudaEventElapsedTime(&st->step_ms, evs[0], evs[1]);
         cudaEventElapsedTime(&st->solve_ms, evs[2], evs[3]);
@@ -1175,9 +1065,6 @@ int32_t mgfb_step_constraints(mgfb_ctx* ctx, uint32_t capacity, uint32_t* body_a
     CU(dl(perm.data(), ctx->perm)); CU(dl(ha.data(), ctx->c_a)); CU(dl(hb.data(), ctx->c_b)); CU(dl(hface.data(), ctx->c_face));
     CU(dl(hsub.data(), ctx->c_sub)); CU(dl(hg.data(), ctx->group));
     CU(cudaStreamSynchronize(ctx->stream));
-    // the order reported is colour-major: the device may keep the rows (CTA, colour)-major (solve_local.cuh), which runs the
-    // same per-body chains -- rows of one colour share no dynamic body and commute exactly
-    std::stable_sort(perm.begin(), perm.end(), [&](unsigned p, unsigned q) { return hg[p] < hg[q]; });
     for (unsigned r = 0; r < m; ++r) {
         unsigned k = perm[r];
         if (body_a) body_a[r] = ctx->tiled ? hgid[ha[k]] : (uint32_t)ha[k];

@@ -650,12 +650,6 @@ struct ColourView {
     unsigned* next;              // [2][cap] successor on the chain of body a / body b: k << 1 | side, or 0xffffffff
     unsigned long long* inbox;   // [2][cap] mask so far at body a / body b, bit 63 = valid
     unsigned cap;
-    // SM-local solver (solve_local.cuh), NULL otherwise: which CTA a constraint's row will live on, decided on the way
-    const unsigned short* home;  // [nbodies] home CTA of every body
-    unsigned* cross;             // [nbodies] constraints of the body whose other body has another home (zeroed per step)
-    unsigned short* cta;         // [m] out: CTA of the constraint's row
-    unsigned* seg_hist;          // [G * 64] out: rows per (CTA, colour), counted as the colours are decided
-    unsigned* seg_slot;          // [m] out: rank of the constraint inside its (CTA, colour) segment
 };
 #define COLOUR_VALID (1ULL << 63)
 __global__ void __launch_bounds__(MGFB_THREADS) k_inc_count(OrderView O, ColourView V, const unsigned* m_ptr, unsigned m_host, Counters* ctr) {
@@ -666,7 +660,6 @@ __global__ void __launch_bounds__(MGFB_THREADS) k_inc_count(OrderView O, ColourV
         atomicAdd(&V.deg[O.a[k]], 1u);
         int b = O.b[k];
         if (b >= 0) atomicAdd(&V.deg[b], 1u);
-        if (V.home && b >= 0 && V.home[O.a[k]] != V.home[b]) { atomicAdd(&V.cross[O.a[k]], 1u); atomicAdd(&V.cross[b], 1u); }
         V.inbox[k] = 0ULL; V.inbox[V.cap + k] = 0ULL;
         V.next[k] = 0xffffffffu; V.next[V.cap + k] = 0xffffffffu;
         O.group[k] = -1;
@@ -679,12 +672,6 @@ __global__ void __launch_bounds__(MGFB_THREADS) k_inc_fill(OrderView O, ColourVi
         int a = O.a[k], b = O.b[k];
         V.csr[V.body_start[a] + (atomicSub(&V.deg[a], 1u) - 1u)] = k;
         if (b >= 0) V.csr[V.body_start[b] + (atomicSub(&V.deg[b], 1u) - 1u)] = k;
-        if (V.home) {
-            // A row between two homes breaks the chain of the body it does not live with (two hand-overs through L2 per
-            // iteration): it goes to the body that already has MORE such rows, so no body collects many breaks.
-            unsigned short ha = V.home[a], hb = b >= 0 ? V.home[b] : ha;
-            V.cta[k] = (ha == hb || V.cross[a] >= V.cross[b]) ? ha : hb;
-        }
     }
 }
 // One thread per body: sort its constraints by key (descending), link the chain, seed the head's inbox.
@@ -768,7 +755,6 @@ __device__ __forceinline__ unsigned colour_one(const OrderView& O, const ColourV
         else O.body_mask[b] = (mb | bit) & ~COLOUR_VALID;
     }
     __stcg(&O.group[k], (int)g);
-    if (V.home) V.seg_slot[k] = atomicAdd(&V.seg_hist[(unsigned)V.cta[k] * 64u + g], 1u);   // SM-local row layout (solve_local.cuh)
     return g;
 }
 // Persistent, all threads co-resident (cooperative launch).  A thread owns constraints tid, tid+nth, ...
@@ -893,9 +879,8 @@ __global__ void __launch_bounds__(1024) k_group_scan(const unsigned* count, unsi
 // histogram of the tile's colours, one global atomic per colour per tile (a handful of colours hold all
 // constraints, so per-constraint global atomics would serialise on ~10 addresses).
 __global__ void __launch_bounds__(MGFB_THREADS) k_scatter_rows(const int* __restrict__ group, unsigned* group_count, const unsigned* __restrict__ group_start,
-                                                              unsigned* perm, const unsigned* m_ptr, unsigned m_host, Counters* ctr, unsigned only_beyond) {
+                                                              unsigned* perm, const unsigned* m_ptr, unsigned m_host, Counters* ctr) {
     if (ctr->overflow | ctr->nan_bounds) return;
-    if (only_beyond && ctr->ngroups <= only_beyond && !ctr->colour_fallback) return;   // the SM-local layout (solve_local.cuh) took this step
     __shared__ unsigned s_cnt[64], s_base[64];
     const unsigned m = m_ptr ? *m_ptr : m_host;
     for (unsigned base = blockIdx.x * blockDim.x; base < m; base += gridDim.x * blockDim.x) {
@@ -1124,8 +1109,7 @@ template <bool TILED>
 __global__ void __launch_bounds__(MGFB_SOLVE_THREADS, 1) k_solve(ConstraintRows R, BodyVel* vel, const unsigned* __restrict__ phase_start,
                                                                 unsigned iters, Counters* ctr, TileLink T, unsigned only_beyond) {
     if (ctr->overflow | ctr->nan_bounds) return;
-    // a dataflow kernel took this step -- unless it declined: > 64 colours, or (bit 31: SM-local layout) the chain colouring fell back to k_order
-    if (only_beyond && ctr->ngroups <= (only_beyond & 0xffffu) && !((only_beyond >> 31) && ctr->colour_fallback)) return;
+    if (only_beyond && ctr->ngroups <= only_beyond) return;   // k_solve_df (dataflow schedule) took this step
     const unsigned P = ctr->n_phases;
     const unsigned Pint = TILED ? ctr->n_int_phases : P;
     if (!TILED && P == 0) return;
@@ -1467,198 +1451,6 @@ __global__ void __launch_bounds__(MGFB_DF_THREADS_LARGE, 1) k_solve_df(Constrain
 #ifdef MGFB_DF_PROFILE
     if (lane == 0) for (int i = 0; i < 5; ++i) atomicAdd(&g_df_prof[i], prof[i]);
     if (lane == 0) atomicAdd(&g_df_prof[5], 1ULL);
-#endif
-}
-
-// ---------------------------------------------------------------- Solver::solve, dataflow schedule, staged through shared memory
-// Same rows, same waits, same arithmetic as k_solve_df -- so the same bits -- but a warp no longer sits through the L2
-// latency of every visit.  Each warp owns DF2_SLOTS slots of shared memory; while it works on visit v it has the
-// immutable row data AND a first look at the inboxes of its visits v+1 .. v+DF2_SLOTS-1 in flight as cp.async copies
-// (LDGSTS: no registers, no stall).  When it arrives at a visit whose inputs had already been pushed at prefetch time
-// -- every row with slack in the dependency graph -- the visit is shared-memory reads + ~300 flops + two stores; only rows on
-// the critical path still poll their inboxes from L2 (same loop as k_solve_df).  The accumulated impulses of the warp's
-// first DF2_IMP warp-rows live in shared memory for the whole solve (it == 0 starts from 0 without a load).
-// Layout per slot: SoA over the 32 lanes (float4[32] per field) so every LDS.128 is conflict-free; a lane only ever touches
-// its own entries, so no cross-lane synchronisation is needed around the copies.
-#ifndef DF2_SLOTS
-#define DF2_SLOTS 2
-#endif
-#ifndef DF2_IMP
-#define DF2_IMP 8
-#endif
-#define DF2_SLOT_BYTES (14 * 512 + 2 * 128)                          // 10 row fields + 4 inbox halves (float4[32] each) + 2 links (u32[32])
-#define DF2_WARP_BYTES (DF2_SLOTS * DF2_SLOT_BYTES + DF2_IMP * 128)  // + impulse cache
-__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
-}
-__device__ __forceinline__ void cp_async4(void* smem, const void* gmem) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-#ifdef MGFB_DF_PROFILE
-__device__ unsigned long long g_df2_prof[8];   // visits, visits whose inputs were in the prefetch, polls, cycles waiting for copies, cycles polling, cycles compute+publish
-#endif
-template <bool TILED>
-__global__ void __launch_bounds__(MGFB_DF_THREADS_LARGE, 1) k_solve_df2(ConstraintRows R, DfArrays D, BodyVel* vel, const unsigned* __restrict__ phase_start,
-                                                                 unsigned iters, unsigned epoch, Counters* ctr, TileLink T) {
-    extern __shared__ __align__(16) unsigned char df2_smem[];
-    if (ctr->overflow | ctr->nan_bounds) return;
-    if (TILED && ctr->comm_error) return;
-    const unsigned P = ctr->n_phases;
-    if (P == 0 || ctr->ngroups > MGFB_DF_MAX_PHASES || iters == 0) return;   // > 64 colours: k_solve takes the step
-    __shared__ unsigned s_row0[MGFB_DF_MAX_PHASES + 1], s_wr0[MGFB_DF_MAX_PHASES + 1];
-    if (threadIdx.x == 0) {
-        unsigned w = 0;
-        for (unsigned p = 0; p < P; ++p) { unsigned r0 = phase_start[p], r1 = phase_start[p + 1]; s_row0[p] = r0; s_wr0[p] = w; w += (r1 - r0 + 31u) >> 5; }
-        s_row0[P] = phase_start[P]; s_wr0[P] = w;
-    }
-    __syncthreads();
-    const unsigned nwr = s_wr0[P];
-    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    const unsigned gw = warp * gridDim.x + blockIdx.x, nW = gridDim.x * (blockDim.x >> 5);
-    if (gw >= nwr) return;
-    const unsigned rc = D.row_cap;
-    unsigned char* wbase = df2_smem + (size_t)warp * DF2_WARP_BYTES;
-    float* imp_cache = reinterpret_cast<float*>(wbase + DF2_SLOTS * DF2_SLOT_BYTES);
-    const unsigned mine = (nwr - gw + nW - 1u) / nW;            // warp-rows this warp owns (the same ones every iteration)
-    const unsigned long long total = (unsigned long long)mine * iters;
-    auto slot_f4 = [&](unsigned slot, unsigned field) { return reinterpret_cast<float4*>(wbase + slot * DF2_SLOT_BYTES + field * 512u) + lane; };
-    auto slot_u32 = [&](unsigned slot, unsigned field) { return reinterpret_cast<unsigned*>(wbase + slot * DF2_SLOT_BYTES + 14u * 512u + field * 128u) + lane; };
-    // visit number -> (warp-row, row of this lane); the phase pointer only moves forward within an iteration
-    unsigned pf_p = 0, pf_j = 0;                                 // prefetch cursor: j-th own warp-row of the current prefetch iteration
-    auto row_of = [&](unsigned wr, unsigned& p, bool* valid) {
-        while (wr >= s_wr0[p + 1]) ++p;
-        unsigned row = s_row0[p] + ((wr - s_wr0[p]) << 5) + lane;
-        *valid = row < s_row0[p + 1];
-        return row;
-    };
-    auto prefetch = [&](unsigned slot) {                        // next visit in order -> slot; always commits a group (possibly empty)
-        bool valid; const unsigned row = row_of(gw + pf_j * nW, pf_p, &valid);
-        if (valid) {
-            cp_async16(slot_f4(slot, 0), R.n + row); cp_async16(slot_f4(slot, 1), R.t0 + row); cp_async16(slot_f4(slot, 2), R.t1 + row);
-            cp_async16(slot_f4(slot, 3), R.ra + row); cp_async16(slot_f4(slot, 4), R.rb + row);
-            cp_async16(slot_f4(slot, 5), D.ia + row); cp_async16(slot_f4(slot, 6), D.ia + rc + row); cp_async16(slot_f4(slot, 7), D.ia + 2 * rc + row);
-            cp_async16(slot_f4(slot, 8), D.ia + 3 * rc + row); cp_async16(slot_f4(slot, 9), D.ia + 4 * rc + row);
-            const float4* ia = reinterpret_cast<const float4*>(D.in_a + row); const float4* ib = reinterpret_cast<const float4*>(D.in_b + row);
-            cp_async16(slot_f4(slot, 10), ia); cp_async16(slot_f4(slot, 11), ia + 1);
-            cp_async16(slot_f4(slot, 12), ib); cp_async16(slot_f4(slot, 13), ib + 1);
-            cp_async4(slot_u32(slot, 0), D.next + row); cp_async4(slot_u32(slot, 1), D.next + rc + row);
-        }
-        cp_async_commit();
-        if (++pf_j == mine) { pf_j = 0; pf_p = 0; }
-    };
-    auto publish = [&](unsigned nx, int body, V3 v, V3 w, float im, const M3& I, unsigned tag, bool last_it) {
-        const bool wrap = (nx & 2u) != 0u;
-        if (wrap && last_it) {
-            BodyVel* dst = vel + body;
-            if (TILED && (unsigned)body >= T.n_own) dst = T.right.vel + T.ridx[(unsigned)body - T.n_own];
-            store_vel(dst, v, w, im, I);
-            return;
-        }
-        const unsigned where = TILED ? (nx >> 2) & 3u : 0u, side = nx & 1u, nr = nx >> 4;
-        Inbox* base = side ? D.in_b : D.in_a;
-        if (TILED && where == DF_LEFT) base = side ? T.left.in_b : T.left.in_a;
-        if (TILED && where == DF_RIGHT) base = side ? T.right.in_b : T.right.in_a;
-        st_inbox<TILED>(base + nr, v, w, tag + (wrap ? 1u : 0u));
-    };
-#ifdef MGFB_DF_PROFILE
-    unsigned long long prof[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-#endif
-    // prime the pipeline: visits 0 .. DF2_SLOTS-1 (groups beyond the last visit are empty, which keeps wait_group's count uniform)
-#pragma unroll
-    for (unsigned s = 0; s < DF2_SLOTS; ++s) {
-        if ((unsigned long long)s < total) prefetch(s); else cp_async_commit();
-    }
-    unsigned cur_p = 0, j = 0, it = 0, slot = 0;
-    for (unsigned long long v = 0; v < total; ++v) {
-        DF_T(t0);
-        cp_async_wait<DF2_SLOTS - 1>();                         // this visit's copies have landed (the younger groups may still fly)
-        bool valid; const unsigned row = row_of(gw + j * nW, cur_p, &valid);
-        const unsigned tag = epoch + it + 1u;
-        const bool last_it = it + 1 == iters;
-        unsigned na = DF_NONE, nb = DF_NONE;
-        Inbox sa, sb;
-        sa.lo = sa.hi = sb.lo = sb.hi = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-        if (valid) { na = *slot_u32(slot, 0); nb = *slot_u32(slot, 1); }
-        const bool needA = na != DF_NONE, needB = nb != DF_NONE;
-        bool okA = !needA, okB = !needB;
-        if (needA) { sa.lo = *slot_f4(slot, 10); sa.hi = *slot_f4(slot, 11); okA = __float_as_uint(sa.lo.w) == tag && __float_as_uint(sa.hi.w) == tag; }
-        if (needB) { sb.lo = *slot_f4(slot, 12); sb.hi = *slot_f4(slot, 13); okB = __float_as_uint(sb.lo.w) == tag && __float_as_uint(sb.hi.w) == tag; }
-        DF_T(t1); DF_ACC(3, t1 - t0); DF_ACC(0, 1);
-        if (!__all_sync(0xffffffffu, okA && okB)) {
-            unsigned long long t_wait0 = 0; unsigned spins = 0;
-            for (;;) {
-                if (!okA) { sa = ld_inbox<TILED>(D.in_a + row); okA = __float_as_uint(sa.lo.w) == tag && __float_as_uint(sa.hi.w) == tag; }
-                if (!okB) { sb = ld_inbox<TILED>(D.in_b + row); okB = __float_as_uint(sb.lo.w) == tag && __float_as_uint(sb.hi.w) == tag; }
-                DF_ACC(2, 1);
-                if (__all_sync(0xffffffffu, okA && okB)) break;
-                if (TILED && (++spins & 1023u) == 0u) {   // a dead or diverged neighbour must never hang the GPU
-                    bool dead = false;
-                    if (lane == 0) {
-                        unsigned long long now = globaltimer_ns();
-                        if (t_wait0 == 0) t_wait0 = now;
-                        if (*reinterpret_cast<volatile unsigned*>(&ctr->comm_error) & COMM_TIMEOUT) dead = true;
-                        else if (now - t_wait0 > T.timeout_ns) { atomicOr(&ctr->comm_error, (unsigned)COMM_TIMEOUT); dead = true; }
-                    }
-                    if (__shfl_sync(0xffffffffu, (int)dead, 0)) { cp_async_wait<0>(); return; }
-                }
-            }
-        } else { DF_ACC(1, 1); }
-        DF_T(t2); DF_ACC(4, t2 - t1);
-        if (valid) {
-            V3 va = mk3(sa.lo.x, sa.lo.y, sa.lo.z), oa = mk3(sa.hi.x, sa.hi.y, sa.hi.z);
-            V3 vb = mk3(sb.lo.x, sb.lo.y, sb.lo.z), ob = mk3(sb.hi.x, sb.hi.y, sb.hi.z);
-            const float4 i0 = *slot_f4(slot, 5), i1 = *slot_f4(slot, 6), i2 = *slot_f4(slot, 7), i3 = *slot_f4(slot, 8), i4 = *slot_f4(slot, 9);
-            const M3 IA = mkm(mk3(i0.x, i0.y, i0.z), mk3(i0.w, i1.x, i1.y), mk3(i1.z, i1.w, i2.x));
-            const float ima = i2.y;
-            const M3 IB = mkm(mk3(i2.z, i2.w, i3.x), mk3(i3.y, i3.z, i3.w), mk3(i4.x, i4.y, i4.z));
-            const float imb = i4.w;
-            const float4 n4 = *slot_f4(slot, 0), t04 = *slot_f4(slot, 1), t14 = *slot_f4(slot, 2), ra4 = *slot_f4(slot, 3), rb4 = *slot_f4(slot, 4);
-            V3 n = f4v(n4), t0v = f4v(t04), t1v = f4v(t14);
-            const int nc = (int)fbits(rb4.w);
-            for (int c = 0; c < nc; ++c) {
-                V3 ra, rb; float bias, nmass, tm0, tm1, imp;
-                if (c == 0) {
-                    ra = f4v(ra4); rb = f4v(rb4); bias = n4.w; nmass = ra4.w; tm0 = t04.w; tm1 = t14.w;
-                    imp = it == 0 ? 0.0f : (j < DF2_IMP ? imp_cache[j * 32u + lane] : __ldcg(&R.impulse[row]));   // k_build_rows zeroes the accumulator
-                } else {
-                    unsigned e = row * 3 + (c - 1);
-                    float4 xa = R.xra[e], xb = R.xrb[e], xt = __ldcg(&R.xtm[e]);
-                    ra = f4v(xa); rb = f4v(xb); nmass = xa.w; bias = xb.w; tm0 = xt.x; tm1 = xt.y; imp = xt.z;
-                }
-                V3 dv = vb + cross3(ob, rb) - va - cross3(oa, ra);        // solver.rs:217-232, same stale dv for both tangents
-                float l0 = -dot3(dv, t0v) * tm0;
-                apply_impulse(t0v * l0, ra, rb, ima, imb, IA, IB, va, oa, vb, ob);
-                float l1 = -dot3(dv, t1v) * tm1;
-                apply_impulse(t1v * l1, ra, rb, ima, imb, IA, IB, va, oa, vb, ob);
-                V3 dv2 = vb + cross3(ob, rb) - va - cross3(oa, ra);       // solver.rs:234-247
-                float vn = dot3(dv2, n);
-                float lambda = nmass * (-vn + bias);
-                float prev = imp;
-                imp = fmaxf(prev + lambda, 0.0f);
-                lambda = imp - prev;
-                apply_impulse(n * lambda, ra, rb, ima, imb, IA, IB, va, oa, vb, ob);
-                if (c == 0) {
-                    if (j < DF2_IMP && !last_it) imp_cache[j * 32u + lane] = imp;
-                    else __stcg(&R.impulse[row], imp);
-                }
-                else { unsigned e = row * 3 + (c - 1); __stcg(&R.xtm[e], make_float4(tm0, tm1, imp, 0.0f)); }
-            }
-            int a = 0, b = 0;
-            if (last_it) { int2 ab = R.ab[row]; a = ab.x; b = ab.y; }
-            if (needA) publish(na, a, va, oa, ima, IA, tag, last_it);
-            if (needB) publish(nb, b, vb, ob, imb, IB, tag, last_it);
-        }
-        // this slot is free again: the visit DF2_SLOTS ahead goes in (every lane has consumed its own entries above)
-        if (v + DF2_SLOTS < total) prefetch(slot); else cp_async_commit();
-        DF_T(t3); DF_ACC(5, t3 - t2);
-        slot = slot + 1 == DF2_SLOTS ? 0 : slot + 1;
-        if (++j == mine) { j = 0; cur_p = 0; ++it; }
-    }
-    cp_async_wait<0>();
-#ifdef MGFB_DF_PROFILE
-    if (lane == 0) { for (int i = 0; i < 6; ++i) atomicAdd(&g_df2_prof[i], prof[i]); atomicAdd(&g_df2_prof[6], 1ULL); }
 #endif
 }
 

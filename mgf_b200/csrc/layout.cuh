@@ -101,8 +101,6 @@ struct Counters {
     unsigned n_int_rows;     // constraints in interior phases
     unsigned df_links;       // dataflow solver: total (body, row) incidences = sum of rows per body
     unsigned colour_fallback; // k_colour_df ran out of colours: k_order (which stacks colours beyond 64) redoes the step's colouring
-    unsigned loc_edges;      // SM-local solver: hand-overs that stay in one CTA's shared memory ...
-    unsigned glob_edges;     // ... and those that cross CTAs through the global inboxes
     unsigned pad1;
     // sticky until the host clears them
     unsigned overflow;       // bit0 pairs, bit1 tpairs, bit2 contacts, bit3 grid entries, bit4 groups, bit5 ghosts

@@ -17,19 +17,17 @@ DT = np.float32(1 / 60)
 
 def main():
     names = sys.argv[1:] or ["C2pile", "C2settled"]
-    variants = [tuple(int(x) for x in v.split(":")) for v in os.environ.get("MGFB_AB", "1:0,3:0").split(",")]
+    variants = os.environ.get("MGFB_AB", "").split(",")
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device="cuda")
     nsteps = int(os.environ.get("MGFB_AB_STEPS", "12"))
     for name in names:
         g, bodies, terrain, iters, snap = bench.gpu_preroll(name)
         g.ctx.close()
         ref_state = None
-        for kernel, warps in variants:
-            os.environ["MGFB_DF_KERNEL"] = str(kernel)
-            if warps:
-                os.environ["MGFB_DF_WARPS"] = str(warps)
-            else:
-                os.environ.pop("MGFB_DF_WARPS", None)
+        for variant in variants:
+            from mgf_b200 import _lib
+            _lib._lib = None   # load the named build
+            os.environ["MGFB_LIB"] = os.path.join(ROOT, "mgf_b200", "lib", f"libmgfb{variant}.so")
             w = mgf_b200.World(device=0)
             w.add_bodies(*bodies); w.set_terrain(*terrain); w.restore(snap)
             w.step(DT, iters, nsteps=3)
@@ -39,7 +37,7 @@ def main():
                 ref_state = st
             same = all(np.array_equal(a.view(np.uint32), b.view(np.uint32)) for a, b in zip(st, ref_state))
             ms = np.mean([r["step_ms"] for r in rows]); sm = np.mean([r["solve_ms"] for r in rows])
-            print(f"{name:10s} kernel {kernel} warps {warps:2d}: step {ms:.4f} ms  solve {sm:.4f} ms  local {np.mean([r['local_handover_permille'] for r in rows]) / 10:.1f}%  constraints {np.mean([r['constraints'] for r in rows]):.0f}"
+            print(f"{name:10s} build '{variant}': step {ms:.4f} ms  solve {sm:.4f} ms  constraints {np.mean([r['constraints'] for r in rows]):.0f}"
                   f"  colours {np.mean([r['phases'] for r in rows]):.2f}  same bits as first variant: {same}", flush=True)
             w.ctx.close()
 
