@@ -205,6 +205,34 @@ int32_t mgfb_bvh_query_batch(mgfb_bvh* bvh, const float* boxes /* nq*6 */, uint3
 int32_t mgfb_bvh_raytrace_batch(mgfb_bvh* bvh, uint32_t particle_kind, const float* particles /* nq*6 */, uint32_t nq, uint32_t* offsets /* nq+1 */,
                                 uint32_t* values, mgfb_intersection* hits, uint32_t capacity, uint32_t* total);
 
+/* ---------------- Compound (src/compound.rs:232-352) ----------------
+ * An aggregate of Components (compound.rs:33-37: a Sphere or a Capsule, given in the compound's own frame) with a
+ * displacement `disp` and a rotation `rot` (assumed normalised, like the reference assumes).  Compound::new inserts the
+ * components one by one into a BVH<AABB, Component>; that tree is grown here exactly as bvh.rs grows it, so the queries
+ * below visit the same leaves in the same ORDER as the reference's callbacks (the last contact delivered is what
+ * `last_contact`, collision.rs:477, returns).  Intersects<Component> itself (compound.rs:150-157) needs no entry point of its
+ * own: a Component is a SPHERE or a CAPSULE shape of mgfb_intersections_batch. */
+typedef struct mgfb_compound mgfb_compound;
+/* Compound::new(components) (compound.rs:247-262); disp = 0, rot = identity. */
+int32_t mgfb_compound_create(mgfb_ctx* ctx, const mgfb_shape* components /* n, SPHERE | CAPSULE */, uint32_t n, mgfb_compound** out);
+void mgfb_compound_destroy(mgfb_compound* c);
+/* the pub fields disp and rot (compound.rs:236-238, AddAssign / SubAssign :265-275); rot = (s, x, y, z) */
+int32_t mgfb_compound_set_transform(mgfb_compound* c, const float disp[3], const float rot[4]);
+/* BoundedBy<AABB> (compound.rs:277-281: the tree's root box rotated, + disp) and BoundedBy<Sphere> (:283-288); either may be NULL.
+ * An empty compound is MGFB_ERR_STATE (the reference panics: "BVH is empty", bvh.rs:263). */
+int32_t mgfb_compound_bounds(const mgfb_compound* c, float aabb[6] /* centre, half extents */, float sphere[4] /* centre, radius */);
+/* Shape::closest_point (compound.rs:299-311) for n points.  Like the reference, the components are taken as stored (disp and
+ * rot are not applied) and ties keep the earlier component. */
+int32_t mgfb_compound_closest_points(mgfb_compound* c, const float* to /* n*3 */, uint32_t n, float* out /* n*3 */);
+/* Intersects<Compound> for Ray / Segment (compound.rs:314-337): the earliest hit over the components the traced tree reaches. */
+int32_t mgfb_compound_intersections_batch(mgfb_compound* c, uint32_t particle_kind, const float* particles /* n*6 */, uint32_t n,
+                                          mgfb_intersection* out /* n */, uint32_t* hit /* n */);
+/* `compound.contacts(&rhs[i], cb)` (compound.rs:339-357) for RHS = Moving<Sphere | Capsule | Triangle | Rectangle> (shape + v):
+ * out[i*slots ..] receives the contacts in callback order (a on the compound's component, b on the rhs), counts[i] how many
+ * callbacks fired (only the first `slots` are stored; 2 * n_components always suffices). */
+int32_t mgfb_compound_contacts_batch(mgfb_compound* c, const mgfb_shape* rhs /* n */, uint32_t n, uint32_t slots, mgfb_contact* out /* n*slots */,
+                                     uint32_t* counts /* n */);
+
 /* ---------------- discrete path: GJK + EPA (simplex.rs:172-553) ---------------- */
 /* `a[i].contacts(&b[i], cb)` for static convex pairs through the generic impl for Convex + Volumetric shapes
  * (collision.rs:497-519): GJK seeded along +-y (simplex.rs:172-200), then EPA (simplex.rs:456-553, at most

@@ -116,6 +116,13 @@ SYMBOLS = [
     ("mgfb_bvh_len", C.c_int32, [_P, C.POINTER(C.c_uint32)]),
     ("mgfb_bvh_query_batch", C.c_int32, [_P, _P, C.c_uint32, _P, _P, C.c_uint32, C.POINTER(C.c_uint32)]),
     ("mgfb_bvh_raytrace_batch", C.c_int32, [_P, C.c_uint32, _P, C.c_uint32, _P, _P, _P, C.c_uint32, C.POINTER(C.c_uint32)]),
+    ("mgfb_compound_create", C.c_int32, [_P, _P, C.c_uint32, C.POINTER(_P)]),
+    ("mgfb_compound_destroy", None, [_P]),
+    ("mgfb_compound_set_transform", C.c_int32, [_P, _P, _P]),
+    ("mgfb_compound_bounds", C.c_int32, [_P, _P, _P]),
+    ("mgfb_compound_closest_points", C.c_int32, [_P, _P, C.c_uint32, _P]),
+    ("mgfb_compound_intersections_batch", C.c_int32, [_P, C.c_uint32, _P, C.c_uint32, _P, _P]),
+    ("mgfb_compound_contacts_batch", C.c_int32, [_P, _P, C.c_uint32, C.c_uint32, _P, _P]),
     ("mgfb_gjk_batch", C.c_int32, [_P, _P, _P, C.c_uint32, _P, _P, _P]),
     ("mgfb_separation_batch", C.c_int32, [_P, _P, _P, C.c_uint32, _P, _P]),
     ("mgfb_bodies_set_gid", C.c_int32, [_P, C.c_uint32, C.c_uint32, _P]),

@@ -231,6 +231,60 @@ class BVH:
                                                                                           L.ptr(val), L.ptr(hits), cap, C.byref(tot)), len(particles), True)
 
 
+class Compound:
+    """src/compound.rs Compound: components (spheres / capsules in the compound's frame) + disp + rot, queried in batches."""
+
+    def __init__(self, ctx, components):
+        self.ctx = ctx
+        comps = np.ascontiguousarray(components, dtype=L.SHAPE_DTYPE)
+        self.n = len(comps)
+        h = C.c_void_p()
+        ctx.check(ctx.lib.mgfb_compound_create(ctx.h, L.ptr(comps), len(comps), C.byref(h)))
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None) and getattr(self.ctx, "h", None):
+            self.ctx.lib.mgfb_compound_destroy(self.h)
+        self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_transform(self, disp, rot):
+        d = np.ascontiguousarray(disp, dtype=np.float32); r = np.ascontiguousarray(rot, dtype=np.float32)
+        assert d.shape == (3,) and r.shape == (4,)
+        self.ctx.check(self.ctx.lib.mgfb_compound_set_transform(self.h, L.ptr(d), L.ptr(r)))
+
+    def bounds(self):
+        """(AABB centre | half extents, bounding sphere centre | radius)."""
+        a = np.zeros(6, np.float32); s = np.zeros(4, np.float32)
+        self.ctx.check(self.ctx.lib.mgfb_compound_bounds(self.h, L.ptr(a), L.ptr(s)))
+        return a, s
+
+    def closest_points(self, to):
+        to = np.ascontiguousarray(to, dtype=np.float32).reshape(-1, 3)
+        out = np.zeros_like(to)
+        self.ctx.check(self.ctx.lib.mgfb_compound_closest_points(self.h, L.ptr(to), len(to), L.ptr(out)))
+        return out
+
+    def intersections(self, particle_kind, particles):
+        particles = np.ascontiguousarray(particles, dtype=np.float32).reshape(-1, 6)
+        out = np.zeros(len(particles), dtype=L.INTERSECTION_DTYPE); hit = np.zeros(len(particles), np.uint32)
+        self.ctx.check(self.ctx.lib.mgfb_compound_intersections_batch(self.h, particle_kind, L.ptr(particles), len(particles), L.ptr(out), L.ptr(hit)))
+        return out, hit
+
+    def contacts(self, rhs, slots=None):
+        """compound.contacts(&rhs[i]): (contacts[n, slots] in callback order, counts[n])."""
+        rhs = np.ascontiguousarray(rhs, dtype=L.SHAPE_DTYPE)
+        slots = slots or max(2 * self.n, 1)
+        out = np.zeros((len(rhs), slots), dtype=L.CONTACT_DTYPE); counts = np.zeros(len(rhs), np.uint32)
+        self.ctx.check(self.ctx.lib.mgfb_compound_contacts_batch(self.h, L.ptr(rhs), len(rhs), slots, L.ptr(out), L.ptr(counts)))
+        return out, counts
+
+
 class World:
     """mgf_demo/world.rs World restricted to the physics: bodies + terrain + step."""
 

@@ -1302,3 +1302,4 @@ int32_t mgfb_device_view_get(mgfb_ctx* ctx, mgfb_device_view* out) {
 #include "bvh.cuh"
 #include "pipeline.cuh"
 #include "selftest.cuh"
+#include "compound.cuh"

@@ -7,6 +7,7 @@
 #include "../include/mgfb.h"
 #include "simplex.hpp"
 #include "world.hpp"
+#include "compound.hpp"
 
 using namespace mgfo;
 
@@ -122,6 +123,58 @@ int32_t mgfo_contacts_batch(uint32_t pair_kind, const mgfb_shape* recv, const mg
                 });
                 break;
             }
+            default: return MGFB_ERR_INVALID_ARG;
+        }
+        counts[i] = cnt;
+    }
+    return MGFB_OK;
+}
+
+// ---- Compound (compound.rs:232-352): the checker of mgfb_compound_* ----
+void* mgfo_compound_create(const mgfb_shape* comps, uint32_t n) {
+    std::vector<Component> v;
+    for (uint32_t i = 0; i < n; ++i) v.push_back(to_component(comps[i]));
+    try { return new Compound(v); } catch (NanBounds&) { return nullptr; }
+}
+void mgfo_compound_destroy(void* h) { delete static_cast<Compound*>(h); }
+void mgfo_compound_set_transform(void* h, const float* disp, const float* rot) {
+    Compound* c = static_cast<Compound*>(h);
+    c->disp = p3(disp); c->rot = Quat{rot[0], p3(rot + 1)};
+}
+void mgfo_compound_bounds(const void* h, float* aabb, float* sphere) {
+    const Compound* c = static_cast<const Compound*>(h);
+    AABB b = c->bounds_aabb(); Sphere s = c->bounds_sphere();
+    put3(aabb, b.c); put3(aabb + 3, b.r); put3(sphere, s.c); sphere[3] = s.r;
+}
+void mgfo_compound_closest_points(const void* h, const float* to, uint32_t n, float* out) {
+    const Compound* c = static_cast<const Compound*>(h);
+    for (uint32_t i = 0; i < n; ++i) put3(out + 3 * i, c->closest_point(p3(to + 3 * i)));
+}
+void mgfo_compound_intersections_batch(const void* h, uint32_t particle_kind, const float* particles, uint32_t n, mgfb_intersection* out, uint32_t* hit) {
+    const Compound* c = static_cast<const Compound*>(h);
+    for (uint32_t i = 0; i < n; ++i) {
+        const float* q = particles + 6 * i;
+        const bool seg = particle_kind == MGFB_SEGMENT;
+        Ray r{p3(q), seg ? p3(q + 3) - p3(q) : p3(q + 3)};
+        Intersection it{v3(0, 0, 0), 0.0f};
+        bool ok = c->intersection(r, seg ? 1.0f : INF, &it);
+        hit[i] = ok ? 1u : 0u;
+        put3(out[i].p, ok ? it.p : v3(0, 0, 0)); out[i].t = ok ? it.t : 0.0f;
+    }
+}
+int32_t mgfo_compound_contacts_batch(const void* h, const mgfb_shape* rhs, uint32_t n, uint32_t slots, mgfb_contact* out, uint32_t* counts) {
+    const Compound* c = static_cast<const Compound*>(h);
+    std::memset(out, 0, (size_t)n * slots * sizeof(mgfb_contact));
+    for (uint32_t i = 0; i < n; ++i) {
+        uint32_t cnt = 0;
+        auto cb = [&](const Contact& k) { if (cnt < slots) put_contact(&out[(size_t)i * slots + cnt], k); ++cnt; };
+        const mgfb_shape& R = rhs[i];
+        Vec3 v = p3(R.v);
+        switch (R.kind) {
+            case MGFB_SPHERE: c->contacts(Moving<Sphere>{to_sphere(R), v}, cb); break;
+            case MGFB_CAPSULE: c->contacts(Moving<Capsule>{to_capsule(R), v}, cb); break;
+            case MGFB_TRIANGLE: c->contacts(Moving<Triangle>{to_tri(R), v}, cb); break;
+            case MGFB_RECTANGLE: c->contacts(Moving<Rectangle>{to_rect(R), v}, cb); break;
             default: return MGFB_ERR_INVALID_ARG;
         }
         counts[i] = cnt;

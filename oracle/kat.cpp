@@ -7,6 +7,7 @@
 #include <vector>
 #include "simplex.hpp"
 #include "world.hpp"
+#include "compound.hpp"
 
 using namespace mgfo;
 
@@ -332,6 +333,21 @@ static void test_compound_rotated_sphere() {  // compound.rs:362-377 restated wi
     RELV(col.a, 0.0f, 6.0f, 0.0f, E);
 }
 
+static void test_compound() {  // compound.rs:362-388, through the restated Compound itself
+    std::vector<Component> comps = {Component::sphere(Sphere{v3(-5, 0, 0), 1.0f}), Component::sphere(Sphere{v3(5, 0, 0), 1.0f})};
+    Compound compound(comps);
+    Moving<Sphere> test_sphere{Sphere{v3(0, 8, 0), 1.0f}, v3(0, -1.5f, 0)};
+    CHECK(!compound.contacts(test_sphere, [&](const Contact&) { CHECK(false); }));
+    compound.rot = qnormalize(from_arc(v3(1, 0, 0), v3(0, 1, 0)));
+    Contact last{}; bool any = compound.contacts(test_sphere, [&](const Contact& c) { last = c; });   // last_contact (collision.rs:477)
+    CHECK(any);
+    REL(last.t, 0.6666663f, E);
+    RELV(last.a, 0.0f, 6.0f, 0.0f, E);
+    Rectangle static_rect{v3(0, -2, 0), {v3(1, 0, 0), v3(0, 0, 1)}, {6.0f, 6.0f}};
+    compound.rot = quat_one();
+    CHECK(compound.contacts(Moving<Rectangle>{static_rect, v3(0, 3, 0)}, [&](const Contact&) {}));   // .unwrap() must not panic
+}
+
 int main() {
     test_ray_intersections();
     test_sphere_penetration();
@@ -348,6 +364,7 @@ int main() {
     test_geom();
     test_tensors();
     test_compound_rotated_sphere();
+    test_compound();
     std::printf("KAT: %d passed, %d failed\n", g_pass, g_fail);
     return g_fail ? 1 : 0;
 }

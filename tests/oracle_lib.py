@@ -40,6 +40,13 @@ def load():
     lib.mgfo_intersections_batch.argtypes = [C.c_uint32, _P, _P, C.c_uint32, _P, _P]
     lib.mgfo_contacts_batch.restype = C.c_int32
     lib.mgfo_contacts_batch.argtypes = [C.c_uint32, _P, _P, C.c_uint32, _P, _P, _P]
+    lib.mgfo_compound_create.restype = _P; lib.mgfo_compound_create.argtypes = [_P, C.c_uint32]
+    lib.mgfo_compound_destroy.restype = None; lib.mgfo_compound_destroy.argtypes = [_P]
+    lib.mgfo_compound_set_transform.restype = None; lib.mgfo_compound_set_transform.argtypes = [_P, _P, _P]
+    lib.mgfo_compound_bounds.restype = None; lib.mgfo_compound_bounds.argtypes = [_P, _P, _P]
+    lib.mgfo_compound_closest_points.restype = None; lib.mgfo_compound_closest_points.argtypes = [_P, _P, C.c_uint32, _P]
+    lib.mgfo_compound_intersections_batch.restype = None; lib.mgfo_compound_intersections_batch.argtypes = [_P, C.c_uint32, _P, C.c_uint32, _P, _P]
+    lib.mgfo_compound_contacts_batch.restype = C.c_int32; lib.mgfo_compound_contacts_batch.argtypes = [_P, _P, C.c_uint32, C.c_uint32, _P, _P]
     lib.mgfo_world_create.restype = _P
     lib.mgfo_world_create.argtypes = [C.c_float]
     lib.mgfo_world_destroy.argtypes = [_P]
@@ -156,6 +163,50 @@ class OracleBVH:
         n = self.lib.mgfo_bvh_raytrace(self.h, kind, L.ptr(particle), L.ptr(out), L.ptr(hits), cap)
         assert n <= cap
         return out[:n], hits[:n]
+
+
+class OracleCompound:
+    """src/compound.rs Compound on the CPU restatement (same methods as mgf_b200.Compound)."""
+
+    def __init__(self, components):
+        self.lib = load()
+        comps = np.ascontiguousarray(components, dtype=L.SHAPE_DTYPE)
+        self.n = len(comps)
+        self.h = self.lib.mgfo_compound_create(L.ptr(comps), len(comps))
+        assert self.h
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.lib.mgfo_compound_destroy(self.h)
+            self.h = None
+
+    def set_transform(self, disp, rot):
+        d = np.ascontiguousarray(disp, dtype=np.float32); r = np.ascontiguousarray(rot, dtype=np.float32)
+        self.lib.mgfo_compound_set_transform(self.h, L.ptr(d), L.ptr(r))
+
+    def bounds(self):
+        a = np.zeros(6, np.float32); s = np.zeros(4, np.float32)
+        self.lib.mgfo_compound_bounds(self.h, L.ptr(a), L.ptr(s))
+        return a, s
+
+    def closest_points(self, to):
+        to = np.ascontiguousarray(to, dtype=np.float32).reshape(-1, 3)
+        out = np.zeros_like(to)
+        self.lib.mgfo_compound_closest_points(self.h, L.ptr(to), len(to), L.ptr(out))
+        return out
+
+    def intersections(self, particle_kind, particles):
+        particles = np.ascontiguousarray(particles, dtype=np.float32).reshape(-1, 6)
+        out = np.zeros(len(particles), dtype=L.INTERSECTION_DTYPE); hit = np.zeros(len(particles), np.uint32)
+        self.lib.mgfo_compound_intersections_batch(self.h, particle_kind, L.ptr(particles), len(particles), L.ptr(out), L.ptr(hit))
+        return out, hit
+
+    def contacts(self, rhs, slots=None):
+        rhs = np.ascontiguousarray(rhs, dtype=L.SHAPE_DTYPE)
+        slots = slots or max(2 * self.n, 1)
+        out = np.zeros((len(rhs), slots), dtype=L.CONTACT_DTYPE); counts = np.zeros(len(rhs), np.uint32)
+        assert self.lib.mgfo_compound_contacts_batch(self.h, L.ptr(rhs), len(rhs), slots, L.ptr(out), L.ptr(counts)) == 0
+        return out, counts
 
 
 class OracleWorld:
