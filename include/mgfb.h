@@ -42,7 +42,9 @@ enum mgfb_shape_kind {
     MGFB_RECTANGLE = 3, /* geom.rs:216   p = c[3], u0[3], u1[3], e0, e1  */
     MGFB_PLANE = 4,     /* geom.rs:32    p = n[3], d                     */
     MGFB_AABB = 5,      /* geom.rs:257   p = c[3], r[3]                  */
-    MGFB_OBB = 6        /* geom.rs:272   p = c[3], r[3], q[4] (s,x,y,z)  */
+    MGFB_OBB = 6,       /* geom.rs:272   p = c[3], r[3], q[4] (s,x,y,z)  */
+    MGFB_CONVEX_MESH = 7 /* mesh.rs:141  p = first vertex, vertex count (whole numbers < 2^24) in the pool of mgfb_convex_vertices_set;
+                            GJK / EPA only */
 };
 
 /* A shape (optionally swept: geom.rs:357 Moving<T>(T, Vector3)). 64 bytes. */
@@ -234,10 +236,14 @@ int32_t mgfb_compound_contacts_batch(mgfb_compound* c, const mgfb_shape* rhs /* 
                                      uint32_t* counts /* n */);
 
 /* ---------------- discrete path: GJK + EPA (simplex.rs:172-553) ---------------- */
+/* The vertices of every ConvexMesh (mesh.rs:141-189: a closed convex point soup, `ConvexMesh::from(verts)` / `push`) the
+ * GJK calls below may name: one pool per context, replaced by each call; a MGFB_CONVEX_MESH shape is a slice of it.  Only
+ * Convex::support (mesh.rs:223-236) reads a ConvexMesh on this path: the vertices as stored, the first of equally good ones. */
+int32_t mgfb_convex_vertices_set(mgfb_ctx* ctx, const float* verts /* n*3 */, uint32_t n);
 /* `a[i].contacts(&b[i], cb)` for static convex pairs through the generic impl for Convex + Volumetric shapes
  * (collision.rs:497-519): GJK seeded along +-y (simplex.rs:172-200), then EPA (simplex.rs:456-553, at most
  * 101 iterations); the contact has t = 0, `a` on shape a, `b = a - depth * n`.  Shapes: SPHERE, CAPSULE, AABB,
- * OBB (the Convex implementors, geom.rs:1027-1072).  status[i]: 0 = no contact (the callback is not invoked),
+ * OBB (the Convex implementors of geom.rs:1027-1072) and CONVEX_MESH (mesh.rs:223).  status[i]: 0 = no contact (the callback is not invoked),
  * 1 = contact in out[i], 2 = EPA polytope outgrew the device's fixed capacity (254 faces), 3 = GJK did not
  * converge in 4096 steps (the reference's loop has no other exit there: NaN input, or separated polytopes whose
  * support point never satisfies |min|^2 >= |support|^2, simplex.rs:195), 4 = the reference panics (EPA indexes a

@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libmgfb.so")
 # enum mgfb_status
 OK, ERR_INVALID_ARG, ERR_SINGULAR_INERTIA, ERR_CAPACITY, ERR_CUDA, ERR_NAN_BOUNDS, ERR_STATE, ERR_TILE = range(8)
 # enum mgfb_shape_kind
-SPHERE, CAPSULE, TRIANGLE, RECTANGLE, PLANE, AABB, OBB = range(7)
+SPHERE, CAPSULE, TRIANGLE, RECTANGLE, PLANE, AABB, OBB, CONVEX_MESH = range(8)
 # enum mgfb_pair_kind
 (SPHERE_X_MSPHERE, CAPSULE_X_MSPHERE, SPHERE_X_MCAPSULE, CAPSULE_X_MCAPSULE, PLANE_X_MSPHERE, PLANE_X_MCAPSULE,
  TRI_X_MSPHERE, TRI_X_MCAPSULE, RECT_X_MSPHERE, RECT_X_MCAPSULE, MCOMP_X_MCOMP, MCOMP_X_TRI) = range(12)
@@ -123,6 +123,7 @@ SYMBOLS = [
     ("mgfb_compound_closest_points", C.c_int32, [_P, _P, C.c_uint32, _P]),
     ("mgfb_compound_intersections_batch", C.c_int32, [_P, C.c_uint32, _P, C.c_uint32, _P, _P]),
     ("mgfb_compound_contacts_batch", C.c_int32, [_P, _P, C.c_uint32, C.c_uint32, _P, _P]),
+    ("mgfb_convex_vertices_set", C.c_int32, [_P, _P, C.c_uint32]),
     ("mgfb_gjk_batch", C.c_int32, [_P, _P, _P, C.c_uint32, _P, _P, _P]),
     ("mgfb_separation_batch", C.c_int32, [_P, _P, _P, C.c_uint32, _P, _P]),
     ("mgfb_bodies_set_gid", C.c_int32, [_P, C.c_uint32, C.c_uint32, _P]),

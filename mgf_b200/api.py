@@ -110,6 +110,17 @@ def obb(c, r, q=(1.0, 0.0, 0.0, 0.0)):
     return _one(L.OBB, [*c, *r, *q])
 
 
+def convex_mesh(first, count):
+    """mesh.rs:141 ConvexMesh as a slice [first, first + count) of the context's vertex pool (convex_vertices_set)."""
+    return _one(L.CONVEX_MESH, [float(first), float(count)])
+
+
+def convex_vertices_set(ctx, verts):
+    """The vertex pool CONVEX_MESH shapes index (mgfb_convex_vertices_set)."""
+    verts = np.ascontiguousarray(verts, dtype=np.float32).reshape(-1, 3)
+    ctx.check(ctx.lib.mgfb_convex_vertices_set(ctx.h, L.ptr(verts), len(verts)))
+
+
 def gjk_batch(ctx, a, b):
     """`a[i].contacts(&b[i], cb)` through the discrete GJK + EPA path (collision.rs:497-519).
     Returns (contacts[n], status[n], epa_iterations[n]); status 1 = a contact was delivered."""

@@ -63,6 +63,7 @@ struct mgfb_ctx {
     Buf cell_count, cell_start, bg_ent, scan_sums, scan_state; unsigned table = 0, ent_cap = 0;
     TerrainData terrain;
     Buf stage;          // packed state staging for get_state / set_velocity
+    Buf convex_pool; unsigned convex_n = 0;   // vertices of the ConvexMeshes the GJK batch may name (mgfb_convex_vertices_set)
     unsigned long long launches = 0;   // kernels launched since the last mgfb_step_totals(reset)
     // user-path staging
     Buf u_a, u_b, u_sc, u_sf, u_n, u_t, u_nc, u_la, u_lb;
@@ -652,7 +653,7 @@ void mgfb_ctx_destroy(mgfb_ctx* ctx) {
                   &ctx->group, &ctx->group_count, &ctx->group_start, &ctx->perm, &ctx->r_ab, &ctx->r_n, &ctx->r_t0, &ctx->r_t1, &ctx->r_ra,
                   &ctx->r_rb, &ctx->r_imp, &ctx->r_xra, &ctx->r_xrb, &ctx->r_xtm, &ctx->r_dep, &ctx->body_deg, &ctx->body_start, &ctx->r_inc, &ctx->r_next, &ctx->r_in_a, &ctx->r_in_b, &ctx->r_ia, &ctx->c_key, &ctx->c_csr, &ctx->c_next, &ctx->c_inbox, &ctx->cell_count, &ctx->cell_start, &ctx->bg_ent,
                   &ctx->scan_sums, &ctx->scan_state, &ctx->u_a, &ctx->u_b, &ctx->u_sc, &ctx->u_sf, &ctx->u_n, &ctx->u_t, &ctx->u_nc, &ctx->u_la,
-                  &ctx->u_lb, &ctx->stage, &ctx->terrain.verts, &ctx->terrain.faces, &ctx->terrain.boxes, &ctx->terrain.cell_count,
+                  &ctx->u_lb, &ctx->stage, &ctx->convex_pool, &ctx->terrain.verts, &ctx->terrain.faces, &ctx->terrain.boxes, &ctx->terrain.cell_count,
                   &ctx->terrain.cell_start, &ctx->terrain.ent_id, &ctx->terrain.ent_key, &ctx->terrain.max_bits,
                   &ctx->gid, &ctx->phase_start, &ctx->edge_idx, &ctx->edge_mark, &ctx->ridx, &ctx->mbox, &ctx->edge_slot, &ctx->tile_df};
     pipe_destroy(ctx);

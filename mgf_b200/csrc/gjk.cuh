@@ -56,6 +56,24 @@ template <> struct GShape<MGFB_OBB> {
     }
 };
 
+template <> struct GShape<MGFB_CONVEX_MESH> {   // mesh.rs:141: a slice of the context's vertex pool (the host wrote its device address into p[2..3])
+    const float* v; unsigned n;
+    __device__ explicit GShape(const mgfb_shape& s) : n((unsigned)s.p[1]) {
+        unsigned long long bits = (unsigned long long)__float_as_uint(s.p[2]) | ((unsigned long long)__float_as_uint(s.p[3]) << 32);
+        v = reinterpret_cast<const float*>(bits);
+    }
+    __device__ V3 support(V3 d) const {   // mesh.rs:223-236: strict >, the first of equally good vertices wins
+        V3 best = mk3(v[0], v[1], v[2]);
+        float best_norm = dot3(d, best);
+        for (unsigned i = 1; i < n; ++i) {
+            V3 p = mk3(v[3 * i], v[3 * i + 1], v[3 * i + 2]);
+            float norm = dot3(d, p);
+            if (norm > best_norm) { best = p; best_norm = norm; }
+        }
+        return best;
+    }
+};
+
 // geom.rs:1099-1133 MinkowskiDiff::support_pt
 template <class A, class B>
 __device__ __forceinline__ SP mink_support(const A& sa, const B& sb, V3 axis) {
@@ -389,29 +407,53 @@ void launch_gjk(bool separation, const mgfb_shape* a, const mgfb_shape* b, const
 }
 typedef void (*gjk_launcher)(bool, const mgfb_shape*, const mgfb_shape*, const unsigned*, unsigned, mgfb_contact*, float*, unsigned*, unsigned*, EpaWork*,
                              unsigned*, int, cudaStream_t);
-const int GJK_KINDS[4] = {MGFB_SPHERE, MGFB_CAPSULE, MGFB_AABB, MGFB_OBB};
-const gjk_launcher GJK_TABLE[4][4] = {
-    {launch_gjk<MGFB_SPHERE, MGFB_SPHERE>, launch_gjk<MGFB_SPHERE, MGFB_CAPSULE>, launch_gjk<MGFB_SPHERE, MGFB_AABB>, launch_gjk<MGFB_SPHERE, MGFB_OBB>},
-    {launch_gjk<MGFB_CAPSULE, MGFB_SPHERE>, launch_gjk<MGFB_CAPSULE, MGFB_CAPSULE>, launch_gjk<MGFB_CAPSULE, MGFB_AABB>, launch_gjk<MGFB_CAPSULE, MGFB_OBB>},
-    {launch_gjk<MGFB_AABB, MGFB_SPHERE>, launch_gjk<MGFB_AABB, MGFB_CAPSULE>, launch_gjk<MGFB_AABB, MGFB_AABB>, launch_gjk<MGFB_AABB, MGFB_OBB>},
-    {launch_gjk<MGFB_OBB, MGFB_SPHERE>, launch_gjk<MGFB_OBB, MGFB_CAPSULE>, launch_gjk<MGFB_OBB, MGFB_AABB>, launch_gjk<MGFB_OBB, MGFB_OBB>}};
+#define GJK_NK 5
+const int GJK_KINDS[GJK_NK] = {MGFB_SPHERE, MGFB_CAPSULE, MGFB_AABB, MGFB_OBB, MGFB_CONVEX_MESH};
+const gjk_launcher GJK_TABLE[GJK_NK][GJK_NK] = {
+    {launch_gjk<MGFB_SPHERE, MGFB_SPHERE>, launch_gjk<MGFB_SPHERE, MGFB_CAPSULE>, launch_gjk<MGFB_SPHERE, MGFB_AABB>, launch_gjk<MGFB_SPHERE, MGFB_OBB>, launch_gjk<MGFB_SPHERE, MGFB_CONVEX_MESH>},
+    {launch_gjk<MGFB_CAPSULE, MGFB_SPHERE>, launch_gjk<MGFB_CAPSULE, MGFB_CAPSULE>, launch_gjk<MGFB_CAPSULE, MGFB_AABB>, launch_gjk<MGFB_CAPSULE, MGFB_OBB>, launch_gjk<MGFB_CAPSULE, MGFB_CONVEX_MESH>},
+    {launch_gjk<MGFB_AABB, MGFB_SPHERE>, launch_gjk<MGFB_AABB, MGFB_CAPSULE>, launch_gjk<MGFB_AABB, MGFB_AABB>, launch_gjk<MGFB_AABB, MGFB_OBB>, launch_gjk<MGFB_AABB, MGFB_CONVEX_MESH>},
+    {launch_gjk<MGFB_OBB, MGFB_SPHERE>, launch_gjk<MGFB_OBB, MGFB_CAPSULE>, launch_gjk<MGFB_OBB, MGFB_AABB>, launch_gjk<MGFB_OBB, MGFB_OBB>, launch_gjk<MGFB_OBB, MGFB_CONVEX_MESH>},
+    {launch_gjk<MGFB_CONVEX_MESH, MGFB_SPHERE>, launch_gjk<MGFB_CONVEX_MESH, MGFB_CAPSULE>, launch_gjk<MGFB_CONVEX_MESH, MGFB_AABB>, launch_gjk<MGFB_CONVEX_MESH, MGFB_OBB>, launch_gjk<MGFB_CONVEX_MESH, MGFB_CONVEX_MESH>}};
 
 int32_t gjk_batch_impl(mgfb_ctx* ctx, bool separation, const mgfb_shape* a, const mgfb_shape* b, uint32_t n, mgfb_contact* out, float* sep,
                        uint32_t* status, uint32_t* epa_iters) {
     if (!ctx) return MGFB_ERR_INVALID_ARG;
     if (n == 0) return MGFB_OK;
     if (!a || !b || !status || (separation ? !sep : !out)) return fail(ctx, MGFB_ERR_INVALID_ARG, "null array");
-    auto slot = [](uint32_t kind) { for (int k = 0; k < 4; ++k) if ((uint32_t)GJK_KINDS[k] == kind) return k; return -1; };
+    auto slot = [](uint32_t kind) { for (int k = 0; k < GJK_NK; ++k) if ((uint32_t)GJK_KINDS[k] == kind) return k; return -1; };
     // bin by (kind_a, kind_b): one divergence-free launch per shape pair
-    std::vector<unsigned> index(n); unsigned count[17] = {0};
+    const int NB = GJK_NK * GJK_NK;
+    std::vector<unsigned> index(n); unsigned count[GJK_NK * GJK_NK + 1] = {0};
+    std::vector<mgfb_shape> ha, hb;   // copies with the vertex pool's device address written into the CONVEX_MESH shapes
+    auto prepare = [&](const mgfb_shape* src, std::vector<mgfb_shape>& dst) -> bool {
+        bool any = false;
+        for (uint32_t i = 0; i < n; ++i) any = any || src[i].kind == MGFB_CONVEX_MESH;
+        if (!any) return true;
+        dst.assign(src, src + n);
+        for (uint32_t i = 0; i < n; ++i) {
+            mgfb_shape& s = dst[i];
+            if (s.kind != MGFB_CONVEX_MESH) continue;
+            const float first = s.p[0], cnt = s.p[1];
+            if (!(first >= 0.0f) || !(cnt >= 1.0f) || first != floorf(first) || cnt != floorf(cnt) || (double)first + (double)cnt > (double)ctx->convex_n) return false;
+            unsigned long long bits = (unsigned long long)(ctx->convex_pool.as<float>() + 3 * (size_t)first);
+            unsigned lo = (unsigned)bits, hi = (unsigned)(bits >> 32);
+            std::memcpy(&s.p[2], &lo, 4); std::memcpy(&s.p[3], &hi, 4);
+        }
+        return true;
+    };
+    if (!prepare(a, ha) || !prepare(b, hb))
+        return fail(ctx, MGFB_ERR_INVALID_ARG, "a CONVEX_MESH names vertices outside the pool of mgfb_convex_vertices_set (verts[0] on an empty mesh panics, mesh.rs:225)");
+    if (!ha.empty()) a = ha.data();
+    if (!hb.empty()) b = hb.data();
     for (uint32_t i = 0; i < n; ++i) {
         int ka = slot(a[i].kind), kb = slot(b[i].kind);
-        if (ka < 0 || kb < 0) return fail(ctx, MGFB_ERR_INVALID_ARG, "GJK shapes must be Sphere, Capsule, AABB or OBB (the Convex + Volumetric implementors, geom.rs:1027-1072)");
-        count[ka * 4 + kb + 1]++;
+        if (ka < 0 || kb < 0) return fail(ctx, MGFB_ERR_INVALID_ARG, "GJK shapes must be Sphere, Capsule, AABB, OBB or ConvexMesh (the Convex implementors, geom.rs:1027-1072, mesh.rs:223)");
+        count[ka * GJK_NK + kb + 1]++;
     }
-    for (int k = 0; k < 16; ++k) count[k + 1] += count[k];
-    { unsigned cur[16]; for (int k = 0; k < 16; ++k) cur[k] = count[k];
-      for (uint32_t i = 0; i < n; ++i) index[cur[slot(a[i].kind) * 4 + slot(b[i].kind)]++] = i; }
+    for (int k = 0; k < NB; ++k) count[k + 1] += count[k];
+    { unsigned cur[GJK_NK * GJK_NK]; for (int k = 0; k < NB; ++k) cur[k] = count[k];
+      for (uint32_t i = 0; i < n; ++i) index[cur[slot(a[i].kind) * GJK_NK + slot(b[i].kind)]++] = i; }
     CU(cudaSetDevice(ctx->device));
     Buf da, db, di, dout, dsep, dst, dit, dwork, dcount;
     int32_t rc = MGFB_OK;
@@ -419,20 +461,20 @@ int32_t gjk_batch_impl(mgfb_ctx* ctx, bool separation, const mgfb_shape* a, cons
     if ((rc = ensure(ctx, da, (size_t)n * sizeof(mgfb_shape))) || (rc = ensure(ctx, db, (size_t)n * sizeof(mgfb_shape))) || (rc = ensure(ctx, di, (size_t)n * 4)) ||
         (rc = ensure(ctx, dout, (size_t)n * sizeof(mgfb_contact))) || (rc = ensure(ctx, dsep, (size_t)n * 4)) || (rc = ensure(ctx, dst, (size_t)n * 4)) ||
         (rc = ensure(ctx, dit, (size_t)n * 4)) || (rc = ensure(ctx, dwork, separation ? sizeof(EpaWork) : (size_t)n * sizeof(EpaWork))) ||
-        (rc = ensure(ctx, dcount, 16 * 4)))
+        (rc = ensure(ctx, dcount, 32 * 4)))
         return done(rc);
     cudaMemcpyAsync(da.p, a, (size_t)n * sizeof(mgfb_shape), cudaMemcpyHostToDevice, ctx->stream);
     cudaMemcpyAsync(db.p, b, (size_t)n * sizeof(mgfb_shape), cudaMemcpyHostToDevice, ctx->stream);
     cudaMemcpyAsync(di.p, index.data(), (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream);
     cudaMemsetAsync(dout.p, 0, (size_t)n * sizeof(mgfb_contact), ctx->stream);
     cudaMemsetAsync(dsep.p, 0, (size_t)n * 4, ctx->stream);
-    cudaMemsetAsync(dcount.p, 0, 16 * 4, ctx->stream);
+    cudaMemsetAsync(dcount.p, 0, 32 * 4, ctx->stream);
     int epa_grid = ctx->num_sms * 4;   // 4 x 52 KB polytopes per SM
-    for (int k = 0; k < 16; ++k) {
+    for (int k = 0; k < NB; ++k) {
         unsigned m = count[k + 1] - count[k];
         if (!m) continue;
         // each bin's EPA work list is a slice of dwork starting at the bin's first pair
-        GJK_TABLE[k / 4][k % 4](separation, da.as<mgfb_shape>(), db.as<mgfb_shape>(), di.as<unsigned>() + count[k], m, dout.as<mgfb_contact>(),
+        GJK_TABLE[k / GJK_NK][k % GJK_NK](separation, da.as<mgfb_shape>(), db.as<mgfb_shape>(), di.as<unsigned>() + count[k], m, dout.as<mgfb_contact>(),
                                 dsep.as<float>(), dst.as<unsigned>(), dit.as<unsigned>(), dwork.as<EpaWork>() + (separation ? 0 : count[k]),
                                 dcount.as<unsigned>() + k, (int)std::min<unsigned>((unsigned)epa_grid, m), ctx->stream);
         ctx->launches += separation ? 1 : 2;
@@ -452,6 +494,19 @@ int32_t gjk_batch_impl(mgfb_ctx* ctx, bool separation, const mgfb_shape* a, cons
 }  // namespace
 
 extern "C" {
+int32_t mgfb_convex_vertices_set(mgfb_ctx* ctx, const float* verts, uint32_t n) {
+    if (!ctx || (n && !verts)) return fail(ctx, MGFB_ERR_INVALID_ARG, "null vertex array");
+    if (n >= (1u << 24)) return fail(ctx, MGFB_ERR_INVALID_ARG, "the vertex pool holds fewer than 2^24 vertices");
+    CU(cudaSetDevice(ctx->device));
+    ctx->convex_n = 0;
+    if (n) {
+        TRY(ensure(ctx, ctx->convex_pool, (size_t)n * 12));
+        CU(cudaMemcpyAsync(ctx->convex_pool.p, verts, (size_t)n * 12, cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+    }
+    ctx->convex_n = n;
+    return MGFB_OK;
+}
 int32_t mgfb_gjk_batch(mgfb_ctx* ctx, const mgfb_shape* a, const mgfb_shape* b, uint32_t n, mgfb_contact* out, uint32_t* status, uint32_t* epa_iters) {
     return gjk_batch_impl(ctx, false, a, b, n, out, nullptr, status, epa_iters);
 }

@@ -376,6 +376,9 @@ double mgfo_world_time_steps(mgfo_world* h, float dt, uint32_t iters, uint32_t n
 }
 
 // ---- discrete path (collision.rs:404-425, 497-519) ----
+static const float* g_convex_pool = nullptr; static uint32_t g_convex_n = 0;
+// the vertex pool MGFB_CONVEX_MESH shapes index (same contract as mgfb_convex_vertices_set); the caller keeps it alive
+void mgfo_convex_vertices_set(const float* verts, uint32_t n) { g_convex_pool = verts; g_convex_n = n; }
 static bool gjk_dispatch(const mgfb_shape& A, const mgfb_shape& B, Contact* c, int* it, int* st);
 int32_t mgfo_gjk_batch(const mgfb_shape* a, const mgfb_shape* b, uint32_t n, mgfb_contact* out, uint32_t* hit, uint32_t* epa_iters) {
     for (uint32_t i = 0; i < n; ++i) {
@@ -403,6 +406,8 @@ int32_t mgfo_separation_batch(const mgfb_shape* a, const mgfb_shape* b, uint32_t
 namespace {
 AABB to_aabb(const mgfb_shape& s) { return AABB{p3(s.p), p3(s.p + 3)}; }
 OBB to_obb(const mgfb_shape& s) { return OBB{p3(s.p), Quat{s.p[6], p3(s.p + 7)}, p3(s.p + 3)}; }
+ConvexMesh to_mesh(const mgfb_shape& s) { return ConvexMesh{g_convex_pool + 3 * (size_t)s.p[0], (unsigned)s.p[1]}; }
+bool mesh_ok(const mgfb_shape& s) { return s.kind != MGFB_CONVEX_MESH || (g_convex_pool && s.p[1] >= 1.0f && (uint64_t)s.p[0] + (uint64_t)s.p[1] <= g_convex_n); }
 template <class SA>
 bool gjk_with(const SA& a, const mgfb_shape& B, Contact* c, int* it, int* st) {
     switch (B.kind) {
@@ -410,16 +415,19 @@ bool gjk_with(const SA& a, const mgfb_shape& B, Contact* c, int* it, int* st) {
         case MGFB_CAPSULE: return gjk_contact(a, to_capsule(B), c, it, st);
         case MGFB_AABB: return gjk_contact(a, to_aabb(B), c, it, st);
         case MGFB_OBB: return gjk_contact(a, to_obb(B), c, it, st);
+        case MGFB_CONVEX_MESH: return gjk_contact(a, to_mesh(B), c, it, st);
         default: return false;
     }
 }
 }  // namespace
 static bool gjk_dispatch(const mgfb_shape& A, const mgfb_shape& B, Contact* c, int* it, int* st) {
+    if (!mesh_ok(A) || !mesh_ok(B)) return false;
     switch (A.kind) {
         case MGFB_SPHERE: return gjk_with(to_sphere(A), B, c, it, st);
         case MGFB_CAPSULE: return gjk_with(to_capsule(A), B, c, it, st);
         case MGFB_AABB: return gjk_with(to_aabb(A), B, c, it, st);
         case MGFB_OBB: return gjk_with(to_obb(A), B, c, it, st);
+        case MGFB_CONVEX_MESH: return gjk_with(to_mesh(A), B, c, it, st);
         default: return false;
     }
 }
@@ -431,16 +439,19 @@ bool sep_with(const SA& a, const mgfb_shape& B, float* d, int* st) {
         case MGFB_CAPSULE: return separation(a, to_capsule(B), d, st);
         case MGFB_AABB: return separation(a, to_aabb(B), d, st);
         case MGFB_OBB: return separation(a, to_obb(B), d, st);
+        case MGFB_CONVEX_MESH: return separation(a, to_mesh(B), d, st);
         default: return false;
     }
 }
 }  // namespace
 static bool sep_dispatch(const mgfb_shape& A, const mgfb_shape& B, float* d, int* st) {
+    if (!mesh_ok(A) || !mesh_ok(B)) return false;
     switch (A.kind) {
         case MGFB_SPHERE: return sep_with(to_sphere(A), B, d, st);
         case MGFB_CAPSULE: return sep_with(to_capsule(A), B, d, st);
         case MGFB_AABB: return sep_with(to_aabb(A), B, d, st);
         case MGFB_OBB: return sep_with(to_obb(A), B, d, st);
+        case MGFB_CONVEX_MESH: return sep_with(to_mesh(A), B, d, st);
         default: return false;
     }
 }

@@ -168,6 +168,19 @@ inline Vec3 support(const OBB& o, Vec3 d0) {
     Vec3 d = rotate_vector(qinvert(o.q), d0);
     return rotate_point(o.q, v3(signum(d.x) * o.r.x, signum(d.y) * o.r.y, signum(d.z) * o.r.z)) + o.c;
 }
+// mesh.rs:141-236 ConvexMesh: a point soup.  Only what Convex::support (mesh.rs:223-236) reads is kept: the vertices as stored
+// (the reference's support ignores `x`); strict > keeps the FIRST of equally good vertices.
+struct ConvexMesh { const float* verts; unsigned n; };
+inline Vec3 support(const ConvexMesh& m, Vec3 d) {
+    Vec3 best_vert = v3(m.verts[0], m.verts[1], m.verts[2]);
+    float best_norm = dot(d, best_vert);
+    for (unsigned i = 1; i < m.n; ++i) {
+        Vec3 vert = v3(m.verts[3 * i], m.verts[3 * i + 1], m.verts[3 * i + 2]);
+        float norm = dot(d, vert);
+        if (norm > best_norm) { best_vert = vert; best_norm = norm; }
+    }
+    return best_vert;
+}
 inline Vec3 support(const Sphere& s, Vec3 d) { return s.c + d * s.r; }
 inline Vec3 support(const Capsule& cp, Vec3 d) {
     Vec3 c = cp.a + cp.d * 0.5f;

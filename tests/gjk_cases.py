@@ -80,3 +80,49 @@ def mixed_pairs(n, seed=7):
         a[idx] = random_shapes(len(idx), KINDS[k // 4], seed + 2 * k)
         b[idx] = random_shapes(len(idx), KINDS[k % 4], seed + 2 * k + 1)
     return a, b
+
+
+def convex_mesh_pool(n_meshes, seed=31):
+    """n_meshes convex point soups (mesh.rs:141 ConvexMesh): box corners (8 vertices), tetrahedra and 12..40 random points on an
+    ellipsoid, each rotated and placed like the random shapes above.  Returns (vertex pool (V, 3) f32, shapes[n_meshes])."""
+    rng = np.random.default_rng(seed)
+    verts = []; shapes = np.zeros(n_meshes, dtype=L.SHAPE_DTYPE)
+    shapes["kind"] = L.CONVEX_MESH
+    first = 0
+    for i in range(n_meshes):
+        c = rng.uniform(-2, 2, 3); size = rng.uniform(0.3, 1.0, 3)
+        kind = i % 3
+        if kind == 0:
+            pts = np.array([[sx, sy, sz] for sx in (-1, 1) for sy in (-1, 1) for sz in (-1, 1)], np.float64) * size
+        elif kind == 1:
+            pts = rng.normal(size=(4, 3)) * size
+        else:
+            p = rng.normal(size=(int(rng.integers(12, 41)), 3)); p /= np.linalg.norm(p, axis=1, keepdims=True)
+            pts = p * size
+        q = rng.normal(size=4); q /= np.linalg.norm(q)
+        w, x, y, z = q
+        R = np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],
+                      [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+                      [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])
+        pts = (pts @ R.T + c).astype(np.float32)
+        verts.append(pts)
+        shapes["p"][i, 0] = first; shapes["p"][i, 1] = len(pts)
+        first += len(pts)
+    return np.concatenate(verts).astype(np.float32), shapes
+
+
+def mesh_pairs(n, seed=7):
+    """n pairs: ConvexMesh against each of the five kinds (both orders), cycling.  Returns (pool, a, b)."""
+    pool, meshes = convex_mesh_pool(2 * n, seed + 100)
+    a = np.zeros(n, dtype=L.SHAPE_DTYPE); b = np.zeros(n, dtype=L.SHAPE_DTYPE)
+    for k in range(9):
+        idx = np.arange(k, n, 9)
+        if len(idx) == 0:
+            continue
+        if k < 4:        # mesh x plain
+            a[idx] = meshes[idx]; b[idx] = random_shapes(len(idx), KINDS[k], seed + 40 + k)
+        elif k < 8:      # plain x mesh
+            a[idx] = random_shapes(len(idx), KINDS[k - 4], seed + 50 + k); b[idx] = meshes[n + idx]
+        else:            # mesh x mesh
+            a[idx] = meshes[idx]; b[idx] = meshes[n + idx]
+    return pool, a, b

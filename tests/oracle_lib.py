@@ -79,12 +79,23 @@ def load():
     lib.mgfo_world_solve_manifolds.argtypes = [_P, C.POINTER(L.Manifolds), C.c_float, C.c_uint32, _P, _P]
     lib.mgfo_world_time_steps.restype = C.c_double
     lib.mgfo_world_time_steps.argtypes = [_P, C.c_float, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+    lib.mgfo_convex_vertices_set.restype = None; lib.mgfo_convex_vertices_set.argtypes = [_P, C.c_uint32]
     lib.mgfo_gjk_batch.restype = C.c_int32
     lib.mgfo_gjk_batch.argtypes = [_P, _P, C.c_uint32, _P, _P, _P]
     lib.mgfo_separation_batch.restype = C.c_int32
     lib.mgfo_separation_batch.argtypes = [_P, _P, C.c_uint32, _P, _P]
     _lib = lib
     return lib
+
+
+_convex_pool = None
+
+
+def convex_vertices_set(verts):
+    """Oracle of mgfb_convex_vertices_set: the vertex pool MGFB_CONVEX_MESH shapes index."""
+    global _convex_pool
+    _convex_pool = np.ascontiguousarray(verts, dtype=np.float32).reshape(-1, 3)   # kept alive here
+    load().mgfo_convex_vertices_set(L.ptr(_convex_pool), len(_convex_pool))
 
 
 def gjk_batch(a, b):
