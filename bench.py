@@ -329,6 +329,42 @@ def short_run(name, torch, flush, device, peak):
     return out
 
 
+def gjk_block(device, with_cpu):
+    """BASELINE configs[4]'s discrete half: 1 M static convex pairs (all 16 kind pairs of Sphere / Capsule / AABB / OBB, centres
+    U(-2,2)^3, sizes U(0.3,1), LCG seed 7) through mgfb_gjk_batch (GJK + EPA, collision.rs:497-519).  Host buffers in and out:
+    the call's wall clock includes both PCIe copies.  The CPU port runs a 20 k sample of the same pairs; that sample is also
+    compared bit for bit."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import numpy as np
+    import gjk_cases   # input generator only (no oracle code)
+    import mgf_b200
+    n = 1 << 20
+    a, b = gjk_cases.mixed_pairs(n, seed=7)
+    ctx = mgf_b200.Context(device=device)
+    mgf_b200.gjk_batch(ctx, a[:4096], b[:4096])
+    best = None
+    for _ in range(3):
+        t0 = time.perf_counter()
+        out, status, iters = mgf_b200.gjk_batch(ctx, a, b)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    blk = {"pairs": n, "pairs_per_second": n / best, "ms_per_batch": 1e3 * best, "contacts": int((status == 1).sum()),
+           "epa_iterations_mean": float(iters[status == 1].mean()), "timing": "wall clock of mgfb_gjk_batch, host buffers (H2D + kernels + D2H), best of 3",
+           "status_histogram": {int(k): int(v) for k, v in zip(*np.unique(status, return_counts=True))}}
+    if with_cpu:
+        import oracle_lib
+        m = 20000
+        t0 = time.perf_counter()
+        oout, ohit, oit = oracle_lib.gjk_batch(a[:m], b[:m])
+        cs = time.perf_counter() - t0
+        same = bool(np.array_equal(ohit, status[:m]) and all(
+            np.array_equal(np.ascontiguousarray(out[f][:m]).view(np.uint32)[~np.isnan(oout[f].reshape(m, -1)).any(axis=1)],
+                           np.ascontiguousarray(oout[f]).view(np.uint32)[~np.isnan(oout[f].reshape(m, -1)).any(axis=1)]) for f in ("a", "b", "n", "t")))
+        blk["cpu_port"] = {"pairs": m, "pairs_per_second": m / cs, "cores": 1, "bit_identical_on_sample": same}
+    ctx.close()
+    return blk
+
+
 # ------------------------------------------------------------------------------------------ main
 def main():
     ap = argparse.ArgumentParser()
@@ -520,6 +556,7 @@ def main():
         for other in WORKLOADS:
             if other != name:
                 others[other] = short_run(other, torch, flush, local_rank, peak)
+        others["gjk_epa_batch"] = gjk_block(local_rank, rank == 0 and not args.no_cpu_baseline)
 
     if rank == 0:
         line = {

@@ -245,7 +245,7 @@ int32_t mgfb_convex_vertices_set(mgfb_ctx* ctx, const float* verts /* n*3 */, ui
  * 101 iterations); the contact has t = 0, `a` on shape a, `b = a - depth * n`.  Shapes: SPHERE, CAPSULE, AABB,
  * OBB (the Convex implementors of geom.rs:1027-1072) and CONVEX_MESH (mesh.rs:223).  status[i]: 0 = no contact (the callback is not invoked),
  * 1 = contact in out[i], 2 = EPA polytope outgrew the device's fixed capacity (254 faces), 3 = GJK did not
- * converge in 4096 steps (the reference's loop has no other exit there: NaN input, or separated polytopes whose
+ * converge in 256 steps (the reference's loop has no other exit there: NaN input, or separated polytopes whose
  * support point never satisfies |min|^2 >= |support|^2, simplex.rs:195), 4 = the reference panics (EPA indexes a
  * free Pool slot, pool.rs:111).  epa_iters may be NULL. */
 int32_t mgfb_gjk_batch(mgfb_ctx* ctx, const mgfb_shape* a, const mgfb_shape* b, uint32_t n, mgfb_contact* out /* n */,
@@ -271,6 +271,18 @@ typedef struct mgfb_manifolds {
     const float* local_a;          /* n*4*3 Manifold.contacts[k].0 */
     const float* local_b;          /* n*4*3 Manifold.contacts[k].1 */
 } mgfb_manifolds;
+
+/* ContactPruner::new + push(contact)* + Manifold::from(pruner) (manifold.rs:42-148) for `ngroups` pairs of objects: group g
+ * owns contacts[offsets[g] .. offsets[g+1]) in push order (what a caller collects from the LocalContacts callbacks of every
+ * collider pair of two objects).  push keeps the earliest collision time (+-1e-6), merges a contact with a kept one when
+ * either pair of global points is within persistent_threshold_sq (mgfb_config; the one further from the centres survives) and
+ * appends it otherwise; the manifold's normal is the mean of the kept normals (not renormalised), its tangents
+ * compute_basis(normal) (geom.rs:1138-1145).  Outputs are laid out like mgfb_manifolds, so they feed mgfb_solver_solve as they
+ * are; ncontacts[g] is the pruner's length (0 for an empty group: the normal is then 0/0 = NaN like the reference's; above 4 only
+ * the first 4 points are stored -- the reference's SmallVec spills to the heap there, a solver row here holds 4).  `time` may be NULL. */
+int32_t mgfb_manifolds_prune(mgfb_ctx* ctx, const mgfb_local_contact* contacts, const uint32_t* offsets /* ngroups+1 */, uint32_t ngroups,
+                             float* time /* ngroups */, float* normal /* ngroups*3 */, float* tangent /* ngroups*6 */, uint32_t* ncontacts /* ngroups */,
+                             float* local_a /* ngroups*12 */, float* local_b /* ngroups*12 */);
 
 enum mgfb_solve_order {
     /* Bit-identical to the reference's sequential Gauss-Seidel over the list as given

@@ -98,6 +98,7 @@ SYMBOLS = [
     ("mgfb_complete_motion", C.c_int32, [_P]),
     ("mgfb_terrain_set", C.c_int32, [_P, _P, C.c_uint32, _P, C.c_uint32, _P]),
     ("mgfb_contacts_batch", C.c_int32, [_P, C.c_uint32, _P, _P, C.c_uint32, _P, _P, _P]),
+    ("mgfb_manifolds_prune", C.c_int32, [_P, _P, _P, C.c_uint32, _P, _P, _P, _P, _P, _P]),
     ("mgfb_solver_solve", C.c_int32, [_P, C.POINTER(Manifolds), C.c_float, C.c_uint32, C.c_uint32, _P, _P, C.POINTER(SolveStats)]),
     ("mgfb_step", C.c_int32, [_P, C.c_float, C.c_uint32, C.POINTER(StepStats)]),
     ("mgfb_step_n", C.c_int32, [_P, C.c_float, C.c_uint32, C.c_uint32, C.POINTER(StepStats)]),

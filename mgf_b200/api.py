@@ -154,6 +154,18 @@ def intersections_batch(ctx, particle_kind, particles, shapes):
     return out, hit
 
 
+def manifolds_prune(ctx, contacts, offsets):
+    """ContactPruner::push over every group's LocalContacts in order + Manifold::from (manifold.rs:42-148).
+    Returns a dict laid out like mgfb_manifolds: time, normal, tangent, ncontacts, local_a, local_b."""
+    contacts = np.ascontiguousarray(contacts, dtype=L.LOCAL_CONTACT_DTYPE)
+    offsets = np.ascontiguousarray(offsets, dtype=np.uint32)
+    g = len(offsets) - 1
+    d = dict(time=np.zeros(g, np.float32), normal=np.zeros((g, 3), np.float32), tangent=np.zeros((g, 6), np.float32), ncontacts=np.zeros(g, np.uint32),
+             local_a=np.zeros((g, 12), np.float32), local_b=np.zeros((g, 12), np.float32))
+    ctx.check(ctx.lib.mgfb_manifolds_prune(ctx.h, L.ptr(contacts), L.ptr(offsets), g, *[L.ptr(d[k]) for k in ("time", "normal", "tangent", "ncontacts", "local_a", "local_b")]))
+    return d
+
+
 def contacts_batch(ctx, pair_kind, recv, arg, want_local=False):
     """`recv[i].contacts(&arg[i], cb)` for a homogeneous batch (collision.rs:471).
 

@@ -209,3 +209,87 @@ extern "C" int32_t mgfb_intersections_batch(mgfb_ctx* ctx, uint32_t particle_kin
     release(dp); release(ds); release(dout); release(dh);
     return s;
 }
+
+// ---------------------------------------------------------------- ContactPruner + Manifold::from (manifold.rs:42-148)
+namespace {
+#define PRUNER_KEEP 8   // contacts a device pruner holds (the reference's SmallVec<[LocalContact; 4]> spills to the heap; a Manifold row holds 4)
+struct PrunedContact { V3 la, lb, ga, gb, n; float t; };
+__device__ __forceinline__ PrunedContact load_lc(const mgfb_local_contact& c) {
+    PrunedContact p;
+    p.la = mk3(c.local_a[0], c.local_a[1], c.local_a[2]); p.lb = mk3(c.local_b[0], c.local_b[1], c.local_b[2]);
+    p.ga = mk3(c.global.a[0], c.global.a[1], c.global.a[2]); p.gb = mk3(c.global.b[0], c.global.b[1], c.global.b[2]);
+    p.n = mk3(c.global.n[0], c.global.n[1], c.global.n[2]); p.t = c.global.t;
+    return p;
+}
+// One thread per group: ContactPruner::new(), push(contact) for the group's contacts in order (manifold.rs:72-102), then
+// Manifold::from(pruner) (manifold.rs:131-148): time, the arithmetic mean of the kept normals, compute_basis of it, the local points.
+__global__ void __launch_bounds__(128) k_manifolds_prune(const mgfb_local_contact* __restrict__ contacts, const unsigned* __restrict__ offsets, unsigned ngroups,
+                                                         float threshold_sq, float* time, float* normal, float* tangent, unsigned* ncontacts, float* local_a,
+                                                         float* local_b) {
+    unsigned g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= ngroups) return;
+    PrunedContact keep[PRUNER_KEEP]; unsigned n = 0;
+    float min_t = __builtin_huge_valf();
+    for (unsigned k = offsets[g]; k < offsets[g + 1]; ++k) {
+        const PrunedContact c = load_lc(contacts[k]);
+        if (c.t < min_t - MGFB_EPS) { n = 1; keep[0] = c; min_t = c.t; continue; }     // an earlier collision replaces everything
+        if (c.t > min_t + MGFB_EPS) continue;
+        bool merged = false;
+        for (unsigned j = 0; j < n && j < PRUNER_KEEP && !merged; ++j) {
+            if (len2(c.ga - keep[j].ga) <= threshold_sq || len2(c.gb - keep[j].gb) <= threshold_sq) {
+                // keep the one whose points are further from the objects' centres
+                if (len2(keep[j].la) + len2(keep[j].lb) < len2(c.la) + len2(c.lb)) keep[j] = c;
+                merged = true;
+            }
+        }
+        if (merged) continue;
+        if (n < PRUNER_KEEP) keep[n] = c;
+        ++n;
+    }
+    V3 sum = zero3();
+    for (unsigned j = 0; j < n && j < PRUNER_KEEP; ++j) sum = sum + keep[j].n;
+    const V3 avg = sum / (float)n;                                                        // 0 / 0 = NaN for an empty pruner, like the reference
+    V3 t0, t1; basis_from_normal(avg, &t0, &t1);
+    time[g] = min_t; ncontacts[g] = n;
+    normal[3 * g] = avg.x; normal[3 * g + 1] = avg.y; normal[3 * g + 2] = avg.z;
+    tangent[6 * g] = t0.x; tangent[6 * g + 1] = t0.y; tangent[6 * g + 2] = t0.z; tangent[6 * g + 3] = t1.x; tangent[6 * g + 4] = t1.y; tangent[6 * g + 5] = t1.z;
+    for (unsigned j = 0; j < 4; ++j) {
+        const bool have = j < n;
+        const V3 a = have ? keep[j].la : zero3(), b = have ? keep[j].lb : zero3();
+        local_a[12 * g + 3 * j] = a.x; local_a[12 * g + 3 * j + 1] = a.y; local_a[12 * g + 3 * j + 2] = a.z;
+        local_b[12 * g + 3 * j] = b.x; local_b[12 * g + 3 * j + 1] = b.y; local_b[12 * g + 3 * j + 2] = b.z;
+    }
+}
+}  // namespace
+
+extern "C" int32_t mgfb_manifolds_prune(mgfb_ctx* ctx, const mgfb_local_contact* contacts, const uint32_t* offsets, uint32_t ngroups, float* time, float* normal,
+                                        float* tangent, uint32_t* ncontacts, float* local_a, float* local_b) {
+    if (!ctx) return MGFB_ERR_INVALID_ARG;
+    if (ngroups == 0) return MGFB_OK;
+    if (!offsets || !normal || !tangent || !ncontacts || !local_a || !local_b) return fail(ctx, MGFB_ERR_INVALID_ARG, "null array");
+    for (uint32_t g = 0; g < ngroups; ++g) if (offsets[g + 1] < offsets[g]) return fail(ctx, MGFB_ERR_INVALID_ARG, "offsets must not decrease");
+    const uint32_t total = offsets[ngroups];
+    if (offsets[0] != 0 || (total && !contacts)) return fail(ctx, MGFB_ERR_INVALID_ARG, "offsets[0] must be 0 and contacts given");
+    CU(cudaSetDevice(ctx->device));
+    Buf dc, dof, dout; int32_t s = MGFB_OK;
+    auto body = [&]() -> int32_t {
+        const size_t per = 4 + 12 + 24 + 4 + 48 + 48;   // bytes of output per group
+        TRY(ensure(ctx, dc, std::max<size_t>((size_t)total * sizeof(mgfb_local_contact), 16))); TRY(ensure(ctx, dof, ((size_t)ngroups + 1) * 4));
+        TRY(ensure(ctx, dout, (size_t)ngroups * per));
+        if (total) CU(cudaMemcpyAsync(dc.p, contacts, (size_t)total * sizeof(mgfb_local_contact), cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaMemcpyAsync(dof.p, offsets, ((size_t)ngroups + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));
+        float* d_time = dout.as<float>(); float* d_n = d_time + ngroups; float* d_t = d_n + 3 * (size_t)ngroups;
+        unsigned* d_nc = reinterpret_cast<unsigned*>(d_t + 6 * (size_t)ngroups); float* d_la = reinterpret_cast<float*>(d_nc + ngroups); float* d_lb = d_la + 12 * (size_t)ngroups;
+        k_manifolds_prune<<<(ngroups + 127) / 128, 128, 0, ctx->stream>>>(dc.as<mgfb_local_contact>(), dof.as<unsigned>(), ngroups, ctx->cfg.persistent_threshold_sq,
+                                                                         d_time, d_n, d_t, d_nc, d_la, d_lb);
+        CU(cudaGetLastError());
+        ctx->launches += 1;
+        auto down = [&](void* dst, const void* src, size_t bytes) { return dst ? cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream) : cudaSuccess; };
+        CU(down(time, d_time, (size_t)ngroups * 4)); CU(down(normal, d_n, (size_t)ngroups * 12)); CU(down(tangent, d_t, (size_t)ngroups * 24));
+        CU(down(ncontacts, d_nc, (size_t)ngroups * 4)); CU(down(local_a, d_la, (size_t)ngroups * 48)); CU(down(local_b, d_lb, (size_t)ngroups * 48));
+        CU(cudaStreamSynchronize(ctx->stream));
+        return MGFB_OK;
+    };
+    s = body(); release(dc); release(dof); release(dout);
+    return s;
+}

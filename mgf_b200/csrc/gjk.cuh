@@ -158,7 +158,7 @@ __device__ __forceinline__ V3 gjk_min_norm(SP simp[4], int state, int* next) {
     *next = next_state;
     return closest;
 }
-#define GJK_MAX_STEPS 4096   // the reference loops until convergence; a NaN input must not hang the GPU
+#define GJK_MAX_STEPS 256    // the reference loops until convergence; a NaN input must not hang the GPU
 // simplex.rs:172-200.  Returns false if the step cap was hit.
 template <class A, class B>
 __device__ bool gjk_closest_point_to_origin(const A& sa, const B& sb, SP simp[4], int* state, V3* out) {

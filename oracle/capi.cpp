@@ -182,6 +182,27 @@ int32_t mgfo_compound_contacts_batch(const void* h, const mgfb_shape* rhs, uint3
     return MGFB_OK;
 }
 
+// Same contract as mgfb_manifolds_prune: ContactPruner::push per group in order, then Manifold::from(pruner) (manifold.rs:42-148).
+int32_t mgfo_manifolds_prune(const mgfb_local_contact* contacts, const uint32_t* offsets, uint32_t ngroups, float* time, float* normal, float* tangent,
+                             uint32_t* ncontacts, float* local_a, float* local_b) {
+    for (uint32_t g = 0; g < ngroups; ++g) {
+        ContactPruner pruner;
+        for (uint32_t k = offsets[g]; k < offsets[g + 1]; ++k) {
+            const mgfb_local_contact& c = contacts[k];
+            pruner.push(LocalContact{p3(c.local_a), p3(c.local_b), Contact{p3(c.global.a), p3(c.global.b), p3(c.global.n), c.global.t}});
+        }
+        Manifold m = manifold_from(pruner);
+        if (time) time[g] = m.time;
+        put3(normal + 3 * g, m.normal); put3(tangent + 6 * g, m.tangent_vector[0]); put3(tangent + 6 * g + 3, m.tangent_vector[1]);
+        ncontacts[g] = (uint32_t)m.len();
+        for (int i = 0; i < 4; ++i) {
+            put3(local_a + 12 * g + 3 * i, i < m.len() ? m.contact(i).first : v3(0, 0, 0));
+            put3(local_b + 12 * g + 3 * i, i < m.len() ? m.contact(i).second : v3(0, 0, 0));
+        }
+    }
+    return MGFB_OK;
+}
+
 // ---- world handle ----
 struct mgfo_world { World w; };
 

@@ -124,7 +124,7 @@ struct Simplex {
     // The reference loops `loop { .. }` until one of the two exits fires; on some inputs (NaN, or a
     // simplex that cycles between two supports) it never does.  Oracle and device both give up after
     // GJK_MAX_STEPS and say so (`*converged = false`), instead of hanging.
-    static constexpr int GJK_MAX_STEPS = 4096;
+    static constexpr int GJK_MAX_STEPS = 256;
     template <class Shape>
     Vec3 closest_point_to_origin(const Shape& shape, bool* converged = nullptr) {
         Vec3 prev_norm = v3(0, 0, 0);

@@ -47,6 +47,7 @@ def load():
     lib.mgfo_compound_closest_points.restype = None; lib.mgfo_compound_closest_points.argtypes = [_P, _P, C.c_uint32, _P]
     lib.mgfo_compound_intersections_batch.restype = None; lib.mgfo_compound_intersections_batch.argtypes = [_P, C.c_uint32, _P, C.c_uint32, _P, _P]
     lib.mgfo_compound_contacts_batch.restype = C.c_int32; lib.mgfo_compound_contacts_batch.argtypes = [_P, _P, C.c_uint32, C.c_uint32, _P, _P]
+    lib.mgfo_manifolds_prune.restype = C.c_int32; lib.mgfo_manifolds_prune.argtypes = [_P, _P, C.c_uint32, _P, _P, _P, _P, _P, _P]
     lib.mgfo_world_create.restype = _P
     lib.mgfo_world_create.argtypes = [C.c_float]
     lib.mgfo_world_destroy.argtypes = [_P]
@@ -116,6 +117,18 @@ def separation_batch(a, b):
     sep = np.zeros(n, np.float32); some = np.zeros(n, np.uint32)
     assert lib.mgfo_separation_batch(L.ptr(a), L.ptr(b), n, L.ptr(sep), L.ptr(some)) == 0
     return sep, some
+
+
+def manifolds_prune(contacts, offsets):
+    """Oracle of mgfb_manifolds_prune."""
+    lib = load()
+    contacts = np.ascontiguousarray(contacts, dtype=L.LOCAL_CONTACT_DTYPE)
+    offsets = np.ascontiguousarray(offsets, dtype=np.uint32)
+    g = len(offsets) - 1
+    d = dict(time=np.zeros(g, np.float32), normal=np.zeros((g, 3), np.float32), tangent=np.zeros((g, 6), np.float32), ncontacts=np.zeros(g, np.uint32),
+             local_a=np.zeros((g, 12), np.float32), local_b=np.zeros((g, 12), np.float32))
+    assert lib.mgfo_manifolds_prune(L.ptr(contacts), L.ptr(offsets), g, *[L.ptr(d[k]) for k in ("time", "normal", "tangent", "ncontacts", "local_a", "local_b")]) == 0
+    return d
 
 
 def contacts_batch(pair_kind, recv, arg, want_local=False):

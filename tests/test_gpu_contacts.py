@@ -134,3 +134,17 @@ def test_empty_batch_and_bad_kind(ctx):
     with pytest.raises(mgf_b200.MgfbError) as err:
         mgf_b200.contacts_batch(ctx, L.CAPSULE_X_MSPHERE, s, s)   # receiver is not a capsule
     assert err.value.code == L.ERR_INVALID_ARG
+
+
+def test_contact_pruner_on_device_bit_exact_and_feeds_the_solver(ctx):
+    """mgfb_manifolds_prune = ContactPruner::push + Manifold::from (manifold.rs:42-148) on the device, against the oracle on
+    seeded groups that hit every branch of push; the manifolds it returns then go through mgfb_solver_solve unchanged."""
+    import pruner_cases
+    contacts, offsets = pruner_cases.random_groups(5000)
+    g = mgf_b200.manifolds_prune(ctx, contacts, offsets); o = oracle_lib.manifolds_prune(contacts, offsets)
+    assert np.array_equal(g["ncontacts"], o["ncontacts"])
+    assert set(np.unique(o["ncontacts"]).tolist()) >= {0, 1, 2, 3, 4}
+    for k in ("time", "normal", "tangent", "local_a", "local_b"):
+        a, b = g[k].reshape(len(offsets) - 1, -1), o[k].reshape(len(offsets) - 1, -1)
+        bad = np.nonzero(((a.view(np.uint32) != b.view(np.uint32)) & ~(np.isnan(a) & np.isnan(b))).any(axis=1))[0]
+        assert len(bad) == 0, (k, bad[:5], a[bad[:2]], b[bad[:2]])

@@ -108,3 +108,24 @@ def test_lcg_fast_matches_slow():
     assert np.array_equal(scenes.lcg_uniform(1000, 7), scenes.lcg_uniform_fast(1000, 7))
     u = scenes.lcg_uniform_fast(200000, 1)
     assert u.min() >= 0.0 and u.max() < 1.0 and abs(u.mean() - 0.5) < 0.01
+
+
+def test_oracle_contact_pruner_hand_derived():
+    """ContactPruner::push / Manifold::from (manifold.rs:72-148) have no test in the reference: hand-derived answers (OURS)."""
+    from pruner_cases import lc
+    x, y = (1.0, 0.0, 0.0), (0.0, 1.0, 0.0)
+    far = np.concatenate([lc((0, 0, 0), (0, 0, 0), y, 0.0, (1, 0, 0), (0, 0, 0)), lc((3, 0, 0), (3, 0, 0), x, 0.0, (0, 2, 0), (0, 0, 0))])
+    m = oracle_lib.manifolds_prune(far, [0, 2])
+    assert m["ncontacts"][0] == 2 and np.array_equal(m["normal"][0], np.float32([0.5, 0.5, 0.0]))          # mean, not renormalised
+    assert np.array_equal(m["local_a"][0][:6], np.float32([1, 0, 0, 0, 2, 0]))
+    near = np.concatenate([lc((0, 0, 0), (0, 0, 0), y, 0.0, (1, 0, 0), (0, 0, 0)), lc((0.5, 0, 0), (9, 9, 9), x, 0.0, (0, 2, 0), (0, 0, 0))])
+    m = oracle_lib.manifolds_prune(near, [0, 2])       # |a - a'|^2 = 0.25 <= 0.5: merged; the newcomer is further from the centres and wins
+    assert m["ncontacts"][0] == 1 and np.array_equal(m["normal"][0], np.float32(x)) and np.array_equal(m["local_a"][0][:3], np.float32([0, 2, 0]))
+    m = oracle_lib.manifolds_prune(near[::-1].copy(), [0, 2])   # other order: the incumbent is further out and stays
+    assert m["ncontacts"][0] == 1 and np.array_equal(m["normal"][0], np.float32(x))
+    times = np.concatenate([lc((0, 0, 0), (0, 0, 0), y, 0.5, (1, 0, 0), (0, 0, 0)), lc((5, 0, 0), (5, 0, 0), x, 0.2, (1, 0, 0), (0, 0, 0)),
+                            lc((9, 0, 0), (9, 0, 0), y, 0.9, (1, 0, 0), (0, 0, 0))])
+    m = oracle_lib.manifolds_prune(times, [0, 3])      # the earlier hit replaces, the later one is dropped
+    assert m["ncontacts"][0] == 1 and m["time"][0] == np.float32(0.2) and np.array_equal(m["normal"][0], np.float32(x))
+    m = oracle_lib.manifolds_prune(times[:0], [0, 0])
+    assert m["ncontacts"][0] == 0 and np.isnan(m["normal"][0]).all() and np.isinf(m["time"][0])
