@@ -211,7 +211,19 @@ def run_reference(args, rank):
         bodies, terrain, iters = build_scene(name)
         config = config_of(name, len(bodies[0]), iters)
         snap, how = reference_snapshot(name)
-    else:   # the same one-box world the N-GPU arm tiles, whole, on one core
+    elif args.bodies_per_gpu == 100000:   # the same one-box world the N-GPU arm tiles, whole, on one core
+        name = "C2settled"
+        b1, _, iters = build_scene(name)
+        one, how = reference_snapshot(name)
+        if not isinstance(one, dict):
+            w1 = oracle_lib.OracleWorld(); w1.add_bodies(*b1); w1.set_terrain(*build_scene(name)[1]); w1.step(dt, iters, WORKLOADS[name][1])
+            one = w1.snapshot()
+        bodies = tuple(np.concatenate([b1[k]] * args.gpus) for k in range(5))
+        parts = [settled_tile_snapshot(one, t, args.gpus) for t in range(args.gpus)]
+        snap = {k: np.concatenate([p[k] for p in parts]) for k in one}
+        terrain = settled_tiles_terrain(args.gpus)
+        config = settled_tiles_config(args.gpus, len(b1[0]), iters)
+    else:   # --bodies-per-gpu 250000: the lattice pile of BASELINE configs[3]
         from mgf_b200 import scenes
         tiles = [scenes.tiled_pile(args.gpus, t, nz=50 * args.bodies_per_gpu // 100000) for t in range(args.gpus)]
         bodies = tuple(np.concatenate([t[0][k] for t in tiles]) for k in range(5))
@@ -253,6 +265,60 @@ def run_reference(args, rank):
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+SEAM_PITCH = 160.5   # the C2 box is 160 wide: copies half a unit further apart start just out of contact across the seam
+
+
+def settled_tile_snapshot(snap, tile, ntiles):
+    """Tile `tile` of the N-GPU workload: the C2settled snapshot translated along x to its place in a row of `ntiles` copies
+    (numpy f32 adds, the same in both arms).  The inner walls are gone, so neighbouring piles lean on each other over the seams."""
+    import numpy as np
+    off = np.float32((tile - (ntiles - 1) / 2.0) * SEAM_PITCH)
+    out = {k: np.array(v, copy=True) for k, v in snap.items()}
+    out["x"][:, 0] += off
+    out["colliders"]["p"][:, 0] += off
+    out["fat"][:, 0] += off
+    return out
+
+
+def settled_tiles_terrain(ntiles):
+    from mgf_b200 import scenes
+    return scenes.box_terrain(SEAM_PITCH * ntiles / 2.0, 40.0, 80.0)
+
+
+def settled_tiles_config(world, n, iters):
+    return {"workload": f"{world} x C2settled: {world} copies of the settled 100000-sphere pile (state of step 600) side by side in one box "
+                        f"{SEAM_PITCH * world:g} x 160, one per GPU, no inner walls: neighbouring piles meet over the tile seams",
+            "bodies": world * n, "solver_iterations": iters, "dt": DT, "window_first_step": 600}
+
+
+def build_settled_tiled(world, rank, local_rank, schedule):
+    """Every rank pre-rolls the C2 scene on its own GPU (identical bits everywhere), moves it to its slot and loads it into its tile."""
+    import numpy as np
+    from mgf_b200 import tiling
+    g, bodies, _, iters, snap = gpu_preroll("C2settled", local_rank)
+    g.ctx.close()
+    if rank == 0:
+        save_snapshot("C2settled", snap)
+    n = len(bodies[0])
+    tw = tiling.TiledWorld(rank, world, device=local_rank, solver_schedule=0 if schedule == "dataflow" else 1)
+    tw.add_owned(np.arange(n, dtype=np.uint32) + np.uint32(rank * n), *bodies)
+    terrain = settled_tiles_terrain(world)
+    tw.set_terrain(*terrain)
+    tw.world.restore(settled_tile_snapshot(snap, rank, world))
+    tw.connect(tiling.all_gather_bytes, ghost_capacity=32768)
+    return tw, bodies, terrain, iters
+
+
+def build_tiled(world, rank, local_rank, bodies_per_gpu, schedule):
+    from mgf_b200 import scenes, tiling
+    nz = 50 * bodies_per_gpu // 100000
+    bodies, ids, terrain = scenes.tiled_pile(world, rank, nz=nz)
+    tw = tiling.TiledWorld(rank, world, device=local_rank, solver_schedule=0 if schedule == "dataflow" else 1)
+    tw.add_owned(ids, *bodies); tw.set_terrain(*terrain)
+    tw.connect(tiling.all_gather_bytes, ghost_capacity=32768 * max(1, nz // 50))
+    return tw, bodies, terrain
 
 
 def tiled_config(world, bodies_per_gpu, iters):
@@ -405,6 +471,7 @@ def main():
 
     dt = np.float32(DT)
     snap = None
+    parity_check = None
     initial_state = "step 0 of the scene (no pre-roll)"
     if world == 1:
         name = args.workload or DEFAULT_WORKLOAD
@@ -420,18 +487,24 @@ def main():
         config = config_of(name, len(bodies[0]), iters)
         parallelism = "single GPU"
     else:
+        # Before anything is timed: a small tiled world lock-stepped against ONE untiled world on the CPU port (the logic of
+        # tests/mp_tiled_check.py, this process group, these GPUs): cross-GPU bit parity shown by the run that is measured.
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import mp_tiled_check
+        parity_check = mp_tiled_check.check(rank, world, local_rank, 3, 0 if args.schedule == "dataflow" else 1)
         # ONE world of `world` x 100 000 spheres in one box, one slab per GPU (weak scaling).  Ghost
         # bodies and boundary velocities cross NVLink inside the kernels (csrc/tile.cuh); torch.distributed
         # only swaps the tiles' memory descriptors once, here.
-        from mgf_b200 import scenes, tiling
-        nz = 50 * args.bodies_per_gpu // 100000
-        bodies, ids, terrain = scenes.tiled_pile(world, rank, nz=nz)
-        iters = 20
-        tw = tiling.TiledWorld(rank, world, device=local_rank, solver_schedule=0 if args.schedule == "dataflow" else 1)
-        tw.add_owned(ids, *bodies); tw.set_terrain(*terrain)
-        tw.connect(tiling.all_gather_bytes, ghost_capacity=32768 * max(1, nz // 50))
+        if args.bodies_per_gpu == 100000:
+            # the N = 1 workload, N times: every GPU holds one settled C2 pile, the piles meet over the tile seams (weak scaling)
+            tw, bodies, terrain, iters = build_settled_tiled(world, rank, local_rank, args.schedule)
+            config = settled_tiles_config(world, len(bodies[0]), iters)
+            initial_state = "every rank runs steps 0..599 of the C2 scene on its own GPU (identical bits) and loads the result, translated to its slot, into its tile"
+        else:
+            iters = 20
+            tw, bodies, terrain = build_tiled(world, rank, local_rank, args.bodies_per_gpu, args.schedule)
+            config = tiled_config(world, args.bodies_per_gpu, iters)
         g = tw.world
-        config = tiled_config(world, args.bodies_per_gpu, iters)
         parallelism = (f"{world} slabs along x, one per GPU; ghost bodies once per step through NVLink peer memory; "
                        + ("solver: the constraint chains of boundary bodies continue on the neighbour GPU, every hand-over one 32-byte "
                           "peer store from inside the solver kernel (no exchange phase, no grid barrier)" if args.schedule == "dataflow"
@@ -479,7 +552,8 @@ def main():
         g.step(dt, iters, nsteps=args.warmup)
     pin = lambda shape: torch.empty(shape, dtype=torch.float32, pin_memory=True).numpy()
     hv, hw = pin((n, 3)), pin((n, 3))
-    outs = [(pin((n, 3)), pin((n, 4)), pin((n, 3)), pin((n, 3))) for _ in range(2)]
+    DEPTH = 3   # steps in flight (mgfb_step_enqueue allows 4): rides out host / PCIe jitter, which lock-stepped neighbour tiles otherwise amplify
+    outs = [(pin((n, 3)), pin((n, 4)), pin((n, 3)), pin((n, 3))) for _ in range(DEPTH)]
     # the per-step inputs are external velocity increments (zero here, so the e2e loop steps the SAME world the
     # device-timed loop stepped)
     hv[:] = 0.0; hw[:] = 0.0
@@ -491,15 +565,17 @@ def main():
     barrier()
     e2e_units = 0.0; e2e_dev_ms = 0.0
     t0 = time.perf_counter()
+    waited = 0
     for k in range(args.steps):
-        hx, hq, ov, ow = outs[k & 1]
+        hx, hq, ov, ow = outs[k % DEPTH]
         g.ctx.check(lib.mgfb_step_enqueue(h, dt, iters, L.INPUT_ADD, L.ptr(hv), L.ptr(hw), L.ptr(hx), L.ptr(hq), L.ptr(ov), L.ptr(ow)))   # H2D + step + D2H queued
-        if k > 0:
-            g.ctx.check(lib.mgfb_step_wait(h, C.byref(st)))   # step k-1's state is in outs[(k-1) & 1]
-            e2e_units += st.constraints * iters; e2e_dev_ms += st.step_ms
-    g.ctx.check(lib.mgfb_step_wait(h, C.byref(st)))
-    e2e_units += st.constraints * iters; e2e_dev_ms += st.step_ms
-    e2e_api = "mgfb_step_enqueue / mgfb_step_wait (pipelined, 2 steps in flight)"
+        if k - waited + 1 >= DEPTH:
+            g.ctx.check(lib.mgfb_step_wait(h, C.byref(st)))   # the oldest queued step's state is in its buffer set (read here by a real consumer)
+            e2e_units += st.constraints * iters; e2e_dev_ms += st.step_ms; waited += 1
+    while waited < args.steps:
+        g.ctx.check(lib.mgfb_step_wait(h, C.byref(st)))
+        e2e_units += st.constraints * iters; e2e_dev_ms += st.step_ms; waited += 1
+    e2e_api = f"mgfb_step_enqueue / mgfb_step_wait (pipelined, {DEPTH} steps in flight)"
     barrier()
     e2e_s = time.perf_counter() - t0
     tot_e2e = g.totals(reset=True)
@@ -507,7 +583,7 @@ def main():
         t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64); dist.all_reduce(t, op=dist.ReduceOp.MAX); e2e_s = t.item()
         u = torch.tensor([e2e_units], device="cuda", dtype=torch.float64); dist.all_reduce(u, op=dist.ReduceOp.SUM); e2e_units = u.item()
     e2e_val = e2e_units / e2e_s
-    assert np.isfinite(outs[0][0]).all() and np.isfinite(outs[(args.steps - 1) & 1][0]).all()
+    assert np.isfinite(outs[0][0]).all() and np.isfinite(outs[(args.steps - 1) % DEPTH][0]).all()
 
     # ---- roofline of the dominant kernel (the solver), live CUDA-event durations
     peak, peak_src = measured_peak()
@@ -558,6 +634,27 @@ def main():
                 others[other] = short_run(other, torch, flush, local_rank, peak)
         others["gjk_epa_batch"] = gjk_block(local_rank, rank == 0 and not args.no_cpu_baseline)
 
+    # ---- N = 8: BASELINE configs[3] (C4: 2 M spheres over 8 GPUs = 250 000 per GPU) as an extra block of the same run
+    c4 = None
+    if world == 8 and args.bodies_per_gpu == 100000:
+        barrier()
+        g.ctx.close()
+        tw4, b4, _ = build_tiled(world, rank, local_rank, 250000, args.schedule)
+        g4 = tw4.world
+        barrier()
+        g4.step(dt, iters, nsteps=args.warmup)
+        barrier()
+        r4 = time_steps_device(g4, torch, flush, dt, iters, min(args.steps, 20))
+        barrier()
+        ms4 = float(sum(r["step_ms"] for r in r4)); u4 = float(sum(r["constraints"] for r in r4)) * iters
+        t = torch.tensor([ms4], device="cuda", dtype=torch.float64); dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        u = torch.tensor([u4], device="cuda", dtype=torch.float64); dist.all_reduce(u, op=dist.ReduceOp.SUM)
+        c4 = {"config": tiled_config(world, 250000, iters), "value": u.item() / (t.item() * 1e-3), "unit": "constraint-iters/s", "steps": len(r4),
+              "ms_per_step": t.item() / len(r4), "constraints_per_step": u.item() / iters / len(r4),
+              "rank0_solve_ms": sum(r["solve_ms"] for r in r4) / len(r4), "rank0_ghosts_per_step": sum(r["ghosts"] for r in r4) / len(r4),
+              "timing": "device (library CUDA events), max over ranks, L2 flushed between steps"}
+        tw4.close()
+
     if rank == 0:
         line = {
             "metric": "contact_constraint_iterations_per_second", "value": value, "unit": "constraint-iters/s", "n_gpus": world,
@@ -578,7 +675,7 @@ def main():
                     "device_ms_per_step": e2e_dev_ms / args.steps, "constraints_per_step": e2e_units / iters / args.steps / max(world, 1),
                     "gpu_launches": tot_e2e["kernel_launches"]},
             "gpu_launches": tot["kernel_launches"], "clocks": clocks, "wall_s_timed_region": t_wall,
-            "other_workloads": others,
+            "other_workloads": others, "parity_check": parity_check, "c4": c4,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -15,16 +15,14 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 from mgf_b200 import scenes, tiling  # noqa: E402
 
 
-def main():
-    rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"]); local = int(os.environ.get("LOCAL_RANK", rank))
-    nsteps = int(sys.argv[1]) if len(sys.argv) > 1 else 20
-    torch.cuda.set_device(local)
-    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+def check(rank, world, local, nsteps, schedule=0):
+    """The lock-step itself; the process group (any backend able to all_gather objects) must exist.  Returns a summary dict on
+    every rank (raises AssertionError on the first difference)."""
     dt = np.float32(1.0 / 60.0); iters = 10
     bodies = scenes.pile_xyz(12 * world, 5, 6, jitter=0.01, seed=11)
     terrain = scenes.box_terrain(10.0 * world, 10.0, 6.0)
     parts = tiling.slab_partition(tiling.shape_centres_x(bodies[0]), world)
-    tw = tiling.TiledWorld(rank, world, device=local, tile_timeout_ms=10000)
+    tw = tiling.TiledWorld(rank, world, device=local, tile_timeout_ms=10000, solver_schedule=schedule)
     tw.add_bodies(parts[rank], *bodies)
     tw.set_terrain(*terrain)
     tw.connect(tiling.all_gather_bytes, ghost_capacity=2048)
@@ -60,10 +58,25 @@ def main():
             so = so[tw.ids]
             bad = np.nonzero((np.ascontiguousarray(sg).view(np.uint32) != np.ascontiguousarray(so).view(np.uint32)).any(axis=1))[0]
             assert len(bad) == 0, f"rank {rank} step {s}: {name} differs for {len(bad)} bodies"
+    summary = [None]
     if rank == 0:
         assert total > 0 and boundary > 0, (total, boundary)
-        print(f"MP_TILED_OK ranks={world} steps={nsteps} constraints={total} boundary={boundary}", flush=True)
+        summary = [{"ranks": world, "steps": nsteps, "bodies": len(bodies[0]), "constraints": total, "boundary_constraints": boundary,
+                    "result": "ok: every rank's bodies bit-identical to ONE untiled world on the CPU port replaying the executed order, every step"}]
+    dist.broadcast_object_list(summary, src=0)
     dist.barrier()
+    tw.close()
+    return summary[0]
+
+
+def main():
+    rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"]); local = int(os.environ.get("LOCAL_RANK", rank))
+    nsteps = int(sys.argv[1]) if len(sys.argv) > 1 else 20
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    out = check(rank, world, local, nsteps)
+    if rank == 0:
+        print(f"MP_TILED_OK ranks={world} steps={nsteps} constraints={out['constraints']} boundary={out['boundary_constraints']}", flush=True)
     dist.destroy_process_group()
 
 

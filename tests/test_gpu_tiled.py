@@ -183,3 +183,35 @@ def test_tiled_pipelined_steps_equal_synchronous_steps():
         for name, a, b, c in zip("x q v omega".split(), ts.state(), tp.state(), out):
             assert np.array_equal(_bits(a), _bits(b)), f"tile {ts.rank}: {name} differs between synchronous and pipelined steps"
             assert np.array_equal(_bits(a), _bits(c)), f"tile {ts.rank}: {name} read back by the pipeline differs"
+
+
+def test_rebin_migrates_bodies_between_tiles_and_stays_bit_exact():
+    """SURVEY 8e "re-bin every k steps": the top layer of the left half slides across the pile into the right half.  Every 8
+    steps the world is re-tiled by the bodies' current x (tiling.rebin_local: snapshot -> new slabs -> restored state); bodies
+    change owner, and the whole run stays bit-identical to the ONE untiled oracle world replaying the executed order."""
+    nx, ny, nz = 16, 4, 4
+    bodies = scenes.pile_xyz(nx, ny, nz, jitter=0.01, seed=13)
+    terrain = scenes.box_terrain(14.0, 10.0, 6.0)
+    tiles, o = _make(bodies, terrain, 2, ctas=24)
+    # push: global id = (ix * ny + iy) * nz + iz ; the whole top layer (iy = ny - 1) gets v = (14, 0, 0) and slides over the pile
+    gid = np.arange(nx * ny * nz)
+    pushed = gid[(gid // nz) % ny == ny - 1]
+    v = np.zeros((len(gid), 3), np.float32); v[pushed, 0] = 14.0
+    w = np.zeros_like(v)
+    o.set_velocity(0, v, w)
+    for t in tiles:
+        t.world.set_velocity(0, v[t.ids], w[t.ids])
+    owners0 = {int(g): t.rank for t in tiles for g in t.ids}
+    total = 0; moved = set()
+    for chunk in range(6):
+        tot, _ = _lockstep(tiles, o, 8, 8, f"rebin chunk {chunk}")
+        total += tot
+        tiles = tiling.rebin_local(tiles, ghost_capacity=256, min_width=2.5)
+        owners = {int(g): t.rank for t in tiles for g in t.ids}
+        assert sorted(owners) == sorted(owners0)                      # every body owned exactly once
+        moved |= {g for g in owners if owners[g] != owners0[g]}
+        for t in tiles:                                              # the restored state is the oracle's, bit for bit
+            for sg, so in zip(t.state(), o.state()):
+                assert np.array_equal(_bits(sg), _bits(so[t.ids]))
+    assert total > 10000
+    assert len(moved) >= 6 and len(moved & set(pushed.tolist())) >= 3, f"bodies that changed owner: {sorted(moved)}"

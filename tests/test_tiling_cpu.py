@@ -20,6 +20,21 @@ def test_slab_partition_is_balanced_sorted_and_deterministic():
     assert all(np.array_equal(p, q) for p, q in zip(parts, again))
 
 
+def test_slab_partition_min_width_widens_thin_slabs():
+    import pytest
+    from mgf_b200 import tiling
+    x = np.concatenate([np.linspace(0.0, 1.0, 90), np.linspace(1.0, 10.0, 10)]).astype(np.float32)   # 90 % of the bodies in the first tenth
+    thin = tiling.slab_partition(x, 4)
+    assert x[thin[1]].max() - x[thin[1]].min() < 0.5
+    wide = tiling.slab_partition(x, 4, min_width=2.0)
+    assert sorted(np.concatenate(wide).tolist()) == list(range(100)) and all(len(p) > 0 for p in wide)
+    firsts = [x[p].min() for p in wide]
+    assert all(b - a >= 2.0 - 1e-6 for a, b in zip(firsts, firsts[1:])) and x.max() - firsts[-1] >= 2.0 - 1e-6
+    assert all(x[wide[r]].max() <= x[wide[r + 1]].min() for r in range(3))
+    with pytest.raises(ValueError):
+        tiling.slab_partition(x, 4, min_width=3.0)
+
+
 def test_tiling_host_logic_two_ranks_gloo():
     procs = []
     for rank in range(2):
