@@ -626,6 +626,23 @@ def main():
                "pairs_per_second": pr / sec, "ms_per_step": 1e3 * sec / ncpu,
                "sample": f"{ncpu} full World::step of the workload (from the same snapshot) after 2 warm-up steps on the C++ port of the reference "
                          f"(the Rust reference cannot be built: no rustc); 1 of {os.cpu_count()} host cores (reference is single-threaded)"}
+    # ---- the north star's parity clause, measured by this very run: C1 stepped 250 times (free fall, impact, settling) in the
+    # reference's own constraint order on the GPU and natively on the CPU port; max relative error of positions / velocities
+    parity = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from mgf_b200 import scenes, _lib as LL
+        cb, ct, ci = scenes.build_config("C1")
+        pg = mgf_b200.World(device=local_rank, step_order=LL.STEP_ORDER_REFERENCE); po = oracle_lib.OracleWorld()
+        for w in (pg, po):
+            w.add_bodies(*cb); w.set_terrain(*ct)
+        pg.step(dt, ci, nsteps=250); po.step(dt, ci, 250)
+        (gx, _, gv, _), (ox, _, ov, _) = pg.state(), po.state()
+        rel = lambda a, b: float((np.linalg.norm(a - b, axis=1) / np.maximum(np.linalg.norm(b, axis=1), 1e-30)).max())
+        parity = {"scene": "C1 (512 spheres, 10 iterations), steps 0..249, mgfb_config.step_order = REFERENCE vs the CPU port's native World::step",
+                  "max_rel_error_x": rel(gx, ox), "max_rel_error_v": rel(gv, ov), "bit_identical": bool(np.array_equal(gx.view(np.uint32), ox.view(np.uint32)) and
+                                                                                                         np.array_equal(gv.view(np.uint32), ov.view(np.uint32))),
+                  "north_star_tolerance": 1e-4}
+        pg.ctx.close()
     if world == 1 and args.workload is None and not args.no_other_workloads:
         g.ctx.close()
         others = {}
@@ -675,7 +692,7 @@ def main():
                     "device_ms_per_step": e2e_dev_ms / args.steps, "constraints_per_step": e2e_units / iters / args.steps / max(world, 1),
                     "gpu_launches": tot_e2e["kernel_launches"]},
             "gpu_launches": tot["kernel_launches"], "clocks": clocks, "wall_s_timed_region": t_wall,
-            "other_workloads": others, "parity_check": parity_check, "c4": c4,
+            "other_workloads": others, "reference_order_parity": parity, "parity_check": parity_check, "c4": c4,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

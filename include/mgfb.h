@@ -88,6 +88,15 @@ enum mgfb_solver_schedule {
                                     geometric class, then hash): a different, equally valid proper colouring */
 };
 
+/* The order in which World::step hands its constraints to the Solver (Gauss-Seidel results depend on it).
+ *   COLOURED   (default) the device's colour-major order, exported by mgfb_step_constraints so that it can be replayed.
+ *   REFERENCE  the demo world's own order (world.rs:233-291): body by body, terrain contacts in the mesh BVH's callback order,
+ *              then body pairs in the body BVH's callback order.  Both trees are replayed on the host exactly as bvh.rs grows
+ *              and re-balances them, step after step, so the state after every step is BIT-IDENTICAL to the reference's own
+ *              World::step.  The tree walk is sequential like the reference's: for parity runs and worlds up to ~10^5 bodies;
+ *              one GPU, synchronous steps only. */
+enum mgfb_step_order { MGFB_STEP_ORDER_COLOURED = 0, MGFB_STEP_ORDER_REFERENCE = 1 };
+
 /* solver.rs:265-279 ContactConstraintParams, manifold.rs:27-39 PruningParams, world.rs:181 */
 typedef struct mgfb_config {
     int32_t device;                 /* CUDA device ordinal */
@@ -100,7 +109,7 @@ typedef struct mgfb_config {
     uint32_t tile_timeout_ms;       /* 0 = 20000: how long a tile waits for a neighbour before MGFB_ERR_TILE */
     uint32_t solver_schedule;       /* mgfb_solver_schedule; coloured order only (as-given order always uses phases); every tile
                                        of a tiled world must use the same value */
-    uint32_t reserved;
+    uint32_t step_order;            /* mgfb_step_order: in which order mgfb_step adds the constraints to the solver */
 } mgfb_config;
 void mgfb_config_default(mgfb_config* cfg);
 

@@ -35,10 +35,11 @@ class Config(C.Structure):
     _fields_ = [("device", C.c_int32), ("penetration_slop", C.c_float), ("baumgarte", C.c_float),
                 ("persistent_threshold_sq", C.c_float), ("fat_margin", C.c_float),
                 ("initial_body_capacity", C.c_uint32), ("max_cooperative_ctas", C.c_uint32), ("tile_timeout_ms", C.c_uint32),
-                ("solver_schedule", C.c_uint32), ("reserved", C.c_uint32)]
+                ("solver_schedule", C.c_uint32), ("step_order", C.c_uint32)]
 
 
 SCHEDULE_DATAFLOW, SCHEDULE_PHASES, SCHEDULE_PHASES_JP = 0, 1, 2
+STEP_ORDER_COLOURED, STEP_ORDER_REFERENCE = 0, 1
 
 
 class Manifolds(C.Structure):

@@ -10,6 +10,7 @@
 #include <vector>
 #include "../../include/mgfb.h"
 #include "kernels.cuh"
+#include "reftree.cuh"
 
 using namespace mgfb;
 
@@ -72,6 +73,7 @@ struct mgfb_ctx {
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t* cur_ev = nullptr;        // the four timing events of the step being enqueued (ev, or a pipeline slot's)
     struct PipeSlot* pipe = nullptr;     // mgfb_step_enqueue / mgfb_step_wait (pipeline.cuh)
+    struct RefOrderState* reforder = nullptr;   // World::step in the reference's own constraint order (reforder.cuh)
     cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
     cudaStream_t s_aux = nullptr;         // the terrain half of the broad/narrowphase runs beside the body half
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
@@ -95,6 +97,17 @@ struct mgfb_ctx {
     unsigned handover_torn = 0, handover_observed = 0;
     bool prof_on = false;
     cudaEvent_t prof_ev[11] = {};
+};
+
+// host state of World::step in reference order (reforder.cuh): the two trees of the demo world, replayed
+struct RefOrderState {
+    RefTree body_tree, mesh_tree;
+    std::vector<int> leaf;            // leaf of every body in body_tree
+    std::vector<Box> fat;             // the fat box each leaf was inserted with
+    std::vector<Box> h_tight, h_fat;  // this step's boxes as the device computed them
+    std::vector<int2> cand;
+    bool mesh_built = false;
+    Buf d_cand, d_la, d_lb, d_nt, d_cnt, d_offs;
 };
 
 namespace {
@@ -546,6 +559,7 @@ M3 capsule_tensor(V3 a, V3 d, float r, float m) {
 }  // namespace
 
 void pipe_destroy(mgfb_ctx* ctx);   // pipeline.cuh
+namespace { void reforder_free(mgfb_ctx* ctx); int32_t step_reference_order(mgfb_ctx* ctx, float dt, unsigned iters, mgfb_step_stats* stats); }   // reforder.cuh
 namespace { int32_t local_handover_selftest(mgfb_ctx* ctx, unsigned rounds, unsigned* torn, unsigned* observed);
             int32_t run_handover_selftest(mgfb_ctx* ctx, Inbox* box, bool sys, unsigned rounds, unsigned* torn, unsigned* observed); }   // selftest.cuh
 
@@ -657,6 +671,7 @@ void mgfb_ctx_destroy(mgfb_ctx* ctx) {
                   &ctx->terrain.cell_start, &ctx->terrain.ent_id, &ctx->terrain.ent_key, &ctx->terrain.max_bits,
                   &ctx->gid, &ctx->phase_start, &ctx->edge_idx, &ctx->edge_mark, &ctx->ridx, &ctx->mbox, &ctx->edge_slot, &ctx->tile_df};
     pipe_destroy(ctx);
+    reforder_free(ctx);
     for (void* ptr : ctx->ipc_opened) cudaIpcCloseMemHandle(ptr);
     for (Buf* b : all) release(*b);
     if (ctx->h_ctr) cudaFreeHost(ctx->h_ctr);
@@ -750,6 +765,15 @@ int32_t mgfb_bodies_add(mgfb_ctx* ctx, uint32_t n, const mgfb_shape* shapes, con
     CU(cudaStreamSynchronize(ctx->stream));
     ctx->n += n; ctx->n_capsules += ncaps;
     if (first_id) *first_id = first;
+    // reference-order replay (reforder.cuh): World::add_body inserts the new leaves into the body BVH as it is (world.rs:178-184)
+    if (ctx->reforder) {
+        RefOrderState* S = ctx->reforder;
+        for (uint32_t i = 0; i < n; ++i) {
+            S->fat.push_back(hfat[i]);
+            S->leaf.push_back(S->body_tree.insert(f4v(hfat[i].c), f4v(hfat[i].r), (int)(first + i)));
+            if (S->leaf.back() < 0) return fail(ctx, MGFB_ERR_NAN_BOUNDS, "AABB::combine: r >= 0 violated (bounds.rs:125-127)");
+        }
+    }
     return MGFB_OK;
 }
 
@@ -869,6 +893,7 @@ int32_t mgfb_bodies_set_state(mgfb_ctx* ctx, uint32_t first, uint32_t n, const f
     CU(cudaGetLastError());
     ctx->launches += 1;
     CU(cudaStreamSynchronize(ctx->stream));
+    if (fat_boxes && ctx->reforder) ctx->reforder->leaf.clear();   // the stored boxes changed: the body tree is rebuilt from them, in body order
     return MGFB_OK;
 }
 
@@ -940,6 +965,7 @@ int32_t mgfb_terrain_set(mgfb_ctx* ctx, const float* verts, uint32_t nverts, con
     CU(cudaStreamSynchronize(ctx->stream));
     release(sums);
     t.present = true;
+    if (ctx->reforder) ctx->reforder->mesh_built = false;
     return MGFB_OK;
 }
 
@@ -972,6 +998,11 @@ int32_t mgfb_step_n(mgfb_ctx* ctx, float dt, uint32_t iters, uint32_t nsteps, mg
     if (!(dt > 0.0f)) return fail(ctx, MGFB_ERR_INVALID_ARG, "dt must be > 0");
     CU(cudaSetDevice(ctx->device));
     if (ctx->n == 0 || nsteps == 0) { if (stats) std::memset(stats, 0, sizeof(*stats)); return MGFB_OK; }
+    if (ctx->cfg.step_order == MGFB_STEP_ORDER_REFERENCE) {
+        if (ctx->pipe_inflight) return fail(ctx, MGFB_ERR_STATE, "steps are in flight: mgfb_step_wait first");
+        for (uint32_t s = 0; s < nsteps; ++s) TRY(step_reference_order(ctx, dt, iters, stats));
+        return MGFB_OK;
+    }
     unsigned scale = ctx->tile_exported ? 2 : 1, overflowed = 0;   // a tile cannot regrow mid-run: sized once, generously
     TRY(ensure_step_buffers(ctx, scale));
     TRY(ensure_grid(ctx, scale));
@@ -1304,3 +1335,4 @@ int32_t mgfb_device_view_get(mgfb_ctx* ctx, mgfb_device_view* out) {
 #include "pipeline.cuh"
 #include "selftest.cuh"
 #include "compound.cuh"
+#include "reforder.cuh"

@@ -6,8 +6,8 @@
 //   BoundedBy<AABB>, <Sphere>   (compound.rs:277-288)    mgfb_compound_bounds
 // The reference keeps the components in a BVH<AABB, Component> grown one insert at a time; which leaves a query visits, and in
 // which ORDER its callback fires (the last contact is what `last_contact` returns), depends on that tree.  A compound holds
-// a handful of components and is built once, so the tree is grown here on the host exactly the way bvh.rs grows it
-// (surface-area descent bvh.rs:125-217, height-balancing rotations :371-480, rounded unions bounds.rs:113-130) and the device
+// a handful of components and is built once, so the tree is grown on the host exactly the way bvh.rs grows it (RefTree,
+// reftree.cuh) and the device
 // threads walk it with the reference's own stack discipline (push left, push right, pop: right child first, bvh.rs:283-310).
 // One thread per query; every contact / intersection primitive is the narrowphase's (narrow.cuh).
 // Included at the end of capi.cu.
@@ -15,21 +15,11 @@
 
 namespace mgfb {
 
-struct CompNode {          // BVHNode<AABB, Component> (bvh.rs:32-46)
-    float4 c, r;           // bounds
-    int left, right;       // BVHNodeType::Parent(l, r); leaf: left = -1, right = index into the component array
-    int parent, height;
-};
 struct CompoundView {
-    const CompNode* nodes; const mgfb_shape* comps;   // comps in insertion order (Compound.shapes)
+    const CompNode* nodes; const mgfb_shape* comps;   // the RefTree's nodes; comps in insertion order (Compound.shapes)
     int root; unsigned ncomp;
     float4 disp; float4 rot;   // rot = (s, x, y, z)
 };
-HD void box_combine(V3 ac, V3 ar, V3 bc, V3 br, V3* oc, V3* orr) {   // bounds.rs:113-130
-    V3 lo = mk3(fminf(ac.x - ar.x, bc.x - br.x), fminf(ac.y - ar.y, bc.y - br.y), fminf(ac.z - ar.z, bc.z - br.z));
-    V3 hi = mk3(fmaxf(ac.x + ar.x, bc.x + br.x), fmaxf(ac.y + ar.y, bc.y + br.y), fmaxf(ac.z + ar.z, bc.z + br.z));
-    *orr = (hi - lo) / 2.0f; *oc = (hi + lo) / 2.0f;
-}
 // geom.rs:940-986: the AABB of the eight rotated corners, folded p1.min(p2.min(...p8))
 HD void box_rotate(V3 c, V3 r, Q4 rot, V3* oc, V3* orr) {
     V3 vx = qrot(rot, mk3(r.x, 0.0f, 0.0f)), vy = qrot(rot, mk3(0.0f, r.y, 0.0f)), vz = qrot(rot, mk3(0.0f, 0.0f, r.z));
@@ -195,95 +185,16 @@ __global__ void __launch_bounds__(128) k_compound_closest(CompoundView C, const 
 
 struct mgfb_compound {
     mgfb_ctx* ctx = nullptr;
-    std::vector<CompNode> nodes;        // host copy of the tree (bounds() reads the root)
+    RefTree tree;                       // host copy of the tree (bounds() reads the root)
     std::vector<mgfb_shape> comps;
-    int root = 0;
     Buf d_nodes, d_comps;
     float disp[3] = {0, 0, 0}, rot[4] = {1, 0, 0, 0};
 };
 
 namespace {
-// BVH::insert for AABB keys exactly as bvh.rs grows the tree: descend by the surface-area heuristic (bvh.rs:137-178), hang the
-// new leaf beside the chosen node under a fresh parent (:180-201), then walk up refitting and rotating (:203-216, balance :371-480).
-struct CompTreeBuilder {
-    std::vector<CompNode>& N; int& root;
-    static V3 c(const CompNode& n) { return f4v(n.c); }
-    static V3 r(const CompNode& n) { return f4v(n.r); }
-    static float area(V3 rr) { return rr.x * rr.y + rr.y * rr.z + rr.z * rr.x; }   // bounds.rs:132-134
-    bool is_leaf(int i) const { return N[i].left < 0; }
-    bool refit(int i) {   // bounds = combine(left, right); false when the reference's assert!(r >= 0) would fire
-        V3 oc, orr; box_combine(c(N[N[i].left]), r(N[N[i].left]), c(N[N[i].right]), r(N[N[i].right]), &oc, &orr);
-        N[i].c = v4(oc, 0); N[i].r = v4(orr, 0);
-        return orr.x >= 0.0f && orr.y >= 0.0f && orr.z >= 0.0f;
-    }
-    int add(V3 bc, V3 br, int left, int right) { CompNode n; n.c = v4(bc, 0); n.r = v4(br, 0); n.left = left; n.right = right; n.parent = 0; n.height = -1; N.push_back(n); return (int)N.size() - 1; }
-    // one rotation of bvh.rs:371-480: `up` (the taller child of a) takes a's place; of up's children the taller stays with up
-    // beside a, the other replaces up under a.  `up_is_right`: up was a's right child (then a keeps its left child first).
-    int rotate(int a, int up, bool up_is_right) {
-        const int keep = up_is_right ? N[a].left : N[a].right;      // a's other child
-        const int x = N[up].left, y = N[up].right;
-        N[up].parent = N[a].parent; N[a].parent = up;
-        if (root == a) root = up;
-        else { CompNode& p = N[N[up].parent]; if (!is_leaf(N[up].parent)) { if (p.left == a) p.left = up; else p.right = up; } }
-        const int stay = N[x].height > N[y].height ? x : y, move = stay == x ? y : x;
-        N[up].left = a; N[up].right = stay;
-        if (up_is_right) { N[a].left = keep; N[a].right = move; } else { N[a].left = move; N[a].right = keep; }
-        N[move].parent = a;
-        // combine(b, g) / combine(c, e): the kept child is the first argument in both mirror cases
-        { V3 oc, orr; box_combine(c(N[keep]), r(N[keep]), c(N[move]), r(N[move]), &oc, &orr); N[a].c = v4(oc, 0); N[a].r = v4(orr, 0); }
-        { V3 oc, orr; box_combine(c(N[a]), r(N[a]), c(N[stay]), r(N[stay]), &oc, &orr); N[up].c = v4(oc, 0); N[up].r = v4(orr, 0); }
-        N[a].height = 1 + std::max(N[keep].height, N[move].height);
-        N[up].height = 1 + std::max(N[a].height, N[stay].height);
-        return up;
-    }
-    int balance(int a) {
-        if (N[a].height < 2 || is_leaf(a)) return a;
-        const int b = N[a].left, cc = N[a].right;
-        if (N[cc].height > N[b].height + 1) return is_leaf(cc) ? cc : rotate(a, cc, true);
-        if (N[b].height > N[cc].height + 1) return is_leaf(b) ? b : rotate(a, b, false);
-        return a;
-    }
-    bool insert(V3 bc, V3 br, int component) {
-        const int leaf = add(bc, br, -1, component);
-        if (N.size() == 1) { root = leaf; return true; }
-        int best = root;
-        while (!is_leaf(best)) {
-            const int c1 = N[best].left, c2 = N[best].right;
-            const float a0 = area(r(N[best]));
-            V3 oc, orr; box_combine(c(N[best]), r(N[best]), bc, br, &oc, &orr);
-            const float combined = area(orr);
-            const float no_descent = combined * 2.0f, inherit = (combined - a0) * 2.0f;
-            auto child_cost = [&](int ch) {
-                V3 qc, qr; box_combine(bc, br, c(N[ch]), r(N[ch]), &qc, &qr);
-                return is_leaf(ch) ? area(qr) + inherit : area(qr) - area(r(N[ch])) + inherit;
-            };
-            const float k1 = child_cost(c1), k2 = child_cost(c2);
-            if (no_descent < k1 && no_descent < k2) break;
-            best = k1 < k2 ? c1 : c2;
-        }
-        const int old_parent = N[best].parent;
-        V3 oc, orr; box_combine(bc, br, c(N[best]), r(N[best]), &oc, &orr);
-        if (!(orr.x >= 0.0f && orr.y >= 0.0f && orr.z >= 0.0f)) return false;
-        const int np = add(oc, orr, best, leaf);
-        N[np].parent = old_parent; N[np].height = N[best].height + 1;
-        if (best != root) { if (!is_leaf(old_parent)) { if (N[old_parent].left == best) N[old_parent].left = np; else N[old_parent].right = np; } }
-        else root = np;
-        N[best].parent = np; N[leaf].parent = np;
-        for (int i = np;;) {
-            i = balance(i);
-            if (!is_leaf(i)) {
-                N[i].height = 1 + std::max(N[N[i].left].height, N[N[i].right].height);
-                if (!refit(i)) return false;
-                if (i == root) break;
-            }
-            i = N[i].parent;
-        }
-        return true;
-    }
-};
 CompoundView compound_view(const mgfb_compound* c) {
     CompoundView V;
-    V.nodes = c->d_nodes.as<CompNode>(); V.comps = c->d_comps.as<mgfb_shape>(); V.root = c->root; V.ncomp = (unsigned)c->comps.size();
+    V.nodes = c->d_nodes.as<CompNode>(); V.comps = c->d_comps.as<mgfb_shape>(); V.root = c->tree.root; V.ncomp = (unsigned)c->comps.size();
     V.disp = make_float4(c->disp[0], c->disp[1], c->disp[2], 0.0f); V.rot = make_float4(c->rot[0], c->rot[1], c->rot[2], c->rot[3]);
     return V;
 }
@@ -296,7 +207,6 @@ int32_t mgfb_compound_create(mgfb_ctx* ctx, const mgfb_shape* components, uint32
     if (n > 4096) return fail(ctx, MGFB_ERR_INVALID_ARG, "a compound holds at most 4096 components");
     CU(cudaSetDevice(ctx->device));
     mgfb_compound* c = new mgfb_compound(); c->ctx = ctx;
-    CompTreeBuilder T{c->nodes, c->root};
     for (uint32_t i = 0; i < n; ++i) {
         mgfb_shape s = components[i]; s.v[0] = s.v[1] = s.v[2] = 0.0f;
         V3 bc, br;
@@ -305,13 +215,13 @@ int32_t mgfb_compound_create(mgfb_ctx* ctx, const mgfb_shape* components, uint32
                                                             bc = mk3(s.p[0], s.p[1], s.p[2]) + d * 0.5f; br = mk3(rr, rr, rr); }
         else { delete c; return fail(ctx, MGFB_ERR_INVALID_ARG, "a Component is a Sphere or a Capsule with radius > 0 (compound.rs:33-37, geom.rs:300,328)"); }
         c->comps.push_back(s);
-        if (!T.insert(bc, br, (int)i)) { delete c; return fail(ctx, MGFB_ERR_NAN_BOUNDS, "AABB::combine: r >= 0 violated (bounds.rs:125-127)"); }
+        if (c->tree.insert(bc, br, (int)i) < 0) { delete c; return fail(ctx, MGFB_ERR_NAN_BOUNDS, "AABB::combine: r >= 0 violated (bounds.rs:125-127)"); }
     }
     int32_t st = MGFB_OK;
     if (n) {
-        st = ensure(ctx, c->d_nodes, c->nodes.size() * sizeof(CompNode));
+        st = ensure(ctx, c->d_nodes, c->tree.N.size() * sizeof(CompNode));
         if (st == MGFB_OK) st = ensure(ctx, c->d_comps, c->comps.size() * sizeof(mgfb_shape));
-        if (st == MGFB_OK && (cudaMemcpyAsync(c->d_nodes.p, c->nodes.data(), c->nodes.size() * sizeof(CompNode), cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess ||
+        if (st == MGFB_OK && (cudaMemcpyAsync(c->d_nodes.p, c->tree.N.data(), c->tree.N.size() * sizeof(CompNode), cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess ||
                               cudaMemcpyAsync(c->d_comps.p, c->comps.data(), c->comps.size() * sizeof(mgfb_shape), cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess ||
                               cudaStreamSynchronize(ctx->stream) != cudaSuccess)) st = fail(ctx, MGFB_ERR_CUDA, "uploading the compound failed");
     }
@@ -333,7 +243,7 @@ int32_t mgfb_compound_set_transform(mgfb_compound* c, const float disp[3], const
 int32_t mgfb_compound_bounds(const mgfb_compound* c, float aabb[6], float sphere[4]) {
     if (!c) return MGFB_ERR_INVALID_ARG;
     if (c->comps.empty()) return fail(c->ctx, MGFB_ERR_STATE, "BVH is empty, there is no root node (bvh.rs:263)");
-    const CompNode& rt = c->nodes[c->root];
+    const CompNode& rt = c->tree.N[c->tree.root];
     const V3 disp = mk3(c->disp[0], c->disp[1], c->disp[2]);
     if (aabb) {   // compound.rs:277-281: root.rotate(rot) + disp
         V3 oc, orr; box_rotate(f4v(rt.c), f4v(rt.r), mkq(c->rot[0], mk3(c->rot[1], c->rot[2], c->rot[3])), &oc, &orr);
