@@ -55,3 +55,10 @@ def test_product_never_touches_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 txt = open(os.path.join(dp, f), errors="ignore").read()
                 assert "liboracle" not in txt and "oracle_lib" not in txt and "oracle/" not in txt, f
+
+
+def test_integration_md_binds_every_symbol():
+    """INTEGRATION.md's Rust `extern "C"` block is the binding a maintainer would paste: it must name every entry point of the header."""
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    missing = [n for n in _declared_symbols() if f"pub fn {n}(" not in doc]
+    assert not missing, missing
