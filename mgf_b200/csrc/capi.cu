@@ -71,6 +71,7 @@ struct mgfb_ctx {
     // cooperative grid sizes
     int coop_order = 0, coop_solve = 0, coop_df = 0, coop_colour = 0;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    Counters* ctr_snap = nullptr;         // pipelined step being enqueued: where k_step_done leaves a copy of its counters
     cudaEvent_t* cur_ev = nullptr;        // the four timing events of the step being enqueued (ev, or a pipeline slot's)
     struct PipeSlot* pipe = nullptr;     // mgfb_step_enqueue / mgfb_step_wait (pipeline.cuh)
     struct RefOrderState* reforder = nullptr;   // World::step in the reference's own constraint order (reforder.cuh)
@@ -499,7 +500,7 @@ int32_t enqueue_step(mgfb_ctx* ctx, float dt, unsigned iters, bool from_integrat
     M.a = L.a; M.b = L.b; M.la = L.la; M.lb = L.lb; M.nt = L.nt; M.user = false;
     M.terrain_center = make_float4(ctx->terrain.x[0], ctx->terrain.x[1], ctx->terrain.x[2], 0.0f);
     TRY(enqueue_order_and_solve(ctx, O, M, &c->contacts, 0, ctx->contact_cap, false, dt, iters, timed));
-    k_step_done<<<1, 1, 0, ctx->stream>>>(c);
+    k_step_done<<<1, 64, 0, ctx->stream>>>(c, ctx->ctr_snap);
     CU(cudaGetLastError());
     // k_integrate, 2x k_grid_insert, scan, k_body_pairs, k_step_done (+ terrain, narrowphase)
     ctx->launches += 6 + (ctx->terrain.present ? 1 : 0) + (sph ? 1 : 0) + (sph && caps ? 2 : 0) + (caps ? 1 : 0) +

@@ -163,6 +163,15 @@ __device__ __forceinline__ unsigned long long mix64(unsigned long long z) {  // 
     return z ^ (z >> 31);
 }
 __device__ __forceinline__ unsigned cell_hash(unsigned long long key, unsigned mask) { return (unsigned)(mix64(key) >> 20) & mask; }
+// Body grid: locality-preserving hash.  A 4x4x4 BLOCK of cells is hashed as one unit onto 64 consecutive buckets, so
+// neighbouring cells sit in neighbouring buckets (same cache lines of cell_start, neighbouring runs of `ent`) and the
+// grid's entry order is spatially coherent: the pair sweep walks the bodies in THAT order, which makes its gathers, the
+// pair lists, the contact list and hence the rows of one colour spatially coherent too, whatever the body numbering.
+// (table size is a power of two >= 4096)
+__device__ __forceinline__ unsigned bcell_hash(int x, int y, int z, unsigned mask) {
+    unsigned blk = (unsigned)(mix64(cell_key(x >> 2, y >> 2, z >> 2)) >> 20) & (mask >> 6);
+    return (blk << 6) | (unsigned)((x & 3) | ((y & 3) << 2) | ((z & 3) << 4));
+}
 struct CellRange { int lo[3], hi[3]; };
 // Cells covered by a stored box.  `slop` widens the range of INSERTED boxes by a few ulps so
 // that a closed, rounded overlap test that passes always finds a shared cell.
@@ -200,7 +209,7 @@ __global__ void __launch_bounds__(MGFB_THREADS) k_bgrid_insert(const Box* __rest
     const unsigned n = ctr->n_total;
     for (unsigned j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
         Box b = fat[j];
-        unsigned h = cell_hash(cell_key(cell_coord(b.c.x, inv), cell_coord(b.c.y, inv), cell_coord(b.c.z, inv)), G.table_mask);
+        unsigned h = bcell_hash(cell_coord(b.c.x, inv), cell_coord(b.c.y, inv), cell_coord(b.c.z, inv), G.table_mask);
         if (!FILL) atomicAdd(&G.cell_count[h], 1u);
         else {
             unsigned pos = G.cell_start[h] + (atomicSub(&G.cell_count[h], 1u) - 1u);
@@ -217,14 +226,14 @@ __global__ void __launch_bounds__(MGFB_THREADS) k_bgrid_insert(const Box* __rest
 #define BP_WARPS (MGFB_THREADS / 32)
 #define BP_BUF 128
 #define BP_PER 4     // bodies per warp between two CTA-wide reservations (3 CTA barriers per 32 bodies instead of per 8)
-__device__ __forceinline__ void bp_flush_warp(unsigned* buf, const unsigned char* sub, unsigned cnt, unsigned i0, const unsigned base[4], PairLists lists,
+__device__ __forceinline__ void bp_flush_warp(unsigned* buf, const unsigned char* sub, unsigned cnt, const unsigned* ids, const unsigned base[4], PairLists lists,
                                               unsigned cap, Counters* ctr, unsigned lane) {
-    // buf entries: j | kind << 30, sub[e] = which of the warp's BP_PER bodies (body i0 + sub * BP_WARPS).  base[k]: where this
+    // buf entries: j | kind << 30, sub[e] = which of the warp's BP_PER bodies (body ids[sub]).  base[k]: where this
     // warp's kind-k entries start in list k.
     unsigned run[4] = {0, 0, 0, 0};
     for (unsigned s0 = 0; s0 < cnt; s0 += 32) {
         unsigned e = s0 + lane < cnt ? buf[s0 + lane] : 0xffffffffu;
-        const unsigned i = i0 + (s0 + lane < cnt ? (unsigned)sub[s0 + lane] : 0u) * BP_WARPS;
+        const unsigned i = ids[s0 + lane < cnt ? (unsigned)sub[s0 + lane] : 0u];
         int kind = e == 0xffffffffu ? -1 : (int)(e >> 30);
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
@@ -244,20 +253,27 @@ __global__ void __launch_bounds__(MGFB_THREADS) k_body_pairs_warp(const Box* __r
     __shared__ unsigned char s_sub[BP_WARPS][BP_BUF];
     __shared__ unsigned s_cnt[BP_WARPS][4];     // per warp, per kind
     __shared__ unsigned s_base[BP_WARPS][4];
+    __shared__ unsigned s_ids[BP_WARPS][BP_PER];   // the warp's bodies of this batch
     if (ctr->overflow | ctr->nan_bounds) return;
     const float inv = grid_inv_cell(ctr);
     const unsigned n = ctr->n_total;
     const unsigned lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
     for (unsigned batch = blockIdx.x * (BP_WARPS * BP_PER); batch < n; batch += gridDim.x * (BP_WARPS * BP_PER)) {   // uniform per block
         unsigned cnt = 0, kcnt[4] = {0, 0, 0, 0};
+        const unsigned* ids = s_ids[w];
         for (unsigned sub = 0; sub < BP_PER; ++sub) {
-        const unsigned i = batch + sub * BP_WARPS + w;
-        if (i < n) {   // (world.rs:256 skips body 0: it has no j < i)
+        // bodies are taken in GRID order (position in `ent` = bucket order: spatially coherent), not in index order
+        const unsigned pos = batch + sub * BP_WARPS + w;
+        if (pos < n) {   // (world.rs:256 skips body 0: it has no j < i)
+            const unsigned iw = __float_as_uint(G.ent[2 * pos].w);
+            const unsigned i = iw & 0x7fffffffu;
+            if (lane == 0) s_ids[w][sub] = i;
+            __syncwarp();
             const unsigned gi = gid[i];
             const bool ghost_i = i >= n_own;
             Box tb = tight[i];
             V3 tc = f4v(tb.c), tr = f4v(tb.r);
-            int ki = col_kind(col[i]);
+            int ki = (int)(iw >> 31);
             int cx = cell_coord(tc.x, inv), cy = cell_coord(tc.y, inv), cz = cell_coord(tc.z, inv);
             unsigned e = 0, e1 = 0;
             {
@@ -267,7 +283,7 @@ __global__ void __launch_bounds__(MGFB_THREADS) k_body_pairs_warp(const Box* __r
                 unsigned h = 0xffffffffu - lane;   // lanes 27..31: unique dummies
                 if (lane < 27) {
                     int x = cx + (int)(lane % 3) - 1, y = cy + (int)((lane / 3) % 3) - 1, z = cz + (int)(lane / 9) - 1;
-                    h = cell_hash(cell_key(x, y, z), G.table_mask);
+                    h = bcell_hash(x, y, z, G.table_mask);
                 }
                 unsigned same = __match_any_sync(0xffffffffu, h);
                 if (lane < 27 && (unsigned)__ffs((int)same) - 1u == lane) { e = G.cell_start[h]; e1 = G.cell_start[h + 1]; }
@@ -314,7 +330,7 @@ __global__ void __launch_bounds__(MGFB_THREADS) k_body_pairs_warp(const Box* __r
                         kcnt[k] = 0;
                     }
                     __syncwarp();
-                    bp_flush_warp(s_buf[w], s_sub[w], cnt, batch + w, base, lists, cap, ctr, lane);
+                    bp_flush_warp(s_buf[w], s_sub[w], cnt, ids, base, lists, cap, ctr, lane);
                     __syncwarp();
                     cnt = 0;
                 }
@@ -338,7 +354,7 @@ __global__ void __launch_bounds__(MGFB_THREADS) k_body_pairs_warp(const Box* __r
         __syncthreads();
         if (cnt) {
             unsigned base[4] = {s_base[w][0], s_base[w][1], s_base[w][2], s_base[w][3]};
-            bp_flush_warp(s_buf[w], s_sub[w], cnt, batch + w, base, lists, cap, ctr, lane);
+            bp_flush_warp(s_buf[w], s_sub[w], cnt, ids, base, lists, cap, ctr, lane);
         }
         __syncthreads();
     }
@@ -1454,13 +1470,23 @@ __global__ void __launch_bounds__(MGFB_DF_THREADS_LARGE, 1) k_solve_df(Constrain
 #endif
 }
 
-__global__ void k_step_done(Counters* ctr) {
-    if (ctr->overflow | ctr->nan_bounds) return;
-    ctr->steps_done++;
-    ctr->acc_steps++;
-    ctr->acc_constraints += ctr->contacts;
-    ctr->acc_pairs += (unsigned long long)ctr->pairs[0] + ctr->pairs[1] + ctr->pairs[2] + ctr->pairs[3] + ctr->tpairs[0] + ctr->tpairs[1];
-    ctr->acc_groups += ctr->ngroups;
+// `snap` (pipelined steps): a copy of the step's counters in a buffer of its own, so that the host copy can ride the
+// D2H stream behind the step instead of sitting in the step's stream (where it would queue behind the previous step's
+// state transfer on the one D2H copy engine and hold the next step back).
+__global__ void __launch_bounds__(64) k_step_done(Counters* ctr, Counters* snap) {
+    if (threadIdx.x == 0 && !(ctr->overflow | ctr->nan_bounds)) {
+        ctr->steps_done++;
+        ctr->acc_steps++;
+        ctr->acc_constraints += ctr->contacts;
+        ctr->acc_pairs += (unsigned long long)ctr->pairs[0] + ctr->pairs[1] + ctr->pairs[2] + ctr->pairs[3] + ctr->tpairs[0] + ctr->tpairs[1];
+        ctr->acc_groups += ctr->ngroups;
+    }
+    __syncthreads();
+    if (snap) {
+        const unsigned* src = reinterpret_cast<const unsigned*>(ctr);
+        unsigned* dst = reinterpret_cast<unsigned*>(snap);
+        for (unsigned k = threadIdx.x; k < sizeof(Counters) / 4; k += blockDim.x) dst[k] = src[k];
+    }
 }
 // state marshalling for the host API: packed f32 arrays <-> SoA records
 __global__ void __launch_bounds__(MGFB_THREADS) k_pack_state(BodyArrays B, unsigned first, unsigned n, float* x, float* q, float* v, float* w) {
@@ -1549,21 +1575,29 @@ __global__ void __launch_bounds__(256) k_scan_lookback(const unsigned* __restric
     unsigned woff = 0, agg = 0;
 #pragma unroll
     for (int w = 0; w < 8; ++w) { if (w < (int)(threadIdx.x >> 5)) woff += ws[w]; agg += ws[w]; }
-    if (threadIdx.x == 0) {
+    if (threadIdx.x < 32) {
+        // look-back by a whole warp: 32 predecessors per L2 round trip (a single thread walking back one tile at a time
+        // made the scan a chain of ~40 dependent round trips at 256 tiles)
+        const unsigned lane = threadIdx.x;
         unsigned excl = 0;
-        if (tile == 0) st_relaxed_u64(status, (2ULL << 62) | agg);
+        if (tile == 0) { if (lane == 0) st_relaxed_u64(status, (2ULL << 62) | agg); }
         else {
-            st_relaxed_u64(status + tile, (1ULL << 62) | agg);
-            for (unsigned p = tile; p-- > 0;) {
-                unsigned long long st;
-                do { st = ld_relaxed_u64(status + p); } while ((st >> 62) == 0ULL);
-                excl += (unsigned)st;
-                if ((st >> 62) == 2ULL) break;
+            if (lane == 0) st_relaxed_u64(status + tile, (1ULL << 62) | agg);
+            for (int p = (int)tile - 1;; p -= 32) {
+                const int idx = p - (int)lane;
+                unsigned long long st = 2ULL << 62;   // before tile 0: an inclusive prefix of 0
+                if (idx >= 0) do { st = ld_relaxed_u64(status + idx); } while ((st >> 62) == 0ULL);
+                const unsigned incl = __ballot_sync(0xffffffffu, (st >> 62) == 2ULL);
+                const unsigned upto = incl ? (unsigned)__ffs((int)incl) - 1u : 31u;   // nearest predecessor that knows its prefix
+                excl += __reduce_add_sync(0xffffffffu, lane <= upto ? (unsigned)st : 0u);
+                if (incl) break;
             }
-            st_relaxed_u64(status + tile, (2ULL << 62) | (unsigned long long)(excl + agg));
+            if (lane == 0) st_relaxed_u64(status + tile, (2ULL << 62) | (unsigned long long)(excl + agg));
         }
-        s_excl = excl;
-        if ((unsigned long long)(tile + 1) * SCAN_ITEMS >= n) { out[n] = excl + agg; if (total_dev) *total_dev = excl + agg; }
+        if (lane == 0) {
+            s_excl = excl;
+            if ((unsigned long long)(tile + 1) * SCAN_ITEMS >= n) { out[n] = excl + agg; if (total_dev) *total_dev = excl + agg; }
+        }
     }
     __syncthreads();
     unsigned run = s_excl + woff + x - sum;

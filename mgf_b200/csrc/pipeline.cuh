@@ -10,6 +10,7 @@
 struct PipeSlot {
     Buf in, out;                       // device staging: v, omega in; x, q, v, omega out
     Counters* h_ctr = nullptr;         // pinned copy of the step's counters
+    Counters* d_ctr = nullptr;         // device copy made by k_step_done; travels to h_ctr on the D2H stream
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};   // step begin / end, solve begin / end
     cudaEvent_t ev_in = nullptr, ev_done = nullptr, ev_out = nullptr;
     // what was asked for, kept so that the step can be re-queued after a work list was regrown
@@ -23,6 +24,7 @@ void pipe_destroy(mgfb_ctx* ctx) {
         PipeSlot& s = ctx->pipe[k];
         release(s.in); release(s.out);
         if (s.h_ctr) cudaFreeHost(s.h_ctr);
+        if (s.d_ctr) cudaFree(s.d_ctr);
         for (auto& e : s.ev) if (e) cudaEventDestroy(e);
         if (s.ev_in) cudaEventDestroy(s.ev_in);
         if (s.ev_done) cudaEventDestroy(s.ev_done);
@@ -43,6 +45,7 @@ int32_t pipe_init(mgfb_ctx* ctx) {
     for (int k = 0; k < MGFB_PIPE_DEPTH; ++k) {
         PipeSlot& s = ctx->pipe[k];
         CU(cudaMallocHost(&s.h_ctr, sizeof(Counters)));
+        CU(cudaMalloc(&s.d_ctr, sizeof(Counters)));
         for (auto& e : s.ev) CU(cudaEventCreate(&e));
         CU(cudaEventCreateWithFlags(&s.ev_in, cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&s.ev_done, cudaEventDisableTiming));
@@ -64,13 +67,12 @@ int32_t pipe_launch(mgfb_ctx* ctx, PipeSlot& s, bool from_integrate) {
         else k_set_velocity<false><<<(n + MGFB_THREADS - 1) / MGFB_THREADS, MGFB_THREADS, 0, ctx->stream>>>(body_arrays(ctx), 0, n, sv, sw, dctr(ctx));
         ctx->launches += 1;
     }
-    ctx->cur_ev = s.ev;
+    ctx->cur_ev = s.ev; ctx->ctr_snap = s.d_ctr;
     CU(cudaEventRecord(s.ev[0], ctx->stream));
     int32_t st = enqueue_step(ctx, s.dt, s.iters, from_integrate, true);
-    ctx->cur_ev = ctx->ev;
+    ctx->cur_ev = ctx->ev; ctx->ctr_snap = nullptr;
     TRY(st);
     CU(cudaEventRecord(s.ev[1], ctx->stream));
-    CU(cudaMemcpyAsync(s.h_ctr, dctr(ctx), sizeof(Counters), cudaMemcpyDeviceToHost, ctx->stream));
     float* sx = s.out.as<float>(); float* sq = sx + (size_t)3 * n; float* sv = sq + (size_t)4 * n; float* sw = sv + (size_t)3 * n;
     if (s.x_out || s.q_out || s.v_out || s.w_out) {
         k_pack_state<<<(n + MGFB_THREADS - 1) / MGFB_THREADS, MGFB_THREADS, 0, ctx->stream>>>(body_arrays(ctx), 0, n, s.x_out ? sx : nullptr,
@@ -80,6 +82,9 @@ int32_t pipe_launch(mgfb_ctx* ctx, PipeSlot& s, bool from_integrate) {
     CU(cudaGetLastError());
     CU(cudaEventRecord(s.ev_done, ctx->stream));
     CU(cudaStreamWaitEvent(ctx->s_d2h, s.ev_done, 0));
+    // nothing host-bound sits in the step's own stream: the one D2H copy engine is busy with the previous step's state for
+    // ~0.1-0.2 ms, and a copy queued behind it there would hold the next step back by as much
+    CU(cudaMemcpyAsync(s.h_ctr, s.d_ctr, sizeof(Counters), cudaMemcpyDeviceToHost, ctx->s_d2h));
     if (s.x_out) CU(cudaMemcpyAsync(s.x_out, sx, (size_t)n * 12, cudaMemcpyDeviceToHost, ctx->s_d2h));
     if (s.q_out) CU(cudaMemcpyAsync(s.q_out, sq, (size_t)n * 16, cudaMemcpyDeviceToHost, ctx->s_d2h));
     if (s.v_out) CU(cudaMemcpyAsync(s.v_out, sv, (size_t)n * 12, cudaMemcpyDeviceToHost, ctx->s_d2h));

@@ -160,7 +160,7 @@ int32_t step_reference_order(mgfb_ctx* ctx, float dt, unsigned iters, mgfb_step_
     M.a = L.a; M.b = L.b; M.la = L.la; M.lb = L.lb; M.nt = L.nt; M.user = false;
     M.terrain_center = make_float4(ctx->terrain.x[0], ctx->terrain.x[1], ctx->terrain.x[2], 0.0f);
     TRY(enqueue_order_and_solve(ctx, O, M, &c->contacts, 0, mcap, true, dt, iters, true));
-    k_step_done<<<1, 1, 0, ctx->stream>>>(c);
+    k_step_done<<<1, 64, 0, ctx->stream>>>(c, nullptr);
     CU(cudaEventRecord(ctx->ev[1], ctx->stream));
     ctx->launches += 3;
     TRY(read_counters(ctx));

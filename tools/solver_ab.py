@@ -39,6 +39,15 @@ def main():
             ms = np.mean([r["step_ms"] for r in rows]); sm = np.mean([r["solve_ms"] for r in rows])
             print(f"{name:10s} build '{variant}': step {ms:.4f} ms  solve {sm:.4f} ms  constraints {np.mean([r['constraints'] for r in rows]):.0f}"
                   f"  colours {np.mean([r['phases'] for r in rows]):.2f}  same bits as first variant: {same}", flush=True)
+            if os.environ.get("MGFB_AB_PHASES", "1") == "1" and hasattr(w, "step_profile"):
+                acc = {}
+                for _ in range(6):
+                    flush.add_(1.0)
+                    _, pr = w.step_profile(DT, iters)
+                    for k, v in pr.items():
+                        if isinstance(v, float):
+                            acc[k] = acc.get(k, 0.0) + v / 6
+                print("           phases (us): " + "  ".join(f"{k} {1e3 * v:.1f}" for k, v in acc.items() if v > 0), flush=True)
             w.ctx.close()
 
 
