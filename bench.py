@@ -177,7 +177,13 @@ def gpu_preroll(name, device=0):
     g.add_bodies(*bodies); g.set_terrain(*terrain)
     pre = WORKLOADS[name][1]
     if pre:
-        g.step(np.float32(DT), iters, nsteps=pre)
+        # profiling runs (ncu launch lists) skip the pre-roll's ~13 000 launches by loading the snapshot an earlier run on this box
+        # cached: restoring it continues bit-identically (tests/test_gpu_step.py snapshot tests)
+        snap = load_snapshot(name) if os.environ.get("MGFB_BENCH_REUSE_SNAPSHOT") == "1" else None
+        if snap is not None:
+            g.restore(snap)
+        else:
+            g.step(np.float32(DT), iters, nsteps=pre)
     return g, bodies, terrain, iters, g.snapshot()
 
 
@@ -708,8 +714,10 @@ def main():
 
 
 # ncu `--set full` captures of one solver launch (profiles/): (workload, dataflow single GPU) -> DRAM bytes, L2 throughput fraction
-NCU_TRAFFIC = {("C2pile", True): 145.2e6}
-NCU_L2_FRAC = {("C2pile", True): 0.32}
+# dram__bytes_read.sum + dram__bytes_write.sum and lts__throughput of ONE k_solve_df launch (ncu --set full, profiles/r02_v1_k_solve_df_raw.csv
+# for C2settled, profiles/r01_v4_k_solve_df_raw.csv for C2pile)
+NCU_TRAFFIC = {("C2pile", True): 145.2e6, ("C2settled", True): 38.2e6}
+NCU_L2_FRAC = {("C2pile", True): 0.32, ("C2settled", True): 0.24}
 
 
 if __name__ == "__main__":

@@ -374,11 +374,17 @@ __global__ void __launch_bounds__(128) k_gjk(const mgfb_shape* __restrict__ a, c
 // Pass 2, one warp (= one CTA) per overlapping pair, persistent over the work list.
 template <int KA, int KB>
 __global__ void __launch_bounds__(32) k_epa(const mgfb_shape* __restrict__ a, const mgfb_shape* __restrict__ b, const EpaWork* __restrict__ work,
-                                            const unsigned* __restrict__ work_count, mgfb_contact* out, unsigned* status, unsigned* epa_iters) {
+                                            const unsigned* __restrict__ work_count, unsigned* work_next, mgfb_contact* out, unsigned* status, unsigned* epa_iters) {
     extern __shared__ __align__(16) unsigned char epa_smem[];
     EpaShared& P = *reinterpret_cast<EpaShared*>(epa_smem);
     const unsigned lane = threadIdx.x, nw = *work_count;
-    for (unsigned k = blockIdx.x; k < nw; k += gridDim.x) {
+    // items are claimed from a shared cursor: one EPA run takes 1..101 iterations over a polytope of 4..4000 faces, so a
+    // fixed stride would leave most warps idle behind the few long ones
+    for (;;) {
+        unsigned k = 0;
+        if (lane == 0) k = atomicAdd(work_next, 1u);
+        k = __shfl_sync(0xffffffffu, k, 0);
+        if (k >= nw) break;
         const unsigned i = work[k].pair;
         GShape<KA> sa(a[i]); GShape<KB> sb(b[i]);
         Hit h; int it = 0;
@@ -398,15 +404,15 @@ __global__ void __launch_bounds__(32) k_epa(const mgfb_shape* __restrict__ a, co
 
 template <int KA, int KB>
 void launch_gjk(bool separation, const mgfb_shape* a, const mgfb_shape* b, const unsigned* index, unsigned n, mgfb_contact* out, float* sep,
-                unsigned* status, unsigned* epa_iters, EpaWork* work, unsigned* work_count, int epa_grid, cudaStream_t s) {
+                unsigned* status, unsigned* epa_iters, EpaWork* work, unsigned* work_count, unsigned* work_next, int epa_grid, cudaStream_t s) {
     unsigned blocks = (n + 127) / 128;
     if (separation) { k_gjk<KA, KB, true><<<blocks, 128, 0, s>>>(a, b, index, n, sep, status, epa_iters, work, work_count); return; }
     k_gjk<KA, KB, false><<<blocks, 128, 0, s>>>(a, b, index, n, sep, status, epa_iters, work, work_count);
     cudaFuncSetAttribute(k_epa<KA, KB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(EpaShared));
-    k_epa<KA, KB><<<epa_grid, 32, sizeof(EpaShared), s>>>(a, b, work, work_count, out, status, epa_iters);
+    k_epa<KA, KB><<<epa_grid, 32, sizeof(EpaShared), s>>>(a, b, work, work_count, work_next, out, status, epa_iters);
 }
 typedef void (*gjk_launcher)(bool, const mgfb_shape*, const mgfb_shape*, const unsigned*, unsigned, mgfb_contact*, float*, unsigned*, unsigned*, EpaWork*,
-                             unsigned*, int, cudaStream_t);
+                             unsigned*, unsigned*, int, cudaStream_t);
 #define GJK_NK 5
 const int GJK_KINDS[GJK_NK] = {MGFB_SPHERE, MGFB_CAPSULE, MGFB_AABB, MGFB_OBB, MGFB_CONVEX_MESH};
 const gjk_launcher GJK_TABLE[GJK_NK][GJK_NK] = {
@@ -461,14 +467,14 @@ int32_t gjk_batch_impl(mgfb_ctx* ctx, bool separation, const mgfb_shape* a, cons
     if ((rc = ensure(ctx, da, (size_t)n * sizeof(mgfb_shape))) || (rc = ensure(ctx, db, (size_t)n * sizeof(mgfb_shape))) || (rc = ensure(ctx, di, (size_t)n * 4)) ||
         (rc = ensure(ctx, dout, (size_t)n * sizeof(mgfb_contact))) || (rc = ensure(ctx, dsep, (size_t)n * 4)) || (rc = ensure(ctx, dst, (size_t)n * 4)) ||
         (rc = ensure(ctx, dit, (size_t)n * 4)) || (rc = ensure(ctx, dwork, separation ? sizeof(EpaWork) : (size_t)n * sizeof(EpaWork))) ||
-        (rc = ensure(ctx, dcount, 32 * 4)))
+        (rc = ensure(ctx, dcount, 64 * 4)))
         return done(rc);
     cudaMemcpyAsync(da.p, a, (size_t)n * sizeof(mgfb_shape), cudaMemcpyHostToDevice, ctx->stream);
     cudaMemcpyAsync(db.p, b, (size_t)n * sizeof(mgfb_shape), cudaMemcpyHostToDevice, ctx->stream);
     cudaMemcpyAsync(di.p, index.data(), (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream);
     cudaMemsetAsync(dout.p, 0, (size_t)n * sizeof(mgfb_contact), ctx->stream);
     cudaMemsetAsync(dsep.p, 0, (size_t)n * 4, ctx->stream);
-    cudaMemsetAsync(dcount.p, 0, 32 * 4, ctx->stream);
+    cudaMemsetAsync(dcount.p, 0, 64 * 4, ctx->stream);   // [0, 32): items per bin, [32, 64): the bins' work cursors
     int epa_grid = ctx->num_sms * 4;   // 4 x 52 KB polytopes per SM
     for (int k = 0; k < NB; ++k) {
         unsigned m = count[k + 1] - count[k];
@@ -476,7 +482,7 @@ int32_t gjk_batch_impl(mgfb_ctx* ctx, bool separation, const mgfb_shape* a, cons
         // each bin's EPA work list is a slice of dwork starting at the bin's first pair
         GJK_TABLE[k / GJK_NK][k % GJK_NK](separation, da.as<mgfb_shape>(), db.as<mgfb_shape>(), di.as<unsigned>() + count[k], m, dout.as<mgfb_contact>(),
                                 dsep.as<float>(), dst.as<unsigned>(), dit.as<unsigned>(), dwork.as<EpaWork>() + (separation ? 0 : count[k]),
-                                dcount.as<unsigned>() + k, (int)std::min<unsigned>((unsigned)epa_grid, m), ctx->stream);
+                                dcount.as<unsigned>() + k, dcount.as<unsigned>() + 32 + k, (int)std::min<unsigned>((unsigned)epa_grid, m), ctx->stream);
         ctx->launches += separation ? 1 : 2;
     }
     cudaError_t e = cudaGetLastError();

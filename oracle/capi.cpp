@@ -401,6 +401,13 @@ static const float* g_convex_pool = nullptr; static uint32_t g_convex_n = 0;
 // the vertex pool MGFB_CONVEX_MESH shapes index (same contract as mgfb_convex_vertices_set); the caller keeps it alive
 void mgfo_convex_vertices_set(const float* verts, uint32_t n) { g_convex_pool = verts; g_convex_n = n; }
 static bool gjk_dispatch(const mgfb_shape& A, const mgfb_shape& B, Contact* c, int* it, int* st);
+// largest Pool slot count / horizon size any EPA run reached since the last call with reset != 0
+int32_t mgfo_epa_high_water(uint32_t* slots, uint32_t* edges, int32_t reset) {
+    if (slots) *slots = epa_high_water(0);
+    if (edges) *edges = epa_high_water(1);
+    if (reset) { epa_high_water(0) = 0; epa_high_water(1) = 0; }
+    return 0;
+}
 int32_t mgfo_gjk_batch(const mgfb_shape* a, const mgfb_shape* b, uint32_t n, mgfb_contact* out, uint32_t* hit, uint32_t* epa_iters) {
     for (uint32_t i = 0; i < n; ++i) {
         Contact c{}; int it = 0;

@@ -14,6 +14,9 @@
 namespace mgfo {
 
 struct SupportPoint { Vec3 p, a, b; };  // geom.rs:1077
+// High-water marks of the EPA polytope (Pool slots, horizon edges) since the last reset: test infrastructure for
+// sizing the CUDA kernel's fixed-capacity polytope (mgfo_epa_high_water).
+inline unsigned& epa_high_water(int which) { static unsigned hw[2] = {0, 0}; return hw[which]; }
 
 template <class S1, class S2>
 struct MinkowskiDiff {
@@ -217,6 +220,7 @@ struct Simplex {
                     to_remove.push_back(i);
                 }
             }
+            if (edges.size() > epa_high_water(1)) epa_high_water(1) = (unsigned)edges.size();
             for (size_t i : to_remove) tris.remove(i);
             for (const Edge& e : edges) {
                 if (!e.live) continue;
@@ -225,6 +229,7 @@ struct Simplex {
                 tris.push({sup, a, b});
             }
             edges.clear();
+            if (tris.entries.size() > epa_high_water(0)) epa_high_water(0) = (unsigned)tris.entries.size();
         }
         return Contact{};  // unreachable
     }
