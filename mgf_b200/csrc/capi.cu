@@ -5,6 +5,7 @@
 #include <unistd.h>
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -71,11 +72,14 @@ struct mgfb_ctx {
     // cooperative grid sizes
     int coop_order = 0, coop_solve = 0, coop_df = 0, coop_colour = 0;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    Buf scan_step;                        // the two look-back scan states of one step (zeroed with the step's scratch)
     Counters* ctr_snap = nullptr;         // pipelined step being enqueued: where k_step_done leaves a copy of its counters
     cudaEvent_t* cur_ev = nullptr;        // the four timing events of the step being enqueued (ev, or a pipeline slot's)
     struct PipeSlot* pipe = nullptr;     // mgfb_step_enqueue / mgfb_step_wait (pipeline.cuh)
     struct RefOrderState* reforder = nullptr;   // World::step in the reference's own constraint order (reforder.cuh)
     cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
+    cudaStream_t gjk_streams[8] = {};     // GJK/EPA batch: the per-shape-pair launches run side by side (an EPA run is one warp for up to ~0.1 s)
+    cudaEvent_t gjk_ev[9] = {};
     cudaStream_t s_aux = nullptr;         // the terrain half of the broad/narrowphase runs beside the body half
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     unsigned pipe_head = 0, pipe_inflight = 0, pipe_scale = 2;
@@ -229,16 +233,40 @@ int32_t ensure_grid(mgfb_ctx* ctx, unsigned scale) {
     }
     (void)ecap;
     if (ctx->cap > ctx->ent_cap) { TRY(ensure(ctx, ctx->bg_ent, (size_t)ctx->cap * 32)); ctx->ent_cap = ctx->cap; }
+    {   // look-back states of the step's two scans (capi.cu step_scan_words): sized here, outside the step
+        size_t w = (((size_t)ctx->table + SCAN_ITEMS - 1) / SCAN_ITEMS + 2) * 2 + (((size_t)body_slots(ctx) + SCAN_ITEMS - 1) / SCAN_ITEMS + 2) * 2;
+        TRY(ensure(ctx, ctx->scan_step, w * 4));
+    }
     return MGFB_OK;
 }
 // exclusive scan of `in[0..n)` into out[0..n], out[n] = total (also stored at *total_dev if given)
 // single-pass scan (decoupled look-back) for the step path: one launch + one small memset
-int32_t scan_u32_lb(mgfb_ctx* ctx, const unsigned* in, unsigned* out, unsigned n, unsigned* total_dev) {
+// `step_state`: a look-back state already zeroed by the step's k_zero_ranges (no memset in the step's stream)
+int32_t scan_u32_lb(mgfb_ctx* ctx, const unsigned* in, unsigned* out, unsigned n, unsigned* total_dev, unsigned long long* step_state = nullptr) {
     unsigned nb = (n + SCAN_ITEMS - 1) / SCAN_ITEMS;
-    TRY(ensure(ctx, ctx->scan_state, ((size_t)nb + 2) * 8));
-    CU(cudaMemsetAsync(ctx->scan_state.p, 0, ((size_t)nb + 1) * 8, ctx->stream));
-    k_scan_lookback<<<nb, 256, 0, ctx->stream>>>(in, n, out, ctx->scan_state.as<unsigned long long>(), total_dev);
+    if (!step_state) {
+        TRY(ensure(ctx, ctx->scan_state, ((size_t)nb + 2) * 8));
+        CU(cudaMemsetAsync(ctx->scan_state.p, 0, ((size_t)nb + 1) * 8, ctx->stream));
+        step_state = ctx->scan_state.as<unsigned long long>();
+    }
+    k_scan_lookback<<<nb, 256, 0, ctx->stream>>>(in, n, out, step_state, total_dev);
     CU(cudaGetLastError());
+    return MGFB_OK;
+}
+// the two look-back states of one step (cell scan, body-degree scan), zeroed together with the rest of the step's scratch
+size_t step_scan_words(const mgfb_ctx* ctx, unsigned which) {
+    size_t n = which == 0 ? ctx->table : body_slots(ctx);
+    return ((n + SCAN_ITEMS - 1) / SCAN_ITEMS + 2) * 2;   // 8-byte entries, in 4-byte words
+}
+unsigned long long* step_scan_state(const mgfb_ctx* ctx, unsigned which) {
+    return ctx->scan_step.as<unsigned long long>() + (which == 0 ? 0 : step_scan_words(ctx, 0) / 2);
+}
+int32_t zero_ranges(mgfb_ctx* ctx, const ZeroRanges& Z) {
+    size_t total = 0;
+    for (unsigned r = 0; r < Z.n; ++r) total += Z.words[r];
+    k_zero_ranges<<<grid_for(ctx, total / 4 + 1), MGFB_THREADS, 0, ctx->stream>>>(Z);
+    CU(cudaGetLastError());
+    ctx->launches += 1;
     return MGFB_OK;
 }
 int32_t scan_u32(mgfb_ctx* ctx, const unsigned* in, unsigned* out, unsigned n, unsigned* sums, unsigned* total_dev) {
@@ -311,7 +339,7 @@ int coop_blocks(const mgfb_ctx* ctx, K kernel, int threads, int max_per_sm) {
 // order -> scan -> scatter -> build -> solve, for `m` constraints counted on the device
 // (m_ptr) or known on the host (m_host).
 int32_t enqueue_order_and_solve(mgfb_ctx* ctx, const OrderView& O, const ManifoldInput& M, const unsigned* m_ptr, unsigned m_host,
-                                unsigned m_bound, bool as_given, float dt, unsigned iters, bool time_solve) {
+                                unsigned m_bound, bool as_given, float dt, unsigned iters, bool time_solve, bool step_scratch_zeroed = false) {
     Counters* c = dctr(ctx);
     ConstraintRows R = rows_view(ctx);
     BodyInfoView BI = body_info(ctx);
@@ -331,9 +359,9 @@ int32_t enqueue_order_and_solve(mgfb_ctx* ctx, const OrderView& O, const Manifol
         ColourView V{};
         V.key = ctx->c_key.as<unsigned long long>(); V.deg = ctx->body_deg.as<unsigned>(); V.body_start = ctx->body_start.as<unsigned>();
         V.csr = ctx->c_csr.as<unsigned>(); V.next = ctx->c_next.as<unsigned>(); V.inbox = ctx->c_inbox.as<unsigned long long>(); V.cap = ctx->row_cap;
-        CU(cudaMemsetAsync(V.deg, 0, (size_t)nb * 4, ctx->stream));
+        if (!step_scratch_zeroed) CU(cudaMemsetAsync(V.deg, 0, (size_t)nb * 4, ctx->stream));
         k_inc_count<<<g, MGFB_THREADS, 0, ctx->stream>>>(O, V, m_ptr, m_host, c);
-        TRY(scan_u32_lb(ctx, V.deg, ctx->body_start.as<unsigned>(), nb, &c->df_links));
+        TRY(scan_u32_lb(ctx, V.deg, ctx->body_start.as<unsigned>(), nb, &c->df_links, step_scratch_zeroed ? step_scan_state(ctx, 1) : nullptr));
         k_inc_fill<<<g, MGFB_THREADS, 0, ctx->stream>>>(O, V, m_ptr, m_host, c);
         k_inc_sort<<<grid_for(ctx, nb), MGFB_THREADS, 0, ctx->stream>>>(O, V, nb, c);
         CU(cudaGetLastError());
@@ -424,13 +452,23 @@ int32_t enqueue_step(mgfb_ctx* ctx, float dt, unsigned iters, bool from_integrat
     Counters* c = dctr(ctx);
     unsigned n = ctx->n;
     BodyArrays B = body_arrays(ctx);
-    CU(cudaMemsetAsync(c, 0, offsetof(Counters, overflow), ctx->stream));
-    CU(cudaMemsetAsync(ctx->body_scratch.p, 0, (size_t)ctx->cap * 12, ctx->stream));
-    CU(cudaMemsetAsync(ctx->group_count.p, 0, (size_t)ctx->group_cap * 4, ctx->stream));
-    CU(cudaMemsetAsync(ctx->cell_count.p, 0, (size_t)ctx->table * 4, ctx->stream));
-    int gb = grid_for(ctx, n);
     const bool tiled = ctx->tiled;
     const unsigned slots = body_slots(ctx);   // upper bound of n_total (device-resident: own + this step's ghosts)
+    {   // the step's scratch, zeroed by ONE kernel (not memsets: see k_zero_ranges)
+        static_assert(offsetof(Counters, overflow) % 4 == 0, "counters are 32-bit words");
+        TRY(ensure(ctx, ctx->scan_step, (step_scan_words(ctx, 0) + step_scan_words(ctx, 1)) * 4));
+        ZeroRanges Z{};
+        auto add = [&](void* p, size_t bytes) { Z.p[Z.n] = reinterpret_cast<unsigned*>(p); Z.words[Z.n] = (unsigned)((bytes + 3) / 4); Z.n++; };
+        add(c, offsetof(Counters, overflow));
+        add(ctx->body_scratch.p, (size_t)ctx->cap * 12);
+        add(ctx->group_count.p, (size_t)ctx->group_cap * 4);
+        add(ctx->cell_count.p, (size_t)ctx->table * 4);
+        add(ctx->scan_step.p, (step_scan_words(ctx, 0) + step_scan_words(ctx, 1)) * 4);
+        add(ctx->body_deg.p, (size_t)slots * 4);
+        if (tiled) add(ctx->edge_mark.p, ctx->n);
+        TRY(zero_ranges(ctx, Z));
+    }
+    int gb = grid_for(ctx, n);
     PROF(MGFB_PHASE_INTEGRATE);
     if (!tiled) {
         if (from_integrate) k_integrate<true, true, true><<<gb, MGFB_THREADS, 0, ctx->stream>>>(B, n, dt, ctx->cfg.fat_margin, c);
@@ -440,7 +478,6 @@ int32_t enqueue_step(mgfb_ctx* ctx, float dt, unsigned iters, bool from_integrat
         ctx->tile_step++;
         ctx->link.step = ctx->tile_step;
         const TileLink& T = ctx->link;
-        CU(cudaMemsetAsync(ctx->edge_mark.p, 0, ctx->n, ctx->stream));
         if ((ctx->tile_step & 0xfffffULL) == 0) CU(cudaMemsetAsync(ctx->tile_df.p, 0, (size_t)ctx->tile_row_cap * 2 * sizeof(Inbox), ctx->stream));
         k_integrate<true, true, true, true><<<gb, MGFB_THREADS, 0, ctx->stream>>>(B, n, dt, ctx->cfg.fat_margin, c);
         k_tile_publish<<<1, 1, 0, ctx->stream>>>(T, c);
@@ -458,7 +495,7 @@ int32_t enqueue_step(mgfb_ctx* ctx, float dt, unsigned iters, bool from_integrat
     PROF(MGFB_PHASE_BODY_GRID);
     BodyGrid G = body_grid(ctx);
     k_bgrid_insert<false><<<gs, MGFB_THREADS, 0, ctx->stream>>>(B.fat, B.col, B.gid, G, c);
-    TRY(scan_u32_lb(ctx, G.cell_count, G.cell_start, ctx->table, &c->grid_entries));
+    TRY(scan_u32_lb(ctx, G.cell_count, G.cell_start, ctx->table, &c->grid_entries, step_scan_state(ctx, 0)));
     k_bgrid_insert<true><<<gs, MGFB_THREADS, 0, ctx->stream>>>(B.fat, B.col, B.gid, G, c);
     PairLists PL; for (int k = 0; k < 4; ++k) PL.p[k] = ctx->pair_list[k].as<int2>();
     PROF(MGFB_PHASE_PAIR_SWEEP);
@@ -499,7 +536,7 @@ int32_t enqueue_step(mgfb_ctx* ctx, float dt, unsigned iters, bool from_integrat
     ManifoldInput M{};
     M.a = L.a; M.b = L.b; M.la = L.la; M.lb = L.lb; M.nt = L.nt; M.user = false;
     M.terrain_center = make_float4(ctx->terrain.x[0], ctx->terrain.x[1], ctx->terrain.x[2], 0.0f);
-    TRY(enqueue_order_and_solve(ctx, O, M, &c->contacts, 0, ctx->contact_cap, false, dt, iters, timed));
+    TRY(enqueue_order_and_solve(ctx, O, M, &c->contacts, 0, ctx->contact_cap, false, dt, iters, timed, true));
     k_step_done<<<1, 64, 0, ctx->stream>>>(c, ctx->ctr_snap);
     CU(cudaGetLastError());
     // k_integrate, 2x k_grid_insert, scan, k_body_pairs, k_step_done (+ terrain, narrowphase)
@@ -667,7 +704,7 @@ void mgfb_ctx_destroy(mgfb_ctx* ctx) {
                   &ctx->c_a, &ctx->c_b, &ctx->c_face, &ctx->c_sub, &ctx->c_la, &ctx->c_lb, &ctx->c_nt, &ctx->body_best, &ctx->body_scratch,
                   &ctx->group, &ctx->group_count, &ctx->group_start, &ctx->perm, &ctx->r_ab, &ctx->r_n, &ctx->r_t0, &ctx->r_t1, &ctx->r_ra,
                   &ctx->r_rb, &ctx->r_imp, &ctx->r_xra, &ctx->r_xrb, &ctx->r_xtm, &ctx->r_dep, &ctx->body_deg, &ctx->body_start, &ctx->r_inc, &ctx->r_next, &ctx->r_in_a, &ctx->r_in_b, &ctx->r_ia, &ctx->c_key, &ctx->c_csr, &ctx->c_next, &ctx->c_inbox, &ctx->cell_count, &ctx->cell_start, &ctx->bg_ent,
-                  &ctx->scan_sums, &ctx->scan_state, &ctx->u_a, &ctx->u_b, &ctx->u_sc, &ctx->u_sf, &ctx->u_n, &ctx->u_t, &ctx->u_nc, &ctx->u_la,
+                  &ctx->scan_sums, &ctx->scan_state, &ctx->scan_step, &ctx->u_a, &ctx->u_b, &ctx->u_sc, &ctx->u_sf, &ctx->u_n, &ctx->u_t, &ctx->u_nc, &ctx->u_la,
                   &ctx->u_lb, &ctx->stage, &ctx->convex_pool, &ctx->terrain.verts, &ctx->terrain.faces, &ctx->terrain.boxes, &ctx->terrain.cell_count,
                   &ctx->terrain.cell_start, &ctx->terrain.ent_id, &ctx->terrain.ent_key, &ctx->terrain.max_bits,
                   &ctx->gid, &ctx->phase_start, &ctx->edge_idx, &ctx->edge_mark, &ctx->ridx, &ctx->mbox, &ctx->edge_slot, &ctx->tile_df};
@@ -681,6 +718,8 @@ void mgfb_ctx_destroy(mgfb_ctx* ctx) {
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
     if (ctx->s_aux) cudaStreamDestroy(ctx->s_aux);
+    for (auto& st : ctx->gjk_streams) if (st) cudaStreamDestroy(st);
+    for (auto& ev : ctx->gjk_ev) if (ev) cudaEventDestroy(ev);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -1243,7 +1282,7 @@ int32_t mgfb_tile_export(mgfb_ctx* ctx, uint32_t ghost_capacity, mgfb_tile_desc*
     TRY(grow_bodies(ctx, ctx->n + ghost_capacity));
     ctx->ghost_cap = ghost_capacity;
     TRY(ensure(ctx, ctx->edge_idx, (size_t)std::max(ctx->n, 1u) * 4));
-    TRY(ensure(ctx, ctx->edge_mark, (size_t)std::max(ctx->n, 1u), false, true));
+    TRY(ensure(ctx, ctx->edge_mark, (size_t)ctx->n + 4, false, true));   // (zeroed in whole words every step)
     TRY(ensure(ctx, ctx->ridx, (size_t)ghost_capacity * 4, false, true));
     TRY(ensure(ctx, ctx->mbox, sizeof(TileMailbox), false, true));
     // every per-step buffer at its final size now: nothing may be reallocated while neighbours hold pointers

@@ -476,15 +476,27 @@ int32_t gjk_batch_impl(mgfb_ctx* ctx, bool separation, const mgfb_shape* a, cons
     cudaMemsetAsync(dsep.p, 0, (size_t)n * 4, ctx->stream);
     cudaMemsetAsync(dcount.p, 0, 64 * 4, ctx->stream);   // [0, 32): items per bin, [32, 64): the bins' work cursors
     int epa_grid = ctx->num_sms * 4;   // 4 x 52 KB polytopes per SM
+    // One EPA run is ONE warp for up to ~10^8 cycles (100 iterations over a polytope of thousands of faces), so a launch lasts
+    // as long as its slowest pair whatever its size: the 25 shape-pair launches run side by side on 8 streams.
+    const int NS = 8;
+    if (!ctx->gjk_streams[0]) {
+        for (int k = 0; k < NS; ++k) if (cudaStreamCreateWithFlags(&ctx->gjk_streams[k], cudaStreamNonBlocking) != cudaSuccess) return done(fail(ctx, MGFB_ERR_CUDA, "cudaStreamCreate"));
+        for (int k = 0; k <= NS; ++k) if (cudaEventCreateWithFlags(&ctx->gjk_ev[k], cudaEventDisableTiming) != cudaSuccess) return done(fail(ctx, MGFB_ERR_CUDA, "cudaEventCreate"));
+    }
+    cudaEventRecord(ctx->gjk_ev[NS], ctx->stream);   // inputs uploaded, outputs cleared
+    for (int k = 0; k < NS; ++k) cudaStreamWaitEvent(ctx->gjk_streams[k], ctx->gjk_ev[NS], 0);
+    int used = 0;
     for (int k = 0; k < NB; ++k) {
         unsigned m = count[k + 1] - count[k];
         if (!m) continue;
+        cudaStream_t bin_stream = ctx->gjk_streams[used++ % NS];
         // each bin's EPA work list is a slice of dwork starting at the bin's first pair
         GJK_TABLE[k / GJK_NK][k % GJK_NK](separation, da.as<mgfb_shape>(), db.as<mgfb_shape>(), di.as<unsigned>() + count[k], m, dout.as<mgfb_contact>(),
                                 dsep.as<float>(), dst.as<unsigned>(), dit.as<unsigned>(), dwork.as<EpaWork>() + (separation ? 0 : count[k]),
-                                dcount.as<unsigned>() + k, dcount.as<unsigned>() + 32 + k, (int)std::min<unsigned>((unsigned)epa_grid, m), ctx->stream);
+                                dcount.as<unsigned>() + k, dcount.as<unsigned>() + 32 + k, (int)std::min<unsigned>((unsigned)epa_grid, m), bin_stream);
         ctx->launches += separation ? 1 : 2;
     }
+    for (int k = 0; k < NS; ++k) { cudaEventRecord(ctx->gjk_ev[k], ctx->gjk_streams[k]); cudaStreamWaitEvent(ctx->stream, ctx->gjk_ev[k], 0); }
     cudaError_t e = cudaGetLastError();
     if (e == cudaSuccess) {
         if (out) cudaMemcpyAsync(out, dout.p, (size_t)n * sizeof(mgfb_contact), cudaMemcpyDeviceToHost, ctx->stream);

@@ -49,7 +49,10 @@ int32_t pipe_init(mgfb_ctx* ctx) {
         for (auto& e : s.ev) CU(cudaEventCreate(&e));
         CU(cudaEventCreateWithFlags(&s.ev_in, cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&s.ev_done, cudaEventDisableTiming));
-        CU(cudaEventCreateWithFlags(&s.ev_out, cudaEventDisableTiming));
+        // mgfb_step_wait sleeps on this one instead of spinning (unless MGFB_PIPE_SPIN=1): with one process per GPU a spinning waiter
+        // per rank takes the cores the other ranks need to keep THEIR launch queues full, and tiles run in lock-step
+        const char* spin = getenv("MGFB_PIPE_SPIN");
+        CU(cudaEventCreateWithFlags(&s.ev_out, cudaEventDisableTiming | ((spin && spin[0] == '1') ? 0u : (unsigned)cudaEventBlockingSync)));
     }
     return MGFB_OK;
 }

@@ -71,10 +71,13 @@ def main():
     hv[:] = 0; hw[:] = 0
     st = L.StepStats()
     g.step(dt, iters, nsteps=3)
-    for depth, with_in, with_out in ((3, True, True), (2, True, True), (4, True, True), (3, False, True), (3, True, False), (3, False, False), (1, True, True)):
+    configs = ((3, True, True), (3, True, True), (2, True, True), (4, True, True), (3, False, True), (3, True, False), (3, False, False), (1, True, True))
+    if os.environ.get("MGFB_DIAG_SHORT") == "1":
+        configs = ((3, True, True), (3, True, True), (4, True, True), (3, False, False))
+    for depth, with_in, with_out in configs:
         outs = [(pin((n, 3)).numpy(), pin((n, 4)).numpy(), pin((n, 3)).numpy(), pin((n, 3)).numpy()) for _ in range(depth)]
         barrier()
-        enq, wai, dev = [], [], []
+        enq, wai, dev, sol = [], [], [], []
         t0 = time.perf_counter()
         waited = 0
         for k in range(steps):
@@ -87,24 +90,25 @@ def main():
             enq.append(tb - ta)
             if k - waited + 1 >= depth:
                 g.ctx.check(lib.mgfb_step_wait(h, C.byref(st))); waited += 1
-                wai.append(time.perf_counter() - tb); dev.append(st.step_ms)
+                wai.append(time.perf_counter() - tb); dev.append(st.step_ms); sol.append(st.solve_ms)
         while waited < steps:
             tb = time.perf_counter()
             g.ctx.check(lib.mgfb_step_wait(h, C.byref(st))); waited += 1
-            wai.append(time.perf_counter() - tb); dev.append(st.step_ms)
+            wai.append(time.perf_counter() - tb); dev.append(st.step_ms); sol.append(st.solve_ms)
         barrier()
         wall = (time.perf_counter() - t0) / steps * 1e3
-        e = np.array(enq) * 1e3; w = np.array(wai) * 1e3; d = np.array(dev)
-        report(f"depth {depth} in {int(with_in)} out {int(with_out)}: wall/step, enqueue mean p99, wait mean p99, device mean p99 (ms):",
-               [wall, e.mean(), np.percentile(e, 99), w.mean(), np.percentile(w, 99), d.mean(), np.percentile(d, 99)])
+        e = np.array(enq) * 1e3; w = np.array(wai) * 1e3; d = np.array(dev); so = np.array(sol)
+        report(f"depth {depth} in {int(with_in)} out {int(with_out)}: wall/step, enqueue mean p99, wait mean p99, device mean p99, solve mean (ms):",
+               [wall, e.mean(), np.percentile(e, 99), w.mean(), np.percentile(w, 99), d.mean(), np.percentile(d, 99), so.mean()])
     # ---- (c) the synchronous call, device-timed, for reference
     barrier()
     t0 = time.perf_counter()
     ms = []
+    sm = []
     for _ in range(steps):
-        ms.append(g.step(dt, iters)["step_ms"])
+        r = g.step(dt, iters); ms.append(r["step_ms"]); sm.append(r["solve_ms"])
     barrier()
-    report("synchronous mgfb_step: wall/step, device mean (ms):", [(time.perf_counter() - t0) / steps * 1e3, float(np.mean(ms))])
+    report("synchronous mgfb_step: wall/step, device mean, solve mean (ms):", [(time.perf_counter() - t0) / steps * 1e3, float(np.mean(ms)), float(np.mean(sm))])
 
 
 if __name__ == "__main__":
