@@ -76,6 +76,7 @@ struct mgfb_ctx {
     Counters* ctr_snap = nullptr;         // pipelined step being enqueued: where k_step_done leaves a copy of its counters
     cudaEvent_t* cur_ev = nullptr;        // the four timing events of the step being enqueued (ev, or a pipeline slot's)
     struct PipeSlot* pipe = nullptr;     // mgfb_step_enqueue / mgfb_step_wait (pipeline.cuh)
+    struct PipeSlot* pipe_pending = nullptr;   // queued step whose host transfers have not been issued yet (pipeline.cuh)
     struct RefOrderState* reforder = nullptr;   // World::step in the reference's own constraint order (reforder.cuh)
     cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
     cudaStream_t gjk_streams[8] = {};     // GJK/EPA batch: the per-shape-pair launches run side by side (an EPA run is one warp for up to ~0.1 s)

@@ -30,7 +30,7 @@ void pipe_destroy(mgfb_ctx* ctx) {
         if (s.ev_done) cudaEventDestroy(s.ev_done);
         if (s.ev_out) cudaEventDestroy(s.ev_out);
     }
-    delete[] ctx->pipe; ctx->pipe = nullptr;
+    delete[] ctx->pipe; ctx->pipe = nullptr; ctx->pipe_pending = nullptr;
     if (ctx->s_h2d) cudaStreamDestroy(ctx->s_h2d);
     if (ctx->s_d2h) cudaStreamDestroy(ctx->s_d2h);
     ctx->s_h2d = ctx->s_d2h = nullptr;
@@ -59,6 +59,33 @@ int32_t pipe_init(mgfb_ctx* ctx) {
 }  // namespace
 
 namespace {
+// Host transfers of a queued step's results: after its own kernels (ev_done) and, when `after` is given, not before that
+// event.  Nothing host-bound sits in the step's own stream (the one D2H copy engine is busy with the previous step's state
+// for 0.1-0.4 ms, and a copy queued behind it there would hold the next step back by as much).
+// On a TILED world the transfers of step k are held until step k+1 reaches its solver (`after` = that step's solve-begin
+// event), and the inputs of step k+2 likewise: the front half of a step is a chain of peer hand-shakes (ghosts, link tables),
+// each a system-scope fence + flag, and a fence issued while PCIe is saturated by a 5 MB transfer waits for it (measured on
+// 8 GPUs sharing PCIe: +0.3 ms of device time per step with the transfers running freely, tools/e2e_diag.py); the solver's
+// own peer hand-overs are fence-free (one 32-byte store each) and do not care.
+bool pipe_defer(const mgfb_ctx* ctx) {
+    static const int env = [] { const char* e = getenv("MGFB_PIPE_DEFER"); return e ? (e[0] == '1' ? 1 : 0) : -1; }();
+    return env < 0 ? ctx->tiled : env == 1;
+}
+int32_t pipe_issue_d2h(mgfb_ctx* ctx, PipeSlot& s, cudaEvent_t after) {
+    const unsigned n = ctx->n;
+    float* sx = s.out.as<float>(); float* sq = sx + (size_t)3 * n; float* sv = sq + (size_t)4 * n; float* sw = sv + (size_t)3 * n;
+    CU(cudaStreamWaitEvent(ctx->s_d2h, s.ev_done, 0));
+    if (after) CU(cudaStreamWaitEvent(ctx->s_d2h, after, 0));
+    CU(cudaMemcpyAsync(s.h_ctr, s.d_ctr, sizeof(Counters), cudaMemcpyDeviceToHost, ctx->s_d2h));
+    if (s.x_out) CU(cudaMemcpyAsync(s.x_out, sx, (size_t)n * 12, cudaMemcpyDeviceToHost, ctx->s_d2h));
+    if (s.q_out) CU(cudaMemcpyAsync(s.q_out, sq, (size_t)n * 16, cudaMemcpyDeviceToHost, ctx->s_d2h));
+    if (s.v_out) CU(cudaMemcpyAsync(s.v_out, sv, (size_t)n * 12, cudaMemcpyDeviceToHost, ctx->s_d2h));
+    if (s.w_out) CU(cudaMemcpyAsync(s.w_out, sw, (size_t)n * 12, cudaMemcpyDeviceToHost, ctx->s_d2h));
+    CU(cudaEventRecord(s.ev_out, ctx->s_d2h));
+    if (ctx->pipe_pending == &s) ctx->pipe_pending = nullptr;
+    return MGFB_OK;
+}
+int32_t pipe_flush_pending(mgfb_ctx* ctx) { return ctx->pipe_pending ? pipe_issue_d2h(ctx, *ctx->pipe_pending, nullptr) : (int32_t)MGFB_OK; }
 // Device side of one queued step: [inputs applied] -> step -> counters -> pack -> D2H.  `from_integrate` = false re-runs only the
 // part after integration (the step overflowed a work list after integrating; the lists have been regrown since).
 int32_t pipe_launch(mgfb_ctx* ctx, PipeSlot& s, bool from_integrate) {
@@ -84,15 +111,11 @@ int32_t pipe_launch(mgfb_ctx* ctx, PipeSlot& s, bool from_integrate) {
     }
     CU(cudaGetLastError());
     CU(cudaEventRecord(s.ev_done, ctx->stream));
-    CU(cudaStreamWaitEvent(ctx->s_d2h, s.ev_done, 0));
-    // nothing host-bound sits in the step's own stream: the one D2H copy engine is busy with the previous step's state for
-    // ~0.1-0.2 ms, and a copy queued behind it there would hold the next step back by as much
-    CU(cudaMemcpyAsync(s.h_ctr, s.d_ctr, sizeof(Counters), cudaMemcpyDeviceToHost, ctx->s_d2h));
-    if (s.x_out) CU(cudaMemcpyAsync(s.x_out, sx, (size_t)n * 12, cudaMemcpyDeviceToHost, ctx->s_d2h));
-    if (s.q_out) CU(cudaMemcpyAsync(s.q_out, sq, (size_t)n * 16, cudaMemcpyDeviceToHost, ctx->s_d2h));
-    if (s.v_out) CU(cudaMemcpyAsync(s.v_out, sv, (size_t)n * 12, cudaMemcpyDeviceToHost, ctx->s_d2h));
-    if (s.w_out) CU(cudaMemcpyAsync(s.w_out, sw, (size_t)n * 12, cudaMemcpyDeviceToHost, ctx->s_d2h));
-    CU(cudaEventRecord(s.ev_out, ctx->s_d2h));
+    if (pipe_defer(ctx)) {
+        // tiled world: the previous step's state goes to the host while THIS step's solver runs (see pipe_issue_d2h)
+        if (ctx->pipe_pending && ctx->pipe_pending != &s) TRY(pipe_issue_d2h(ctx, *ctx->pipe_pending, s.ev[2]));
+        ctx->pipe_pending = &s;
+    } else TRY(pipe_issue_d2h(ctx, s, nullptr));
     return MGFB_OK;
 }
 int32_t pipe_ensure_lists(mgfb_ctx* ctx) {
@@ -124,6 +147,7 @@ int32_t mgfb_step_enqueue(mgfb_ctx* ctx, float dt, uint32_t iters, uint32_t inpu
     s.x_out = x_out; s.q_out = q_out; s.v_out = v_out; s.w_out = omega_out;
     if (v_in) {
         float* sv = s.in.as<float>(); float* sw = sv + (size_t)3 * n;
+        if (pipe_defer(ctx) && ctx->pipe_pending) CU(cudaStreamWaitEvent(ctx->s_h2d, ctx->pipe_pending->ev[2], 0));   // ride the youngest queued step's solver
         CU(cudaMemcpyAsync(sv, v_in, (size_t)n * 12, cudaMemcpyHostToDevice, ctx->s_h2d));
         CU(cudaMemcpyAsync(sw, omega_in, (size_t)n * 12, cudaMemcpyHostToDevice, ctx->s_h2d));
         CU(cudaEventRecord(s.ev_in, ctx->s_h2d));
@@ -138,12 +162,14 @@ int32_t mgfb_step_wait(mgfb_ctx* ctx, mgfb_step_stats* stats) {
     if (!ctx->pipe || ctx->pipe_inflight == 0) return fail(ctx, MGFB_ERR_STATE, "no step in flight");
     CU(cudaSetDevice(ctx->device));
     PipeSlot& s = ctx->pipe[ctx->pipe_head % MGFB_PIPE_DEPTH];
+    if (ctx->pipe_pending == &s) TRY(pipe_flush_pending(ctx));   // no younger step was queued behind it: nothing to wait for
     CU(cudaEventSynchronize(s.ev_out));
     auto drain = [&]() {   // after a sticky flag every queued kernel is a no-op: wait them out
+        pipe_flush_pending(ctx);
         for (unsigned k = 1; k < ctx->pipe_inflight; ++k) cudaEventSynchronize(ctx->pipe[(ctx->pipe_head + k) % MGFB_PIPE_DEPTH].ev_out);
         cudaStreamSynchronize(ctx->stream);
     };
-    auto drop_all = [&]() { ctx->pipe_head += ctx->pipe_inflight; ctx->pipe_inflight = 0; };
+    auto drop_all = [&]() { ctx->pipe_head += ctx->pipe_inflight; ctx->pipe_inflight = 0; ctx->pipe_pending = nullptr; };
     unsigned overflowed = 0;
     if (ctx->tiled && !(s.h_ctr->nan_bounds | s.h_ctr->overflow) && s.h_ctr->comm_error) {   // same reports as mgfb_step_n
         const unsigned ce = s.h_ctr->comm_error;
@@ -174,6 +200,7 @@ int32_t mgfb_step_wait(mgfb_ctx* ctx, mgfb_step_stats* stats) {
             TRY(clear_sticky(ctx));
             TRY(pipe_ensure_lists(ctx));
             TRY(pipe_launch(ctx, s, false));
+            TRY(pipe_flush_pending(ctx));
             CU(cudaEventSynchronize(s.ev_out));
             if (s.h_ctr->nan_bounds) { drop_all(); clear_sticky(ctx); return fail(ctx, MGFB_ERR_NAN_BOUNDS, "AABB::combine: r >= 0 violated (bounds.rs:125-127)"); }
             if (!s.h_ctr->overflow) break;
