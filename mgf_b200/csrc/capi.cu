@@ -410,10 +410,8 @@ int32_t enqueue_order_and_solve(mgfb_ctx* ctx, const OrderView& O, const Manifol
         // were cleared at step start whenever the 2^20-step cycle restarts)
         epoch = 0x80000000u | (unsigned)((ctx->tile_step & 0xfffffULL) << 11);
         k_tile_links_send<<<1, 1024, 0, ctx->stream>>>(TL, D, R.ab, c);
-        if (TL.has_left) k_tile_wait<<<1, 1, 0, ctx->stream>>>(&TL.mine->links_from_left.flag, TL.step, TL.timeout_ns, c);
-        if (TL.has_right) k_tile_wait<<<1, 1, 0, ctx->stream>>>(&TL.mine->links_from_right.flag, TL.step, TL.timeout_ns, c);
-        k_df_init<true><<<g, MGFB_THREADS, 0, ctx->stream>>>(vel, nb, R.ab, D, epoch, m_ptr, m_host, c, TL);
-        ctx->launches += 2 + (TL.has_left ? 1 : 0) + (TL.has_right ? 1 : 0);
+        k_df_init<true><<<g, MGFB_THREADS, 0, ctx->stream>>>(vel, nb, R.ab, D, epoch, m_ptr, m_host, c, TL);   // waits for both neighbours' link tables itself
+        ctx->launches += 2;
     }
     CU(cudaGetLastError());
     if (time_solve) CU(cudaEventRecord(ctx->cur_ev[2], ctx->stream));
@@ -482,13 +480,9 @@ int32_t enqueue_step(mgfb_ctx* ctx, float dt, unsigned iters, bool from_integrat
         if ((ctx->tile_step & 0xfffffULL) == 0) CU(cudaMemsetAsync(ctx->tile_df.p, 0, (size_t)ctx->tile_row_cap * 2 * sizeof(Inbox), ctx->stream));
         k_integrate<true, true, true, true><<<gb, MGFB_THREADS, 0, ctx->stream>>>(B, n, dt, ctx->cfg.fat_margin, c);
         k_tile_publish<<<1, 1, 0, ctx->stream>>>(T, c);
-        if (T.has_left) {
-            k_tile_wait<<<1, 1, 0, ctx->stream>>>(&T.mine->xr.flag, T.step, T.timeout_ns, c);
-            k_ghost_send<<<gb, 256, 0, ctx->stream>>>(B, T, c);
-        }
-        if (T.has_right) k_tile_wait<<<1, 1, 0, ctx->stream>>>(&T.mine->ghosts.flag, T.step, T.timeout_ns, c);
-        k_ghost_recv<<<grid_for(ctx, std::max(ctx->ghost_cap, 1u)), 256, 0, ctx->stream>>>(B, T, c);
-        ctx->launches += 2 + (T.has_left ? 2 : 0) + (T.has_right ? 1 : 0);
+        if (T.has_left) k_ghost_send<<<gb, 256, 0, ctx->stream>>>(B, T, c);   // waits for the left extent itself
+        k_ghost_recv<<<grid_for(ctx, std::max(ctx->ghost_cap, 1u)), 256, 0, ctx->stream>>>(B, T, c);   // waits for the right neighbour's ghosts itself
+        ctx->launches += 2 + (T.has_left ? 1 : 0);
     }
     int gs = grid_for(ctx, slots);
     if (ctx->terrain.present) CU(cudaEventRecord(ctx->ev_fork, ctx->stream));   // tight boxes are final: the terrain half may start

@@ -1268,7 +1268,13 @@ __global__ void __launch_bounds__(MGFB_THREADS) k_df_init(const BodyVel* __restr
                                                          unsigned epoch, const unsigned* m_ptr, unsigned m_host, Counters* ctr, TileLink T) {
     if (ctr->overflow | ctr->nan_bounds) return;
     if (ctr->ngroups > 64u) return;   // k_solve takes this step
-    if (TILED) n = ctr->n_total;
+    if (TILED) {
+        n = ctr->n_total;
+        // the neighbours' link tables (k_tile_links_send over there): every CTA waits for the flags itself
+        if (T.has_left) tile_wait_cta(&T.mine->links_from_left.flag, T.step, T.timeout_ns, ctr);
+        if (T.has_right) tile_wait_cta(&T.mine->links_from_right.flag, T.step, T.timeout_ns, ctr);
+        if (*reinterpret_cast<volatile unsigned*>(&ctr->comm_error) & COMM_TIMEOUT) return;
+    }
     const unsigned tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
     for (unsigned i = tid; i < n; i += nth) {
         unsigned s0 = D.body_start[i], s1 = D.body_start[i + 1];

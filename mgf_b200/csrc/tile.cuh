@@ -122,8 +122,12 @@ __global__ void k_tile_wait(const unsigned long long* flag, unsigned long long t
 // neighbour's right extent is written into the neighbour's arrays at n_own_left + k.
 __global__ void __launch_bounds__(256) k_ghost_send(BodyArrays B, TileLink T, Counters* ctr) {
     if (ctr->overflow | ctr->nan_bounds | ctr->comm_error) return;
+    // every CTA waits for the left neighbour's extent itself (one launch less than a wait kernel in front)
+    tile_wait_cta(&T.mine->xr.flag, T.step, T.timeout_ns, ctr);
+    if (*reinterpret_cast<volatile unsigned*>(&ctr->comm_error)) return;
     const float xr = T.mine->xr.f;
     const TilePeer& P = T.left;
+    bool wrote = false;
     for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < T.n_own; i += gridDim.x * blockDim.x) {
         Box fb = B.fat[i];
         float lo = fb.c.x - fb.r.x;
@@ -143,9 +147,12 @@ __global__ void __launch_bounds__(256) k_ghost_send(BodyArrays B, TileLink T, Co
         P.col[d] = B.col[i]; P.tight[d] = B.tight[i]; P.fat[d] = fb;
         P.gid[d] = B.gid[i];
         P.ridx[k] = i;
+        wrote = true;
     }
-    // last block done -> publish the count
-    __threadfence_system();
+    // last block done -> publish the count.  Only warps that wrote to the neighbour pay for a system-scope fence (a few
+    // hundred of 100 k bodies are edge bodies); the chain writer fence -> CTA barrier -> blocks_done -> last block's fence +
+    // release orders every ghost record before the flag (fences are cumulative).
+    if (__any_sync(0xffffffffu, wrote)) __threadfence_system();
     __syncthreads();
     if (threadIdx.x == 0) {
         __threadfence();
@@ -163,6 +170,7 @@ __global__ void __launch_bounds__(256) k_ghost_send(BodyArrays B, TileLink T, Co
 // n_total and folds the ghosts' extents into the grid cell size.
 __global__ void __launch_bounds__(256) k_ghost_recv(BodyArrays B, TileLink T, Counters* ctr) {
     if (ctr->overflow | ctr->nan_bounds) return;
+    if (T.has_right) tile_wait_cta(&T.mine->ghosts.flag, T.step, T.timeout_ns, ctr);   // the right neighbour's ghosts are in
     unsigned ng = T.has_right ? min(T.mine->ghosts.u, T.ghost_cap) : 0u;
     if (blockIdx.x == 0 && threadIdx.x == 0) ctr->n_total = T.n_own + ng;
     float my_fat = 0.0f, my_tight = 0.0f;

@@ -74,6 +74,8 @@ def main():
     configs = ((3, True, True), (3, True, True), (2, True, True), (4, True, True), (3, False, True), (3, True, False), (3, False, False), (1, True, True))
     if os.environ.get("MGFB_DIAG_SHORT") == "1":
         configs = ((3, True, True), (3, True, True), (4, True, True), (3, False, False))
+    if os.environ.get("MGFB_DIAG_SHORT") == "2":
+        configs = ((3, True, True), (3, True, True))
     for depth, with_in, with_out in configs:
         outs = [(pin((n, 3)).numpy(), pin((n, 4)).numpy(), pin((n, 3)).numpy(), pin((n, 3)).numpy()) for _ in range(depth)]
         barrier()
@@ -100,6 +102,16 @@ def main():
         e = np.array(enq) * 1e3; w = np.array(wai) * 1e3; d = np.array(dev); so = np.array(sol)
         report(f"depth {depth} in {int(with_in)} out {int(with_out)}: wall/step, enqueue mean p99, wait mean p99, device mean p99, solve mean (ms):",
                [wall, e.mean(), np.percentile(e, 99), w.mean(), np.percentile(w, 99), d.mean(), np.percentile(d, 99), so.mean()])
+    # ---- per-phase device time of the synchronous step (mgfb_step_profile), every rank
+    acc = {}
+    for _ in range(20):
+        _, pr = g.step_profile(dt, iters)
+        for k, v in pr.items():
+            if isinstance(v, float):
+                acc[k] = acc.get(k, 0.0) + v / 20
+    if rank == 0:
+        print("phases:", " ".join(acc.keys()), flush=True)
+    report("phase ms per rank:", [acc[k] for k in acc])
     # ---- (c) the synchronous call, device-timed, for reference
     barrier()
     t0 = time.perf_counter()
