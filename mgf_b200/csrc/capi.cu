@@ -72,6 +72,9 @@ struct mgfb_ctx {
     // cooperative grid sizes
     int coop_order = 0, coop_solve = 0, coop_df = 0, coop_colour = 0;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    // coherent broadphase (bpcache.cuh): on unless MGFB_BROADPHASE=sweep
+    bool bp_on = true, bp_invalidate = true;
+    Buf bp_state, bp_s[2], bp_stale, bp_c0, bp_ovf, bp_ref_flag, bp_ref_list; unsigned bp_s_cap = 0, bp_slots = 0;
     Buf scan_step;                        // the two look-back scan states of one step (zeroed with the step's scratch)
     Counters* ctr_snap = nullptr;         // pipelined step being enqueued: where k_step_done leaves a copy of its counters
     cudaEvent_t* cur_ev = nullptr;        // the four timing events of the step being enqueued (ev, or a pipeline slot's)
@@ -158,7 +161,17 @@ BodyArrays body_arrays(const mgfb_ctx* ctx) {
     B.force = ctx->force.as<float4>(); B.torque = ctx->torque.as<float4>(); B.imb = ctx->imb.as<float4>();
     B.col = ctx->col.as<Collider>(); B.tight = ctx->tight.as<Box>(); B.fat = ctx->fat.as<Box>();
     B.gid = ctx->gid.as<unsigned>();
+    B.ref_flag = nullptr; B.ref_list = nullptr; B.ref_cap = 0;
+    if (ctx->bp_on && ctx->bp_ref_flag.p) { B.ref_flag = ctx->bp_ref_flag.as<unsigned char>(); B.ref_list = ctx->bp_ref_list.as<unsigned>(); B.ref_cap = BP_REF_CAP; }
     return B;
+}
+BpView bp_view(const mgfb_ctx* ctx) {
+    BpView V;
+    V.st = ctx->bp_state.as<BpState>();
+    V.S[0] = ctx->bp_s[0].as<int2>(); V.S[1] = ctx->bp_s[1].as<int2>(); V.s_cap = ctx->bp_s_cap;
+    V.stale = ctx->bp_stale.as<unsigned char>(); V.c0 = ctx->bp_c0.as<float4>(); V.ovf = ctx->bp_ovf.as<unsigned>(); V.ovf_cap = BP_OVF_CAP;
+    V.ref_flag = ctx->bp_ref_flag.as<unsigned char>(); V.ref_list = ctx->bp_ref_list.as<unsigned>(); V.ref_cap = BP_REF_CAP;
+    return V;
 }
 // bodies this ctx may hold in a step: its own plus the ghosts a tiled world sends it
 unsigned body_slots(const mgfb_ctx* ctx) { return ctx->n + ctx->ghost_cap; }
@@ -189,6 +202,16 @@ int32_t ensure_step_buffers(mgfb_ctx* ctx, unsigned scale) {
     unsigned pc = n * 8 * scale, tc = n * 8 * scale, cc = n * 8 * scale;
     if (pc > ctx->pair_cap) { for (auto& b : ctx->pair_list) TRY(ensure(ctx, b, (size_t)pc * sizeof(int2))); ctx->pair_cap = pc; }
     if (tc > ctx->tpair_cap) { for (auto& b : ctx->tpair_list) TRY(ensure(ctx, b, (size_t)tc * sizeof(int2))); ctx->tpair_cap = tc; }
+    if (ctx->bp_on) {   // the cached superset S (two buffers), stale marks, overflow list, this step's replaced bodies
+        unsigned sc = n * 16 * scale, slots = body_slots(ctx);
+        if (sc > ctx->bp_s_cap) { for (auto& b : ctx->bp_s) TRY(ensure(ctx, b, (size_t)sc * sizeof(int2))); ctx->bp_s_cap = sc; ctx->bp_invalidate = true; }
+        if (slots > ctx->bp_slots || !ctx->bp_state.p) {
+            TRY(ensure(ctx, ctx->bp_stale, (size_t)slots + 4, false, true)); TRY(ensure(ctx, ctx->bp_c0, (size_t)slots * 16)); TRY(ensure(ctx, ctx->bp_ref_flag, (size_t)slots + 4, false, true));
+            TRY(ensure(ctx, ctx->bp_ovf, (size_t)BP_OVF_CAP * 4)); TRY(ensure(ctx, ctx->bp_ref_list, (size_t)BP_REF_CAP * 4));
+            TRY(ensure(ctx, ctx->bp_state, sizeof(BpState), false, true));
+            ctx->bp_slots = slots; ctx->bp_invalidate = true;
+        }
+    }
     if (cc > ctx->contact_cap) {
         TRY(ensure(ctx, ctx->c_a, (size_t)cc * 4)); TRY(ensure(ctx, ctx->c_b, (size_t)cc * 4));
         TRY(ensure(ctx, ctx->c_face, (size_t)cc * 4)); TRY(ensure(ctx, ctx->c_sub, (size_t)cc * 4));
@@ -465,6 +488,10 @@ int32_t enqueue_step(mgfb_ctx* ctx, float dt, unsigned iters, bool from_integrat
         add(ctx->scan_step.p, (step_scan_words(ctx, 0) + step_scan_words(ctx, 1)) * 4);
         add(ctx->body_deg.p, (size_t)slots * 4);
         if (tiled) add(ctx->edge_mark.p, ctx->n);
+        if (ctx->bp_on) {
+            add(ctx->bp_ref_flag.p, slots);
+            if (ctx->bp_invalidate) { add(&ctx->bp_state.as<BpState>()->valid, 4); ctx->bp_invalidate = false; }   // rebuild from scratch this step
+        }
         TRY(zero_ranges(ctx, Z));
     }
     int gb = grid_for(ctx, n);
@@ -489,15 +516,42 @@ int32_t enqueue_step(mgfb_ctx* ctx, float dt, unsigned iters, bool from_integrat
     // broadphase over the stored fat boxes
     PROF(MGFB_PHASE_BODY_GRID);
     BodyGrid G = body_grid(ctx);
+    PairLists PL; for (int k = 0; k < 4; ++k) PL.p[k] = ctx->pair_list[k].as<int2>();
+    if (ctx->bp_on) {
+        // coherent broadphase (bpcache.cuh): the device picks this step's path; the kernels of the other one return at once
+        BpView V = bp_view(ctx);
+        const int gn = grid_for(ctx, slots);
+        k_bp_decide<<<1, 1, 0, ctx->stream>>>(V, c, n);
+        // -- rebuild: grid over the own bodies' fat boxes; one sweep writes S and this step's pair lists
+        k_bp_grid<false><<<gn, MGFB_THREADS, 0, ctx->stream>>>(B.fat, B.col, B.gid, n, G, V, c);
+        {
+            unsigned nbk = (ctx->table + SCAN_ITEMS - 1) / SCAN_ITEMS;
+            k_scan_lookback<<<nbk, 256, 0, ctx->stream>>>(G.cell_count, ctx->table, G.cell_start, step_scan_state(ctx, 0), &c->grid_entries, &V.st->mode, (unsigned)BP_COHERENT);
+        }
+        k_bp_grid<true><<<gn, MGFB_THREADS, 0, ctx->stream>>>(B.fat, B.col, B.gid, n, G, V, c);
+        {
+            int gw = std::max(1, std::min((int)((slots + BP_WARPS * BP_PER - 1) / (BP_WARPS * BP_PER)), ctx->num_sms * 8));
+            if (ctx->max_ctas) gw = std::min(gw, ctx->max_ctas * 4);
+            k_body_pairs_warp<true><<<gw, MGFB_THREADS, 0, ctx->stream>>>(B.tight, B.col, B.gid, tiled ? n : 0xffffffffu, G, PL, ctx->pair_cap, c, V, n);
+        }
+        PROF(MGFB_PHASE_PAIR_SWEEP);
+        // -- coherent: S -> this step's pair lists; both: replaced bodies and ghosts queried against the cached grid
+        k_bp_mark<<<grid_for(ctx, BP_REF_CAP), MGFB_THREADS, 0, ctx->stream>>>(B.fat, V, c);
+        k_bp_filter<<<grid_for(ctx, (size_t)ctx->bp_s_cap / BP_FILTER_ITEMS / 4 + 1), MGFB_THREADS, 0, ctx->stream>>>(B.tight, B.fat, V, PL, ctx->pair_cap, c);
+        k_bp_query<<<grid_for(ctx, (size_t)(BP_REF_CAP / 4 + ctx->ghost_cap) * 32), MGFB_THREADS, 0, ctx->stream>>>(B.tight, B.fat, B.col, B.gid, n, G, V, PL, ctx->pair_cap, c);
+        k_bp_query_ovf<<<ctx->num_sms * 4, MGFB_THREADS, 0, ctx->stream>>>(B.tight, B.fat, B.col, B.gid, n, V, PL, ctx->pair_cap, c);
+        k_bp_finish<<<1, 1, 0, ctx->stream>>>(V, c);
+        ctx->launches += 6;   // (10 launches where the sweep path has 4)
+    } else {
     k_bgrid_insert<false><<<gs, MGFB_THREADS, 0, ctx->stream>>>(B.fat, B.col, B.gid, G, c);
     TRY(scan_u32_lb(ctx, G.cell_count, G.cell_start, ctx->table, &c->grid_entries, step_scan_state(ctx, 0)));
     k_bgrid_insert<true><<<gs, MGFB_THREADS, 0, ctx->stream>>>(B.fat, B.col, B.gid, G, c);
-    PairLists PL; for (int k = 0; k < 4; ++k) PL.p[k] = ctx->pair_list[k].as<int2>();
     PROF(MGFB_PHASE_PAIR_SWEEP);
     {
         int gw = std::max(1, std::min((int)((slots + BP_WARPS * BP_PER - 1) / (BP_WARPS * BP_PER)), ctx->num_sms * 8));
         if (ctx->max_ctas) gw = std::min(gw, ctx->max_ctas * 4);
-        k_body_pairs_warp<<<gw, MGFB_THREADS, 0, ctx->stream>>>(B.tight, B.col, B.gid, tiled ? n : 0xffffffffu, G, PL, ctx->pair_cap, c);
+        k_body_pairs_warp<false><<<gw, MGFB_THREADS, 0, ctx->stream>>>(B.tight, B.col, B.gid, tiled ? n : 0xffffffffu, G, PL, ctx->pair_cap, c, BpView{}, 0u);
+    }
     }
     ContactList L = contact_list(ctx);
     TerrainView T{};
@@ -546,6 +600,7 @@ int32_t read_counters(mgfb_ctx* ctx) {
     return MGFB_OK;
 }
 int32_t clear_sticky(mgfb_ctx* ctx) {
+    ctx->bp_invalidate = true;   // whatever tripped the flag, the cached broadphase starts over (bpcache.cuh)
     CU(cudaMemsetAsync(reinterpret_cast<char*>(dctr(ctx)) + offsetof(Counters, overflow), 0, 8, ctx->stream));
     return MGFB_OK;
 }
@@ -619,6 +674,7 @@ int32_t mgfb_ctx_create(const mgfb_config* cfg, mgfb_ctx** out) {
     *out = nullptr;
     mgfb_ctx* ctx = new mgfb_ctx();
     if (cfg) ctx->cfg = *cfg; else mgfb_config_default(&ctx->cfg);
+    { const char* e = getenv("MGFB_BROADPHASE"); ctx->bp_on = !(e && std::strcmp(e, "sweep") == 0); }   // "sweep": grid + sweep every step (A/B)
     ctx->device = ctx->cfg.device;
     auto bail = [&](cudaError_t e, const char* what) {
         g_create_err = std::string(what) + ": " + cudaGetErrorString(e);
@@ -651,12 +707,14 @@ int32_t mgfb_ctx_create(const mgfb_config* cfg, mgfb_ctx** out) {
                              (const void*)k_integrate<false, false, true, false>, (const void*)k_tile_publish, (const void*)k_tile_wait,
                              (const void*)k_ghost_send, (const void*)k_ghost_recv, (const void*)k_bgrid_insert<false>,
                              (const void*)k_bgrid_insert<true>, (const void*)k_scan_reduce, (const void*)k_scan_sums, (const void*)k_scan_final, (const void*)k_scan_lookback,
-                             (const void*)k_body_pairs_warp, (const void*)k_terrain_pairs, (const void*)k_narrow_bodies<0, 0>,
+                             (const void*)k_body_pairs_warp<false>, (const void*)k_terrain_pairs, (const void*)k_narrow_bodies<0, 0>,
                              (const void*)k_narrow_bodies<0, 1>, (const void*)k_narrow_bodies<1, 0>, (const void*)k_narrow_bodies<1, 1>,
                              (const void*)k_narrow_terrain<0>, (const void*)k_narrow_terrain<1>, (const void*)k_order, (const void*)k_group_scan,
                              (const void*)k_scatter_rows, (const void*)k_build_rows, (const void*)k_solve<false>, (const void*)k_solve<true>,
                              (const void*)k_solve_df<false>, (const void*)k_solve_df<true>, (const void*)k_df_init<false>, (const void*)k_df_init<true>,
                              (const void*)k_tile_links_send, (const void*)k_tile_solve_done, (const void*)k_inc_count, (const void*)k_inc_fill, (const void*)k_inc_sort, (const void*)k_colour_df,
+                             (const void*)k_zero_ranges, (const void*)k_bp_decide, (const void*)k_bp_finish, (const void*)k_bp_grid<false>, (const void*)k_bp_grid<true>,
+                             (const void*)k_body_pairs_warp<true>, (const void*)k_bp_mark, (const void*)k_bp_filter, (const void*)k_bp_query, (const void*)k_bp_query_ovf,
                              (const void*)k_step_done, (const void*)k_pack_state, (const void*)k_set_velocity<false>, (const void*)k_set_velocity<true>, (const void*)k_set_state};
         cudaFuncAttributes fa;
         for (const void* f : fns) if ((e = cudaFuncGetAttributes(&fa, f)) != cudaSuccess) return bail(e, "cudaFuncGetAttributes");
@@ -699,7 +757,7 @@ void mgfb_ctx_destroy(mgfb_ctx* ctx) {
                   &ctx->c_a, &ctx->c_b, &ctx->c_face, &ctx->c_sub, &ctx->c_la, &ctx->c_lb, &ctx->c_nt, &ctx->body_best, &ctx->body_scratch,
                   &ctx->group, &ctx->group_count, &ctx->group_start, &ctx->perm, &ctx->r_ab, &ctx->r_n, &ctx->r_t0, &ctx->r_t1, &ctx->r_ra,
                   &ctx->r_rb, &ctx->r_imp, &ctx->r_xra, &ctx->r_xrb, &ctx->r_xtm, &ctx->r_dep, &ctx->body_deg, &ctx->body_start, &ctx->r_inc, &ctx->r_next, &ctx->r_in_a, &ctx->r_in_b, &ctx->r_ia, &ctx->c_key, &ctx->c_csr, &ctx->c_next, &ctx->c_inbox, &ctx->cell_count, &ctx->cell_start, &ctx->bg_ent,
-                  &ctx->scan_sums, &ctx->scan_state, &ctx->scan_step, &ctx->u_a, &ctx->u_b, &ctx->u_sc, &ctx->u_sf, &ctx->u_n, &ctx->u_t, &ctx->u_nc, &ctx->u_la,
+                  &ctx->scan_sums, &ctx->scan_state, &ctx->scan_step, &ctx->bp_state, &ctx->bp_s[0], &ctx->bp_s[1], &ctx->bp_stale, &ctx->bp_c0, &ctx->bp_ovf, &ctx->bp_ref_flag, &ctx->bp_ref_list, &ctx->u_a, &ctx->u_b, &ctx->u_sc, &ctx->u_sf, &ctx->u_n, &ctx->u_t, &ctx->u_nc, &ctx->u_la,
                   &ctx->u_lb, &ctx->stage, &ctx->convex_pool, &ctx->terrain.verts, &ctx->terrain.faces, &ctx->terrain.boxes, &ctx->terrain.cell_count,
                   &ctx->terrain.cell_start, &ctx->terrain.ent_id, &ctx->terrain.ent_key, &ctx->terrain.max_bits,
                   &ctx->gid, &ctx->phase_start, &ctx->edge_idx, &ctx->edge_mark, &ctx->ridx, &ctx->mbox, &ctx->edge_slot, &ctx->tile_df};
@@ -733,6 +791,7 @@ int32_t mgfb_bodies_count(const mgfb_ctx* ctx, uint32_t* n) {
 
 int32_t mgfb_bodies_add(mgfb_ctx* ctx, uint32_t n, const mgfb_shape* shapes, const float* mass, const float* restitution,
                         const float* friction, const float* world_force, uint32_t* first_id) {
+    if (ctx) ctx->bp_invalidate = true;   // the stored fat boxes / the body set change under the cached broadphase
     if (!ctx) return MGFB_ERR_INVALID_ARG;
     if (n == 0) { if (first_id) *first_id = ctx->n; return MGFB_OK; }
     if (!shapes || !mass || !restitution || !friction || !world_force) return fail(ctx, MGFB_ERR_INVALID_ARG, "null input array");
@@ -894,6 +953,7 @@ int32_t mgfb_bodies_get_fat_bounds(mgfb_ctx* ctx, uint32_t first, uint32_t n, fl
 
 int32_t mgfb_bodies_set_state(mgfb_ctx* ctx, uint32_t first, uint32_t n, const float* x, const float* q, const float* v, const float* omega,
                               const mgfb_shape* colliders, const float* fat_boxes) {
+    if (ctx) ctx->bp_invalidate = true;   // the stored fat boxes / the body set change under the cached broadphase
     if (!ctx || (uint64_t)first + n > ctx->n) return fail(ctx, MGFB_ERR_INVALID_ARG, "body range out of bounds");
     if (n == 0) return MGFB_OK;
     if (ctx->pipe_inflight) return fail(ctx, MGFB_ERR_STATE, "steps are in flight: mgfb_step_wait first");
@@ -1270,6 +1330,7 @@ int32_t mgfb_bodies_set_gid(mgfb_ctx* ctx, uint32_t first, uint32_t n, const uin
 }
 
 int32_t mgfb_tile_export(mgfb_ctx* ctx, uint32_t ghost_capacity, mgfb_tile_desc* out) {
+    if (ctx) ctx->bp_invalidate = true;   // the stored fat boxes / the body set change under the cached broadphase
     if (!ctx || !out) return MGFB_ERR_INVALID_ARG;
     if (ctx->tile_exported) return fail(ctx, MGFB_ERR_STATE, "tile already exported");
     CU(cudaSetDevice(ctx->device));
@@ -1330,6 +1391,7 @@ static int32_t tile_open_peer(mgfb_ctx* ctx, const mgfb_tile_desc* desc, TilePee
 }
 
 int32_t mgfb_tile_connect(mgfb_ctx* ctx, uint32_t rank, uint32_t nranks, const mgfb_tile_desc* descs) {
+    if (ctx) ctx->bp_invalidate = true;   // the stored fat boxes / the body set change under the cached broadphase
     if (!ctx || !descs || nranks == 0 || rank >= nranks) return fail(ctx, MGFB_ERR_INVALID_ARG, "bad arguments");
     if (!ctx->tile_exported) return fail(ctx, MGFB_ERR_STATE, "mgfb_tile_export first");
     if (ctx->tiled) return fail(ctx, MGFB_ERR_STATE, "tile already connected");

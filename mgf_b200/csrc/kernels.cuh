@@ -118,6 +118,11 @@ __global__ void __launch_bounds__(MGFB_THREADS) k_integrate(BodyArrays B, unsign
                 fb.c = v4(tc, 0.0f); fb.r = v4(fr, 0.0f);
                 B.fat[i] = fb;
                 refreshed++;
+                if (B.ref_flag) {
+                    B.ref_flag[i] = 1;
+                    unsigned k = atomicAdd(&ctr->n_ref, 1u);
+                    if (k < B.ref_cap) B.ref_list[k] = i;
+                }
             }
             my_fat = fmaxf(my_fat, fmaxf(fr.x, fmaxf(fr.y, fr.z)));
             my_tight = fmaxf(my_tight, fmaxf(tr.x, fmaxf(tr.y, tr.z)));
@@ -226,46 +231,77 @@ __global__ void __launch_bounds__(MGFB_THREADS) k_bgrid_insert(const Box* __rest
 #define BP_WARPS (MGFB_THREADS / 32)
 #define BP_BUF 128
 #define BP_PER 4     // bodies per warp between two CTA-wide reservations (3 CTA barriers per 32 bodies instead of per 8)
-__device__ __forceinline__ void bp_flush_warp(unsigned* buf, const unsigned char* sub, unsigned cnt, const unsigned* ids, const unsigned base[4], PairLists lists,
-                                              unsigned cap, Counters* ctr, unsigned lane) {
-    // buf entries: j | kind << 30, sub[e] = which of the warp's BP_PER bodies (body ids[sub]).  base[k]: where this
-    // warp's kind-k entries start in list k.
-    unsigned run[4] = {0, 0, 0, 0};
+// buf entries: j | in_P << 29 | kind << 30 (bodies < 2^29), sub[e] = which of the warp's BP_PER bodies (body ids[sub]).
+// base[k], k < 4: where this warp's kind-k entries start in list k; base[4]: where its entries start in the cached superset
+// S (BUILD: every staged entry goes there, those with in_P set also to their kind's list).
+template <bool CACHED>
+__device__ __forceinline__ void bp_flush_warp(unsigned* buf, const unsigned char* sub, unsigned cnt, const unsigned* ids, const unsigned base[5], PairLists lists,
+                                              unsigned cap, int2* s_list, unsigned s_cap, Counters* ctr, unsigned lane) {
+    unsigned run[5] = {0, 0, 0, 0, 0};
     for (unsigned s0 = 0; s0 < cnt; s0 += 32) {
-        unsigned e = s0 + lane < cnt ? buf[s0 + lane] : 0xffffffffu;
-        const unsigned i = ids[s0 + lane < cnt ? (unsigned)sub[s0 + lane] : 0u];
-        int kind = e == 0xffffffffu ? -1 : (int)(e >> 30);
+        const bool have = s0 + lane < cnt;
+        unsigned e = have ? buf[s0 + lane] : 0u;
+        const unsigned i = ids[have ? (unsigned)sub[s0 + lane] : 0u];
+        const int kind_all = have ? (int)(e >> 30) : -1;
+        const int kind = (have && ((e >> 29) & 1u)) ? kind_all : -1;
+        const unsigned j = e & 0x1fffffffu;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             unsigned m = __ballot_sync(0xffffffffu, kind == k);
             if (kind == k) {
                 unsigned pos = base[k] + run[k] + __popc(m & ((1u << lane) - 1u));
-                if (pos < cap) lists.p[k][pos] = make_int2((int)i, (int)(e & 0x3fffffffu));   // (bodies < 2^30)
+                if (pos < cap) lists.p[k][pos] = make_int2((int)i, (int)j);
                 else atomicOr(&ctr->overflow, (unsigned)OVF_PAIRS);
             }
             run[k] += __popc(m);
         }
+        if (CACHED && s_list) {
+            unsigned m = __ballot_sync(0xffffffffu, have);
+            if (have) {
+                unsigned pos = base[4] + run[4] + __popc(m & ((1u << lane) - 1u));
+                const unsigned ki = (unsigned)kind_all >> 1, kj = (unsigned)kind_all & 1u;
+                if (pos < s_cap) s_list[pos] = make_int2((int)(i | (ki << 31)), (int)(j | (kj << 31)));
+                else atomicOr(&ctr->overflow, (unsigned)OVF_PAIRS);
+            }
+            run[4] += __popc(m);
+        }
     }
 }
+}  // namespace mgfb
+#include "bpcache.cuh"
+namespace mgfb {
+// CACHED = launched by the coherent broadphase (bpcache.cuh), whose k_bp_decide picked this step's path:
+//   BP_REBUILD  the grid holds the own bodies binned by fat centre with cell edge s0; the sweep runs around the FAT centre and
+//               stages every pair whose fat boxes overlap (-> S), marking those that also pass this step's exact test (-> lists);
+//   BP_SWEEP    the plain sweep (tight box against stored fat boxes, ghosts in the grid), nothing kept;
+//   BP_COHERENT nothing to do.
+// !CACHED: the plain sweep.
+template <bool CACHED>
 __global__ void __launch_bounds__(MGFB_THREADS) k_body_pairs_warp(const Box* __restrict__ tight, const Collider* __restrict__ col, const unsigned* __restrict__ gid,
-                                                                 unsigned n_own, BodyGrid G, PairLists lists, unsigned cap, Counters* ctr) {
+                                                                 unsigned n_own, BodyGrid G, PairLists lists, unsigned cap, Counters* ctr, BpView V, unsigned n_build) {
     __shared__ unsigned s_buf[BP_WARPS][BP_BUF];
     __shared__ unsigned char s_sub[BP_WARPS][BP_BUF];
-    __shared__ unsigned s_cnt[BP_WARPS][4];     // per warp, per kind
-    __shared__ unsigned s_base[BP_WARPS][4];
+    __shared__ unsigned s_cnt[BP_WARPS][5];     // per warp, per kind (+ S)
+    __shared__ unsigned s_base[BP_WARPS][5];
     __shared__ unsigned s_ids[BP_WARPS][BP_PER];   // the warp's bodies of this batch
     if (ctr->overflow | ctr->nan_bounds) return;
-    const float inv = grid_inv_cell(ctr);
-    const unsigned n = ctr->n_total;
+    if (CACHED && V.st->mode == BP_COHERENT) return;
+    const bool BUILD = CACHED && V.st->mode == BP_REBUILD;
+    const float inv = CACHED ? 1.0f / V.st->s0 : grid_inv_cell(ctr);
+    const unsigned n = BUILD ? n_build : ctr->n_total;
+    int2* s_list = BUILD ? V.S[V.st->cur] : nullptr;
+    unsigned* s_count = BUILD ? &V.st->s_count[V.st->cur] : nullptr;
+    const unsigned s_cap = BUILD ? V.s_cap : 0u;
     const unsigned lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
     for (unsigned batch = blockIdx.x * (BP_WARPS * BP_PER); batch < n; batch += gridDim.x * (BP_WARPS * BP_PER)) {   // uniform per block
-        unsigned cnt = 0, kcnt[4] = {0, 0, 0, 0};
+        unsigned cnt = 0, kcnt[5] = {0, 0, 0, 0, 0};
         const unsigned* ids = s_ids[w];
         for (unsigned sub = 0; sub < BP_PER; ++sub) {
         // bodies are taken in GRID order (position in `ent` = bucket order: spatially coherent), not in index order
         const unsigned pos = batch + sub * BP_WARPS + w;
         if (pos < n) {   // (world.rs:256 skips body 0: it has no j < i)
-            const unsigned iw = __float_as_uint(G.ent[2 * pos].w);
+            const float4 me0 = G.ent[2 * pos];
+            const unsigned iw = __float_as_uint(me0.w);
             const unsigned i = iw & 0x7fffffffu;
             if (lane == 0) s_ids[w][sub] = i;
             __syncwarp();
@@ -273,8 +309,11 @@ __global__ void __launch_bounds__(MGFB_THREADS) k_body_pairs_warp(const Box* __r
             const bool ghost_i = i >= n_own;
             Box tb = tight[i];
             V3 tc = f4v(tb.c), tr = f4v(tb.r);
+            V3 fc = mk3(me0.x, me0.y, me0.z), fr = zero3();
+            if (BUILD) { const float4 me1 = G.ent[2 * pos + 1]; fr = mk3(me1.x, me1.y, me1.z); }
             int ki = (int)(iw >> 31);
-            int cx = cell_coord(tc.x, inv), cy = cell_coord(tc.y, inv), cz = cell_coord(tc.z, inv);
+            const V3 qc = BUILD ? fc : tc;   // the query's centre
+            int cx = cell_coord(qc.x, inv), cy = cell_coord(qc.y, inv), cz = cell_coord(qc.z, inv);
             unsigned e = 0, e1 = 0;
             {
                 // lanes 0..26: the 27 cells around the centre.  Two of them may hash to the same bucket: only the
@@ -287,6 +326,7 @@ __global__ void __launch_bounds__(MGFB_THREADS) k_body_pairs_warp(const Box* __r
                 }
                 unsigned same = __match_any_sync(0xffffffffu, h);
                 if (lane < 27 && (unsigned)__ffs((int)same) - 1u == lane) { e = G.cell_start[h]; e1 = G.cell_start[h + 1]; }
+                e1 = min(e1, n); e = min(e, e1);   // (a grid that was not built must not turn into an endless walk)
             }
             // Flatten the (at most 27) bucket ranges: lane l owns [e, e1); an inclusive warp scan of the lengths
             // gives every candidate a global number t, and lane t%32 tests candidate t -- all 32 lanes busy
@@ -308,53 +348,61 @@ __global__ void __launch_bounds__(MGFB_THREADS) k_body_pairs_warp(const Box* __r
                 const unsigned src_incl = __shfl_sync(0xffffffffu, incl, (int)lo);
                 const unsigned src_len = __shfl_sync(0xffffffffu, len_l, (int)lo);
                 const unsigned src_e = __shfl_sync(0xffffffffu, e, (int)lo);
-                int kind = -1; unsigned j = 0;
+                int kind = -1; unsigned j = 0; bool in_p = false;   // kind >= 0: staged
                 if (t < total) {
                     const unsigned ee = src_e + (t - (src_incl - src_len));
                     float4 a = G.ent[2 * ee], b = G.ent[2 * ee + 1];
                     unsigned jw = __float_as_uint(a.w);
                     j = jw & 0x7fffffffu;
-                    if (__float_as_uint(b.w) < gi && !(ghost_i && j >= n_own) && box_overlaps(tc, tr, mk3(a.x, a.y, a.z), mk3(b.x, b.y, b.z)))
-                        kind = ki * 2 + (int)(jw >> 31);
+                    if (__float_as_uint(b.w) < gi && !(ghost_i && j >= n_own)) {
+                        const V3 jc = mk3(a.x, a.y, a.z), jr = mk3(b.x, b.y, b.z);
+                        in_p = box_overlaps(tc, tr, jc, jr);
+                        if (in_p || (BUILD && box_overlaps_slop(fc, fr, jc, jr))) kind = ki * 2 + (int)(jw >> 31);
+                    }
                 }
                 unsigned m = __ballot_sync(0xffffffffu, kind >= 0);
                 if (!m) continue;
                 unsigned nh = __popc(m);
                 if (cnt + nh > BP_BUF) {   // staging full (a very dense blob): spill with a per-warp reservation
-                    unsigned base[4];
+                    unsigned base[5];
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {
+                    for (int k = 0; k < 5; ++k) {
                         unsigned b0 = 0;
-                        if (lane == 0 && kcnt[k]) b0 = atomicAdd(&ctr->pairs[k], kcnt[k]);
+                        if (lane == 0 && kcnt[k]) b0 = atomicAdd(k < 4 ? &ctr->pairs[k] : s_count, kcnt[k]);
                         base[k] = __shfl_sync(0xffffffffu, b0, 0);
                         kcnt[k] = 0;
                     }
                     __syncwarp();
-                    bp_flush_warp(s_buf[w], s_sub[w], cnt, ids, base, lists, cap, ctr, lane);
+                    bp_flush_warp<CACHED>(s_buf[w], s_sub[w], cnt, ids, base, lists, cap, s_list, s_cap, ctr, lane);
                     __syncwarp();
                     cnt = 0;
                 }
-                if (kind >= 0) { unsigned slot = cnt + __popc(m & ((1u << lane) - 1u)); s_buf[w][slot] = j | ((unsigned)kind << 30); s_sub[w][slot] = (unsigned char)sub; }
+                if (kind >= 0) {
+                    unsigned slot = cnt + __popc(m & ((1u << lane) - 1u));
+                    s_buf[w][slot] = j | (in_p ? (1u << 29) : 0u) | ((unsigned)kind << 30); s_sub[w][slot] = (unsigned char)sub;
+                }
                 cnt += nh;
+                if (BUILD) kcnt[4] += nh;
                 // hits per kind: body i has ONE kind, so only kinds 2*ki and 2*ki+1 can occur
-                unsigned n1 = __popc(__ballot_sync(0xffffffffu, kind == ki * 2 + 1));
+                unsigned np = __popc(__ballot_sync(0xffffffffu, in_p));
+                unsigned n1 = __popc(__ballot_sync(0xffffffffu, in_p && kind == ki * 2 + 1));
 #pragma unroll
-                for (int k = 0; k < 4; ++k) kcnt[k] += k == ki * 2 + 1 ? n1 : (k == ki * 2 ? nh - n1 : 0u);
+                for (int k = 0; k < 4; ++k) kcnt[k] += k == ki * 2 + 1 ? n1 : (k == ki * 2 ? np - n1 : 0u);
             }
         }
         }
-        if (lane < 4) s_cnt[w][lane] = kcnt[lane];
+        if (lane < 5) s_cnt[w][lane] = kcnt[lane];
         __syncthreads();
-        if (threadIdx.x < 4) {   // one reservation per kind for the whole block
+        if (threadIdx.x < (BUILD ? 5 : 4)) {   // one reservation per kind (and for S) for the whole block
             unsigned tot = 0;
             for (int ww = 0; ww < BP_WARPS; ++ww) { s_base[ww][threadIdx.x] = tot; tot += s_cnt[ww][threadIdx.x]; }
-            unsigned b0 = tot ? atomicAdd(&ctr->pairs[threadIdx.x], tot) : 0u;
+            unsigned b0 = tot ? atomicAdd(threadIdx.x < 4 ? &ctr->pairs[threadIdx.x] : s_count, tot) : 0u;
             for (int ww = 0; ww < BP_WARPS; ++ww) s_base[ww][threadIdx.x] += b0;
         }
         __syncthreads();
         if (cnt) {
-            unsigned base[4] = {s_base[w][0], s_base[w][1], s_base[w][2], s_base[w][3]};
-            bp_flush_warp(s_buf[w], s_sub[w], cnt, ids, base, lists, cap, ctr, lane);
+            unsigned base[5] = {s_base[w][0], s_base[w][1], s_base[w][2], s_base[w][3], BUILD ? s_base[w][4] : 0u};
+            bp_flush_warp<CACHED>(s_buf[w], s_sub[w], cnt, ids, base, lists, cap, s_list, s_cap, ctr, lane);
         }
         __syncthreads();
     }
@@ -1564,11 +1612,11 @@ __global__ void __launch_bounds__(MGFB_THREADS) k_set_state(BodyArrays B, unsign
 }
 
 // ---------------------------------------------------------------- single-pass exclusive scan (u32)
-// Zero-fill of up to 8 ranges in one launch: the step's scratch (counters, cell counts, group counts, per-body masks,
+// Zero-fill of up to 12 ranges in one launch: the step's scratch (counters, cell counts, group counts, per-body masks,
 // scan states ...).  A kernel, not cudaMemsetAsync: memsets ride a copy engine, and with the pipelined step API that
 // engine is busy for 0.1-0.4 ms per step moving the previous step's state to the host -- every memset in the step's
 // stream then waits for it (measured: +0.33 ms of device time per step on 8 GPUs sharing PCIe, tools/e2e_diag.py).
-struct ZeroRanges { unsigned* p[8]; unsigned words[8]; unsigned n; };
+struct ZeroRanges { unsigned* p[12]; unsigned words[12]; unsigned n; };
 __global__ void __launch_bounds__(MGFB_THREADS) k_zero_ranges(ZeroRanges Z) {
     const unsigned tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
     for (unsigned r = 0; r < Z.n; ++r) {
@@ -1584,8 +1632,10 @@ __global__ void __launch_bounds__(MGFB_THREADS) k_zero_ranges(ZeroRanges Z) {
 // prefix, in one 64-bit word (flag << 62 | value).  `state` = [ticket, pad, status[ntiles]] zeroed before
 // the launch.  out[n] = total (also *total_dev when given).
 #define SCAN_ITEMS 2048
-__global__ void __launch_bounds__(256) k_scan_lookback(const unsigned* __restrict__ in, unsigned n, unsigned* out, unsigned long long* state, unsigned* total_dev) {
+__global__ void __launch_bounds__(256) k_scan_lookback(const unsigned* __restrict__ in, unsigned n, unsigned* out, unsigned long long* state, unsigned* total_dev,
+                                                       const unsigned* skip_if = nullptr, unsigned skip_value = 0u) {
     __shared__ unsigned s_tile, s_excl, ws[8];
+    if (skip_if && *skip_if == skip_value) return;   // (a coherent broadphase step keeps its grid: bpcache.cuh)
     unsigned long long* status = state + 1;
     if (threadIdx.x == 0) s_tile = atomicAdd(reinterpret_cast<unsigned*>(state), 1u);
     __syncthreads();

@@ -101,7 +101,7 @@ struct Counters {
     unsigned n_int_rows;     // constraints in interior phases
     unsigned df_links;       // dataflow solver: total (body, row) incidences = sum of rows per body
     unsigned colour_fallback; // k_colour_df ran out of colours: k_order (which stacks colours beyond 64) redoes the step's colouring
-    unsigned pad1;
+    unsigned n_ref;          // bodies whose stored fat box was replaced this step and that are listed for the coherent broadphase (bpcache.cuh)
     // sticky until the host clears them
     unsigned overflow;       // bit0 pairs, bit1 tpairs, bit2 contacts, bit3 grid entries, bit4 groups, bit5 ghosts
     unsigned nan_bounds;     // AABB::combine assert (bounds.rs:125-127)
@@ -131,6 +131,8 @@ struct BodyArrays {
     Box* tight;
     Box* fat;
     unsigned* gid;    // global body id (= index when the world is not tiled): orders pairs (j < i, world.rs:266)
+    // coherent broadphase (bpcache.cuh), or NULL: which bodies replaced their stored fat box this step
+    unsigned char* ref_flag; unsigned* ref_list; unsigned ref_cap;
 };
 
 }  // namespace mgfb
