@@ -53,14 +53,18 @@ __device__ __forceinline__ bool box_overlaps_slop(V3 ac, V3 ar, V3 bc, V3 br) {
     return fabsf(ac.x - bc.x) <= (ar.x + br.x) + ex && fabsf(ac.y - bc.y) <= (ar.y + br.y) + ey && fabsf(ac.z - bc.z) <= (ar.z + br.z) + ez;
 }
 
-__global__ void k_bp_decide(BpView V, Counters* ctr, unsigned n_own) {
+// `force_rebuild`: tiled worlds rebuild on a common schedule (every BP_TILED_PERIOD steps, by the tiles' shared step number):
+// tiles run in lock-step, so a tile that rebuilds alone makes its neighbours wait inside their solvers for as long as the
+// rebuild takes -- measured on 2 GPUs: +50 us per step with every tile on its own schedule, more than the cache saves.
+#define BP_TILED_PERIOD 8u
+__global__ void k_bp_decide(BpView V, Counters* ctr, unsigned n_own, unsigned force_rebuild) {
     if (ctr->overflow | ctr->nan_bounds) return;
     BpState& s = *V.st;
     const float mf = __uint_as_float(ctr->max_fat_bits);   // own bodies (k_integrate) and this step's ghosts (k_ghost_recv)
     const bool sane = mf > 0.0f && mf < 1.0e18f;
     const unsigned nr = ctr->n_ref;
     const bool calm = sane && nr <= V.ref_cap && nr * 8u <= n_own + 64u && nr + BP_OVF_SOFT <= V.ovf_cap;
-    const bool ok = calm && s.valid && s.n_grid == n_own && s.n_ovf <= BP_OVF_SOFT && s.n_ovf + nr <= V.ovf_cap &&
+    const bool ok = calm && !force_rebuild && s.valid && s.n_grid == n_own && s.n_ovf <= BP_OVF_SOFT && s.n_ovf + nr <= V.ovf_cap &&
                     2.0f * mf * 1.001f + s.drift <= s.s0 && s.s_count[s.cur] <= V.s_cap;
     if (ok) { s.mode = BP_COHERENT; s.coherent_steps++; s.s_count[s.cur ^ 1u] = 0u; }
     else if (calm) {

@@ -73,7 +73,7 @@ struct mgfb_ctx {
     int coop_order = 0, coop_solve = 0, coop_df = 0, coop_colour = 0;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     // coherent broadphase (bpcache.cuh): on unless MGFB_BROADPHASE=sweep
-    bool bp_on = true, bp_invalidate = true;
+    bool bp_on = true, bp_forced = false, bp_invalidate = true;
     Buf bp_state, bp_s[2], bp_stale, bp_c0, bp_ovf, bp_ref_flag, bp_ref_list; unsigned bp_s_cap = 0, bp_slots = 0;
     Buf scan_step;                        // the two look-back scan states of one step (zeroed with the step's scratch)
     Counters* ctr_snap = nullptr;         // pipelined step being enqueued: where k_step_done leaves a copy of its counters
@@ -521,7 +521,7 @@ int32_t enqueue_step(mgfb_ctx* ctx, float dt, unsigned iters, bool from_integrat
         // coherent broadphase (bpcache.cuh): the device picks this step's path; the kernels of the other one return at once
         BpView V = bp_view(ctx);
         const int gn = grid_for(ctx, slots);
-        k_bp_decide<<<1, 1, 0, ctx->stream>>>(V, c, n);
+        k_bp_decide<<<1, 1, 0, ctx->stream>>>(V, c, n, (tiled && ctx->tile_step % BP_TILED_PERIOD == 0) ? 1u : 0u);
         // -- rebuild: grid over the own bodies' fat boxes; one sweep writes S and this step's pair lists
         k_bp_grid<false><<<gn, MGFB_THREADS, 0, ctx->stream>>>(B.fat, B.col, B.gid, n, G, V, c);
         {
@@ -674,7 +674,8 @@ int32_t mgfb_ctx_create(const mgfb_config* cfg, mgfb_ctx** out) {
     *out = nullptr;
     mgfb_ctx* ctx = new mgfb_ctx();
     if (cfg) ctx->cfg = *cfg; else mgfb_config_default(&ctx->cfg);
-    { const char* e = getenv("MGFB_BROADPHASE"); ctx->bp_on = !(e && std::strcmp(e, "sweep") == 0); }   // "sweep": grid + sweep every step (A/B)
+    // "sweep": grid + sweep every step; "cache": the coherent broadphase even on tiled worlds (default: untiled worlds only)
+    { const char* e = getenv("MGFB_BROADPHASE"); ctx->bp_on = !(e && std::strcmp(e, "sweep") == 0); ctx->bp_forced = e && std::strcmp(e, "cache") == 0; }
     ctx->device = ctx->cfg.device;
     auto bail = [&](cudaError_t e, const char* what) {
         g_create_err = std::string(what) + ": " + cudaGetErrorString(e);
@@ -1330,6 +1331,9 @@ int32_t mgfb_bodies_set_gid(mgfb_ctx* ctx, uint32_t first, uint32_t n, const uin
 }
 
 int32_t mgfb_tile_export(mgfb_ctx* ctx, uint32_t ghost_capacity, mgfb_tile_desc* out) {
+    // Tiled worlds keep the plain grid + sweep: measured on 2 GPUs, the coherent broadphase saves ~30 us in the broadphase but the
+    // dataflow solver -- whose chains cross the tiles in lock-step -- runs ~50 us longer behind it (tools/e2e_diag.py phases).
+    if (ctx && !ctx->bp_forced) ctx->bp_on = false;
     if (ctx) ctx->bp_invalidate = true;   // the stored fat boxes / the body set change under the cached broadphase
     if (!ctx || !out) return MGFB_ERR_INVALID_ARG;
     if (ctx->tile_exported) return fail(ctx, MGFB_ERR_STATE, "tile already exported");
