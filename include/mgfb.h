@@ -337,7 +337,8 @@ typedef struct mgfb_step_stats {
     uint32_t ghosts;              /* tiled world: bodies received from the right neighbour this step */
     uint32_t boundary_constraints;/* tiled world: constraints between an owned body and a ghost */
     uint32_t phases;              /* non-empty groups = grid-wide phases per solver iteration */
-    uint32_t reserved;
+    uint32_t broadphase_path;     /* how the pair set was found: 0 grid + sweep, 1 coherent (cached superset filtered, replaced bodies queried),
+                                   * 2 cache rebuilt, 3 grid + sweep chosen by the cache (too much moved); the set is the same */
 } mgfb_step_stats;
 
 /* One World::step(dt) with `iters` solver iterations (the demo hard-codes 20, world.rs:293).

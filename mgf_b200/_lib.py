@@ -58,10 +58,10 @@ class StepStats(C.Structure):
                 ("constraints", C.c_uint32), ("terrain_constraints", C.c_uint32), ("groups", C.c_uint32),
                 ("iterations", C.c_uint32), ("fat_refreshes", C.c_uint32), ("step_ms", C.c_float),
                 ("solve_ms", C.c_float), ("overflow", C.c_uint32), ("colouring_rounds", C.c_uint32), ("ghosts", C.c_uint32),
-                ("boundary_constraints", C.c_uint32), ("phases", C.c_uint32), ("reserved", C.c_uint32)]
+                ("boundary_constraints", C.c_uint32), ("phases", C.c_uint32), ("broadphase_path", C.c_uint32)]
 
     def as_dict(self):
-        return {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}
+        return {k: getattr(self, k) for k, _ in self._fields_}
 
 
 class PhaseProfile(C.Structure):

@@ -66,6 +66,7 @@ __global__ void k_bp_decide(BpView V, Counters* ctr, unsigned n_own, unsigned fo
     const bool calm = sane && nr <= V.ref_cap && nr * 8u <= n_own + 64u && nr + BP_OVF_SOFT <= V.ovf_cap;
     const bool ok = calm && !force_rebuild && s.valid && s.n_grid == n_own && s.n_ovf <= BP_OVF_SOFT && s.n_ovf + nr <= V.ovf_cap &&
                     2.0f * mf * 1.001f + s.drift <= s.s0 && s.s_count[s.cur] <= V.s_cap;
+    ctr->bp_path = ok ? 1u : (calm ? 2u : 3u);
     if (ok) { s.mode = BP_COHERENT; s.coherent_steps++; s.s_count[s.cur ^ 1u] = 0u; }
     else if (calm) {
         s.mode = BP_REBUILD; s.rebuilds++;

@@ -1083,6 +1083,7 @@ static void fill_step_stats(mgfb_ctx* ctx, mgfb_step_stats* st, unsigned iters, 
     st->ghosts = h.n_total - ctx->n;
     st->boundary_constraints = h.contacts - h.n_int_rows;
     st->phases = h.n_phases;
+    st->broadphase_path = h.bp_path;
     if (timed) {
         cudaEventElapsedTime(&st->step_ms, evs[0], evs[1]);
         cudaEventElapsedTime(&st->solve_ms, evs[2], evs[3]);

@@ -101,6 +101,7 @@ struct Counters {
     unsigned n_int_rows;     // constraints in interior phases
     unsigned df_links;       // dataflow solver: total (body, row) incidences = sum of rows per body
     unsigned colour_fallback; // k_colour_df ran out of colours: k_order (which stacks colours beyond 64) redoes the step's colouring
+    unsigned bp_path;        // which broadphase path ran: 0 plain sweep (cache off), 1 coherent, 2 rebuild, 3 sweep chosen by the cache (bpcache.cuh)
     unsigned n_ref;          // bodies whose stored fat box was replaced this step and that are listed for the coherent broadphase (bpcache.cuh)
     // sticky until the host clears them
     unsigned overflow;       // bit0 pairs, bit1 tpairs, bit2 contacts, bit3 grid entries, bit4 groups, bit5 ghosts
