@@ -1,13 +1,5 @@
-# INTEGRATION — using libmgfb from mgf (Rust)
-
-`libmgfb.so` exports the C ABI declared in `include/mgfb.h` (POD structs, plain pointers and
-sizes, `int32_t` status, no callbacks, no unwinding).  A maintainer of mgf would add a tiny
-`mgf-sys`-style module and re-implement the hot-path types as thin wrappers.  This could not be
-compiled here (no Rust toolchain in this image); it is written against the header 1:1.
-
-## 1. Raw binding (`src/gpu/sys.rs`)
-
-```rust
+//! Raw binding of include/mgfb.h (libmgfb.so).  Kept identical to the block in INTEGRATION.md section 1 by
+//! tests/test_abi.py::test_rust_binding_matches_integration_md; not compiled in this repository's CI (no Rust toolchain in the image).
 #![allow(non_camel_case_types)]
 use std::os::raw::{c_char, c_void};
 
@@ -125,92 +117,3 @@ extern "C" {
     pub fn mgfb_selftest_handover(ctx: *mut mgfb_ctx, rounds: u32, torn: *mut u32, observed: *mut u32) -> i32;
     pub fn mgfb_device_view_get(ctx: *mut mgfb_ctx, out: *mut mgfb_device_view) -> i32;
 }
-```
-
-## 2. The `Shape` trait and the shape structs (geom.rs:451-466)
-
-The north star names `Shape` (`center`, `set_pos`, `closest_point`, `+= / -= Vector3`).  These are host-side value operations on
-small POD structs; they stay in Rust untouched.  What crosses the boundary is the struct itself, flattened into `mgfb_shape`:
-
-| mgf type (geom.rs / compound.rs / mesh.rs) | `mgfb_shape.kind` | `p[..]` | `From` impl a maintainer adds |
-|---|---|---|---|
-| `Sphere { c, r }` :290 | `MGFB_SPHERE` | `c.x c.y c.z r` | `impl From<Sphere> for mgfb_shape` |
-| `Capsule { a, d, r }` :316 | `MGFB_CAPSULE` | `a, d, r` | idem |
-| `Triangle { a, b, c }` :128 | `MGFB_TRIANGLE` | `a, b, c` | idem |
-| `Rectangle { c, u, e }` :216 | `MGFB_RECTANGLE` | `c, u[0], u[1], e[0], e[1]` | idem |
-| `Plane { n, d }` :32 | `MGFB_PLANE` | `n, d` | idem |
-| `AABB { c, r }` :257, `OBB { c, q, r }` :272 | `MGFB_AABB`, `MGFB_OBB` | `c, r` / `c, r, q(s,x,y,z)` | idem |
-| `Moving<T>(T, Vector3)` :357 | the kind of `T` | as `T`, and `v = .1` | `impl<T: Into<mgfb_shape>> From<Moving<T>>` |
-| `Component::{Sphere, Capsule}` compound.rs:33 | `MGFB_SPHERE` / `MGFB_CAPSULE` | as above | `match` |
-| `ConvexMesh { verts, .. }` mesh.rs:141 | `MGFB_CONVEX_MESH` | first vertex, vertex count in the pool given to `mgfb_convex_vertices_set` | the wrapper appends `verts` to the pool |
-| `Ray { p, d }` :63, `Segment { a, b }` :91 | (particles) | 6 floats, `mgfb_particle_kind` | — |
-
-`Shape::center / set_pos / closest_point` of a `Compound` (compound.rs:290-311) are `mgfb_compound_set_transform` (the pub fields
-`disp`, `rot`) and `mgfb_compound_closest_points`; for the other shapes they never needed the GPU.
-
-## 3. Safe wrappers that keep mgf's surface
-
-| mgf item (file:line) | wrapper |
-|---|---|
-| `RigidBodyVec::new()` physics.rs:181 | `GpuRigidBodyVec::new()` → `mgfb_ctx_create` |
-| `add_body(Component, mass, restitution, friction, world_force) -> RigidBodyRef` physics.rs:200 | fills one `mgfb_shape` from `Component::{Sphere,Capsule}` (`kind`, `p = [c, r]` or `[a, d, r]`) → `mgfb_bodies_add(n=1)`; returns `RigidBodyRef::Dynamic(first_id)` |
-| `integrate(dt)`, `complete_motion()` physics.rs:222,262 | `mgfb_integrate`, `mgfb_complete_motion` |
-| pub fields `x`, `q`, `collider`; `colliders()` physics.rs:142-154,256 | `sync_to_host()` → `mgfb_bodies_get_state` / `mgfb_bodies_get_colliders` into the existing `Vec<Point3<f32>>`, `Vec<Quaternion<f32>>` (cgmath's `Quaternion{s, v}` has the same `(s,x,y,z)` order) |
-| `ConstrainedSet::get / set` physics.rs:272-315 | `get_state` / `mgfb_bodies_set_velocity` |
-| `Mesh::new / push_vert / push_face / set_pos` mesh.rs:40-73 | unchanged on the host; `World::set_terrain(&Mesh)` → `mgfb_terrain_set(verts, faces, x)` |
-| `Contacts::contacts(&self, &RHS, FnMut(Contact)) -> bool` collision.rs:471 | `contacts_batch(kind, recv, arg)` → `mgfb_contacts_batch`; the callback form is a loop over `counts[i]` outputs in order |
-| `Intersects<RHS>::intersection(&self, &RHS) -> Option<Intersection>` collision.rs:163-373 (Ray, Segment × Plane, Triangle, Rectangle, AABB, OBB, Sphere, Capsule, Moving<Sphere>) | `intersections_batch(kind, particles, shapes)` → `mgfb_intersections_batch`; `hit[i]` is the `Option` discriminant |
-| `BVH::{new, insert(&K, V) -> usize, remove(usize), query(&Arg, FnMut(&V)), raytrace(&Arg, FnMut(&V, Intersection)), Index}` bvh.rs:88-369,483 | `GpuBvh` over `mgfb_bvh_*`: `insert` takes `key.bounds()` (c, r) and the value (`V = u32`, e.g. an index into a host `Vec<V>`), `query`/`raytrace` call the closure for `values[offsets[q]..offsets[q+1]]` |
-| `Solver::new / add_constraint / solve(&mut T, iters)` solver.rs:57-78 + `ContactConstraint::new(&pool, a, b, Manifold, dt)` :101 | `GpuSolver` collects `(obj_a, obj_b, Manifold)` triples (SoA `Vec`s) in `add_constraint`, `solve` passes them as `mgfb_manifolds` with `MGFB_ORDER_AS_GIVEN` (bit-identical to the sequential sweep) or `MGFB_ORDER_COLOURED` |
-| `ContactPruner::{new, push}` + `Manifold::from(pruner)` manifold.rs:42-148 | `GpuPruner`: collect the `LocalContact`s of every object pair in push order, `mgfb_manifolds_prune` → arrays laid out like `mgfb_manifolds` (straight into `GpuSolver`) |
-| `Compound::{new, contacts, intersection, closest_point, bounds}`, pub `disp` / `rot` compound.rs:232-352 | `GpuCompound` over `mgfb_compound_*`; the tree is grown like `BVH::insert` grows it, so callback order (and `last_contact`) is the reference's |
-| generic `Contacts for Convex x Convex`, `Penetrates::separation` collision.rs:404-425, 497-519 (Sphere, Capsule, AABB, OBB, ConvexMesh) | `mgfb_gjk_batch`, `mgfb_separation_batch` |
-| checkpoint / restore (serde-derived structs hold the same fields) | `mgfb_bodies_get_state` + `get_colliders` + `get_fat_bounds` ↔ `mgfb_bodies_set_state` |
-| `World::step(dt)` world.rs:227 | `mgfb_step(ctx, dt, 20, &mut stats)` — the whole loop body (BVH refresh, mesh query, body-pair query, pruner, constraints, solve) runs on the device.  `mgfb_config.step_order = MGFB_STEP_ORDER_REFERENCE` makes it add the constraints in the demo world's own order: bit-identical to the Rust `World::step`, for parity runs |
-
-```rust
-pub struct GpuWorld { ctx: *mut sys::mgfb_ctx }
-impl GpuWorld {
-    pub fn step(&mut self, dt: f32) -> Result<sys::mgfb_step_stats, Error> {
-        let mut st = Default::default();
-        check(self.ctx, unsafe { sys::mgfb_step(self.ctx, dt, 20, &mut st) })?;   // world.rs:293: 20 iterations
-        Ok(st)
-    }
-}
-fn check(ctx: *mut sys::mgfb_ctx, code: i32) -> Result<(), Error> {
-    if code == 0 { return Ok(()); }
-    let msg = unsafe { std::ffi::CStr::from_ptr(sys::mgfb_last_error(ctx)) }.to_string_lossy().into_owned();
-    Err(match code {      // the panics of the reference, as values
-        1 => Error::InvalidArg(msg), 2 => Error::SingularInertia(msg), 3 => Error::Capacity(msg),
-        4 => Error::Cuda(msg), 5 => Error::NanBounds(msg), _ => Error::State(msg) })
-}
-impl Drop for GpuWorld { fn drop(&mut self) { unsafe { sys::mgfb_ctx_destroy(self.ctx) } } }
-// mgfb_ctx is not thread-safe: GpuWorld is Send but not Sync.
-```
-
-The crate sketched above is in the tree as `bindings/rust/mgf-b200/` (`src/sys.rs` = the block of section 1, checked against it and
-against the header by `tests/test_abi.py`; `src/lib.rs` = `GpuWorld`, `GpuSolver`, `contacts_batch`; `build.rs` links
-`mgf_b200/lib/libmgfb.so`).  It has never been compiled: this image has no Rust toolchain.
-
-## 4. Python (what tests and bench use)
-
-`mgf_b200/_lib.py` is the same binding in ctypes (`SYMBOLS` lists every prototype and
-`tests/test_abi.py` checks it against the header); `mgf_b200/api.py` mirrors the names above.
-
-```python
-import mgf_b200
-from mgf_b200 import scenes
-w = mgf_b200.World(device=0)
-w.add_bodies(*scenes.balls_scene(num=8)[:5])       # shapes, mass, restitution, friction, world_force
-w.set_terrain(*scenes.box_terrain())
-stats = w.step(1/60, iters=10)                     # World::step
-x, q, v, omega = w.state()
-```
-
-## 5. Build
-
-`python -c "import __graft_entry__ as g; g.build()"` →
-`nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo --fmad=false -Xcompiler
--fPIC,-ffp-contract=off -shared -o mgf_b200/lib/libmgfb.so mgf_b200/csrc/capi.cu`.
-`--fmad=false` is what makes the device arithmetic bit-identical to the CPU reference; it costs
-nothing measurable on this memory/latency-bound path.

@@ -62,3 +62,14 @@ def test_integration_md_binds_every_symbol():
     doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
     missing = [n for n in _declared_symbols() if f"pub fn {n}(" not in doc]
     assert not missing, missing
+
+
+def test_rust_binding_matches_integration_md():
+    """bindings/rust/mgf-b200/src/sys.rs is the extern block of INTEGRATION.md, verbatim (the crate cannot be compiled here: no rustc)."""
+    import re
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    block = re.findall(r"```rust\n(.*?)```", doc, re.S)[0]
+    rs = open(os.path.join(ROOT, "bindings", "rust", "mgf-b200", "src", "sys.rs")).read()
+    assert rs.endswith(block), "regenerate sys.rs from INTEGRATION.md section 1"
+    missing = [n for n in _declared_symbols() if f"pub fn {n}(" not in rs]
+    assert not missing, missing
