@@ -86,6 +86,8 @@ struct mgfb_ctx {
     cudaEvent_t gjk_ev[9] = {};
     cudaStream_t s_aux = nullptr;         // the terrain half of the broad/narrowphase runs beside the body half
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    // coherent broadphase: its mutually exclusive paths run side by side (the one not chosen returns at once)
+    cudaStream_t s_bp[2] = {nullptr, nullptr}; cudaEvent_t ev_bp[4] = {nullptr, nullptr, nullptr, nullptr};
     unsigned pipe_head = 0, pipe_inflight = 0, pipe_scale = 2;
     // last step
     unsigned last_constraints = 0;
@@ -522,24 +524,38 @@ int32_t enqueue_step(mgfb_ctx* ctx, float dt, unsigned iters, bool from_integrat
         BpView V = bp_view(ctx);
         const int gn = grid_for(ctx, slots);
         k_bp_decide<<<1, 1, 0, ctx->stream>>>(V, c, n, (tiled && ctx->tile_step % BP_TILED_PERIOD == 0) ? 1u : 0u);
-        // -- rebuild: grid over the own bodies' fat boxes; one sweep writes S and this step's pair lists
-        k_bp_grid<false><<<gn, MGFB_THREADS, 0, ctx->stream>>>(B.fat, B.col, B.gid, n, G, V, c);
+        // The paths exclude each other at run time (the kernels of the one not chosen return at once), so they are queued
+        // side by side: [A] rebuild: grid + one sweep, on s_bp[0]; [B] coherent: mark + filter, on the step's stream;
+        // [C] the queries, on s_bp[1], after the marks and -- for a rebuild's ghosts -- after the grid.
+        cudaStream_t sA = ctx->s_bp[0], sC = ctx->s_bp[1];
+        CU(cudaEventRecord(ctx->ev_bp[0], ctx->stream));
+        CU(cudaStreamWaitEvent(sA, ctx->ev_bp[0], 0));
+        // -- [A] rebuild: grid over the own bodies' fat boxes; one sweep writes S and this step's pair lists
+        k_bp_grid<false><<<gn, MGFB_THREADS, 0, sA>>>(B.fat, B.col, B.gid, n, G, V, c);
         {
             unsigned nbk = (ctx->table + SCAN_ITEMS - 1) / SCAN_ITEMS;
-            k_scan_lookback<<<nbk, 256, 0, ctx->stream>>>(G.cell_count, ctx->table, G.cell_start, step_scan_state(ctx, 0), &c->grid_entries, &V.st->mode, (unsigned)BP_COHERENT);
+            k_scan_lookback<<<nbk, 256, 0, sA>>>(G.cell_count, ctx->table, G.cell_start, step_scan_state(ctx, 0), &c->grid_entries, &V.st->mode, (unsigned)BP_COHERENT);
         }
-        k_bp_grid<true><<<gn, MGFB_THREADS, 0, ctx->stream>>>(B.fat, B.col, B.gid, n, G, V, c);
+        k_bp_grid<true><<<gn, MGFB_THREADS, 0, sA>>>(B.fat, B.col, B.gid, n, G, V, c);
         {
             int gw = std::max(1, std::min((int)((slots + BP_WARPS * BP_PER - 1) / (BP_WARPS * BP_PER)), ctx->num_sms * 8));
             if (ctx->max_ctas) gw = std::min(gw, ctx->max_ctas * 4);
-            k_body_pairs_warp<true><<<gw, MGFB_THREADS, 0, ctx->stream>>>(B.tight, B.col, B.gid, tiled ? n : 0xffffffffu, G, PL, ctx->pair_cap, c, V, n);
+            k_body_pairs_warp<true><<<gw, MGFB_THREADS, 0, sA>>>(B.tight, B.col, B.gid, tiled ? n : 0xffffffffu, G, PL, ctx->pair_cap, c, V, n);
         }
+        CU(cudaEventRecord(ctx->ev_bp[1], sA));
         PROF(MGFB_PHASE_PAIR_SWEEP);
-        // -- coherent: S -> this step's pair lists; both: replaced bodies and ghosts queried against the cached grid
+        // -- [B] coherent: S -> this step's pair lists
         k_bp_mark<<<grid_for(ctx, BP_REF_CAP), MGFB_THREADS, 0, ctx->stream>>>(B.fat, V, c);
-        k_bp_filter<<<grid_for(ctx, (size_t)ctx->bp_s_cap / BP_FILTER_ITEMS / 4 + 1), MGFB_THREADS, 0, ctx->stream>>>(B.tight, B.fat, V, PL, ctx->pair_cap, c);
-        k_bp_query<<<grid_for(ctx, (size_t)(BP_REF_CAP / 4 + ctx->ghost_cap) * 32), MGFB_THREADS, 0, ctx->stream>>>(B.tight, B.fat, B.col, B.gid, n, G, V, PL, ctx->pair_cap, c);
-        k_bp_query_ovf<<<ctx->num_sms * 4, MGFB_THREADS, 0, ctx->stream>>>(B.tight, B.fat, B.col, B.gid, n, V, PL, ctx->pair_cap, c);
+        CU(cudaEventRecord(ctx->ev_bp[2], ctx->stream));
+        k_bp_filter<<<grid_for(ctx, (size_t)ctx->bp_s_cap / BP_FILTER_ITEMS + 1), MGFB_THREADS, 0, ctx->stream>>>(B.tight, B.fat, V, PL, ctx->pair_cap, c);
+        // -- [C] replaced bodies (and ghosts) queried against the cached grid and the overflow list
+        CU(cudaStreamWaitEvent(sC, ctx->ev_bp[1], 0));
+        CU(cudaStreamWaitEvent(sC, ctx->ev_bp[2], 0));
+        k_bp_query<<<grid_for(ctx, (size_t)(BP_REF_CAP / 4 + ctx->ghost_cap) * 32), MGFB_THREADS, 0, sC>>>(B.tight, B.fat, B.col, B.gid, n, G, V, PL, ctx->pair_cap, c);
+        k_bp_query_ovf<<<ctx->num_sms * 4, MGFB_THREADS, 0, sC>>>(B.tight, B.fat, B.col, B.gid, n, V, PL, ctx->pair_cap, c);
+        CU(cudaEventRecord(ctx->ev_bp[3], sC));
+        CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_bp[1], 0));
+        CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_bp[3], 0));
         k_bp_finish<<<1, 1, 0, ctx->stream>>>(V, c);
         ctx->launches += 6;   // (10 launches where the sweep path has 4)
     } else {
@@ -696,6 +712,8 @@ int32_t mgfb_ctx_create(const mgfb_config* cfg, mgfb_ctx** out) {
     if ((e = cudaStreamCreateWithFlags(&ctx->s_aux, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "cudaStreamCreate");
     if ((e = cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming)) != cudaSuccess) return bail(e, "cudaEventCreate");
     if ((e = cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming)) != cudaSuccess) return bail(e, "cudaEventCreate");
+    for (auto& st : ctx->s_bp) if ((e = cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "cudaStreamCreate");
+    for (auto& ev : ctx->ev_bp) if ((e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)) != cudaSuccess) return bail(e, "cudaEventCreate");
     if ((e = cudaMallocHost(&ctx->h_ctr, sizeof(Counters))) != cudaSuccess) return bail(e, "cudaMallocHost");
     if ((e = cudaMalloc(&ctx->ctr.p, sizeof(Counters))) != cudaSuccess) return bail(e, "cudaMalloc");
     ctx->ctr.bytes = sizeof(Counters);
@@ -771,6 +789,8 @@ void mgfb_ctx_destroy(mgfb_ctx* ctx) {
     for (auto& e : ctx->prof_ev) if (e) cudaEventDestroy(e);
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
+    for (auto& st : ctx->s_bp) if (st) cudaStreamDestroy(st);
+    for (auto& ev : ctx->ev_bp) if (ev) cudaEventDestroy(ev);
     if (ctx->s_aux) cudaStreamDestroy(ctx->s_aux);
     for (auto& st : ctx->gjk_streams) if (st) cudaStreamDestroy(st);
     for (auto& ev : ctx->gjk_ev) if (ev) cudaEventDestroy(ev);
