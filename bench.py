@@ -694,6 +694,9 @@ def main():
             "config": config,
             "work": {"constraints_per_step": units_all / iters / args.steps, "candidate_pairs_per_step": pairs_all / args.steps,
                      "colour_groups": sum(groups) / len(groups), "l2": "flushed between timed steps (256 MB write)",
+                     # how the body pair set was found in the timed steps (mgfb_step_stats.broadphase_path; the set is the same on every path)
+                     "broadphase_steps": {label: sum(1 for r in rows if r.get("broadphase_path") == code)
+                                          for code, label in ((0, "grid_and_sweep"), (1, "coherent_cache"), (2, "cache_rebuilt"), (3, "sweep_chosen_by_cache"))},
                      "parallelism": parallelism, "bodies_per_gpu": n,
                      "rank0_ghosts_per_step": sum(ghosts) / len(ghosts), "rank0_boundary_constraints_per_step": sum(bcons) / len(bcons),
                      "arithmetic": "--fmad=false, IEEE div/sqrt: bit-exact vs the CPU port",
