@@ -205,7 +205,7 @@ int32_t ensure_step_buffers(mgfb_ctx* ctx, unsigned scale) {
     if (pc > ctx->pair_cap) { for (auto& b : ctx->pair_list) TRY(ensure(ctx, b, (size_t)pc * sizeof(int2))); ctx->pair_cap = pc; }
     if (tc > ctx->tpair_cap) { for (auto& b : ctx->tpair_list) TRY(ensure(ctx, b, (size_t)tc * sizeof(int2))); ctx->tpair_cap = tc; }
     if (ctx->bp_on) {   // the cached superset S (two buffers), stale marks, overflow list, this step's replaced bodies
-        unsigned sc = n * 16 * scale, slots = body_slots(ctx);
+        unsigned sc = n * 24 * scale, slots = body_slots(ctx);   // fat-box overlaps per body: ~11 in a settled pile of equal spheres, more for mixed sizes
         if (sc > ctx->bp_s_cap) { for (auto& b : ctx->bp_s) TRY(ensure(ctx, b, (size_t)sc * sizeof(int2))); ctx->bp_s_cap = sc; ctx->bp_invalidate = true; }
         if (slots > ctx->bp_slots || !ctx->bp_state.p) {
             TRY(ensure(ctx, ctx->bp_stale, (size_t)slots + 4, false, true)); TRY(ensure(ctx, ctx->bp_c0, (size_t)slots * 16)); TRY(ensure(ctx, ctx->bp_ref_flag, (size_t)slots + 4, false, true));
