@@ -365,7 +365,8 @@ int coop_blocks(const mgfb_ctx* ctx, K kernel, int threads, int max_per_sm) {
 // order -> scan -> scatter -> build -> solve, for `m` constraints counted on the device
 // (m_ptr) or known on the host (m_host).
 int32_t enqueue_order_and_solve(mgfb_ctx* ctx, const OrderView& O, const ManifoldInput& M, const unsigned* m_ptr, unsigned m_host,
-                                unsigned m_bound, bool as_given, float dt, unsigned iters, bool time_solve, bool step_scratch_zeroed = false) {
+                                unsigned m_bound, bool as_given, float dt, unsigned iters, bool time_solve, bool step_scratch_zeroed = false,
+                                bool count_fused = false) {
     Counters* c = dctr(ctx);
     ConstraintRows R = rows_view(ctx);
     BodyInfoView BI = body_info(ctx);
@@ -386,7 +387,7 @@ int32_t enqueue_order_and_solve(mgfb_ctx* ctx, const OrderView& O, const Manifol
         V.key = ctx->c_key.as<unsigned long long>(); V.deg = ctx->body_deg.as<unsigned>(); V.body_start = ctx->body_start.as<unsigned>();
         V.csr = ctx->c_csr.as<unsigned>(); V.next = ctx->c_next.as<unsigned>(); V.inbox = ctx->c_inbox.as<unsigned long long>(); V.cap = ctx->row_cap;
         if (!step_scratch_zeroed) CU(cudaMemsetAsync(V.deg, 0, (size_t)nb * 4, ctx->stream));
-        k_inc_count<<<g, MGFB_THREADS, 0, ctx->stream>>>(O, V, m_ptr, m_host, c);
+        if (!count_fused) k_inc_count<<<g, MGFB_THREADS, 0, ctx->stream>>>(O, V, m_ptr, m_host, c);   // (the step's narrowphase did it while emitting: EmitHook)
         TRY(scan_u32_lb(ctx, V.deg, ctx->body_start.as<unsigned>(), nb, &c->df_links, step_scratch_zeroed ? step_scan_state(ctx, 1) : nullptr));
         k_inc_fill<<<g, MGFB_THREADS, 0, ctx->stream>>>(O, V, m_ptr, m_host, c);
         k_inc_sort<<<grid_for(ctx, nb), MGFB_THREADS, 0, ctx->stream>>>(O, V, nb, c);
@@ -394,7 +395,7 @@ int32_t enqueue_order_and_solve(mgfb_ctx* ctx, const OrderView& O, const Manifol
         OrderView Ov = O; unsigned mh = m_host; const unsigned* mp = m_ptr;
         void* args[] = {&Ov, &V, &mp, &mh, &c};
         CU(cudaLaunchCooperativeKernel((void*)k_colour_df, dim3(ctx->coop_colour), dim3(MGFB_THREADS), args, 0, ctx->stream));
-        ctx->launches += 5;
+        ctx->launches += count_fused ? 4 : 5;
     }
     {
         OrderView Ov = O; bool ag = as_given; unsigned mh = m_host; const unsigned* mp = m_ptr;
@@ -570,6 +571,14 @@ int32_t enqueue_step(mgfb_ctx* ctx, float dt, unsigned iters, bool from_integrat
     }
     }
     ContactList L = contact_list(ctx);
+    // the chain colouring's per-constraint setup rides on the contact emission (one launch and one pass less)
+    EmitHook H{};
+    const bool count_fused = ctx->cfg.solver_schedule != MGFB_SCHEDULE_PHASES_JP;
+    if (count_fused) {
+        H.gid = B.gid; H.x = B.x; H.col = B.col;
+        H.key = ctx->c_key.as<unsigned long long>(); H.deg = ctx->body_deg.as<unsigned>(); H.inbox = ctx->c_inbox.as<unsigned long long>();
+        H.next = ctx->c_next.as<unsigned>(); H.group = ctx->group.as<int>(); H.cap = ctx->row_cap;
+    }
     TerrainView T{};
     bool caps = ctx->n_capsules > 0, sph = ctx->n_capsules < ctx->n;
     int gp = grid_for(ctx, (size_t)slots * 4);
@@ -581,19 +590,19 @@ int32_t enqueue_step(mgfb_ctx* ctx, float dt, unsigned iters, bool from_integrat
         CU(cudaStreamWaitEvent(ctx->s_aux, ctx->ev_fork, 0));
         if (ctx->prof_on) CU(cudaEventRecord(ctx->prof_ev[9], ctx->s_aux));
         k_terrain_pairs<<<gb, MGFB_THREADS, 0, ctx->s_aux>>>(B.tight, B.col, n, T, TL, ctx->tpair_cap, c);
-        if (sph) k_narrow_terrain<0><<<gp, MGFB_THREADS, 0, ctx->s_aux>>>(B.col, ctx->tpair_list[0].as<int2>(), T, L, ctx->contact_cap, c);
-        if (caps) k_narrow_terrain<1><<<gp, MGFB_THREADS, 0, ctx->s_aux>>>(B.col, ctx->tpair_list[1].as<int2>(), T, L, ctx->contact_cap, c);
+        if (sph) k_narrow_terrain<0><<<gp, MGFB_THREADS, 0, ctx->s_aux>>>(B.col, ctx->tpair_list[0].as<int2>(), T, L, ctx->contact_cap, c, H);
+        if (caps) k_narrow_terrain<1><<<gp, MGFB_THREADS, 0, ctx->s_aux>>>(B.col, ctx->tpair_list[1].as<int2>(), T, L, ctx->contact_cap, c, H);
         if (ctx->prof_on) CU(cudaEventRecord(ctx->prof_ev[10], ctx->s_aux));
         CU(cudaEventRecord(ctx->ev_join, ctx->s_aux));
     }
     // narrowphase, one specialisation per shape pair
     PROF(MGFB_PHASE_NARROW_BODIES);
-    if (sph) k_narrow_bodies<0, 0><<<gp, MGFB_THREADS, 0, ctx->stream>>>(B.col, PL.p[0], L, ctx->contact_cap, c);
+    if (sph) k_narrow_bodies<0, 0><<<gp, MGFB_THREADS, 0, ctx->stream>>>(B.col, PL.p[0], L, ctx->contact_cap, c, H);
     if (sph && caps) {
-        k_narrow_bodies<0, 1><<<gp, MGFB_THREADS, 0, ctx->stream>>>(B.col, PL.p[1], L, ctx->contact_cap, c);
-        k_narrow_bodies<1, 0><<<gp, MGFB_THREADS, 0, ctx->stream>>>(B.col, PL.p[2], L, ctx->contact_cap, c);
+        k_narrow_bodies<0, 1><<<gp, MGFB_THREADS, 0, ctx->stream>>>(B.col, PL.p[1], L, ctx->contact_cap, c, H);
+        k_narrow_bodies<1, 0><<<gp, MGFB_THREADS, 0, ctx->stream>>>(B.col, PL.p[2], L, ctx->contact_cap, c, H);
     }
-    if (caps) k_narrow_bodies<1, 1><<<gp, MGFB_THREADS, 0, ctx->stream>>>(B.col, PL.p[3], L, ctx->contact_cap, c);
+    if (caps) k_narrow_bodies<1, 1><<<gp, MGFB_THREADS, 0, ctx->stream>>>(B.col, PL.p[3], L, ctx->contact_cap, c, H);
     if (ctx->terrain.present) CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
     CU(cudaGetLastError());
     // constraints: colour, build rows in solve order, solve
@@ -601,7 +610,7 @@ int32_t enqueue_step(mgfb_ctx* ctx, float dt, unsigned iters, bool from_integrat
     ManifoldInput M{};
     M.a = L.a; M.b = L.b; M.la = L.la; M.lb = L.lb; M.nt = L.nt; M.user = false;
     M.terrain_center = make_float4(ctx->terrain.x[0], ctx->terrain.x[1], ctx->terrain.x[2], 0.0f);
-    TRY(enqueue_order_and_solve(ctx, O, M, &c->contacts, 0, ctx->contact_cap, false, dt, iters, timed, true));
+    TRY(enqueue_order_and_solve(ctx, O, M, &c->contacts, 0, ctx->contact_cap, false, dt, iters, timed, true, count_fused));
     k_step_done<<<1, 64, 0, ctx->stream>>>(c, ctx->ctr_snap);
     CU(cudaGetLastError());
     // k_integrate, 2x k_grid_insert, scan, k_body_pairs, k_step_done (+ terrain, narrowphase)

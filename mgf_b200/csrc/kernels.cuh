@@ -489,12 +489,20 @@ __global__ void k_face_boxes(const float4* verts, const uint4* faces, unsigned n
 }
 
 // ---------------------------------------------------------------- narrowphase
+// What the chain colouring needs of a fresh constraint (key, body degrees, cleared links: the loop body of k_inc_count), done
+// by the thread that emits the contact: one pass over the contact list and one launch less per step.  NULL key: not fused.
+struct EmitHook {
+    const unsigned* gid; const float4* x; const Collider* col;   // for the key (chain_key)
+    unsigned long long* key; unsigned* deg; unsigned long long* inbox; unsigned* next; int* group; unsigned cap;
+};
+__device__ __forceinline__ void emit_hook(const EmitHook& H, unsigned k, int a, int b, unsigned face, unsigned sub);
 __device__ __forceinline__ void emit_contact(const ContactList& L, unsigned cap, Counters* ctr, int a, int b, unsigned face,
-                                             unsigned sub, V3 la, V3 lb, V3 n, float t) {
+                                             unsigned sub, V3 la, V3 lb, V3 n, float t, const EmitHook& H) {
     unsigned k = atomicAdd(&ctr->contacts, 1u);
     if (k >= cap) { atomicOr(&ctr->overflow, (unsigned)OVF_CONTACTS); return; }
     L.a[k] = a; L.b[k] = b; L.face[k] = face; L.sub[k] = sub;
     L.la[k] = v4(la, n.x); L.lb[k] = v4(lb, n.y); L.nt[k] = make_float4(n.z, t, 0.0f, 0.0f);
+    if (H.key) emit_hook(H, k, a, b, face, sub);
 }
 
 // Body i (receiver, kind KI) vs body j (argument, kind KJ): compound.rs:192-207 resolved per
@@ -517,7 +525,7 @@ __device__ __forceinline__ bool body_pair_contact(const Collider& A, const Colli
 }
 template <int KI, int KJ>
 __global__ void __launch_bounds__(MGFB_THREADS) k_narrow_bodies(const Collider* __restrict__ col, const int2* __restrict__ pairs,
-                                                               ContactList L, unsigned cap, Counters* ctr) {
+                                                               ContactList L, unsigned cap, Counters* ctr, EmitHook H) {
     if (ctr->overflow | ctr->nan_bounds) return;
     unsigned np = ctr->pairs[KI * 2 + KJ];
     for (unsigned p = blockIdx.x * blockDim.x + threadIdx.x; p < np; p += gridDim.x * blockDim.x) {
@@ -527,7 +535,7 @@ __global__ void __launch_bounds__(MGFB_THREADS) k_narrow_bodies(const Collider* 
         if (!body_pair_contact<KI, KJ>(A, Bc, &h, &la, &lb)) continue;
         // ContactPruner with one contact -> Manifold::from(pruner): normal = (0 + n) / 1  (manifold.rs:135-140)
         V3 n = (zero3() + h.n) / 1.0f;
-        emit_contact(L, cap, ctr, ij.x, ij.y, 0u, 0u, la, lb, n, h.t);
+        emit_contact(L, cap, ctr, ij.x, ij.y, 0u, 0u, la, lb, n, h.t, H);
     }
 }
 // Body i vs terrain face f: mesh.rs:119-137 + collision.rs:1490-1506 + compound.rs:179-190.
@@ -551,7 +559,7 @@ __device__ __forceinline__ int body_tri_contacts(const Collider& A, const Tri& t
 }
 template <int KI>
 __global__ void __launch_bounds__(MGFB_THREADS) k_narrow_terrain(const Collider* __restrict__ col, const int2* __restrict__ pairs,
-                                                                TerrainView T, ContactList L, unsigned cap, Counters* ctr) {
+                                                                TerrainView T, ContactList L, unsigned cap, Counters* ctr, EmitHook H) {
     if (ctr->overflow | ctr->nan_bounds) return;
     unsigned np = ctr->tpairs[KI];
     V3 mx = f4v(T.x);
@@ -563,7 +571,7 @@ __global__ void __launch_bounds__(MGFB_THREADS) k_narrow_terrain(const Collider*
         Hit hs[2]; V3 la[2], lb[2];
         int nh = body_tri_contacts<KI>(A, tri, mx, hs, la, lb);
         for (int k = 0; k < nh; ++k) {
-            emit_contact(L, cap, ctr, bf.x, -1, (unsigned)bf.y, (unsigned)k, la[k], lb[k], hs[k].n, hs[k].t);
+            emit_contact(L, cap, ctr, bf.x, -1, (unsigned)bf.y, (unsigned)k, la[k], lb[k], hs[k].n, hs[k].t, H);
             atomicAdd(&ctr->tcontacts, 1u);
         }
     }
@@ -687,24 +695,38 @@ __global__ void __launch_bounds__(MGFB_THREADS) k_order(OrderView O, const unsig
 // parity -- so a class costs about one colour: 7 colours instead of 10 at C2 (the maximum degree is 7), and the
 // chains the colours travel down are 7-10 links deep instead of ~26.  On irregular piles it is neutral (+-1 colour).
 // Depends only on the two bodies' state, which ghosts copy exactly: the same key on every tile.
-__device__ __forceinline__ unsigned long long chain_key(const OrderView& O, unsigned k) {
-    unsigned long long h = order_key(O, k, false);
-    if (!O.x) return h;
-    const int a = O.a[k], b = O.b[k];
+__device__ __forceinline__ unsigned long long chain_key_geo(unsigned long long h, int a, int b, const float4* x, const Collider* col) {
     unsigned cls = 6u;
     if (b >= 0) {
-        float4 xa = O.x[a], xb = O.x[b];
+        float4 xa = x[a], xb = x[b];
         float dx = xa.x - xb.x, dy = xa.y - xb.y, dz = xa.z - xb.z;
         float ax = fabsf(dx), ay = fabsf(dy), az = fabsf(dz);
         unsigned axis = (ay > ax) ? ((az > ay) ? 2u : 1u) : ((az > ax) ? 2u : 0u);
         // parity of the LOWER body's place in a row of touching bodies along that axis: round(x_lo / diameter_lo)
         float ca = axis == 0u ? xa.x : (axis == 1u ? xa.y : xa.z), cb = axis == 0u ? xb.x : (axis == 1u ? xb.y : xb.z);
         const bool lo_a = ca < cb;
-        float q = floorf((lo_a ? ca : cb) / (2.0f * (lo_a ? O.col[a].p0.w : O.col[b].p0.w)) + 0.5f);
+        float q = floorf((lo_a ? ca : cb) / (2.0f * (lo_a ? col[a].p0.w : col[b].p0.w)) + 0.5f);
         unsigned par = (fabsf(q) < 1.0e9f) ? ((unsigned)(long long)q & 1u) : 0u;
         cls = axis * 2u + par;
     }
     return ((unsigned long long)(7u - cls) << 61) | (h >> 3);
+}
+__device__ __forceinline__ unsigned long long chain_key(const OrderView& O, unsigned k) {
+    unsigned long long h = order_key(O, k, false);
+    if (!O.x) return h;
+    return chain_key_geo(h, O.a[k], O.b[k], O.x, O.col);
+}
+// the step path's constraint, initialised by the thread that emitted its contact (same values as k_inc_count computes)
+__device__ __forceinline__ void emit_hook(const EmitHook& H, unsigned k, int a, int b, unsigned face, unsigned sub) {
+    unsigned lo = b >= 0 ? H.gid[b] : (0x80000000u | (face << 1) | sub);
+    unsigned long long h = mix64(((unsigned long long)H.gid[a] << 32) | lo);
+    if (!h) h = 1ULL;
+    H.key[k] = chain_key_geo(h, a, b, H.x, H.col);
+    atomicAdd(&H.deg[a], 1u);
+    if (b >= 0) atomicAdd(&H.deg[b], 1u);
+    H.inbox[k] = 0ULL; H.inbox[H.cap + k] = 0ULL;
+    H.next[k] = 0xffffffffu; H.next[H.cap + k] = 0xffffffffu;
+    H.group[k] = -1;
 }
 struct ColourView {
     unsigned long long* key;     // [m] priority (bijective hash of the constraint's identity)
