@@ -11,10 +11,11 @@ n = len(shapes)
 w = mgf_b200.World(device=0)
 w.add_bodies(shapes, np.ones(n, np.float32), np.full(n, 0.3, np.float32), np.full(n, 0.6, np.float32), np.tile(np.array([0, -9.8, 0], np.float32), (n, 1)))
 w.set_terrain(*scenes.box_terrain(6.0, 10.0, 6.0))
-tot = 0
-for _ in range(40):
-    tot += w.step(np.float32(1 / 60), 8)["constraints"]
-print("constraints", tot)
+tot = 0; paths = {}
+for _ in range(int(os.environ.get("MGFB_SAN_STEPS", "90"))):
+    st = w.step(np.float32(1 / 60), 8)
+    tot += st["constraints"]; paths[st["broadphase_path"]] = paths.get(st["broadphase_path"], 0) + 1
+print("constraints", tot, "broadphase paths (1 coherent, 2 rebuilt, 3 sweep):", paths)
 import ray_cases
 rays, segs, shp = ray_cases.random_queries(500, 1)
 out, hit = mgf_b200.intersections_batch(w.ctx, L.RAY, rays, shp); print("ray hits", int(hit.sum()))
