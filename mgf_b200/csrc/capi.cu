@@ -550,7 +550,7 @@ int32_t enqueue_step(mgfb_ctx* ctx, float dt, unsigned iters, bool from_integrat
         CU(cudaEventRecord(ctx->ev_bp[2], ctx->stream));
         k_bp_filter<<<grid_for(ctx, (size_t)ctx->bp_s_cap / BP_FILTER_ITEMS + 1), MGFB_THREADS, 0, ctx->stream>>>(B.tight, B.fat, V, PL, ctx->pair_cap, c);
         // -- [C] replaced bodies (and ghosts) queried against the cached grid and the overflow list
-        CU(cudaStreamWaitEvent(sC, ctx->ev_bp[1], 0));
+        if (tiled) CU(cudaStreamWaitEvent(sC, ctx->ev_bp[1], 0));   // (only a rebuild's ghost queries need the new grid; untiled worlds have no ghosts)
         CU(cudaStreamWaitEvent(sC, ctx->ev_bp[2], 0));
         k_bp_query<<<grid_for(ctx, (size_t)(BP_REF_CAP / 4 + ctx->ghost_cap) * 32), MGFB_THREADS, 0, sC>>>(B.tight, B.fat, B.col, B.gid, n, G, V, PL, ctx->pair_cap, c);
         k_bp_query_ovf<<<ctx->num_sms * 4, MGFB_THREADS, 0, sC>>>(B.tight, B.fat, B.col, B.gid, n, V, PL, ctx->pair_cap, c);
