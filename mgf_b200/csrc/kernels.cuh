@@ -1400,7 +1400,9 @@ struct DfRow { RowData d; float4 i0, i1, i2, i3, i4; unsigned na, nb, row; float
 #define MGFB_DF_MAX_PHASES 64
 // Block size is chosen at launch: 10 warps/SM measured best while the rows are L2-resident (100 k .. 300 k bodies;
 // 256: +20 %, 384: +6 % solve time), 16 warps/SM once they stream from HBM (> ~1 M rows).
+#ifndef MGFB_DF_THREADS_SMALL
 #define MGFB_DF_THREADS_SMALL 320
+#endif
 #define MGFB_DF_THREADS_LARGE 512
 #define MGFB_DF_LARGE_ROWS 1000000u
 template <bool TILED>
