@@ -125,7 +125,8 @@ int32_t mgfb_synchronize(mgfb_ctx* ctx);
  * shapes[i].v is ignored (a new collider is Moving::sweep(collider, 0)).  world_force is the
  * per-unit-mass force (force = world_force * mass).  *first_id receives the index of the first
  * new body (RigidBodyRef::Dynamic(id)).  Also inserts the fat AABB (bounds + fat_margin) that
- * the demo world keeps in its body BVH (world.rs:178-184). */
+ * the demo world keeps in its body BVH (world.rs:178-184).  A context holds fewer than 2^29 bodies (ghosts included) and
+ * 2^27 constraints per step (bits of the pair and chain-link words); more is MGFB_ERR_CAPACITY. */
 int32_t mgfb_bodies_add(mgfb_ctx* ctx, uint32_t n, const mgfb_shape* shapes, const float* mass,
                         const float* restitution, const float* friction, const float* world_force /* n*3 */,
                         uint32_t* first_id);

@@ -825,6 +825,7 @@ int32_t mgfb_bodies_add(mgfb_ctx* ctx, uint32_t n, const mgfb_shape* shapes, con
     if (!ctx) return MGFB_ERR_INVALID_ARG;
     if (n == 0) { if (first_id) *first_id = ctx->n; return MGFB_OK; }
     if (!shapes || !mass || !restitution || !friction || !world_force) return fail(ctx, MGFB_ERR_INVALID_ARG, "null input array");
+    if ((unsigned long long)ctx->n + n >= (1ULL << 29)) return fail(ctx, MGFB_ERR_CAPACITY, "a context holds fewer than 2^29 bodies (bits of the pair words)");
     CU(cudaSetDevice(ctx->device));
     std::vector<float4> hx(n), hq(n), hforce(n), htorque(n), himb((size_t)n * 3);
     std::vector<BodyVel> hvel(n);
