@@ -357,8 +357,10 @@ def phase_rooflines(g, torch, flush, dt, iters, nsteps, peak):
         bytes_ = {
             "integrate": 272.0 * st["bodies"],
             "body_grid": None, "pair_sweep": None, "colouring": None,
-            "narrow_bodies": 64.0 * pb[0] + 72.0 * (pb[1] + pb[2]) + 88.0 * pb[3] + 64.0 * pr["body_contacts"],
-            "terrain": 72.0 * tp[0] + 84.0 * tp[1] + 64.0 * pr["terrain_contacts"],
+            # (+ 76 B per contact: the chain colouring's per-constraint setup -- key 8, links 24, group 4, two degree counters 8, the two
+            # positions the key's class is read from 32 -- is done by the thread that emits the contact since round 2)
+            "narrow_bodies": 64.0 * pb[0] + 72.0 * (pb[1] + pb[2]) + 88.0 * pb[3] + (64.0 + 76.0) * pr["body_contacts"],
+            "terrain": 72.0 * tp[0] + 84.0 * tp[1] + (64.0 + 44.0) * pr["terrain_contacts"],
             "build_rows": (2 * 84.0 + 64.0 + 100.0) * st["constraints"],
             "solve": ALGO_BYTES_PER_CONSTRAINT_ITER * st["constraints"] * iters,
         }
